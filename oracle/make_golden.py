@@ -1,0 +1,187 @@
+"""ORACLE SCAFFOLDING — regenerates tests/golden/* from the UNMODIFIED reference code.
+
+Run in the build container only (`python oracle/make_golden.py`); needs /root/reference.
+The fixtures are small: network weights are not stored, they are re-derived on any machine
+from `seeded_state()` (numpy PCG64, platform independent), only inputs/outputs/losses/gradient
+digests are.  tests/test_oracle_vs_golden.py replays them through oracle/resenc_oracle.py
+(CPU) and tests/test_gpu_parity.py through the CUDA product path.
+"""
+import hashlib
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import reference_loader as rl          # noqa: E402
+from oracle import resenc_oracle as O              # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+NET_CASES = {
+    # name: (patch, in_channels, tasks, model_config, se_reduce_dims, batch)
+    "sheet_normals_16": ([16, 16, 16], 1,
+                         {"sheet": {"channels": 1, "activation": "sigmoid"},
+                          "normals": {"channels": 3, "activation": "none"}}, {}, "all", 2),
+    "ink_se_16": ([16, 16, 16], 4, {"ink": {"channels": 1, "activation": "sigmoid"}},
+                  {"squeeze_excitation": True, "conv_bias": True}, "all", 2),
+    "ink_se23_16": ([16, 16, 16], 4, {"ink": {"channels": 1, "activation": "sigmoid"}},
+                    {"squeeze_excitation": True}, (2, 3), 1),
+    "aniso_8x32x32": ([8, 32, 32], 1, {"sheet": {"channels": 2, "activation": "softmax"}}, {}, "all", 1),
+    "affine_16": ([16, 16, 16], 2, {"sheet": {"channels": 1, "activation": "none"}},
+                  {"norm_op_kwargs": {"affine": True, "eps": 1e-5}}, "all", 1),
+}
+
+
+def seeded_state(named_shapes, seed):
+    """Deterministic, platform-independent weights for a list of (name, shape)."""
+    out = {}
+    for name, shape in named_shapes:
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        shape = tuple(shape)
+        if len(shape) > 1:
+            fan_in = int(np.prod(shape[1:]))
+            if "transpconvs" in name:
+                fan_in = int(shape[0])
+            b = 1.0 / np.sqrt(fan_in)
+            a = rng.uniform(-b, b, size=shape)
+        elif name.endswith("norm.weight"):
+            a = 1.0 + rng.uniform(-0.2, 0.2, size=shape)
+        else:
+            a = rng.uniform(-0.1, 0.1, size=shape)
+        out[name] = torch.from_numpy(a.astype(np.float32))
+    return out
+
+
+def seeded_inputs(case, seed=1234):
+    patch, cin, tasks, _, _, batch = NET_CASES[case]
+    rng = np.random.default_rng([seed, zlib.crc32(case.encode())])
+    x = rng.random((batch, cin, *patch), dtype=np.float32)
+    tgt = {}
+    for t, info in tasks.items():
+        c = info["channels"]
+        if t == "normals":
+            v = rng.standard_normal((batch, c, *patch)).astype(np.float32)
+            v /= np.linalg.norm(v, axis=1, keepdims=True)
+            tgt[t] = v
+        else:
+            tgt[t] = (rng.random((batch, c, *patch)) > 0.8).astype(np.float32)
+    return x, tgt
+
+
+def loss_for(task, pred, target):
+    if task == "normals":
+        return O.masked_cosine_loss(pred, target)
+    return O.bce_dice_loss(pred, target)
+
+
+def unique_named_params(model):
+    return [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+
+
+def make_net_case(case):
+    patch, cin, tasks, mc, rd, batch = NET_CASES[case]
+    model = rl.build_reference(rl.make_mgr(patch, tasks, in_channels=cin, batch=batch, model_config=mc),
+                               se_reduce_dims=rd)
+    names = unique_named_params(model)
+    st = seeded_state(names, seed=7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(st[n])
+    x, tgt = seeded_inputs(case)
+    xt = torch.from_numpy(x)
+    model.train()
+    out = model(xt)
+    # reference losses through the reference's own loss classes (training/losses/losses.py)
+    losses_mod = rl.reference_module("training/losses/losses.py", "ref_losses")
+    total = 0.0
+    per = {}
+    for t in tasks:
+        fn = losses_mod.MaskedCosineLoss() if t == "normals" else losses_mod.BCEDiceLoss(0.5, 0.5)
+        l = fn(out[t], torch.from_numpy(tgt[t]))
+        per[t] = float(l)
+        total = total + l
+    total.backward()
+    grads = {n: p.grad for n, p in model.named_parameters()}
+    gnorm = np.array([0.0 if grads[n] is None else float(grads[n].double().norm()) for n, _ in names])
+    has_grad = np.array([grads[n] is not None for n, _ in names])
+    model.eval()
+    with torch.no_grad():
+        ev = model(xt)
+    rec = {"x": x, "loss_total": np.float64(float(total)), "grad_norms": gnorm, "has_grad": has_grad,
+           "param_names": np.array([n for n, _ in names])}
+    # a few full gradients (first conv, a deep conv, a transposed conv, a head)
+    picks = [n for n, _ in names if n.endswith("stem.convs.0.conv.weight")
+             or n.endswith("stages.1.blocks.0.conv1.conv.weight")
+             or n.endswith("transpconvs.0.weight") or "seg_layers" in n and n.endswith(".1.weight")
+             or n.endswith("squeeze_excitation.fc1.weight") and ".stages.1.blocks.0." in n]
+    for n in picks:
+        if grads[n] is not None and grads[n].numel() <= 200000:
+            rec["grad::" + n] = grads[n].numpy()
+    for t in tasks:
+        rec["target::" + t] = tgt[t]
+        rec["train::" + t] = out[t].detach().numpy()
+        rec["eval::" + t] = ev[t].numpy()
+        rec["loss::" + t] = np.float64(per[t])
+    np.savez_compressed(os.path.join(GOLD, f"net_{case}.npz"), **rec)
+    # state-dict key census (drop-in contract)
+    keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, f"keys_{case}.json"), "w") as f:
+        json.dump({"state_dict": keys, "parameters": [[n, list(s)] for n, s in names]}, f)
+    print(case, "loss", float(total), {t: per[t] for t in per}, "params", len(names), "keys", len(keys))
+
+
+def sha16(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def make_host_goldens():
+    gen = rl.reference_function("helpers.py", "generate_positions")
+    pos_cases = [((1024,) * 3, (128,) * 3, 0.5), ((1000,) * 3, (128,) * 3, 0.5),
+                 ((300, 200, 130), (128,) * 3, 0.25), ((2000, 1500, 1750), (64, 192, 192), 0.05),
+                 ((256,) * 3, (128,) * 3, 0.1), ((128, 128, 128), (128,) * 3, 0.5),
+                 ((130, 257, 129), (64, 128, 64), 0.5), ((96, 96, 96), (32, 32, 32), 0.3)]
+    pos = []
+    for vol, patch, ov in pos_cases:
+        # inference_dataset.py:44-56 executed literally with the reference's generate_positions
+        steps = [int(round(p * (1 - ov))) for p in patch]
+        axes = [gen(0, vol[i], patch[i], steps[i]) for i in range(3)]
+        table = np.array([(z, y, x) for z in axes[0] for y in axes[1] for x in axes[2]], dtype=np.int64)
+        pos.append({"vol": list(vol), "patch": list(patch), "overlap": ov, "steps": steps,
+                    "axes": [list(map(int, a)) for a in axes], "count": int(len(table)),
+                    "sha1": sha16(table)})
+    ih = rl.reference_module("inference/helpers.py", "ref_inf_helpers")
+    gau = []
+    for tile in [(128, 128, 128), (64, 64, 64), (64, 192, 192), (32, 32, 32), (16, 24, 40), (14, 256, 256)]:
+        g = ih.compute_gaussian_3d(tile).numpy()
+        gau.append({"tile": list(tile), "sha1": sha16(g), "sum": float(g.astype(np.float64).sum()),
+                    "min": float(g.min()), "max": float(g.max()),
+                    "argmax": [int(i) for i in np.unravel_index(g.argmax(), g.shape)],
+                    "edge_center": float(g[0, tile[1] // 2, tile[2] // 2])})
+    np.save(os.path.join(GOLD, "gaussian_16x24x40.npy"), ih.compute_gaussian_3d((16, 24, 40)).numpy())
+    topo = []
+    for patch in [(64, 64, 64), (96, 96, 96), (128, 128, 128), (192, 192, 192), (14, 256, 256), (16, 16, 16),
+                  (8, 32, 32), (32, 64, 160)]:
+        um = rl.reference_module("builders/utils.py", "ref_utils")
+        npa, strides, kernels, final, div = um.get_pool_and_conv_props((1.0, 1.0, 1.0), list(patch), 4, 999999)
+        topo.append({"patch": list(patch), "num_pool": [int(v) for v in npa],
+                     "strides": [list(map(int, s)) for s in strides],
+                     "kernels": [list(map(int, k)) for k in kernels],
+                     "final_patch": [int(v) for v in final],
+                     "blocks": um.get_n_blocks_per_stage(len(strides))})
+    with open(os.path.join(GOLD, "host_goldens.json"), "w") as f:
+        json.dump({"positions": pos, "gaussian": gau, "topology": topo}, f, indent=1)
+    print("host goldens:", len(pos), "position cases,", len(gau), "gaussian,", len(topo), "topology")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    make_host_goldens()
+    for c in NET_CASES:
+        make_net_case(c)
