@@ -1,0 +1,285 @@
+// Shape-generic implicit-GEMM gather convolution and weight-gradient kernels on the legacy
+// warp-level tensor path (mma.sync m16n8k16 bf16, fp32 accumulate).  They take any channel
+// count that is a multiple of 8 and any grid, and serve (a) shapes the tcgen05 kernels do not
+// cover (Cout < 32, C % 16 != 0, bottleneck widths) and (b) as the on-device cross-check the
+// GPU tests run the tcgen05 kernels against.  Same operand conventions as conv_tc5.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+struct GConvParams {
+    const bf16* src[2];
+    int srcC[2];
+    int nsrc;
+    int ID, IH, IW, NB;  // input grid
+    const bf16* w;       // [taps][Nout][Ctot]
+    int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
+    int OD, OH, OW;  // output class grid
+    int Nout;
+    int mode, ostrD, ostrH, ostrW, ooffD, ooffH, ooffW, FD, FH, FW;
+    bf16* out0;
+    bf16* out1;
+    int outC0, outC1, psC, psD, psH, psW;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+static constexpr int GC_BM = 128, GC_BN = 64, GC_BK = 32, GC_PITCH = 40, GC_THREADS = 256;
+
+__global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConvParams p) {
+    __shared__ __align__(16) bf16 As[GC_BM * GC_PITCH];
+    __shared__ __align__(16) bf16 Bs[GC_BN * GC_PITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp & 3, warp_n = warp >> 2;
+    const long long Mtot = (long long)p.NB * p.OD * p.OH * p.OW;
+    const long long m0 = (long long)blockIdx.x * GC_BM;
+    const int n0 = blockIdx.y * GC_BN;
+    const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
+    const int ntaps = p.tapD * p.tapH * p.tapW;
+    const int kchunks = (Ctot + GC_BK - 1) / GC_BK;
+    const int nIt = ntaps * kchunks;
+
+    // the two A rows this thread stages, decomposed once
+    int rnb[2], rod[2], roh[2], row_[2];
+    bool rvalid[2];
+    const int kvec = tid & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = (tid >> 2) + i * 64;
+        long long m = m0 + r;
+        rvalid[i] = m < Mtot;
+        if (!rvalid[i]) m = 0;
+        row_[i] = (int)(m % p.OW); m /= p.OW;
+        roh[i] = (int)(m % p.OH); m /= p.OH;
+        rod[i] = (int)(m % p.OD); m /= p.OD;
+        rnb[i] = (int)m;
+    }
+    const int bn = tid >> 2;  // B row staged by this thread
+
+    uint4 ra[2], rb_;
+    auto prefetch = [&](int it) {
+        const int t = it / kchunks, kc = it - t * kchunks;
+        const int kw = t % p.tapW, kh = (t / p.tapW) % p.tapH, kd = t / (p.tapW * p.tapH);
+        const int c = kc * GC_BK + kvec * 8;
+        const bf16* sp = p.src[0];
+        int cs = c, sC = p.srcC[0];
+        if (p.nsrc > 1 && c >= p.srcC[0]) { sp = p.src[1]; cs = c - p.srcC[0]; sC = p.srcC[1]; }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int iz = rod[i] * p.istrD + p.offD + kd;
+            const int iy = roh[i] * p.istrH + p.offH + kh;
+            const int ix = row_[i] * p.istrW + p.offW + kw;
+            const bool ok = rvalid[i] && c < Ctot && iz >= 0 && iz < p.ID && iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW;
+            ra[i] = make_uint4(0, 0, 0, 0);
+            if (ok) {
+                const size_t vox = (((size_t)rnb[i] * p.ID + iz) * p.IH + iy) * p.IW + ix;
+                ra[i] = __ldg(reinterpret_cast<const uint4*>(sp + vox * sC + cs));
+            }
+        }
+        rb_ = make_uint4(0, 0, 0, 0);
+        if (n0 + bn < p.Nout && c < Ctot)
+            rb_ = __ldg(reinterpret_cast<const uint4*>(p.w + ((size_t)t * p.Nout + n0 + bn) * Ctot + c));
+    };
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+    prefetch(0);
+    for (int it = 0; it < nIt; ++it) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<uint4*>(&As[((tid >> 2) + i * 64) * GC_PITCH + kvec * 8]) = ra[i];
+        *reinterpret_cast<uint4*>(&Bs[bn * GC_PITCH + kvec * 8]) = rb_;
+        __syncthreads();
+        if (it + 1 < nIt) prefetch(it + 1);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int r = warp_m * 32 + mi * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                const int c = ks * 16 + (lane >> 4) * 8;
+                ldsm_x4(smem_u32(&As[r * GC_PITCH + c]), af[mi][0], af[mi][1], af[mi][2], af[mi][3]);
+            }
+            uint32_t bfr[4][2];
+#pragma unroll
+            for (int nj = 0; nj < 2; ++nj) {
+                const int r = warp_n * 32 + nj * 16 + (lane >> 4) * 8 + (lane & 7);
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldsm_x4(smem_u32(&Bs[r * GC_PITCH + c]), bfr[nj * 2][0], bfr[nj * 2][1], bfr[nj * 2 + 1][0],
+                        bfr[nj * 2 + 1][1]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(acc[mi][ni], af[mi], bfr[ni][0], bfr[ni][1]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = warp_m * 32 + mi * 16 + half * 8 + g;
+            long long m = m0 + r;
+            if (m >= Mtot) continue;
+            const int ow = (int)(m % p.OW); m /= p.OW;
+            const int oh = (int)(m % p.OH); m /= p.OH;
+            const int od = (int)(m % p.OD); m /= p.OD;
+            const int nb = (int)m;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int col = n0 + warp_n * 32 + ni * 8 + q * 2;
+                if (col >= p.Nout) continue;
+                int fd, fh, fw, ch;
+                if (p.mode == 1) {
+                    const int par = col / p.psC;
+                    ch = col - par * p.psC;
+                    const int pw = par % p.psW, ph = (par / p.psW) % p.psH, pd = par / (p.psW * p.psH);
+                    fd = od * p.ostrD + pd; fh = oh * p.ostrH + ph; fw = ow * p.ostrW + pw;
+                } else {
+                    ch = col;
+                    fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
+                }
+                const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
+                bf16* dst = (ch < p.outC0) ? p.out0 + vox * p.outC0 + ch : p.out1 + vox * p.outC1 + (ch - p.outC0);
+                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight gradient:  dW[tap][a][b] += sum_m P[m][a] * Q[gather(m, tap)][b]
+//   conv wgrad : P = dy (a = Cout) on the output grid, Q = x (b = Cin, two sources allowed)
+//   convT wgrad: P = x  (a = Cin) on the input grid,  Q = dy gathered at 2i+p (b = Cout)
+// fp32 atomics into a zero-initialised [taps][A][B] buffer (split over the voxel dimension).
+// ---------------------------------------------------------------------------------------
+struct GWgradParams {
+    const bf16* P; int PC;        // [NB, GD, GH, GW, PC]
+    const bf16* Q[2]; int QC[2]; int nq;   // gathered operand(s), grid QD x QH x QW
+    int NB, GD, GH, GW, QD, QH, QW;
+    int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
+    float* dw;                    // [taps][PC][QCtot]
+    int mPerSplit;                // voxels handled by one blockIdx.z
+};
+
+static constexpr int GW_BA = 64, GW_BB = 64, GW_BK = 32, GW_PITCH = 72;
+
+__global__ void __launch_bounds__(256) gather_wgrad_mma_kernel(const GWgradParams p) {
+    __shared__ __align__(16) bf16 Ps[GW_BK * GW_PITCH];
+    __shared__ __align__(16) bf16 Qs[GW_BK * GW_PITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_a = warp & 3, warp_b = warp >> 2;
+    const int QCtot = p.QC[0] + (p.nq > 1 ? p.QC[1] : 0);
+    const int tilesB = (QCtot + GW_BB - 1) / GW_BB;
+    const int a0 = (blockIdx.x / tilesB) * GW_BA;
+    const int b0 = (blockIdx.x % tilesB) * GW_BB;
+    const int t = blockIdx.y;
+    const int kw = t % p.tapW, kh = (t / p.tapW) % p.tapH, kd = t / (p.tapW * p.tapH);
+    const long long Mtot = (long long)p.NB * p.GD * p.GH * p.GW;
+    const long long mBeg = (long long)blockIdx.z * p.mPerSplit;
+    const long long mEnd = min(Mtot, mBeg + p.mPerSplit);
+    if (mBeg >= mEnd) return;
+
+    const int lr = tid >> 3, lv = tid & 7;  // staged row (voxel within chunk) and 16-byte vector
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    uint4 rp, rq;
+    auto prefetch = [&](long long mc) {
+        const long long m = mc + lr;
+        rp = make_uint4(0, 0, 0, 0);
+        rq = make_uint4(0, 0, 0, 0);
+        if (m < mEnd) {
+            long long mm = m;
+            const int gw = (int)(mm % p.GW); mm /= p.GW;
+            const int gh = (int)(mm % p.GH); mm /= p.GH;
+            const int gd = (int)(mm % p.GD); mm /= p.GD;
+            const int nb = (int)mm;
+            const int ca = a0 + lv * 8;
+            if (ca < p.PC) rp = __ldg(reinterpret_cast<const uint4*>(p.P + (size_t)m * p.PC + ca));
+            const int qz = gd * p.istrD + p.offD + kd, qy = gh * p.istrH + p.offH + kh, qx = gw * p.istrW + p.offW + kw;
+            const int cb = b0 + lv * 8;
+            if (cb < QCtot && qz >= 0 && qz < p.QD && qy >= 0 && qy < p.QH && qx >= 0 && qx < p.QW) {
+                const bf16* qp = p.Q[0];
+                int cs = cb, qc = p.QC[0];
+                if (p.nq > 1 && cb >= p.QC[0]) { qp = p.Q[1]; cs = cb - p.QC[0]; qc = p.QC[1]; }
+                const size_t vox = (((size_t)nb * p.QD + qz) * p.QH + qy) * p.QW + qx;
+                rq = __ldg(reinterpret_cast<const uint4*>(qp + vox * qc + cs));
+            }
+        }
+    };
+
+    prefetch(mBeg);
+    for (long long mc = mBeg; mc < mEnd; mc += GW_BK) {
+        *reinterpret_cast<uint4*>(&Ps[lr * GW_PITCH + lv * 8]) = rp;
+        *reinterpret_cast<uint4*>(&Qs[lr * GW_PITCH + lv * 8]) = rq;
+        __syncthreads();
+        if (mc + GW_BK < mEnd) prefetch(mc + GW_BK);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[4];
+            {
+                // A'[a][k] stored as Ps[k][a]: transposed 8x8 loads
+                const int kr = ks * 16 + (lane >> 4) * 8 + (lane & 7);
+                const int ac = warp_a * 16 + ((lane >> 3) & 1) * 8;
+                ldsm_x4_t(smem_u32(&Ps[kr * GW_PITCH + ac]), af[0], af[1], af[2], af[3]);
+            }
+#pragma unroll
+            for (int nj = 0; nj < 2; ++nj) {
+                uint32_t b00, b01, b10, b11;
+                const int kr = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                const int bc = warp_b * 32 + nj * 16 + (lane >> 4) * 8;
+                ldsm_x4_t(smem_u32(&Qs[kr * GW_PITCH + bc]), b00, b01, b10, b11);
+                mma_bf16_16816(acc[nj * 2], af, b00, b01);
+                mma_bf16_16816(acc[nj * 2 + 1], af, b10, b11);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int a = a0 + warp_a * 16 + half * 8 + g;
+            const int b = b0 + warp_b * 32 + ni * 8 + q * 2;
+            if (a < p.PC) {
+                float* d = p.dw + ((size_t)t * p.PC + a) * QCtot + b;
+                if (b < QCtot) atomicAdd(d, acc[ni][half * 2]);
+                if (b + 1 < QCtot) atomicAdd(d + 1, acc[ni][half * 2 + 1]);
+            }
+        }
+    }
+}
+
+}  // namespace rb

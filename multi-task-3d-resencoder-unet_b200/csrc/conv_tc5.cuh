@@ -1,0 +1,278 @@
+// tcgen05 / TMEM / TMA implicit-GEMM "gather convolution" for sm_100a.
+//
+// One kernel covers every dense contraction of the ResEnc U-Net forward and data-gradient:
+//   out[m, n] = sum_{tap, c} A[src(m, tap), c] * W[tap][n][c]
+// where m runs over a grid of output voxels (N, OD, OH, OW), the input coordinate of a tap
+// is  i = o * istr + off + k  (out-of-range => 0, provided by TMA zero fill), A is the
+// channels-last bf16 activation (optionally two tensors concatenated along C) and W the
+// packed bf16 weight [taps][Nout][Ctot].
+//
+// Reference ops realised through it (reference file:line):
+//   Conv3d k3 s1/s2 fprop        simple_conv_blocks.py:43-51   (istr = stride, off = -1)
+//   Conv3d k1 fprop (skip, bottleneck)  resblocks.py:97-100,187-195
+//   Conv3d dgrad (stride 1: flipped taps; stride 2: 8 output-parity classes)
+//   ConvTranspose3d k=s=2 fprop   decoder.py:110-113 (pixel-shuffle epilogue, N = 8*Cout)
+//   ConvTranspose3d dgrad         (= k2 s2 p0 conv)
+//   cat((up, skip), 1)            decoder.py:147 (two A sources, no copy)
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2..5 epilogue.
+// A tile  = 128 output voxels (tw x th x td x tn box) x KW channels, landed by one 5-D TMA
+// box per (tap, channel chunk) in the canonical K-major swizzled layout UMMA consumes.
+// Accumulators live in TMEM, double buffered (2 x Ntile fp32 columns) so the epilogue of tile
+// i overlaps the MMAs of tile i+1.  Persistent grid, static round-robin tile schedule.
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+struct Tc5ConvParams {
+    CUtensorMap mapA[2];  // rank 5 (C, W, H, D, N)
+    CUtensorMap mapB;     // rank 3 (Ctot, Nout, taps)
+    int nsrc, srcC[2];
+    int KW;  // K elements per pipeline step (16/32/64) == swizzle span / 2
+    int tapD, tapH, tapW;
+    int offD, offH, offW;
+    int istrD, istrH, istrW;
+    int tw, th, td, tn;  // tile box, product 128
+    int tilesW, tilesH, tilesD, tilesNB;
+    int OW, OH, OD, NB;  // output class grid
+    int Nout, Ntile, nTilesN;
+    int mode;  // 0 direct, 1 pixel shuffle (column = parity * psC + channel)
+    int ostrD, ostrH, ostrW, ooffD, ooffH, ooffW;
+    int FD, FH, FW;  // full output spatial dims
+    bf16* out0;
+    bf16* out1;
+    int outC0, outC1;  // channel split of the destination (out1 may be null)
+    int psC;
+    int psD, psH, psW;  // pixel-shuffle factors per dim (1 or 2)
+    int stages;
+    float* stat_sum;  // optional [NB][Nout] per-(n,c) sum of outputs   (fp32, atomics)
+    float* stat_sq;   // optional [NB][Nout] per-(n,c) sum of squares
+};
+
+static constexpr int TC5_THREADS = 192;
+
+__global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const __grid_constant__ Tc5ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: barriers first (small), then 1024-aligned tiles
+    // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
+    uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
+    // full[8], empty[8], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + 192);
+    uint8_t* tiles = smem_al + 1024;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t bytesA = 128u * p.KW * 2u;
+    const uint32_t bytesB = (uint32_t)p.Ntile * p.KW * 2u;
+    const uint32_t stageBytes = bytesA + bytesB;
+    const uint32_t tile_base = smem_u32(tiles);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * p.Ntile) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA[0]);
+        if (p.nsrc > 1) tma_prefetch_desc(&p.mapA[1]);
+        tma_prefetch_desc(&p.mapB);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int spatialTiles = p.tilesW * p.tilesH * p.tilesD * p.tilesNB;
+    const int totalTiles = spatialTiles * p.nTilesN;
+    const int ntaps = p.tapD * p.tapH * p.tapW;
+    const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+                // n-tile fastest so CTAs that share an activation tile run close in time (L2 reuse)
+                const int nt = tile % p.nTilesN;
+                int sp = tile / p.nTilesN;
+                const int tiw = sp % p.tilesW; sp /= p.tilesW;
+                const int tih = sp % p.tilesH; sp /= p.tilesH;
+                const int tid = sp % p.tilesD; sp /= p.tilesD;
+                const int tib = sp;
+                const int ow0 = tiw * p.tw, oh0 = tih * p.th, od0 = tid * p.td, nb0 = tib * p.tn;
+                const int n0 = nt * p.Ntile;
+                for (int t = 0; t < ntaps; ++t) {
+                    const int kw = t % p.tapW;
+                    const int kh = (t / p.tapW) % p.tapH;
+                    const int kd = t / (p.tapW * p.tapH);
+                    const int ix = ow0 * p.istrW + p.offW + kw;
+                    const int iy = oh0 * p.istrH + p.offH + kh;
+                    const int iz = od0 * p.istrD + p.offD + kd;
+                    int cbase = 0;
+                    for (int s = 0; s < p.nsrc; ++s) {
+                        for (int c = 0; c < p.srcC[s]; c += p.KW) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY);
+                            const uint32_t dstA = tile_base + stage * stageBytes;
+                            const uint32_t dstB = dstA + bytesA;
+                            mbar_expect_tx(full_bar(stage), stageBytes);
+                            tma_load_5d(dstA, &p.mapA[s], full_bar(stage), c, ix, iy, iz, nb0);
+                            tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);
+                            if (++stage == S) { stage = 0; phase ^= 1u; }
+                        }
+                        cbase += p.srcC[s];
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
+            const uint32_t lay = swizzle_layout_code(p.KW * 2);
+            const uint32_t sbo = 8u * p.KW * 2u;  // 8 rows of one swizzle span
+            const int kPerStep = p.KW / 16;
+            const int stepsPerTile = ntaps * (Ctot / p.KW);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
+                for (int ks = 0; ks < stepsPerTile; ++ks) {
+                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL);
+                    tc_fence_after();
+                    const uint32_t aAddr = tile_base + stage * stageBytes;
+                    const uint32_t bAddr = aAddr + bytesA;
+                    for (int k = 0; k < kPerStep; ++k) {
+                        const uint64_t da = make_smem_desc(aAddr + k * 32u, 16u, sbo, lay);
+                        const uint64_t db = make_smem_desc(bAddr + k * 32u, 16u, sbo, lay);
+                        umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int iw = row % p.tw;
+        const int ih = (row / p.tw) % p.th;
+        const int id = (row / (p.tw * p.th)) % p.td;
+        const int in = row / (p.tw * p.th * p.td);
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            const int nt = tile % p.nTilesN;
+            int sp = tile / p.nTilesN;
+            const int tiw = sp % p.tilesW; sp /= p.tilesW;
+            const int tih = sp % p.tilesH; sp /= p.tilesH;
+            const int tid = sp % p.tilesD; sp /= p.tilesD;
+            const int tib = sp;
+            const int ow = tiw * p.tw + iw, oh = tih * p.th + ih, od = tid * p.td + id, nb = tib * p.tn + in;
+            const bool valid = (ow < p.OW) && (oh < p.OH) && (od < p.OD) && (nb < p.NB);
+            const int n0 = nt * p.Ntile;
+
+            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.Ntile);
+            for (int cg = 0; cg < p.Ntile; cg += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_addr + cg, v);
+                tmem_ld_wait();
+                const int col0 = n0 + cg;
+                if (col0 < p.Nout) {
+                    if (p.stat_sum != nullptr) {
+                        // per-(sample, channel) sum / sum of squares over the 32 rows of this warp;
+                        // rows of one warp may straddle samples only when tn > 1, handled per lane.
+#pragma unroll 4
+                        for (int j = 0; j < 32; ++j) {
+                            float x = valid ? __uint_as_float(v[j]) : 0.f;
+                            float s1, s2;
+                            if (p.tn == 1) {
+                                s1 = warp_sum(x);
+                                s2 = warp_sum(x * x);
+                                if (lane == 0 && col0 + j < p.Nout) {
+                                    atomicAdd(p.stat_sum + (size_t)nb * p.Nout + col0 + j, s1);
+                                    atomicAdd(p.stat_sq + (size_t)nb * p.Nout + col0 + j, s2);
+                                }
+                            } else if (valid && col0 + j < p.Nout) {
+                                atomicAdd(p.stat_sum + (size_t)nb * p.Nout + col0 + j, x);
+                                atomicAdd(p.stat_sq + (size_t)nb * p.Nout + col0 + j, x * x);
+                            }
+                        }
+                    }
+                    if (valid) {
+                        int fd, fh, fw, ch0;
+                        if (p.mode == 1) {
+                            const int par = col0 / p.psC;
+                            ch0 = col0 - par * p.psC;
+                            const int pw = par % p.psW;
+                            const int ph = (par / p.psW) % p.psH;
+                            const int pd = par / (p.psW * p.psH);
+                            fd = od * p.ostrD + pd; fh = oh * p.ostrH + ph; fw = ow * p.ostrW + pw;
+                        } else {
+                            ch0 = col0;
+                            fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
+                        }
+                        const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
+                        bf16* dst;
+                        int lim;  // channels available from ch0 in the chosen destination
+                        if (ch0 < p.outC0) { dst = p.out0 + vox * p.outC0 + ch0; lim = p.outC0 - ch0; }
+                        else { dst = p.out1 + vox * p.outC1 + (ch0 - p.outC0); lim = p.outC1 - (ch0 - p.outC0); }
+                        if (p.mode == 1) lim = min(lim, p.psC - ch0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q * 8 < lim) {
+                                uint4 o;
+                                o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                                o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                                o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                                o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                                *reinterpret_cast<uint4*>(dst + q * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace rb

@@ -1,0 +1,549 @@
+// HBM-bound kernels of the ResEnc U-Net hot path: InstanceNorm statistics, the fused
+// normalise + affine/SE-gate + residual + LeakyReLU pass and its backward, AvgPool, the
+// 1x1x1 task heads, stem im2col and weight (un)packing.  All activations are channels-last
+// (NDHWC) bf16 with C % 8 == 0; every access is a 16-byte vector, coalesced along C.
+//
+// Reference arithmetic (file:line in /root/reference):
+//   InstanceNorm3d(affine=False|True, eps)          build_network_from_config.py:172, simple_conv_blocks.py:58-60
+//   LeakyReLU(0.01), out += residual                 resblocks.py:76,113-114
+//   SqueezeExcite gate (DNA, not vendored)           resblocks.py:86-87,111-112
+//   AvgPool3d(stride, stride) in the ResNet-D skip   resblocks.py:92-95
+//   seg head Conv3d(C, classes, 1, bias=True)        decoder.py:131,151-152
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+    f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    return o;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-(sample, [w], channel) reductions.  out is double [NB][G][C][2] with G = 1 or W.
+//   kind 0: (sum y, sum y^2)                        -> InstanceNorm statistics / SE squeeze
+//   kind 1: (sum g, sum g*y), g = dz * lrelu'(z)    -> InstanceNorm / gate / affine backward
+// grid = (blocks per sample, NB); a block strides over voxels, thread = (voxel row, 8 channels).
+// ---------------------------------------------------------------------------------------
+struct ReduceParams {
+    const bf16* y;   // [NB, S, C]
+    const bf16* dz;  // kind 1
+    const bf16* z;   // kind 1 with act: sign source (may be null => g = dz)
+    double* out;
+    long long S;
+    int C, W, perW;
+    float slope;
+    int kind;
+};
+
+__global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p) {
+    extern __shared__ float red[];  // [rows][cg*16]
+    const int cg = p.C >> 3;
+    const int rows = 256 / cg > 0 ? 256 / cg : 1;
+    const int nb = blockIdx.y;
+    // when C/8 > 256 a thread loops over several channel groups
+    for (int cbase = 0; cbase < cg; cbase += 256) {
+        const int mycg = cbase + (threadIdx.x % (cg < 256 ? cg : 256));
+        const int myrow = threadIdx.x / (cg < 256 ? cg : 256);
+        const bool active = myrow < rows && mycg < cg;
+        if (!p.perW) {
+            float s1[8], s2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            if (active) {
+                const size_t base = (size_t)nb * p.S;
+                for (long long v = (long long)blockIdx.x * rows + myrow; v < p.S; v += (long long)gridDim.x * rows) {
+                    const size_t off = (base + v) * p.C + (size_t)mycg * 8;
+                    float a[8], b[8];
+                    unpack8(ld_stream(reinterpret_cast<const uint4*>(p.y + off)), a);
+                    if (p.kind == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
+                    } else {
+                        unpack8(ld_stream(reinterpret_cast<const uint4*>(p.dz + off)), b);
+                        if (p.z != nullptr) {
+                            float zz[8];
+                            unpack8(ld_stream(reinterpret_cast<const uint4*>(p.z + off)), zz);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) b[j] = zz[j] > 0.f ? b[j] : b[j] * p.slope;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s1[j] += b[j]; s2[j] += b[j] * a[j]; }
+                    }
+                }
+            }
+            // reduce over rows through shared memory
+            const int width = (cg < 256 ? cg : 256) * 16;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    red[myrow * width + (threadIdx.x % (cg < 256 ? cg : 256)) * 16 + j] = s1[j];
+                    red[myrow * width + (threadIdx.x % (cg < 256 ? cg : 256)) * 16 + 8 + j] = s2[j];
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < width; i += blockDim.x) {
+                float acc = 0.f;
+                for (int r = 0; r < rows; ++r) acc += red[r * width + i];
+                const int g = i >> 4, j = i & 15;
+                const int c = (cbase + g) * 8 + (j & 7);
+                if (c < p.C) atomicAdd(p.out + ((size_t)nb * p.C + c) * 2 + (j >> 3), (double)acc);
+            }
+            __syncthreads();
+        } else {
+            // per-w variant: blockIdx.x enumerates w; rows stride over (d,h)
+            const int w = blockIdx.x;
+            const long long DH = p.S / p.W;
+            float s1[8], s2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            if (active) {
+                for (long long dh = myrow; dh < DH; dh += rows) {
+                    const size_t off = ((size_t)nb * p.S + dh * p.W + w) * p.C + (size_t)mycg * 8;
+                    float a[8], b[8];
+                    unpack8(ld_stream(reinterpret_cast<const uint4*>(p.y + off)), a);
+                    if (p.kind == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
+                    } else {
+                        unpack8(ld_stream(reinterpret_cast<const uint4*>(p.dz + off)), b);
+                        if (p.z != nullptr) {
+                            float zz[8];
+                            unpack8(ld_stream(reinterpret_cast<const uint4*>(p.z + off)), zz);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) b[j] = zz[j] > 0.f ? b[j] : b[j] * p.slope;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s1[j] += b[j]; s2[j] += b[j] * a[j]; }
+                    }
+                }
+            }
+            const int width = (cg < 256 ? cg : 256) * 16;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    red[myrow * width + (threadIdx.x % (cg < 256 ? cg : 256)) * 16 + j] = s1[j];
+                    red[myrow * width + (threadIdx.x % (cg < 256 ? cg : 256)) * 16 + 8 + j] = s2[j];
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < width; i += blockDim.x) {
+                float acc = 0.f;
+                for (int r = 0; r < rows; ++r) acc += red[r * width + i];
+                const int g = i >> 4, j = i & 15;
+                const int c = (cbase + g) * 8 + (j & 7);
+                if (c < p.C) p.out[(((size_t)nb * p.W + w) * p.C + c) * 2 + (j >> 3)] = (double)acc;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused apply:   z = act( y * scale[n,(w),c] + shift[n,(w),c] + res )
+// scale/shift fold mean, rstd, affine gamma/beta and the SE gate (host glue builds them
+// from the statistics; they are [NB][G][C] fp32 with G = 1 or W).
+// ---------------------------------------------------------------------------------------
+struct ApplyParams {
+    const bf16* y;
+    const bf16* res;  // may be null
+    bf16* z;
+    const float* scale;
+    const float* shift;
+    long long S;
+    int NB, C, W, perW, act;
+    float slope;
+};
+
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) {
+    // grid = (blocks, NB); 32-bit index math inside one sample (S * C/8 < 2^31, checked on the host)
+    const uint32_t cg = (uint32_t)p.C >> 3;
+    const uint32_t per = (uint32_t)p.S * cg;
+    const int nb = blockIdx.y;
+    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + (size_t)nb * per;
+    const uint4* rv = p.res ? reinterpret_cast<const uint4*>(p.res) + (size_t)nb * per : nullptr;
+    uint4* zv = reinterpret_cast<uint4*>(p.z) + (size_t)nb * per;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        const uint32_t g = i % cg;
+        const uint32_t v = i / cg;
+        const size_t cidx = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
+        float a[8], sc[8], sh[8];
+        unpack8(ld_stream(yv + i), a);
+        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx));
+        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx + 4));
+        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx));
+        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sh[j]);
+        if (rv != nullptr) {
+            float r[8];
+            unpack8(ld_stream(rv + i), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += r[j];
+        }
+        if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] > 0.f ? a[j] : a[j] * p.slope;
+        }
+        zv[i] = pack8(a);
+    }
+}
+
+// Backward of the fused apply + InstanceNorm:
+//   g    = dz * lrelu'(z)                 (z = saved output; act==0 => g = dz)
+//   dres = g                              (only when dres != null)
+//   dy   = g * k1[n,(w),c] + y * k2[n,c] + k3[n,c]
+struct ApplyBwdParams {
+    const bf16* dz;
+    const bf16* z;
+    const bf16* y;
+    bf16* dy;
+    bf16* dres;
+    const float* k1;
+    const float* k2;
+    const float* k3;
+    long long S;
+    int NB, C, W, perW, act;
+    float slope;
+};
+
+__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams p) {
+    const uint32_t cg = (uint32_t)p.C >> 3;
+    const uint32_t per = (uint32_t)p.S * cg;
+    const int nb = blockIdx.y;
+    const size_t base = (size_t)nb * per;
+    const uint4* dzv = reinterpret_cast<const uint4*>(p.dz) + base;
+    const uint4* zv = p.z ? reinterpret_cast<const uint4*>(p.z) + base : nullptr;
+    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + base;
+    uint4* dyv = reinterpret_cast<uint4*>(p.dy) + base;
+    uint4* drv = p.dres ? reinterpret_cast<uint4*>(p.dres) + base : nullptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        const uint32_t g = i % cg;
+        const uint32_t v = i / cg;
+        const size_t c2 = (size_t)nb * p.C + g * 8;
+        const size_t c1 = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : c2;
+        float gd[8], yy[8], a1[8], a2[8], a3[8];
+        unpack8(ld_stream(dzv + i), gd);
+        if (p.act) {
+            float zz[8];
+            unpack8(ld_stream(zv + i), zz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd[j] = zz[j] > 0.f ? gd[j] : gd[j] * p.slope;
+        }
+        if (drv != nullptr) drv[i] = pack8(gd);
+        unpack8(ld_stream(yv + i), yy);
+        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1));
+        *reinterpret_cast<float4*>(a1 + 4) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1 + 4));
+        *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(p.k2 + c2));
+        *reinterpret_cast<float4*>(a2 + 4) = __ldg(reinterpret_cast<const float4*>(p.k2 + c2 + 4));
+        *reinterpret_cast<float4*>(a3) = __ldg(reinterpret_cast<const float4*>(p.k3 + c2));
+        *reinterpret_cast<float4*>(a3 + 4) = __ldg(reinterpret_cast<const float4*>(p.k3 + c2 + 4));
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(gd[j], a1[j], fmaf(yy[j], a2[j], a3[j]));
+        dyv[i] = pack8(o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// AvgPool3d(kernel = stride) forward / backward, window (sd, sh, sw) in {1,2}^3.
+// ---------------------------------------------------------------------------------------
+struct PoolParams {
+    const bf16* in;
+    bf16* out;
+    int NB, D, H, W, C;  // dims of the full-resolution tensor
+    int sd, sh, sw;
+};
+
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const PoolParams p) {
+    const int cg = p.C >> 3;
+    const int OD = p.D / p.sd, OH = p.H / p.sh, OW = p.W / p.sw;
+    const long long total = (long long)p.NB * OD * OH * OW * cg;
+    const float inv = 1.f / (float)(p.sd * p.sh * p.sw);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int g = (int)(t % cg); t /= cg;
+        const int ow = (int)(t % OW); t /= OW;
+        const int oh = (int)(t % OH); t /= OH;
+        const int od = (int)(t % OD); t /= OD;
+        const int nb = (int)t;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int a = 0; a < p.sd; ++a)
+            for (int b = 0; b < p.sh; ++b)
+                for (int c = 0; c < p.sw; ++c) {
+                    const size_t vox = (((size_t)nb * p.D + od * p.sd + a) * p.H + oh * p.sh + b) * p.W + ow * p.sw + c;
+                    float f[8];
+                    unpack8(ld_stream(reinterpret_cast<const uint4*>(p.in + vox * p.C + g * 8)), f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        reinterpret_cast<uint4*>(p.out)[i] = pack8(acc);
+    }
+}
+
+// in = d(pooled) [NB, D/sd, H/sh, W/sw, C]; out = d(full) [NB, D, H, W, C]
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const PoolParams p) {
+    const int cg = p.C >> 3;
+    const int OD = p.D / p.sd, OH = p.H / p.sh, OW = p.W / p.sw;
+    const long long total = (long long)p.NB * p.D * p.H * p.W * cg;
+    const float inv = 1.f / (float)(p.sd * p.sh * p.sw);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int g = (int)(t % cg); t /= cg;
+        const int w = (int)(t % p.W); t /= p.W;
+        const int h = (int)(t % p.H); t /= p.H;
+        const int d = (int)(t % p.D); t /= p.D;
+        const int nb = (int)t;
+        const size_t vox = (((size_t)nb * OD + d / p.sd) * OH + h / p.sh) * OW + w / p.sw;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.in + vox * p.C + g * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= inv;
+        reinterpret_cast<uint4*>(p.out)[i] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Task head: 1x1x1 conv with bias, K <= 8 classes, output NCDHW fp32 (what the trainer's
+// losses and the blend consume).  act: 0 none, 1 sigmoid, 2 softmax over classes
+// (build_network_from_config.py:6-18,322-323).
+// ---------------------------------------------------------------------------------------
+static constexpr int HEAD_MAXK = 8;
+struct HeadParams {
+    const bf16* x;    // [NB, S, C]
+    const float* w;   // [K][C]
+    const float* b;   // [K]
+    float* out;       // [NB][K][S]
+    long long S;
+    int NB, C, K, act;
+};
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams p) {
+    extern __shared__ float hw[];  // [K][C] + [K]
+    for (int i = threadIdx.x; i < p.K * p.C; i += blockDim.x) hw[i] = p.w[i];
+    for (int i = threadIdx.x; i < p.K; i += blockDim.x) hw[p.K * p.C + i] = p.b ? p.b[i] : 0.f;
+    __syncthreads();
+    const long long total = (long long)p.NB * p.S;
+    const int cg = p.C >> 3;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+        float acc[HEAD_MAXK];
+#pragma unroll
+        for (int k = 0; k < HEAD_MAXK; ++k) acc[k] = k < p.K ? hw[p.K * p.C + k] : 0.f;
+        for (int g = 0; g < cg; ++g) {
+            float f[8];
+            unpack8(ld_stream(reinterpret_cast<const uint4*>(p.x + (size_t)v * p.C) + g), f);
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXK; ++k) {
+                if (k < p.K) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], hw[k * p.C + g * 8 + j], acc[k]);
+                }
+            }
+        }
+        if (p.act == 1) {
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXK; ++k) acc[k] = 1.f / (1.f + expf(-acc[k]));
+        } else if (p.act == 2) {
+            float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXK; ++k) if (k < p.K) mx = fmaxf(mx, acc[k]);
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXK; ++k) if (k < p.K) { acc[k] = expf(acc[k] - mx); sum += acc[k]; }
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXK; ++k) acc[k] /= sum;
+        }
+        const long long nb = v / p.S, s = v % p.S;
+#pragma unroll
+        for (int k = 0; k < HEAD_MAXK; ++k)
+            if (k < p.K) p.out[((size_t)nb * p.K + k) * p.S + s] = acc[k];
+    }
+}
+
+// Backward of the head (on raw logits): dx = dl . W (bf16), dW += dl^T x, db += sum dl.
+// thread = (voxel, 8-channel group); block-level reduction of dW / db, then fp32 atomics.
+struct HeadBwdParams {
+    const bf16* x;
+    const float* w;
+    const float* dl;  // [NB][K][S]
+    bf16* dx;         // [NB, S, C]
+    float* dw;        // [K][C]   (accumulated)
+    float* db;        // [K]
+    long long S;
+    int NB, C, K;
+};
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdParams p) {
+    extern __shared__ float sm[];  // [K][C] weights, then [K][C] + [K] block accumulators
+    float* wS = sm;
+    float* accS = sm + p.K * p.C;
+    for (int i = threadIdx.x; i < p.K * p.C; i += blockDim.x) wS[i] = p.w[i];
+    for (int i = threadIdx.x; i < p.K * p.C + p.K; i += blockDim.x) accS[i] = 0.f;
+    __syncthreads();
+    const int cg = p.C >> 3;
+    const long long total = (long long)p.NB * p.S * cg;
+    float dwl[HEAD_MAXK][8];
+    float dbl[HEAD_MAXK];
+#pragma unroll
+    for (int k = 0; k < HEAD_MAXK; ++k) {
+        dbl[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwl[k][j] = 0.f;
+    }
+    // all threads of a block keep the same channel group across iterations when the stride is a
+    // multiple of cg, so round the stride
+    const long long stride = ((long long)gridDim.x * blockDim.x / cg) * cg;
+    const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % cg);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long v = i / cg;
+        const long long nb = v / p.S, s = v % p.S;
+        float f[8], o[8];
+        unpack8(ld_stream(reinterpret_cast<const uint4*>(p.x) + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < HEAD_MAXK; ++k) {
+            if (k < p.K) {
+                const float d = __ldg(p.dl + ((size_t)nb * p.K + k) * p.S + s);
+                if (g == 0) dbl[k] += d;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = fmaf(d, wS[k * p.C + g * 8 + j], o[j]);
+                    dwl[k][j] = fmaf(d, f[j], dwl[k][j]);
+                }
+            }
+        }
+        reinterpret_cast<uint4*>(p.dx)[i] = pack8(o);
+    }
+#pragma unroll
+    for (int k = 0; k < HEAD_MAXK; ++k) {
+        if (k < p.K) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&accS[k * p.C + g * 8 + j], dwl[k][j]);
+            if (g == 0) atomicAdd(&accS[p.K * p.C + k], dbl[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.K * p.C; i += blockDim.x) atomicAdd(p.dw + i, accS[i]);
+    if (p.db != nullptr)
+        for (int i = threadIdx.x; i < p.K; i += blockDim.x) atomicAdd(p.db + i, accS[p.K * p.C + i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Stem im2col: x NCDHW fp32 (the trainer's input layout) -> col [NB, D, H, W, Kp] bf16 with
+// column index k = tap * Cin + ci (zero padded to Kp, a multiple of 16), so the stem
+// convolution (encoder.py:81-86) and its weight gradient become 1x1x1 GEMMs.
+// ---------------------------------------------------------------------------------------
+struct Im2colParams {
+    const float* x;
+    bf16* col;
+    int NB, Cin, D, H, W, kd, kh, kw, Kp;
+};
+
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const Im2colParams p) {
+    const int kg = p.Kp >> 3;
+    const long long S = (long long)p.D * p.H * p.W;
+    const long long total = (long long)p.NB * S * kg;
+    const int K = p.kd * p.kh * p.kw * p.Cin;
+    const int pd = (p.kd - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % kg);
+        long long v = i / kg;
+        const int w = (int)(v % p.W); v /= p.W;
+        const int h = (int)(v % p.H); v /= p.H;
+        const int d = (int)(v % p.D); v /= p.D;
+        const int nb = (int)v;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < K) {
+                const int ci = k % p.Cin;
+                const int t = k / p.Cin;
+                const int tw = t % p.kw, th = (t / p.kw) % p.kh, td = t / (p.kw * p.kh);
+                const int z = d + td - pd, y = h + th - ph, x = w + tw - pw;
+                if (z >= 0 && z < p.D && y >= 0 && y < p.H && x >= 0 && x < p.W)
+                    val = __ldg(p.x + (((size_t)nb * p.Cin + ci) * p.D + z) * p.H * p.W + (size_t)y * p.W + x);
+            }
+            f[j] = val;
+        }
+        reinterpret_cast<uint4*>(p.col)[i] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight packing.  Canonical parameters keep the reference layout and dtype
+// ([Cout, Cin, kd, kh, kw] fp32; ConvTranspose3d [Cin, Cout, 2, 2, 2]); kernels consume
+// bf16 [taps][rows][cols].  The gather is fully described by strides so one kernel covers
+// fprop, flipped / parity-class dgrad and the transposed convolution.
+//   out[((t * R) + r) * Cc + c] = bf16( w[ r*sr + c*sc + kidx(t) ] )   (c >= Cvalid => 0)
+// with kidx(t) = mapD[td]*kHW + mapH[th]*kW + mapW[tw].
+// ---------------------------------------------------------------------------------------
+struct PackParams {
+    const float* w;
+    bf16* out;
+    int nD, nH, nW;       // taps per dim in the packed tensor
+    int mapD[3], mapH[3], mapW[3];
+    int kH, kW;           // canonical kernel dims (for kidx)
+    int R, Cc, Cvalid;    // packed rows / cols (cols padded to Cc)
+    long long sr, sc;     // canonical strides (elements) of the row / col index
+    long long tapStrideR; // extra row offset per tap (pixel-shuffle packing: rows = par*Cout+co) -- unused => 0
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackParams p) {
+    const long long total = (long long)p.nD * p.nH * p.nW * p.R * p.Cc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % p.Cc);
+        long long t = i / p.Cc;
+        const int r = (int)(t % p.R); t /= p.R;
+        const int tw = (int)(t % p.nW); t /= p.nW;
+        const int th = (int)(t % p.nH); t /= p.nH;
+        const int td = (int)t;
+        float v = 0.f;
+        if (c < p.Cvalid) {
+            const long long kidx = ((long long)p.mapD[td] * p.kH + p.mapH[th]) * p.kW + p.mapW[tw];
+            v = p.w[(long long)r * p.sr + (long long)c * p.sc + kidx];
+        }
+        p.out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// Weight-gradient unpack:  grad[a*sa + b*sb + t] (+)= dwp[t][a][b]   (b < Bvalid)
+struct UnpackParams {
+    const float* dwp;  // [T][A][B]
+    float* grad;
+    int T, A, B, Bvalid;
+    long long sa, sb;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackParams p) {
+    const long long total = (long long)p.A * p.Bvalid * p.T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % p.T);
+        long long r = i / p.T;
+        const int b = (int)(r % p.Bvalid);
+        const int a = (int)(r / p.Bvalid);
+        const float v = p.dwp[((size_t)t * p.A + a) * p.B + b];
+        float* d = p.grad + (long long)a * p.sa + (long long)b * p.sb + t;
+        *d = p.accumulate ? *d + v : v;
+    }
+}
+
+}  // namespace rb
