@@ -1,0 +1,175 @@
+/* resenc_b200.h — C ABI of the B200-native (sm_100a) ResEnc U-Net hot path.
+ *
+ * The reference (bruniss/multi-task-3d-resencoder-unet) is pure Python on top of torch.nn; it has
+ * no FFI of its own.  Each entry point below therefore names the reference *call site* whose
+ * arithmetic it replaces (path:line relative to the reference tree); the Python host mirror in
+ * multi-task-3d-resencoder-unet_b200/builders/ binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; all pointers are DEVICE pointers unless noted
+ *   - activations: channels-last NDHWC bf16, C % 8 == 0, 16-byte aligned
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - every function returns 0 on success or a negative RbStatus; rb_last_error() gives the text
+ *   - nothing is allocated persistently; workspaces are passed in by the caller
+ *   - re-entrant across threads and streams
+ */
+#ifndef RESENC_B200_H
+#define RESENC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum RbStatus {
+    RB_OK = 0,
+    RB_ERR_INVALID = -1,      /* bad descriptor / unsupported shape */
+    RB_ERR_CUDA = -2,         /* CUDA runtime or driver error */
+    RB_ERR_UNSUPPORTED = -3,  /* requested implementation cannot run this shape */
+    RB_ERR_DEVICE = -4        /* device-side pipeline timeout recorded by a kernel */
+};
+
+enum RbConvImpl {
+    RB_IMPL_AUTO = 0,     /* tcgen05 when the shape qualifies, else mma.sync */
+    RB_IMPL_MMA_SYNC = 1, /* shape-generic warp-level tensor path (cross-check + odd shapes) */
+    RB_IMPL_TCGEN05 = 2   /* TMA + tcgen05.mma + TMEM; RB_ERR_UNSUPPORTED if the shape does not qualify */
+};
+
+const char* rb_last_error(void);
+int rb_version(void);
+/* Synchronises `stream`, returns RB_ERR_DEVICE (and clears the flag) if any kernel recorded a
+ * pipeline timeout since the last call. */
+int rb_device_error(void* stream);
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+ * gpu_launches). */
+long long rb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Gather convolution: one implicit GEMM covers every dense contraction of the network.
+ *   out[m, n] = sum_{tap, c} A[src(m, tap), c] * W[tap][n][c]
+ *   m over the output class grid (NB, OD, OH, OW); input coordinate i = o*istr + off + k,
+ *   out-of-range reads as 0; A = one or two NDHWC tensors concatenated along C (virtual
+ *   torch.cat); W packed bf16 [taps][Nout][Ctot].
+ * Replaces:
+ *   nn.Conv3d k3/k1, stride 1/2, pad (k-1)/2      builders/simple_conv_blocks.py:43-51
+ *   its data gradient (flipped taps / 8 parity classes for stride 2)
+ *   nn.ConvTranspose3d k == stride                builders/decoder.py:110-113 (mode 1: pixel shuffle)
+ *   its data gradient (= k2 s2 p0 conv)
+ *   torch.cat((up, skip), 1)                      builders/decoder.py:147 (nsrc == 2)
+ * Output: direct (mode 0) to voxel (o*ostr + ooff) of an [NB, FD, FH, FW, outC0 (+outC1)] tensor
+ * (two destinations split the channel range: used to route the concat gradient), or pixel
+ * shuffle (mode 1): column = parity * psC + channel, voxel = o*ostr + parity offset.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct RbConvDesc {
+    int nsrc, srcC0, srcC1;
+    int NB, ID, IH, IW;
+    int tapD, tapH, tapW;
+    int offD, offH, offW;
+    int istrD, istrH, istrW;
+    int OD, OH, OW;
+    int Nout;
+    int mode;
+    int ostrD, ostrH, ostrW, ooffD, ooffH, ooffW;
+    int FD, FH, FW;
+    int outC0, outC1;
+    int psC, psD, psH, psW;
+    int impl;   /* RbConvImpl */
+    int splitK; /* 0 = library heuristic, 1 = never, >1 = forced (mma.sync path only) */
+} RbConvDesc;
+
+/* fp32 workspace bytes needed by rb_conv_gather for this descriptor (0 when no split-K). */
+size_t rb_conv_gather_workspace(const RbConvDesc* d);
+/* stat_sum / stat_sq: optional fp32 [NB][Nout] accumulators (caller zeroes them) receiving the
+ * per-(sample, channel) sum and sum of squares of the fp32 accumulators — the InstanceNorm
+ * statistics (build_network_from_config.py:172) fused into the producing conv's epilogue.
+ * Only the tcgen05 path fills them; returns RB_ERR_UNSUPPORTED if requested on mma.sync. */
+int rb_conv_gather(const RbConvDesc* d, const void* src0, const void* src1, const void* w_packed,
+                   void* out0, void* out1, float* stat_sum, float* stat_sq,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* 1 if the tcgen05 kernel can run this descriptor. */
+int rb_conv_gather_tc5_supported(const RbConvDesc* d);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight gradient:  dW[tap][a][b] += sum_m P[m][a] * Q[gather(m, tap)][b]      (fp32 atomics)
+ *   conv  wgrad: P = dy on the output grid (a = Cout), Q = x (b = Cin; two sources allowed)
+ *   convT wgrad: P = x on the input grid (a = Cin), Q = dy gathered at 2i + p (b = Cout)
+ * Replaces the weight half of aten::convolution_backward for the call sites listed above
+ * (train.py:224 `scaler.scale(loss).backward()`).  dw must be zeroed by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct RbWgradDesc {
+    int PC;
+    int nq, QC0, QC1;
+    int NB, GD, GH, GW;
+    int QD, QH, QW;
+    int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
+    int splits; /* 0 = heuristic */
+} RbWgradDesc;
+int rb_wgrad_gather(const RbWgradDesc* d, const void* P, const void* Q0, const void* Q1, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InstanceNorm3d(affine=False|True, eps) + LeakyReLU + residual add + SE gate
+ *   builders/simple_conv_blocks.py:58-64, builders/resblocks.py:106-114, DNA SqueezeExcite
+ * rb_plane_reduce   per-(n,[w],c) reductions in double: kind 0 (sum y, sum y^2); kind 1
+ *                   (sum g, sum g*y) with g = dz * lrelu'(z).  out: [NB][G][C][2], G = 1 or W.
+ * rb_in_finalize_*  tiny: statistics -> folded scale/shift (fwd) or backward coefficients.
+ * rb_norm_act_fwd   z = act(y * scale + shift + res)              one read of y (+res), one write
+ * rb_norm_act_bwd   g = dz*act'(z); dres = g; dy = g*k1 + y*k2 + k3
+ * ------------------------------------------------------------------------------------------ */
+int rb_plane_reduce(int kind, const void* y, const void* dz, const void* z, double* out,
+                    int NB, long long S, int C, int W, int perW, float slope, void* stream);
+int rb_in_finalize_fwd(const double* sums, const float* gamma, const float* beta, float* mean, float* rstd,
+                       float* scale, float* shift, int NB, int C, double S, double eps, void* stream);
+int rb_in_finalize_bwd(const double* red, const float* mean, const float* rstd, const float* gamma,
+                       float* k1, float* k2, float* k3, float* dgamma, float* dbeta,
+                       int NB, int C, double S, void* stream);
+int rb_norm_act_fwd(const void* y, const void* res, void* z, const float* scale, const float* shift,
+                    int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
+int rb_norm_act_bwd(const void* dz, const void* z, const void* y, void* dy, void* dres,
+                    const float* k1, const float* k2, const float* k3,
+                    int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
+
+/* AvgPool3d(stride, stride) of the ResNet-D skip, builders/resblocks.py:92-95.  D,H,W = full-res dims. */
+int rb_avgpool_fwd(const void* in, void* out, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream);
+int rb_avgpool_bwd(const void* dout, void* din, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream);
+
+/* Task head Conv3d(C, K<=8, 1, bias=True) (+ eval-mode activation), builders/decoder.py:131,151-152,
+ * builders/build_network_from_config.py:6-18,322-323.  x NDHWC bf16 -> out NCDHW fp32.
+ * act: 0 none, 1 sigmoid, 2 softmax over K. */
+int rb_head_fwd(const void* x, const float* w, const float* b, float* out, int NB, long long S, int C, int K, int act, void* stream);
+int rb_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db,
+                int NB, long long S, int C, int K, void* stream);
+
+/* Stem im2col (builders/encoder.py:81-86, Cin not a multiple of 8): x NCDHW fp32 ->
+ * col [NB,D,H,W,Kp] bf16, column = tap*Cin + ci, zero padded to Kp (multiple of 16). */
+int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream);
+
+/* Layout conversion at module boundaries: NCDHW fp32 <-> NDHWC bf16 (C % 8 == 0). */
+int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream);
+int rb_cl_to_ncdhw(const void* src, float* dst, int NB, int C, long long S, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sliding-window blend, inference.py:135-157 (accumulate), :166-210 (finalise), :213-263 (cast),
+ * inference/helpers.py:8-68 (gaussian weight).  fp32, no FMA contraction: weight == NULL is
+ * bit-identical to the reference numpy loop.  One call = one patch; calls on one stream apply
+ * in order (the reference's z-major order).
+ * activation (fused inference.py:124-133): 0 none, 1 sigmoid, 2 softmax over C.
+ * kind: 0 average -> uint8, 1 "normals" -> uint16.
+ * ------------------------------------------------------------------------------------------ */
+int rb_blend_accumulate(const float* pred, const float* weight, float* sum, float* wsum,
+                        int C, int PZ, int PY, int PX, int VZ, int VY, int VX,
+                        int z0, int y0, int x0, int activation, void* stream);
+int rb_blend_finalize_cast(const float* sum, const float* wsum, void* out, float* favg,
+                           long long V, int C, int kind, void* stream);
+int rb_blend_add(float* dst, const float* src, long long n, void* stream);
+
+/* Patch extraction + per-patch standardisation, dataloading/inference_dataset.py:62-75.
+ * vol: device uint8/uint16 [VZ][VY][VX]; stats: device double[2] scratch; out: fp32 [PZ][PY][PX]. */
+int rb_extract_patch(const void* vol, int is_u16, int VZ, int VY, int VX, int z0, int y0, int x0,
+                     int PZ, int PY, int PX, int standardize, double* stats, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESENC_B200_H */

@@ -1,0 +1,180 @@
+"""NetworkFromConfig — drop-in for the reference's builders/build_network_from_config.py:20-326.
+
+Same constructor contract (reads `mgr.tasks`, `train_patch_size`, `train_batch_size`,
+`in_channels`, `vram_max`, `autoconfigure`, `model_config`), same attributes, same children
+(`shared_encoder`, `task_decoders`, `task_activations`) and therefore the same state_dict keys;
+`forward(x)` takes the trainer's NCDHW float input and returns `{task: NCDHW fp32}` — raw logits
+in train mode, activated in eval mode (:312-326).  All arithmetic runs on the sm_100a kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .decoder import Decoder
+from .encoder import Encoder
+from .utils import get_n_blocks_per_stage, get_pool_and_conv_props
+
+_MANUAL_KEYS = ("basic_encoder_block", "basic_decoder_block", "bottleneck_block", "features_per_stage",
+                "num_stages", "n_blocks_per_stage", "kernel_sizes", "n_conv_per_stage_decoder", "strides")
+_ACTIVATIONS = {"none": lambda: None, "sigmoid": nn.Sigmoid, "softmax": lambda: nn.Softmax(dim=1)}
+
+
+def get_activation_module(activation_str: str):
+    """nn.Module for 'sigmoid' / 'softmax', None for 'none'; anything else is a ValueError."""
+    try:
+        return _ACTIVATIONS[activation_str.lower()]()
+    except KeyError:
+        raise ValueError(f"Unknown activation type: {activation_str}")
+
+
+def _report(title, obj, names):
+    print("-" * 61)
+    print(title)
+    for n in names:
+        print(f"{n}: {getattr(obj, n)}")
+    print("-" * 61)
+
+
+class NetworkFromConfig(nn.Module):
+    def __init__(self, mgr):
+        super().__init__()
+        self.mgr = mgr
+        self.tasks = mgr.tasks
+        self.patch_size = mgr.train_patch_size
+        self.batch_size = mgr.train_batch_size
+        self.in_channels = mgr.in_channels
+        self.vram_target = mgr.vram_max
+        self.autoconfigure = mgr.autoconfigure
+        cfg = mgr.model_config
+        self.model_name = cfg.get("model_name", "Model")
+        # the rank check comes first here (the reference reaches it only after autoconfiguration,
+        # which already fails with an IndexError for ranks other than 3)
+        if len(self.patch_size) == 2:
+            raise NotImplementedError("2-D patches are not implemented on the B200 path (3-D only)")
+        if len(self.patch_size) != 3:
+            raise ValueError("Patch size must have either 2 or 3 dimensions!")
+        self.op_dims = 3
+
+        if mgr.autoconfigure:
+            # nnU-Net-style residual encoder preset: 32..512 features, pool until < 8 voxels per axis
+            print("--- Autoconfiguring network from config ---")
+            self.use_timm = False
+            self.basic_encoder_block = "BasicBlockD"
+            self.basic_decoder_block = "ConvBlock"
+            self.bottleneck_block = "BasicBlockD"
+            npool, pool_kernels, conv_kernels, final_patch_size, _ = get_pool_and_conv_props(
+                spacing=(1.0, 1.0, 1.0), patch_size=mgr.train_patch_size, min_feature_map_size=4, max_numpool=999999)
+            self.num_stages = len(pool_kernels)
+            self.num_pool_per_axis = npool
+            self.pool_op_kernel_sizes = pool_kernels
+            self.kernel_sizes = conv_kernels
+            self.features_per_stage = [min(32 * 2 ** i, 512) for i in range(self.num_stages)]
+            self.n_blocks_per_stage = get_n_blocks_per_stage(self.num_stages)
+            self.n_conv_per_stage_decoder = [1] * (self.num_stages - 1)
+            self.strides = pool_kernels
+            self.final_patch_size = final_patch_size
+            _report("Final Autoconfigured Parameters:", self,
+                    ("num_stages", "features_per_stage", "n_blocks_per_stage", "n_conv_per_stage_decoder", "strides",
+                     "final_patch_size"))
+        else:
+            print("--- Configuring network from config file ---")
+            self.use_timm = cfg.get("use_timm_encoder", False)
+            for key in _MANUAL_KEYS:
+                if key not in cfg:
+                    raise ValueError(f"autoconfigure=False, but '{key}' was not provided in the config!")
+            self.basic_encoder_block = cfg["basic_encoder_block"]
+            self.basic_decoder_block = cfg["basic_decoder_block"]
+            self.bottleneck_block = cfg["bottleneck_block"]
+            self.features_per_stage = cfg["features_per_stage"]
+            self.num_stages = cfg["num_stages"]
+            self.n_blocks_per_stage = cfg["n_blocks_per_stage"]
+            self.kernel_sizes = cfg["kernel_sizes"]
+            self.n_conv_per_stage_decoder = cfg["n_conv_per_stage_decoder"]
+            self.strides = cfg["strides"]
+            _report("Final Manual Parameters:", self,
+                    ("use_timm", "basic_encoder_block", "basic_decoder_block", "bottleneck_block", "features_per_stage",
+                     "num_stages", "n_blocks_per_stage", "kernel_sizes", "n_conv_per_stage_decoder", "strides"))
+        if self.use_timm:
+            raise NotImplementedError("use_timm_encoder is not implemented on the B200 path")
+
+        # read but overridden below from the patch rank, like the reference (:165-206)
+        self.conv_op = cfg.get("conv_op", "nn.Conv3d")
+        self.conv_op_kwargs = cfg.get("conv_op_kwargs", {"bias": False})
+        self.pool_op = cfg.get("pool_op", "nn.AvgPool3d")
+        self.dropout_op = cfg.get("dropout_op", "nn.Dropout3d")
+        self.dropout_op_kwargs = cfg.get("dropout_op_kwargs", {"p": 0.0})
+        self.norm_op = cfg.get("norm_op", "nn.InstanceNorm3d")
+        self.norm_op_kwargs = cfg.get("norm_op_kwargs", {"affine": False, "eps": 1e-5})
+        self.conv_bias = cfg.get("conv_bias", False)
+        self.nonlin = cfg.get("nonlin", "nn.LeakyReLU")
+        self.nonlin_kwargs = cfg.get("nonlin_kwargs", {"inplace": True})
+        self.return_skips = cfg.get("return_skips", True)
+        self.do_stem = cfg.get("do_stem", True)
+        self.stem_channels = cfg.get("stem_channels", None)
+        self.bottleneck_channels = cfg.get("bottleneck_channels", None)
+        self.stochastic_depth_p = cfg.get("stochastic_depth_p", 0.0)
+        self.squeeze_excitation = cfg.get("squeeze_excitation", False)
+        self.squeeze_excitation_reduction_ratio = 1.0 / 16.0 if self.squeeze_excitation else None
+        self.stem_n_channels = self.features_per_stage[0]
+
+        self.conv_op, self.pool_op = nn.Conv3d, nn.AvgPool3d
+        self.norm_op, self.dropout_op = nn.InstanceNorm3d, nn.Dropout3d
+
+        if self.nonlin == "nn.LeakyReLU":
+            self.nonlin, self.nonlin_kwargs = nn.LeakyReLU, {"negative_slope": 1e-2, "inplace": True}
+        elif self.nonlin == "nn.ReLU":
+            raise NotImplementedError("nn.ReLU is not implemented on the B200 path (LeakyReLU only)")
+
+        if self.bottleneck_block == "BottleneckBlockD":
+            if self.bottleneck_channels is None:
+                self.bottleneck_channels = [f // 4 for f in self.features_per_stage]
+            elif isinstance(self.bottleneck_channels, int):
+                self.bottleneck_channels = [self.bottleneck_channels] * len(self.features_per_stage)
+        else:
+            self.bottleneck_channels = None
+
+        self.shared_encoder = Encoder(
+            input_channels=self.in_channels, basic_block=self.basic_encoder_block, n_stages=self.num_stages,
+            features_per_stage=self.features_per_stage, n_blocks_per_stage=self.n_blocks_per_stage,
+            bottleneck_block=self.bottleneck_block, conv_op=self.conv_op, kernel_sizes=self.kernel_sizes,
+            conv_bias=self.conv_bias, norm_op=self.norm_op, norm_op_kwargs=self.norm_op_kwargs,
+            dropout_op=self.dropout_op, dropout_op_kwargs=self.dropout_op_kwargs, nonlin=self.nonlin,
+            nonlin_kwargs=self.nonlin_kwargs, strides=self.strides, return_skips=self.return_skips,
+            do_stem=self.do_stem, stem_channels=self.stem_n_channels, bottleneck_channels=self.bottleneck_channels,
+            stochastic_depth_p=self.stochastic_depth_p, squeeze_excitation=self.squeeze_excitation,
+            squeeze_excitation_reduction_ratio=self.squeeze_excitation_reduction_ratio)
+
+        self.task_decoders = nn.ModuleDict()
+        self.task_activations = nn.ModuleDict()
+        self._activation_names = {}
+        for name, info in self.tasks.items():
+            act = info.get("activation", "none")
+            self.task_decoders[name] = Decoder(encoder=self.shared_encoder, basic_block=self.basic_decoder_block,
+                                               num_classes=info["channels"],
+                                               n_conv_per_stage=self.n_conv_per_stage_decoder, deep_supervision=False)
+            self.task_activations[name] = get_activation_module(act)
+            self._activation_names[name] = act.lower()
+
+        _report("--- NetworkFromConfig initialized with the following settings ---", self,
+                ("model_name", "use_timm", "basic_encoder_block", "basic_decoder_block", "features_per_stage",
+                 "num_stages", "n_blocks_per_stage", "n_conv_per_stage_decoder", "bottleneck_block", "op_dims",
+                 "kernel_sizes", "conv_bias", "norm_op_kwargs", "dropout_op_kwargs", "nonlin", "nonlin_kwargs",
+                 "strides", "return_skips", "do_stem", "stem_channels", "bottleneck_channels", "stochastic_depth_p",
+                 "squeeze_excitation", "squeeze_excitation_reduction_ratio", "patch_size", "batch_size", "in_channels",
+                 "vram_target", "autoconfigure", "tasks"))
+
+    @torch.compiler.disable
+    def forward(self, x):
+        """The kernels are launched through ctypes; under torch.compile this method runs eagerly."""
+        if not self.return_skips:
+            raise NotImplementedError("return_skips=False leaves the decoders without skips (as in the reference)")
+        with torch.autocast("cuda", enabled=False):
+            skips = self.shared_encoder(x)
+            results = {}
+            for name, decoder in self.task_decoders.items():
+                act = None
+                if self.task_activations[name] is not None and not self.training:
+                    act = self._activation_names[name]      # fused into the head kernel
+                results[name] = decoder(skips, activation=act)
+        return results

@@ -1,0 +1,578 @@
+// C ABI of the B200-native ResEnc U-Net hot path (see include/resenc_b200.h for the contract
+// and the reference call sites each entry point replaces).  Host side only: argument checks,
+// launch geometry, TMA descriptor encoding.  Single translation unit: all kernels are included.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/resenc_b200.h"
+#include "common.cuh"
+#include "conv_tc5.cuh"
+#include "conv_generic.cuh"
+#include "elementwise.cuh"
+#include "blend.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return RB_OK;
+}
+
+#define RB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail(RB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int num_sms() {
+    static int n = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    });
+    return n;
+}
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+    long long b = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * max_waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ----------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda
+// dependency, so the library also loads on a machine without a driver).
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kw) {
+    return kw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+struct Tc5Plan {
+    bool ok = false;
+    int KW = 0, Ntile = 0, nTilesN = 0, stages = 0;
+    int tw = 0, th = 0, td = 0, tn = 0, tilesW = 0, tilesH = 0, tilesD = 0, tilesNB = 0;
+    size_t smem = 0;
+    long long tiles = 0;
+    int ksteps = 0;
+};
+
+Tc5Plan plan_tc5(const RbConvDesc& d) {
+    Tc5Plan pl;
+    if (d.nsrc < 1 || d.nsrc > 2) return pl;
+    if (d.srcC0 % 16 != 0 || (d.nsrc == 2 && d.srcC1 % 16 != 0)) return pl;
+    if (d.Nout % 32 != 0) return pl;
+    if (d.mode == 1 && (d.psC % 32 != 0)) return pl;
+    if (d.outC1 > 0 && d.outC0 % 32 != 0) return pl;
+    if (d.outC0 % 8 != 0 || d.outC1 % 8 != 0) return pl;
+    int kw = 64;
+    while (kw > 16 && (d.srcC0 % kw != 0 || (d.nsrc == 2 && d.srcC1 % kw != 0))) kw >>= 1;
+    pl.KW = kw;
+    if (d.Nout <= 256) pl.Ntile = d.Nout;
+    else if (d.Nout % 256 == 0) pl.Ntile = 256;
+    else if (d.Nout % 128 == 0) pl.Ntile = 128;
+    else if (d.Nout % 64 == 0) pl.Ntile = 64;
+    else pl.Ntile = 32;
+    pl.nTilesN = d.Nout / pl.Ntile;
+    // tile box: power-of-two factorisation of 128 output voxels minimising the tile count
+    long long best = -1;
+    for (int tw = 1; tw <= 128; tw <<= 1)
+        for (int th = 1; tw * th <= 128; th <<= 1)
+            for (int td = 1; tw * th * td <= 128; td <<= 1) {
+                const int tn = 128 / (tw * th * td);
+                if ((tw - 1) * d.istrW + 1 > 256 || (th - 1) * d.istrH + 1 > 256 || (td - 1) * d.istrD + 1 > 256 || tn > 256) continue;
+                const long long t = (long long)((d.OW + tw - 1) / tw) * ((d.OH + th - 1) / th) * ((d.OD + td - 1) / td) *
+                                    ((d.NB + tn - 1) / tn);
+                // ties: prefer the widest tw (longer contiguous runs for TMA and the epilogue stores)
+                if (best < 0 || t < best || (t == best && tw > pl.tw)) {
+                    best = t;
+                    pl.tw = tw; pl.th = th; pl.td = td; pl.tn = tn;
+                }
+            }
+    if (best < 0) return pl;
+    pl.tilesW = (d.OW + pl.tw - 1) / pl.tw;
+    pl.tilesH = (d.OH + pl.th - 1) / pl.th;
+    pl.tilesD = (d.OD + pl.td - 1) / pl.td;
+    pl.tilesNB = (d.NB + pl.tn - 1) / pl.tn;
+    pl.tiles = best * pl.nTilesN;
+    const size_t stageBytes = (size_t)(128 + pl.Ntile) * pl.KW * 2;
+    int st = (int)((200 * 1024) / stageBytes);
+    if (st > 8) st = 8;
+    if (st < 2) return pl;
+    pl.stages = st;
+    pl.smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)st * stageBytes;
+    const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+    pl.ksteps = d.tapD * d.tapH * d.tapW * (ctot / pl.KW);
+    pl.ok = true;
+    return pl;
+}
+
+int validate_conv(const RbConvDesc& d) {
+    if (d.nsrc < 1 || d.nsrc > 2) return fail(RB_ERR_INVALID, "conv: nsrc must be 1 or 2");
+    if (d.srcC0 <= 0 || d.srcC0 % 8 != 0 || (d.nsrc == 2 && (d.srcC1 <= 0 || d.srcC1 % 8 != 0)))
+        return fail(RB_ERR_INVALID, "conv: source channels must be positive multiples of 8");
+    if (d.Nout <= 0 || d.Nout % 8 != 0) return fail(RB_ERR_INVALID, "conv: Nout must be a positive multiple of 8");
+    if (d.NB <= 0 || d.ID <= 0 || d.IH <= 0 || d.IW <= 0 || d.OD <= 0 || d.OH <= 0 || d.OW <= 0)
+        return fail(RB_ERR_INVALID, "conv: empty grid");
+    if (d.tapD < 1 || d.tapH < 1 || d.tapW < 1 || d.tapD > 3 || d.tapH > 3 || d.tapW > 3)
+        return fail(RB_ERR_INVALID, "conv: taps per axis must be 1..3");
+    if (d.istrD < 1 || d.istrH < 1 || d.istrW < 1 || d.ostrD < 1 || d.ostrH < 1 || d.ostrW < 1)
+        return fail(RB_ERR_INVALID, "conv: strides must be >= 1");
+    if (d.outC0 <= 0 || d.outC0 % 8 != 0 || d.outC1 < 0 || d.outC1 % 8 != 0)
+        return fail(RB_ERR_INVALID, "conv: destination channels must be multiples of 8");
+    if (d.mode == 0) {
+        if (d.Nout != d.outC0 + d.outC1) return fail(RB_ERR_INVALID, "conv: Nout != outC0 + outC1");
+        if ((long long)(d.OD - 1) * d.ostrD + d.ooffD >= d.FD || (long long)(d.OH - 1) * d.ostrH + d.ooffH >= d.FH ||
+            (long long)(d.OW - 1) * d.ostrW + d.ooffW >= d.FW || d.ooffD < 0 || d.ooffH < 0 || d.ooffW < 0)
+            return fail(RB_ERR_INVALID, "conv: output class grid exceeds the destination");
+    } else if (d.mode == 1) {
+        if (d.psC <= 0 || d.psC % 8 != 0 || d.psD < 1 || d.psH < 1 || d.psW < 1 || d.psD > 2 || d.psH > 2 || d.psW > 2)
+            return fail(RB_ERR_INVALID, "conv: bad pixel-shuffle factors");
+        if (d.Nout != d.psC * d.psD * d.psH * d.psW) return fail(RB_ERR_INVALID, "conv: Nout != psC * parities");
+        if (d.psC != d.outC0 + d.outC1) return fail(RB_ERR_INVALID, "conv: psC != outC0 + outC1");
+        if (d.ostrD != d.psD || d.ostrH != d.psH || d.ostrW != d.psW) return fail(RB_ERR_INVALID, "conv: pixel shuffle needs ostr == ps");
+        if (d.OD * d.psD > d.FD || d.OH * d.psH > d.FH || d.OW * d.psW > d.FW) return fail(RB_ERR_INVALID, "conv: pixel shuffle exceeds the destination");
+    } else {
+        return fail(RB_ERR_INVALID, "conv: mode must be 0 or 1");
+    }
+    return RB_OK;
+}
+
+int generic_splitk(const RbConvDesc& d) {
+    if (d.splitK == 1) return 1;
+    const long long M = (long long)d.NB * d.OD * d.OH * d.OW;
+    const long long ctas = ((M + rb::GC_BM - 1) / rb::GC_BM) * ((d.Nout + rb::GC_BN - 1) / rb::GC_BN);
+    const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+    const int nIt = d.tapD * d.tapH * d.tapW * ((ctot + rb::GC_BK - 1) / rb::GC_BK);
+    if (d.splitK > 1) return d.splitK < nIt ? d.splitK : nIt;
+    if (ctas >= num_sms() || nIt < 16) return 1;
+    long long s = (2LL * num_sms() + ctas - 1) / ctas;
+    if (s > nIt / 4) s = nIt / 4;
+    if (s > 64) s = 64;
+    return s < 2 ? 1 : (int)s;
+}
+
+bool auto_prefers_tc5(const RbConvDesc& d, const Tc5Plan& pl) {
+    if (!pl.ok) return false;
+    // a handful of 128-row tiles with a very long K loop is latency bound on one CTA each:
+    // the split-K mma.sync path spreads it over the whole chip instead
+    if (pl.tiles < 48 && pl.ksteps > 64) return false;
+    return true;
+}
+
+int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const void* src1, const void* w, void* out0,
+               void* out1, float* stat_sum, float* stat_sq, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    rb::Tc5ConvParams p;
+    memset(&p, 0, sizeof(p));
+    const void* srcs[2] = {src0, src1};
+    const int srcC[2] = {d.srcC0, d.srcC1};
+    for (int s = 0; s < d.nsrc; ++s) {
+        const cuuint64_t C = (cuuint64_t)srcC[s];
+        cuuint64_t dims[5] = {C, (cuuint64_t)d.IW, (cuuint64_t)d.IH, (cuuint64_t)d.ID, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {C * 2, C * 2 * d.IW, C * 2 * d.IW * d.IH, C * 2 * d.IW * d.IH * d.ID};
+        cuuint32_t box[5] = {(cuuint32_t)pl.KW, (cuuint32_t)((pl.tw - 1) * d.istrW + 1), (cuuint32_t)((pl.th - 1) * d.istrH + 1),
+                             (cuuint32_t)((pl.td - 1) * d.istrD + 1), (cuuint32_t)pl.tn};
+        cuuint32_t estr[5] = {1, (cuuint32_t)d.istrW, (cuuint32_t)d.istrH, (cuuint32_t)d.istrD, 1};
+        CUresult r = enc(&p.mapA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(A%d) failed: %d", s, (int)r);
+    }
+    {
+        const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+        const int ntaps = d.tapD * d.tapH * d.tapW;
+        cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, (cuuint64_t)ntaps};
+        cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
+        cuuint32_t box[3] = {(cuuint32_t)pl.KW, (cuuint32_t)pl.Ntile, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+    p.nsrc = d.nsrc; p.srcC[0] = d.srcC0; p.srcC[1] = d.nsrc == 2 ? d.srcC1 : 0;
+    p.KW = pl.KW;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW;
+    p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.istrD = d.istrD; p.istrH = d.istrH; p.istrW = d.istrW;
+    p.tw = pl.tw; p.th = pl.th; p.td = pl.td; p.tn = pl.tn;
+    p.tilesW = pl.tilesW; p.tilesH = pl.tilesH; p.tilesD = pl.tilesD; p.tilesNB = pl.tilesNB;
+    p.OW = d.OW; p.OH = d.OH; p.OD = d.OD; p.NB = d.NB;
+    p.Nout = d.Nout; p.Ntile = pl.Ntile; p.nTilesN = pl.nTilesN;
+    p.mode = d.mode;
+    p.ostrD = d.ostrD; p.ostrH = d.ostrH; p.ostrW = d.ostrW; p.ooffD = d.ooffD; p.ooffH = d.ooffH; p.ooffW = d.ooffW;
+    p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
+    p.out0 = (rb::bf16*)out0; p.out1 = (rb::bf16*)out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
+    p.psC = d.psC; p.psD = d.psD; p.psH = d.psH; p.psW = d.psW;
+    p.stages = pl.stages;
+    p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(rb::tc5_gather_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tc5): %s", cudaGetErrorString(attr_err));
+    long long grid = pl.tiles < num_sms() ? pl.tiles : num_sms();
+    rb::tc5_gather_conv_kernel<<<(int)grid, rb::TC5_THREADS, pl.smem, st>>>(p);
+    return check_launch("tc5_gather_conv_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rb_last_error(void) { return g_err; }
+int rb_version(void) { return 100; }
+long long rb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rb_device_error(void* stream) {
+    RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    int h = 0;
+    RB_CUDA(cudaMemcpyFromSymbol(&h, rb::g_dev_error, sizeof(int)));
+    if (h != 0) {
+        int z = 0;
+        RB_CUDA(cudaMemcpyToSymbol(rb::g_dev_error, &z, sizeof(int)));
+        return fail(RB_ERR_DEVICE, "device pipeline timeout, code %d", h);
+    }
+    return RB_OK;
+}
+
+int rb_conv_gather_tc5_supported(const RbConvDesc* d) {
+    if (!d) return 0;
+    return plan_tc5(*d).ok ? 1 : 0;
+}
+
+size_t rb_conv_gather_workspace(const RbConvDesc* d) {
+    if (!d) return 0;
+    if (d->impl == RB_IMPL_TCGEN05) return 0;
+    if (d->impl == RB_IMPL_AUTO && auto_prefers_tc5(*d, plan_tc5(*d))) return 0;
+    if (generic_splitk(*d) <= 1) return 0;
+    return (size_t)d->NB * d->OD * d->OH * d->OW * d->Nout * sizeof(float);
+}
+
+int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, const void* w, void* out0, void* out1,
+                   float* stat_sum, float* stat_sq, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dp) return fail(RB_ERR_INVALID, "conv: null descriptor");
+    const RbConvDesc& d = *dp;
+    int rc = validate_conv(d);
+    if (rc) return rc;
+    if (!src0 || !w || !out0 || (d.nsrc == 2 && !src1) || (d.outC1 > 0 && !out1)) return fail(RB_ERR_INVALID, "conv: null pointer");
+    if (!aligned16(src0) || !aligned16(src1) || !aligned16(w) || !aligned16(out0) || !aligned16(out1))
+        return fail(RB_ERR_INVALID, "conv: pointers must be 16-byte aligned");
+    if ((stat_sum == nullptr) != (stat_sq == nullptr)) return fail(RB_ERR_INVALID, "conv: stat_sum and stat_sq go together");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    bool use_tc5 = false;
+    Tc5Plan pl;
+    if (d.impl == RB_IMPL_TCGEN05 || d.impl == RB_IMPL_AUTO) {
+        pl = plan_tc5(d);
+        if (d.impl == RB_IMPL_TCGEN05) {
+            if (!pl.ok) return fail(RB_ERR_UNSUPPORTED, "conv: shape does not qualify for the tcgen05 kernel");
+            use_tc5 = true;
+        } else {
+            use_tc5 = auto_prefers_tc5(d, pl);
+        }
+    } else if (d.impl != RB_IMPL_MMA_SYNC) {
+        return fail(RB_ERR_INVALID, "conv: unknown impl %d", d.impl);
+    }
+    if (use_tc5) return launch_tc5(d, pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
+    if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");
+
+    rb::GConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.src[0] = (const rb::bf16*)src0; p.src[1] = (const rb::bf16*)src1;
+    p.srcC[0] = d.srcC0; p.srcC[1] = d.nsrc == 2 ? d.srcC1 : 0; p.nsrc = d.nsrc;
+    p.ID = d.ID; p.IH = d.IH; p.IW = d.IW; p.NB = d.NB;
+    p.w = (const rb::bf16*)w;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.istrD = d.istrD; p.istrH = d.istrH; p.istrW = d.istrW;
+    p.OD = d.OD; p.OH = d.OH; p.OW = d.OW; p.Nout = d.Nout;
+    p.mode = d.mode; p.ostrD = d.ostrD; p.ostrH = d.ostrH; p.ostrW = d.ostrW;
+    p.ooffD = d.ooffD; p.ooffH = d.ooffH; p.ooffW = d.ooffW; p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
+    p.out0 = (rb::bf16*)out0; p.out1 = (rb::bf16*)out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
+    p.psC = d.psC; p.psD = d.psD; p.psH = d.psH; p.psW = d.psW;
+    const long long M = (long long)d.NB * d.OD * d.OH * d.OW;
+    int sk = generic_splitk(d);
+    const size_t need = (size_t)M * d.Nout * sizeof(float);
+    if (sk > 1 && (workspace == nullptr || workspace_bytes < need)) sk = 1;
+    p.splitK = sk;
+    p.ws = sk > 1 ? (float*)workspace : nullptr;
+    const long long gx = (M + rb::GC_BM - 1) / rb::GC_BM;
+    if (gx > 2147483647LL) return fail(RB_ERR_INVALID, "conv: grid too large");
+    dim3 grid((unsigned)gx, (unsigned)((d.Nout + rb::GC_BN - 1) / rb::GC_BN), (unsigned)sk);
+    if (sk > 1) RB_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    rb::gather_conv_mma_kernel<<<grid, rb::GC_THREADS, 0, st>>>(p);
+    rc = check_launch("gather_conv_mma_kernel");
+    if (rc) return rc;
+    if (sk > 1) {
+        rb::gather_finish_kernel<<<grid_for(M * (d.Nout / 2), 256), 256, 0, st>>>(p);
+        rc = check_launch("gather_finish_kernel");
+    }
+    return rc;
+}
+
+int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const void* Q1, float* dw, void* stream) {
+    if (!dp) return fail(RB_ERR_INVALID, "wgrad: null descriptor");
+    const RbWgradDesc& d = *dp;
+    if (d.PC <= 0 || d.PC % 8 != 0 || d.nq < 1 || d.nq > 2 || d.QC0 <= 0 || d.QC0 % 8 != 0 || (d.nq == 2 && (d.QC1 <= 0 || d.QC1 % 8 != 0)))
+        return fail(RB_ERR_INVALID, "wgrad: channel counts must be positive multiples of 8");
+    if (!P || !Q0 || !dw || (d.nq == 2 && !Q1)) return fail(RB_ERR_INVALID, "wgrad: null pointer");
+    if (!aligned16(P) || !aligned16(Q0) || !aligned16(Q1)) return fail(RB_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
+    if (d.NB <= 0 || d.GD <= 0 || d.GH <= 0 || d.GW <= 0 || d.QD <= 0 || d.QH <= 0 || d.QW <= 0) return fail(RB_ERR_INVALID, "wgrad: empty grid");
+    rb::GWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = (const rb::bf16*)P; p.PC = d.PC;
+    p.Q[0] = (const rb::bf16*)Q0; p.Q[1] = (const rb::bf16*)Q1; p.QC[0] = d.QC0; p.QC[1] = d.nq == 2 ? d.QC1 : 0; p.nq = d.nq;
+    p.NB = d.NB; p.GD = d.GD; p.GH = d.GH; p.GW = d.GW; p.QD = d.QD; p.QH = d.QH; p.QW = d.QW;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.istrD = d.istrD; p.istrH = d.istrH; p.istrW = d.istrW;
+    p.dw = dw;
+    const int qct = p.QC[0] + p.QC[1];
+    const int tiles = ((d.PC + rb::GW_BA - 1) / rb::GW_BA) * ((qct + rb::GW_BB - 1) / rb::GW_BB);
+    const int taps = d.tapD * d.tapH * d.tapW;
+    const long long M = (long long)d.NB * d.GD * d.GH * d.GW;
+    long long splits = d.splits;
+    if (splits <= 0) {
+        splits = (4LL * num_sms() + (long long)tiles * taps - 1) / ((long long)tiles * taps);
+        const long long maxs = (M + 255) / 256;  // at least 256 voxels per slice
+        if (splits > maxs) splits = maxs;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > 65535) splits = 65535;
+    long long per = (M + splits - 1) / splits;
+    per = (per + rb::GW_BK - 1) / rb::GW_BK * rb::GW_BK;
+    splits = (M + per - 1) / per;
+    p.mPerSplit = (int)per;
+    dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)splits);
+    rb::gather_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("gather_wgrad_mma_kernel");
+}
+
+int rb_plane_reduce(int kind, const void* y, const void* dz, const void* z, double* out, int NB, long long S, int C, int W,
+                    int perW, float slope, void* stream) {
+    if (!y || !out || (kind == 1 && !dz)) return fail(RB_ERR_INVALID, "plane_reduce: null pointer");
+    if (C <= 0 || C % 8 != 0 || NB <= 0 || S <= 0) return fail(RB_ERR_INVALID, "plane_reduce: bad shape");
+    if (perW && (W <= 0 || S % W != 0)) return fail(RB_ERR_INVALID, "plane_reduce: S must be a multiple of W");
+    if (kind != 0 && kind != 1) return fail(RB_ERR_INVALID, "plane_reduce: kind must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    rb::ReduceParams p;
+    p.y = (const rb::bf16*)y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out;
+    p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind;
+    const int cg = C / 8;
+    const int rows = 256 / cg > 0 ? 256 / cg : 1;
+    int gx;
+    if (perW) {
+        gx = W;
+    } else {
+        RB_CUDA(cudaMemsetAsync(out, 0, (size_t)NB * C * 2 * sizeof(double), st));
+        long long want = (4LL * num_sms() + NB - 1) / NB;
+        const long long maxb = (S + rows - 1) / rows;
+        if (want > maxb) want = maxb;
+        gx = (int)(want < 1 ? 1 : want);
+    }
+    const size_t smem = (size_t)256 * 16 * sizeof(float);
+    rb::plane_reduce_kernel<<<dim3(gx, NB), 256, smem, st>>>(p);
+    return check_launch("plane_reduce_kernel");
+}
+
+int rb_in_finalize_fwd(const double* sums, const float* gamma, const float* beta, float* mean, float* rstd, float* scale,
+                       float* shift, int NB, int C, double S, double eps, void* stream) {
+    if (!sums || !mean || !rstd || !scale || !shift) return fail(RB_ERR_INVALID, "in_finalize_fwd: null pointer");
+    rb::FinalizeParams p{sums, gamma, beta, mean, rstd, scale, shift, NB, C, S, eps};
+    rb::in_finalize_fwd_kernel<<<(NB * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("in_finalize_fwd_kernel");
+}
+
+int rb_in_finalize_bwd(const double* red, const float* mean, const float* rstd, const float* gamma, float* k1, float* k2,
+                       float* k3, float* dgamma, float* dbeta, int NB, int C, double S, void* stream) {
+    if (!red || !mean || !rstd || !k1 || !k2 || !k3) return fail(RB_ERR_INVALID, "in_finalize_bwd: null pointer");
+    rb::FinalizeBwdParams p{red, mean, rstd, gamma, k1, k2, k3, dgamma, dbeta, NB, C, S};
+    rb::in_finalize_bwd_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("in_finalize_bwd_kernel");
+}
+
+static int check_apply_shape(const char* who, int NB, long long S, int C, int W, int perW) {
+    if (C <= 0 || C % 8 != 0 || NB <= 0 || S <= 0) return fail(RB_ERR_INVALID, "%s: bad shape", who);
+    if (S * (C / 8) >= (1LL << 31)) return fail(RB_ERR_INVALID, "%s: one sample exceeds 2^31 vectors", who);
+    if (perW && (W <= 0 || S % W != 0)) return fail(RB_ERR_INVALID, "%s: S must be a multiple of W", who);
+    return RB_OK;
+}
+
+int rb_norm_act_fwd(const void* y, const void* res, void* z, const float* scale, const float* shift, int NB, long long S,
+                    int C, int W, int perW, int act, float slope, void* stream) {
+    if (!y || !z || !scale || !shift) return fail(RB_ERR_INVALID, "norm_act_fwd: null pointer");
+    int rc = check_apply_shape("norm_act_fwd", NB, S, C, W, perW);
+    if (rc) return rc;
+    rb::ApplyParams p{(const rb::bf16*)y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope};
+    const long long per = S * (C / 8);
+    int gx = grid_for(per, 256, 8);
+    rb::norm_act_fwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("norm_act_fwd_kernel");
+}
+
+int rb_norm_act_bwd(const void* dz, const void* z, const void* y, void* dy, void* dres, const float* k1, const float* k2,
+                    const float* k3, int NB, long long S, int C, int W, int perW, int act, float slope, void* stream) {
+    if (!dz || !y || !dy || !k1 || !k2 || !k3 || (act && !z)) return fail(RB_ERR_INVALID, "norm_act_bwd: null pointer");
+    int rc = check_apply_shape("norm_act_bwd", NB, S, C, W, perW);
+    if (rc) return rc;
+    rb::ApplyBwdParams p{(const rb::bf16*)dz, (const rb::bf16*)z, (const rb::bf16*)y, (rb::bf16*)dy, (rb::bf16*)dres,
+                         k1, k2, k3, S, NB, C, W, perW, act, slope};
+    const long long per = S * (C / 8);
+    int gx = grid_for(per, 256, 8);
+    rb::norm_act_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("norm_act_bwd_kernel");
+}
+
+static int check_pool(int NB, int D, int H, int W, int C, int sd, int sh, int sw) {
+    if (NB <= 0 || C <= 0 || C % 8 != 0) return fail(RB_ERR_INVALID, "avgpool: bad shape");
+    if (sd < 1 || sh < 1 || sw < 1 || sd > 2 || sh > 2 || sw > 2) return fail(RB_ERR_INVALID, "avgpool: window must be 1 or 2 per axis");
+    if (D % sd || H % sh || W % sw) return fail(RB_ERR_INVALID, "avgpool: dims must be divisible by the window");
+    return RB_OK;
+}
+
+int rb_avgpool_fwd(const void* in, void* out, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream) {
+    if (!in || !out) return fail(RB_ERR_INVALID, "avgpool_fwd: null pointer");
+    int rc = check_pool(NB, D, H, W, C, sd, sh, sw);
+    if (rc) return rc;
+    rb::PoolParams p{(const rb::bf16*)in, (rb::bf16*)out, NB, D, H, W, C, sd, sh, sw};
+    const long long total = (long long)NB * (D / sd) * (H / sh) * (W / sw) * (C / 8);
+    rb::avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("avgpool_fwd_kernel");
+}
+
+int rb_avgpool_bwd(const void* dout, void* din, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream) {
+    if (!dout || !din) return fail(RB_ERR_INVALID, "avgpool_bwd: null pointer");
+    int rc = check_pool(NB, D, H, W, C, sd, sh, sw);
+    if (rc) return rc;
+    rb::PoolParams p{(const rb::bf16*)dout, (rb::bf16*)din, NB, D, H, W, C, sd, sh, sw};
+    const long long total = (long long)NB * D * H * W * (C / 8);
+    rb::avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("avgpool_bwd_kernel");
+}
+
+int rb_head_fwd(const void* x, const float* w, const float* b, float* out, int NB, long long S, int C, int K, int act, void* stream) {
+    if (!x || !w || !out) return fail(RB_ERR_INVALID, "head_fwd: null pointer");
+    if (K < 1 || K > rb::HEAD_MAXK || C <= 0 || C % 8 != 0 || C > 1024) return fail(RB_ERR_INVALID, "head_fwd: need 1 <= K <= 8, C %% 8 == 0, C <= 1024");
+    rb::HeadParams p{(const rb::bf16*)x, w, b, out, S, NB, C, K, act};
+    const size_t smem = (size_t)(K * C + K) * sizeof(float);
+    rb::head_fwd_kernel<<<grid_for((long long)NB * S, 256), 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("head_fwd_kernel");
+}
+
+int rb_head_bwd(const void* x, const float* w, const float* dl, void* dx, float* dw, float* db, int NB, long long S, int C,
+                int K, void* stream) {
+    if (!x || !w || !dl || !dx || !dw) return fail(RB_ERR_INVALID, "head_bwd: null pointer");
+    if (K < 1 || K > rb::HEAD_MAXK || C <= 0 || C % 8 != 0 || C > 1024) return fail(RB_ERR_INVALID, "head_bwd: need 1 <= K <= 8, C %% 8 == 0, C <= 1024");
+    rb::HeadBwdParams p{(const rb::bf16*)x, w, dl, (rb::bf16*)dx, dw, db, S, NB, C, K};
+    const size_t smem = (size_t)(2 * K * C + K) * sizeof(float);
+    rb::head_bwd_kernel<<<grid_for((long long)NB * S * (C / 8), 256, 4), 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("head_bwd_kernel");
+}
+
+int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream) {
+    if (!x || !col) return fail(RB_ERR_INVALID, "stem_im2col: null pointer");
+    if (Kp % 8 != 0 || Kp < kd * kh * kw * Cin) return fail(RB_ERR_INVALID, "stem_im2col: Kp must be a multiple of 8 covering taps*Cin");
+    rb::Im2colParams p{x, (rb::bf16*)col, NB, Cin, D, H, W, kd, kh, kw, Kp};
+    const long long total = (long long)NB * D * H * W * (Kp / 8);
+    rb::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("stem_im2col_kernel");
+}
+
+int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream) {
+    if (!src || !dst || C <= 0 || C % 8 != 0) return fail(RB_ERR_INVALID, "ncdhw_to_cl: bad arguments");
+    rb::LayoutParams p{src, (rb::bf16*)dst, S, NB, C};
+    rb::ncdhw_to_cl_kernel<<<grid_for((long long)NB * (C / 8) * S, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ncdhw_to_cl_kernel");
+}
+
+int rb_cl_to_ncdhw(const void* src, float* dst, int NB, int C, long long S, void* stream) {
+    if (!src || !dst || C <= 0 || C % 8 != 0) return fail(RB_ERR_INVALID, "cl_to_ncdhw: bad arguments");
+    rb::LayoutBackParams p{(const rb::bf16*)src, dst, S, NB, C};
+    rb::cl_to_ncdhw_kernel<<<grid_for((long long)NB * (C / 8) * S, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("cl_to_ncdhw_kernel");
+}
+
+int rb_blend_accumulate(const float* pred, const float* weight, float* sum, float* wsum, int C, int PZ, int PY, int PX, int VZ,
+                        int VY, int VX, int z0, int y0, int x0, int activation, void* stream) {
+    if (!pred || !sum) return fail(RB_ERR_INVALID, "blend_accumulate: null pointer");
+    if (C < 1 || PZ < 1 || PY < 1 || PX < 1 || VZ < 1 || VY < 1 || VX < 1) return fail(RB_ERR_INVALID, "blend_accumulate: bad shape");
+    if (activation < 0 || activation > 2) return fail(RB_ERR_INVALID, "blend_accumulate: bad activation");
+    rb::BlendParams p{pred, weight, sum, wsum, C, PZ, PY, PX, VZ, VY, VX, z0, y0, x0, activation};
+    rb::blend_accumulate_kernel<<<grid_for((long long)PZ * PY * PX, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("blend_accumulate_kernel");
+}
+
+int rb_blend_finalize_cast(const float* sum, const float* wsum, void* out, float* favg, long long V, int C, int kind, void* stream) {
+    if (!sum || !wsum || !out) return fail(RB_ERR_INVALID, "blend_finalize_cast: null pointer");
+    if (kind != 0 && kind != 1) return fail(RB_ERR_INVALID, "blend_finalize_cast: kind must be 0 or 1");
+    if (C < 1 || V < 1) return fail(RB_ERR_INVALID, "blend_finalize_cast: bad shape");
+    rb::FinalizeCastParams p{sum, wsum, out, favg, V, C, kind};
+    rb::blend_finalize_cast_kernel<<<grid_for(V, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("blend_finalize_cast_kernel");
+}
+
+int rb_blend_add(float* dst, const float* src, long long n, void* stream) {
+    if (!dst || !src || n < 0) return fail(RB_ERR_INVALID, "blend_add: bad arguments");
+    if (n == 0) return RB_OK;
+    rb::blend_add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    return check_launch("blend_add_kernel");
+}
+
+int rb_extract_patch(const void* vol, int is_u16, int VZ, int VY, int VX, int z0, int y0, int x0, int PZ, int PY, int PX,
+                     int standardize, double* stats, float* out, void* stream) {
+    if (!vol || !out || (standardize && !stats)) return fail(RB_ERR_INVALID, "extract_patch: null pointer");
+    if (z0 < 0 || y0 < 0 || x0 < 0 || z0 + PZ > VZ || y0 + PY > VY || x0 + PX > VX) return fail(RB_ERR_INVALID, "extract_patch: patch outside the volume");
+    cudaStream_t st = (cudaStream_t)stream;
+    rb::ExtractParams p{vol, is_u16, VZ, VY, VX, z0, y0, x0, PZ, PY, PX, stats, out, standardize};
+    const long long PS = (long long)PZ * PY * PX;
+    if (standardize) {
+        RB_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), st));
+        rb::patch_stats_kernel<<<grid_for(PS, 256, 2), 256, 0, st>>>(p);
+        int rc = check_launch("patch_stats_kernel");
+        if (rc) return rc;
+    }
+    rb::patch_write_kernel<<<grid_for(PS, 256), 256, 0, st>>>(p);
+    return check_launch("patch_write_kernel");
+}
+
+}  // extern "C"

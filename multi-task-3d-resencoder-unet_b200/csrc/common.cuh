@@ -15,7 +15,7 @@ typedef __nv_bfloat16 bf16;
 // timeout they record a code here and fall through so the launch drains.  The host API reads
 // it back after synchronising (rb_check_device_error).
 // ---------------------------------------------------------------------------------------
-extern __device__ int g_dev_error;
+static __device__ int g_dev_error = 0;  // single translation unit (api.cu)
 
 enum DevErr : int {
     DEVERR_NONE = 0,
@@ -68,14 +68,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait (about 2 s at 2 GHz).  Returns false and records `code` on timeout.
+// Bounded wait (about 0.5 s at 2 GHz).  Returns false and records `code` on timeout; once any
+// wait in the grid has timed out every later wait gives up at once, so a broken pipeline drains in
+// well under a second instead of hanging the GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return true;
-    long long t0 = clock64();
+    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            atomicCAS(&g_dev_error, 0, code);
-            return false;
+        if ((++spins & 63u) == 0) {
+            if (*reinterpret_cast<volatile int*>(&g_dev_error) != 0) return false;
+            if (clock64() - t0 > 1000000000LL) {
+                atomicCAS(&g_dev_error, 0, code);
+                return false;
+            }
         }
     }
     return true;

@@ -21,6 +21,8 @@ struct GConvParams {
     bf16* out0;
     bf16* out1;
     int outC0, outC1, psC, psD, psH, psW;
+    int splitK;  // > 1: blockIdx.z takes a contiguous slice of the (tap, k-chunk) loop and adds fp32
+    float* ws;   //      partials into ws[m][Nout] (zeroed by the host); gather_finish_kernel stores
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -53,7 +55,14 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
     const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
     const int ntaps = p.tapD * p.tapH * p.tapW;
     const int kchunks = (Ctot + GC_BK - 1) / GC_BK;
-    const int nIt = ntaps * kchunks;
+    const int nItAll = ntaps * kchunks;
+    int itBeg = 0, nIt = nItAll;
+    if (p.splitK > 1) {
+        const int per = (nItAll + p.splitK - 1) / p.splitK;
+        itBeg = blockIdx.z * per;
+        nIt = min(nItAll, itBeg + per);
+        if (itBeg >= nIt) return;
+    }
 
     // the two A rows this thread stages, decomposed once
     int rnb[2], rod[2], roh[2], row_[2];
@@ -105,8 +114,8 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
-    prefetch(0);
-    for (int it = 0; it < nIt; ++it) {
+    prefetch(itBeg);
+    for (int it = itBeg; it < nIt; ++it) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
             *reinterpret_cast<uint4*>(&As[((tid >> 2) + i * 64) * GC_PITCH + kvec * 8]) = ra[i];
@@ -147,6 +156,17 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
             const int r = warp_m * 32 + mi * 16 + half * 8 + g;
             long long m = m0 + r;
             if (m >= Mtot) continue;
+            if (p.splitK > 1) {
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = n0 + warp_n * 32 + ni * 8 + q * 2;
+                    if (col >= p.Nout) continue;
+                    float* d = p.ws + (size_t)m * p.Nout + col;
+                    atomicAdd(d, acc[mi][ni][half * 2]);
+                    atomicAdd(d + 1, acc[mi][ni][half * 2 + 1]);
+                }
+                continue;
+            }
             const int ow = (int)(m % p.OW); m /= p.OW;
             const int oh = (int)(m % p.OH); m /= p.OH;
             const int od = (int)(m % p.OD); m /= p.OD;
@@ -170,6 +190,35 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
                 *reinterpret_cast<uint32_t*>(dst) = pack_bf16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
             }
         }
+    }
+}
+
+// Split-K finish: ws[m][Nout] fp32 -> bf16 destination(s) with the same addressing as above.
+__global__ void __launch_bounds__(256) gather_finish_kernel(const GConvParams p) {
+    const long long Mtot = (long long)p.NB * p.OD * p.OH * p.OW;
+    const int half = p.Nout >> 1;
+    const long long total = Mtot * half;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % half) * 2;
+        long long m = i / half;
+        const float2 v = *reinterpret_cast<const float2*>(p.ws + (size_t)m * p.Nout + col);
+        const int ow = (int)(m % p.OW); m /= p.OW;
+        const int oh = (int)(m % p.OH); m /= p.OH;
+        const int od = (int)(m % p.OD); m /= p.OD;
+        const int nb = (int)m;
+        int fd, fh, fw, ch;
+        if (p.mode == 1) {
+            const int par = col / p.psC;
+            ch = col - par * p.psC;
+            const int pw = par % p.psW, ph = (par / p.psW) % p.psH, pd = par / (p.psW * p.psH);
+            fd = od * p.ostrD + pd; fh = oh * p.ostrH + ph; fw = ow * p.ostrW + pw;
+        } else {
+            ch = col;
+            fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
+        }
+        const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
+        bf16* dst = (ch < p.outC0) ? p.out0 + vox * p.outC0 + ch : p.out1 + vox * p.outC1 + (ch - p.outC0);
+        *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v.x, v.y);
     }
 }
 

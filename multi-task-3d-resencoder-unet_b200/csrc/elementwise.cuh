@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) 
 // Backward of the fused apply + InstanceNorm:
 //   g    = dz * lrelu'(z)                 (z = saved output; act==0 => g = dz)
 //   dres = g                              (only when dres != null)
-//   dy   = g * k1[n,(w),c] + y * k2[n,c] + k3[n,c]
+//   dy   = g * k1[n,(w),c] + y * k2[n,(w),c] + k3[n,(w),c]
 struct ApplyBwdParams {
     const bf16* dz;
     const bf16* z;
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
         const uint32_t g = i % cg;
         const uint32_t v = i / cg;
-        const size_t c2 = (size_t)nb * p.C + g * 8;
-        const size_t c1 = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : c2;
+        const size_t c1 = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
+        const size_t c2 = c1;
         float gd[8], yy[8], a1[8], a2[8], a3[8];
         unpack8(ld_stream(dzv + i), gd);
         if (p.act) {
@@ -488,61 +488,122 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const Im2colParams p) 
 }
 
 // ---------------------------------------------------------------------------------------
-// Weight packing.  Canonical parameters keep the reference layout and dtype
-// ([Cout, Cin, kd, kh, kw] fp32; ConvTranspose3d [Cin, Cout, 2, 2, 2]); kernels consume
-// bf16 [taps][rows][cols].  The gather is fully described by strides so one kernel covers
-// fprop, flipped / parity-class dgrad and the transposed convolution.
-//   out[((t * R) + r) * Cc + c] = bf16( w[ r*sr + c*sc + kidx(t) ] )   (c >= Cvalid => 0)
-// with kidx(t) = mapD[td]*kHW + mapH[th]*kW + mapW[tw].
+// InstanceNorm finalisation (tiny, one thread per (n, c)).
+//   fwd: sums[n][c] = (sum y, sum y^2) over S voxels (double) -> mean, rstd and the folded
+//        scale = gamma * rstd, shift = beta - mean * scale consumed by norm_act_fwd_kernel.
+//   bwd: red[n][c] = (G1 = sum g, Gy = sum g*y) -> coefficients of
+//        dy = g*k1 + y*k2 + k3  (closed-form InstanceNorm backward, biased variance) and the
+//        affine parameter gradients dgamma[c] = sum_n sum g*xhat, dbeta[c] = sum_n sum g.
 // ---------------------------------------------------------------------------------------
-struct PackParams {
-    const float* w;
-    bf16* out;
-    int nD, nH, nW;       // taps per dim in the packed tensor
-    int mapD[3], mapH[3], mapW[3];
-    int kH, kW;           // canonical kernel dims (for kidx)
-    int R, Cc, Cvalid;    // packed rows / cols (cols padded to Cc)
-    long long sr, sc;     // canonical strides (elements) of the row / col index
-    long long tapStrideR; // extra row offset per tap (pixel-shuffle packing: rows = par*Cout+co) -- unused => 0
+struct FinalizeParams {
+    const double* sums;   // [NB][C][2]
+    const float* gamma;   // [C] or null
+    const float* beta;    // [C] or null
+    float* mean;          // [NB][C]
+    float* rstd;          // [NB][C]
+    float* scale;         // [NB][C]
+    float* shift;         // [NB][C]
+    int NB, C;
+    double S;
+    double eps;
 };
 
-__global__ void __launch_bounds__(256) pack_weights_kernel(const PackParams p) {
-    const long long total = (long long)p.nD * p.nH * p.nW * p.R * p.Cc;
+__global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const FinalizeParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.NB * p.C) return;
+    const int c = i % p.C;
+    const double m = p.sums[2 * (size_t)i] / p.S;
+    double var = p.sums[2 * (size_t)i + 1] / p.S - m * m;
+    if (var < 0.0) var = 0.0;
+    const double r = 1.0 / sqrt(var + p.eps);
+    const double ga = p.gamma ? (double)p.gamma[c] : 1.0;
+    const double be = p.beta ? (double)p.beta[c] : 0.0;
+    p.mean[i] = (float)m;
+    p.rstd[i] = (float)r;
+    p.scale[i] = (float)(ga * r);
+    p.shift[i] = (float)(be - m * ga * r);
+}
+
+struct FinalizeBwdParams {
+    const double* red;    // [NB][C][2] = (sum g, sum g*y)
+    const float* mean;
+    const float* rstd;
+    const float* gamma;   // or null
+    float* k1;            // [NB][C]
+    float* k2;
+    float* k3;
+    float* dgamma;        // [C] accumulated (or null)
+    float* dbeta;         // [C] accumulated (or null)
+    int NB, C;
+    double S;
+};
+
+__global__ void __launch_bounds__(256) in_finalize_bwd_kernel(const FinalizeBwdParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.C) return;
+    double dg = 0.0, db = 0.0;
+    for (int n = 0; n < p.NB; ++n) {
+        const size_t i = (size_t)n * p.C + c;
+        const double G1 = p.red[2 * i], Gy = p.red[2 * i + 1];
+        const double m = p.mean[i], r = p.rstd[i];
+        const double G2 = r * (Gy - m * G1);  // sum g * xhat
+        const double a = (p.gamma ? (double)p.gamma[c] : 1.0) * r;
+        p.k1[i] = (float)a;
+        p.k2[i] = (float)(-a * r * G2 / p.S);
+        p.k3[i] = (float)(-a * G1 / p.S + a * m * r * G2 / p.S);
+        dg += G2;
+        db += G1;
+    }
+    if (p.dgamma) p.dgamma[c] += (float)dg;
+    if (p.dbeta) p.dbeta[c] += (float)db;
+}
+
+// ---------------------------------------------------------------------------------------
+// Layout conversion at the network boundary: NCDHW fp32 <-> NDHWC bf16 (C % 8 == 0).
+// One thread = one voxel x 8 channels; reads are coalesced along the voxel index per channel,
+// writes are 16-byte vectors.
+// ---------------------------------------------------------------------------------------
+struct LayoutParams {
+    const float* f32;  // [NB][C][S]
+    bf16* cl;          // [NB][S][C]
+    long long S;
+    int NB, C;
+};
+
+__global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const LayoutParams p) {
+    const int cg = p.C >> 3;
+    const long long total = (long long)p.NB * cg * p.S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % p.Cc);
-        long long t = i / p.Cc;
-        const int r = (int)(t % p.R); t /= p.R;
-        const int tw = (int)(t % p.nW); t /= p.nW;
-        const int th = (int)(t % p.nH); t /= p.nH;
-        const int td = (int)t;
-        float v = 0.f;
-        if (c < p.Cvalid) {
-            const long long kidx = ((long long)p.mapD[td] * p.kH + p.mapH[th]) * p.kW + p.mapW[tw];
-            v = p.w[(long long)r * p.sr + (long long)c * p.sc + kidx];
-        }
-        p.out[i] = __float2bfloat16_rn(v);
+        const long long s = i % p.S;
+        long long t = i / p.S;
+        const int g = (int)(t % cg);
+        const int nb = (int)(t / cg);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __ldg(p.f32 + ((size_t)nb * p.C + g * 8 + j) * p.S + s);
+        *reinterpret_cast<uint4*>(p.cl + ((size_t)nb * p.S + s) * p.C + g * 8) = pack8(f);
     }
 }
 
-// Weight-gradient unpack:  grad[a*sa + b*sb + t] (+)= dwp[t][a][b]   (b < Bvalid)
-struct UnpackParams {
-    const float* dwp;  // [T][A][B]
-    float* grad;
-    int T, A, B, Bvalid;
-    long long sa, sb;
-    int accumulate;
+struct LayoutBackParams {
+    const bf16* cl;
+    float* f32;
+    long long S;
+    int NB, C;
 };
 
-__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const UnpackParams p) {
-    const long long total = (long long)p.A * p.Bvalid * p.T;
+__global__ void __launch_bounds__(256) cl_to_ncdhw_kernel(const LayoutBackParams p) {
+    const int cg = p.C >> 3;
+    const long long total = (long long)p.NB * cg * p.S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i % p.T);
-        long long r = i / p.T;
-        const int b = (int)(r % p.Bvalid);
-        const int a = (int)(r / p.Bvalid);
-        const float v = p.dwp[((size_t)t * p.A + a) * p.B + b];
-        float* d = p.grad + (long long)a * p.sa + (long long)b * p.sb + t;
-        *d = p.accumulate ? *d + v : v;
+        const long long s = i % p.S;
+        long long t = i / p.S;
+        const int g = (int)(t % cg);
+        const int nb = (int)(t / cg);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.cl + ((size_t)nb * p.S + s) * p.C + g * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p.f32[((size_t)nb * p.C + g * 8 + j) * p.S + s] = f[j];
     }
 }
 

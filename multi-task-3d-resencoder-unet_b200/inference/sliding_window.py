@@ -1,0 +1,371 @@
+"""Sliding-window inference on the B200 path.
+
+Host logic (bit-exact with the reference, checked against tests/golden/host_goldens.json):
+  * patch enumeration      dataloading/inference_dataset.py:38-56 + helpers.py:200-216
+  * Gaussian importance    inference/helpers.py:8-68 (scipy gaussian_filter of a centred delta)
+Device kernels (csrc/blend.cuh through the C ABI):
+  * patch extraction + per-patch standardisation   dataloading/inference_dataset.py:62-75
+  * accumulate / finalise / cast                   inference.py:135-157, :166-210, :213-263
+Multi-GPU: the z-start list is split into contiguous runs, one per rank; each rank owns slab-local
+accumulators, the overlapping planes are added once at the end (neighbour exchange) and every rank
+finalises a disjoint z-range.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+_ACT = {None: 0, "none": 0, "sigmoid": 1, "softmax": 2}
+
+
+# ------------------------------------------------------------------------------------------
+# enumeration (pure Python integers; Python's round() is round-half-even on the double product,
+# exactly what the reference evaluates)
+# ------------------------------------------------------------------------------------------
+def generate_positions(min_val: int, max_val: int, patch_size: int, step: int) -> List[int]:
+    """Start offsets covering [min_val, max_val): regular grid plus a final patch flush with the end."""
+    if max_val - min_val < patch_size:
+        raise ValueError(f"volume extent {max_val - min_val} is smaller than the patch size {patch_size} "
+                         "(the reference fails with IndexError here)")
+    if step <= 0:
+        raise ValueError(f"step must be positive, got {step} (overlap too close to 1)")
+    starts = list(range(min_val, max_val - patch_size + 1, step))
+    tail = max_val - patch_size
+    if tail > starts[-1]:
+        starts.append(tail)
+    return starts
+
+
+def patch_steps(patch_size: Sequence[int], overlap: float) -> List[int]:
+    return [int(round(p * (1 - overlap))) for p in patch_size]
+
+
+def axis_positions(vol_shape, patch_size, overlap) -> List[List[int]]:
+    steps = patch_steps(patch_size, overlap)
+    return [generate_positions(0, int(vol_shape[a]), int(patch_size[a]), steps[a]) for a in range(3)]
+
+
+def all_positions(vol_shape, patch_size, overlap) -> List[Tuple[int, int, int]]:
+    """z-major nested enumeration of patch origins."""
+    zs, ys, xs = axis_positions(vol_shape, patch_size, overlap)
+    return [(z, y, x) for z in zs for y in ys for x in xs]
+
+
+def shard_z_starts(z_starts: Sequence[int], world_size: int) -> List[List[int]]:
+    """Contiguous, near-equal runs of z-starts; earlier ranks take the remainder."""
+    n = len(z_starts)
+    base, extra = divmod(n, world_size)
+    out, i = [], 0
+    for r in range(world_size):
+        k = base + (1 if r < extra else 0)
+        out.append(list(z_starts[i:i + k]))
+        i += k
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Gaussian importance map
+# ------------------------------------------------------------------------------------------
+def _delta_response_1d(n: int, sigma: float) -> np.ndarray:
+    """Response along one axis of scipy.ndimage's truncated (4 sigma), normalised Gaussian FIR to a
+    unit impulse at n // 2 with zero ("constant") boundary handling, in float64."""
+    radius = int(4.0 * sigma + 0.5)
+    taps = np.exp(-0.5 / (sigma * sigma) * np.arange(-radius, radius + 1) ** 2)
+    taps /= taps.sum()
+    idx = np.arange(n) - n // 2
+    resp = np.zeros(n, np.float64)
+    inside = np.abs(idx) <= radius
+    resp[inside] = taps[idx[inside] + radius]
+    return resp
+
+
+def compute_gaussian_3d(tile_size, sigma_scale: float = 1. / 8, value_scaling_factor: float = 1.0,
+                        dtype=np.float32) -> np.ndarray:
+    """Importance map of inference/helpers.py:8-68 as a numpy array.  The separable filter is applied
+    axis by axis on a float32 array, i.e. one float32 rounding per pass, which is reproduced here."""
+    tile = [int(t) for t in tile_size]
+    acc = None
+    for ax, n in enumerate(tile):
+        line = _delta_response_1d(n, n * sigma_scale)
+        shape = [1] * len(tile)
+        shape[ax] = n
+        if acc is None:
+            acc = line.astype(np.float32).reshape(shape)
+        else:
+            acc = (acc.astype(np.float64) * line.reshape(shape)).astype(np.float32)
+    g = np.array(np.broadcast_to(acc, tile), dtype=np.float32, order="C")
+    g /= (g.max() / value_scaling_factor)
+    positive_min = g[g > 0].min()
+    g[g == 0] = positive_min
+    return g.astype(dtype, copy=False)
+
+
+_gauss_map_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def get_gaussian_map(tile_size, device, sigma_scale: float = 1. / 8) -> torch.Tensor:
+    """Cached device copy (the reference's helper of the same name references an undefined cache,
+    inference/helpers.py:82)."""
+    key = (tuple(int(t) for t in tile_size), str(device), float(sigma_scale))
+    if key not in _gauss_map_cache:
+        _gauss_map_cache[key] = torch.from_numpy(compute_gaussian_3d(tile_size, sigma_scale)).to(device)
+    return _gauss_map_cache[key]
+
+
+# ------------------------------------------------------------------------------------------
+# device accumulators
+# ------------------------------------------------------------------------------------------
+class SlabBlender:
+    """Running sum / weight volumes for one z-slab [z_lo, z_hi) of the output, on one GPU.
+
+    targets: {name: {"channels": c, "activation": "none"|"sigmoid"|"softmax"}} (infer_output_targets).
+    weight:  "uniform" (the reference's sum/count blend, bit-exact) or "gaussian".
+    """
+
+    def __init__(self, targets: Dict[str, dict], vol_shape, patch_size, z_lo: int, z_hi: int, device,
+                 weight: str = "uniform"):
+        if weight not in ("uniform", "gaussian"):
+            raise ValueError("weight must be 'uniform' or 'gaussian'")
+        self.targets = targets
+        self.vol_shape = tuple(int(v) for v in vol_shape)
+        self.patch = tuple(int(p) for p in patch_size)
+        self.z_lo, self.z_hi = int(z_lo), int(z_hi)
+        self.device = torch.device(device)
+        self.weight_kind = weight
+        self.weight = get_gaussian_map(self.patch, self.device) if weight == "gaussian" else None
+        depth = self.z_hi - self.z_lo
+        _, Y, X = self.vol_shape
+        self.sums = {t: torch.zeros((info["channels"], depth, Y, X), dtype=torch.float32, device=self.device)
+                     for t, info in targets.items()}
+        # the reference keeps one count array per target; they are identical, one is enough
+        self.wsum = torch.zeros((depth, Y, X), dtype=torch.float32, device=self.device)
+        self._lib = L.load()
+
+    def add(self, preds: Dict[str, torch.Tensor], index: int, position, apply_activation: bool = True):
+        """Accumulate sample `index` of a batch of predictions {target: [B, c, pz, py, px] fp32}
+        at volume position (z0, y0, x0)."""
+        z0, y0, x0 = (int(v) for v in position)
+        st = L.stream_ptr(self.device)
+        _, Y, X = self.vol_shape
+        depth = self.z_hi - self.z_lo
+        first = True
+        for t, info in self.targets.items():
+            p = preds[t]
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                p = p.float().contiguous()
+            L.require_cuda(p, "blend")
+            c = info["channels"]
+            if p.shape[1] != c:
+                raise ValueError(f"target {t}: prediction has {p.shape[1]} channels, config says {c}")
+            pz, py, px = p.shape[2:]
+            act = _ACT[str(info.get("activation", "none")).lower()] if apply_activation else 0
+            one = p[index]
+            L.check(self._lib.rb_blend_accumulate(
+                one.data_ptr(), L.ptr(self.weight), self.sums[t].data_ptr(), self.wsum.data_ptr() if first else None,
+                c, pz, py, px, depth, Y, X, z0 - self.z_lo, y0, x0, act, st), "rb_blend_accumulate")
+            first = False
+
+    def finalize(self, z_from: Optional[int] = None, z_to: Optional[int] = None, keep_float: bool = False):
+        """Finalise + cast the planes [z_from, z_to) (volume coordinates, default: whole slab).
+        Returns {target: uint8 | uint16 tensor [c, z, Y, X]} (c == 1 squeezed like the reference's
+        arrays) and, if keep_float, the finalised fp32 values as well."""
+        z_from = self.z_lo if z_from is None else int(z_from)
+        z_to = self.z_hi if z_to is None else int(z_to)
+        _, Y, X = self.vol_shape
+        nz = z_to - z_from
+        V = nz * Y * X
+        out, flt = {}, {}
+        st = L.stream_ptr(self.device)
+        a = z_from - self.z_lo
+        wsum = self.wsum[a:a + nz].contiguous()
+        for t, info in self.targets.items():
+            c = info["channels"]
+            normals = t.lower() == "normals"
+            s = self.sums[t][:, a:a + nz].contiguous()
+            res = torch.empty((c, nz, Y, X), dtype=torch.uint16 if normals else torch.uint8, device=self.device)
+            f = torch.empty((c, nz, Y, X), dtype=torch.float32, device=self.device) if keep_float else None
+            L.check(self._lib.rb_blend_finalize_cast(s.data_ptr(), wsum.data_ptr(), res.data_ptr(), L.ptr(f), V, c,
+                                                     1 if normals else 0, st), "rb_blend_finalize_cast")
+            out[t] = res[0] if c == 1 else res
+            if keep_float:
+                flt[t] = f[0] if c == 1 else f
+        return (out, flt) if keep_float else out
+
+
+class DeviceVolume:
+    """A z-range of the input volume resident in HBM, with on-device patch extraction."""
+
+    def __init__(self, volume, z_lo: int, z_hi: int, device, chunk_planes: int = 64):
+        shape = tuple(int(s) for s in volume.shape[-3:])
+        self.shape = shape
+        self.z_lo, self.z_hi = int(z_lo), int(z_hi)
+        self.device = torch.device(device)
+        dt = np.dtype(volume.dtype)
+        if dt == np.uint8:
+            tdt, self.is_u16 = torch.uint8, 0
+        elif dt == np.uint16:
+            tdt, self.is_u16 = torch.uint16, 1
+        else:
+            raise NotImplementedError(f"input volumes must be uint8 or uint16, got {dt}")
+        self.data = torch.empty((self.z_hi - self.z_lo, shape[1], shape[2]), dtype=tdt, device=self.device)
+        self.h2d_bytes = 0
+        for z in range(self.z_lo, self.z_hi, chunk_planes):
+            z1 = min(z + chunk_planes, self.z_hi)
+            blk = np.ascontiguousarray(volume[z:z1])          # zarr-style slicing interface
+            host = torch.from_numpy(blk)
+            if self.device.type == "cuda":
+                host = host.pin_memory()
+            self.data[z - self.z_lo:z1 - self.z_lo].copy_(host, non_blocking=True)
+            self.h2d_bytes += blk.nbytes
+        self._stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._lib = L.load()
+
+    def extract(self, position, patch_size, out: torch.Tensor, standardize: bool = True):
+        """out: fp32 [pz, py, px] slice of the batch buffer."""
+        z0, y0, x0 = (int(v) for v in position)
+        pz, py, px = (int(p) for p in patch_size)
+        L.check(self._lib.rb_extract_patch(self.data.data_ptr(), self.is_u16, self.z_hi - self.z_lo, self.shape[1],
+                                           self.shape[2], z0 - self.z_lo, y0, x0, pz, py, px, 1 if standardize else 0,
+                                           self._stats.data_ptr(), out.data_ptr(), L.stream_ptr(self.device)),
+                "rb_extract_patch")
+
+
+# ------------------------------------------------------------------------------------------
+# the sweep
+# ------------------------------------------------------------------------------------------
+class SlidingWindowInferer:
+    """Runs `model` (eval mode) over every patch of `volume` and blends the predictions.
+
+    Mirrors the loop body of the reference's ZarrInferenceHandler.infer (inference.py:116-263):
+    model(patches) -> optional second activation from `targets[...]['activation']` -> accumulate ->
+    finalise -> cast.  `rank`/`world_size` select a contiguous run of z-starts (z-slab sharding).
+    """
+
+    def __init__(self, model, targets: Dict[str, dict], patch_size, overlap: float = 0.5, batch_size: int = 1,
+                 weight: str = "uniform", standardize: bool = True, in_channels: int = 1, rank: int = 0,
+                 world_size: int = 1, device=None):
+        self.model = model
+        self.targets = targets
+        self.patch = tuple(int(p) for p in patch_size)
+        self.overlap = float(overlap)
+        self.batch_size = int(batch_size)
+        self.weight = weight
+        self.standardize = standardize
+        self.in_channels = in_channels
+        self.rank, self.world = int(rank), int(world_size)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if in_channels != 1:
+            raise NotImplementedError("the reference's InferenceDataset yields single-channel patches "
+                                      "(inference_dataset.py:73); multi-channel sweeps are not implemented")
+
+    def plan(self, vol_shape):
+        zs, ys, xs = axis_positions(vol_shape, self.patch, self.overlap)
+        mine = shard_z_starts(zs, self.world)[self.rank]
+        positions = [(z, y, x) for z in mine for y in ys for x in xs]
+        if mine:
+            z_lo, z_hi = mine[0], mine[-1] + self.patch[0]
+        else:
+            z_lo = z_hi = 0
+        return positions, z_lo, z_hi, (zs, ys, xs)
+
+    @torch.no_grad()
+    def sweep(self, volume):
+        """Accumulate this rank's patches.  Returns the SlabBlender (un-finalised)."""
+        vol_shape = tuple(int(s) for s in volume.shape[-3:])
+        positions, z_lo, z_hi, _ = self.plan(vol_shape)
+        blender = SlabBlender(self.targets, vol_shape, self.patch, z_lo, z_hi, self.device, self.weight)
+        if not positions:
+            return blender
+        dvol = DeviceVolume(volume, z_lo, z_hi, self.device)
+        self.h2d_bytes = dvol.h2d_bytes
+        was_training = self.model.training
+        self.model.eval()
+        B = self.batch_size
+        try:
+            for i in range(0, len(positions), B):
+                chunk = positions[i:i + B]
+                batch = torch.empty((len(chunk), 1, *self.patch), dtype=torch.float32, device=self.device)
+                for j, pos in enumerate(chunk):
+                    dvol.extract(pos, self.patch, batch[j, 0], self.standardize)
+                preds = self.model(batch)
+                for j, pos in enumerate(chunk):
+                    blender.add(preds, j, pos, apply_activation=True)
+        finally:
+            self.model.train(was_training)
+        return blender
+
+    def run(self, volume, keep_float: bool = False):
+        """Single-process convenience: sweep + finalise the whole volume (world_size must be 1)."""
+        if self.world != 1:
+            raise RuntimeError("run() is single-rank; use sweep() + merge_slabs() under torch.distributed")
+        return self.sweep(volume).finalize(keep_float=keep_float)
+
+
+def plan_slab_exchange(z_starts: Sequence[int], patch_z: int, vol_z: int, world_size: int):
+    """Pure host logic of the end-of-sweep exchange.  Returns (pairs, own) where own[r] = [lo, hi) is the
+    z-range rank r finalises and pairs = [(src, dst, lo, hi)]: planes [lo, hi) of src's slab that must be
+    added into dst's slab (src < dst)."""
+    runs = shard_z_starts(z_starts, world_size)
+    first = [run[0] if run else None for run in runs]
+    nonempty = [r for r in range(world_size) if runs[r]]
+    own = []
+    for r in range(world_size):
+        if not runs[r]:
+            own.append((0, 0))
+            continue
+        later = [first[q] for q in nonempty if q > r]
+        own.append((first[r], later[0] if later else int(vol_z)))
+    pairs = []
+    for src in nonempty:
+        s_lo, s_hi = runs[src][0], runs[src][-1] + patch_z
+        for dst in nonempty:
+            if dst <= src:
+                continue
+            lo, hi = max(s_lo, own[dst][0]), min(s_hi, own[dst][1])
+            if lo < hi:
+                pairs.append((src, dst, lo, hi))
+    return pairs, own
+
+
+def _device_add(dst: torch.Tensor, src: torch.Tensor):
+    """dst += src through the C ABI (fp32, CUDA only)."""
+    L.require_cuda(dst, "slab merge")
+    lib = L.load()
+    if dst.is_contiguous():
+        L.check(lib.rb_blend_add(dst.data_ptr(), src.data_ptr(), dst.numel(), L.stream_ptr(dst.device)), "rb_blend_add")
+    else:   # [c, a:b] slice of a slab: every channel block is contiguous
+        for ch in range(dst.shape[0]):
+            L.check(lib.rb_blend_add(dst[ch].data_ptr(), src[ch].data_ptr(), dst[ch].numel(),
+                                     L.stream_ptr(dst.device)), "rb_blend_add")
+
+
+def merge_slabs(blender: SlabBlender, z_starts: Sequence[int], rank: int, world_size: int, group=None,
+                add_fn=_device_add):
+    """Add the planes a slab shares with later slabs' owners so that every output plane is complete on
+    exactly one rank, then return that rank's owned z-range [own_lo, own_hi).
+
+    Ownership: rank r owns [first z-start of r, first z-start of r+1) (the last non-empty rank owns
+    up to the end of the volume).  A slab extends patch_z beyond its last start, so it overlaps the
+    next ranks' owned ranges: those planes are sent forward and added there.  Uses point-to-point
+    torch.distributed (NCCL on GPUs, gloo in the CPU tests); no collective touches the sweep."""
+    import torch.distributed as dist
+    pairs, own = plan_slab_exchange(z_starts, blender.patch[0], blender.vol_shape[0], world_size)
+    names = list(blender.sums.keys())
+    for src, dst, lo, hi in pairs:
+        a, b = lo - blender.z_lo, hi - blender.z_lo
+        if rank == src:
+            for t in names:
+                dist.send(blender.sums[t][:, a:b].contiguous(), dst, group=group)
+            dist.send(blender.wsum[a:b].contiguous(), dst, group=group)
+        elif rank == dst:
+            for t in names + [None]:
+                tgt = blender.wsum[a:b] if t is None else blender.sums[t][:, a:b]
+                buf = torch.empty(tgt.shape, dtype=tgt.dtype, device=tgt.device)
+                dist.recv(buf, src, group=group)
+                add_fn(tgt, buf)
+    return own[rank]

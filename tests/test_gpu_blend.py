@@ -1,0 +1,164 @@
+"""GPU parity of the sliding-window path against the oracle's restatement of the reference loop
+(inference.py:116-263).  Integer / index work and the uniform blend are BIT-EXACT; the Gaussian
+blend is bit-exact too (fp32 multiply-then-add without contraction, same order as numpy)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import case_mgr, golden_state, make_mgr, quiet_build, state_dict_from_params
+from oracle import resenc_oracle as O   # checker only
+
+pytestmark = pytest.mark.gpu
+
+TARGETS = {"sheet": {"channels": 1, "activation": "none"}, "normals": {"channels": 3, "activation": "none"}}
+
+
+@pytest.fixture(autouse=True)
+def _device_error_guard(rb):
+    yield
+    rb._lib.device_error_check()
+
+
+def _random_preds(n, patch, seed):
+    rng = np.random.default_rng(seed)
+    return {"sheet": rng.random((n, 1, *patch), dtype=np.float32),
+            "normals": rng.standard_normal((n, 3, *patch)).astype(np.float32)}
+
+
+@pytest.mark.parametrize("vol,patch,overlap", [((24, 20, 28), (16, 16, 16), 0.5), ((16, 16, 16), (16, 16, 16), 0.5),
+                                               ((40, 17, 33), (16, 16, 32), 0.25), ((19, 23, 21), (8, 8, 8), 0.1)])
+@pytest.mark.parametrize("weight", ["uniform", "gaussian"])
+def test_blend_bit_exact(rb, vol, patch, overlap, weight):
+    inf = rb.inference
+    pos = inf.all_positions(vol, patch, overlap)
+    assert pos == O.all_positions(vol, patch, overlap)
+    preds = _random_preds(len(pos), patch, 11)
+    if weight == "uniform":
+        sums, cnt = O.blend_reference(preds, pos, vol, TARGETS)
+    else:
+        sums, cnt = O.blend_weighted_reference(preds, pos, vol, TARGETS, O.gaussian_map(patch))
+    exp = O.finalize_reference(sums, cnt, TARGETS)
+    bl = inf.SlabBlender(TARGETS, vol, patch, 0, vol[0], "cuda", weight)
+    dev = {t: torch.from_numpy(v).cuda() for t, v in preds.items()}
+    B = 3
+    for i in range(0, len(pos), B):
+        chunk = {t: v[i:i + B].contiguous() for t, v in dev.items()}
+        for j in range(min(B, len(pos) - i)):
+            bl.add(chunk, j, pos[i + j])
+    for t in TARGETS:
+        got = bl.sums[t].cpu().numpy()
+        ref = sums[t] if sums[t].ndim == 4 else sums[t][None]
+        assert np.array_equal(got, ref), t
+    assert np.array_equal(bl.wsum.cpu().numpy(), cnt["sheet"])
+    out = bl.finalize()
+    for t in TARGETS:
+        assert out[t].cpu().numpy().dtype == exp[t].dtype
+        assert np.array_equal(out[t].cpu().numpy(), exp[t]), t
+
+
+def test_finalize_edge_cases(rb):
+    """zeros (count == 0 stays untouched), values outside [0, 1] clip, zero-length normals, NaN-free."""
+    inf = rb.inference
+    vol, patch = (8, 8, 8), (4, 4, 4)
+    bl = inf.SlabBlender(TARGETS, vol, patch, 0, 8, "cuda", "uniform")
+    preds = {"sheet": np.full((1, 1, 4, 4, 4), 1.7, np.float32), "normals": np.zeros((1, 3, 4, 4, 4), np.float32)}
+    preds["sheet"][0, 0, 0, 0, 0] = -0.3
+    pos = [(0, 0, 0), (2, 2, 2)]
+    both = {t: np.concatenate([v, v]) for t, v in preds.items()}
+    sums, cnt = O.blend_reference(both, pos, vol, TARGETS)
+    exp = O.finalize_reference(sums, cnt, TARGETS)
+    dev = {t: torch.from_numpy(v).cuda() for t, v in both.items()}
+    for j, p in enumerate(pos):
+        bl.add(dev, j, p)
+    out = bl.finalize()
+    for t in TARGETS:
+        assert np.array_equal(out[t].cpu().numpy(), exp[t]), t
+    assert out["sheet"].max().item() == 255 and out["sheet"][7, 7, 7].item() == 0
+    assert out["normals"][0, 0, 0, 0].item() == 32767
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_extract_and_standardize(rb, dtype):
+    inf = rb.inference
+    rng = np.random.default_rng(5)
+    hi = 255 if dtype == np.uint8 else 65535
+    vol = rng.integers(0, hi + 1, size=(20, 24, 28)).astype(dtype)
+    dv = inf.DeviceVolume(vol, 4, 20, "cuda")
+    out = torch.empty((8, 16, 12), dtype=torch.float32, device="cuda")
+    dv.extract((6, 3, 9), (8, 16, 12), out, standardize=True)
+    ref = O.standardize_patch(vol[6:14, 3:19, 9:21].astype(np.float32) / np.float32(hi))
+    assert np.allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+    dv.extract((6, 3, 9), (8, 16, 12), out, standardize=False)
+    assert np.array_equal(out.cpu().numpy(), vol[6:14, 3:19, 9:21].astype(np.float32) / np.float32(hi))
+    const = np.full((8, 8, 8), 7, dtype)
+    dc = inf.DeviceVolume(const, 0, 8, "cuda")
+    o2 = torch.empty((8, 8, 8), dtype=torch.float32, device="cuda")
+    dc.extract((0, 0, 0), (8, 8, 8), o2, standardize=True)
+    assert torch.isfinite(o2).all() and float(o2.abs().max()) < 1e-3   # std clipped at 1e-10, numerator ~0
+
+
+def test_sliding_window_end_to_end_and_slab_sharding(rb):
+    """Whole sweep on a 48x32x32 volume with the 16^3 golden network: single slab == oracle blend of the
+    same per-patch predictions (bit-exact), and a 2-slab z-sharded sweep merged on one GPU gives the same
+    finalised volume up to fp32 re-association in the overlap planes."""
+    inf = rb.inference
+    case = "sheet_normals_16"
+    mgr, _ = case_mgr(case)
+    model = quiet_build(rb.NetworkFromConfig, mgr)
+    model.load_state_dict(state_dict_from_params(model, golden_state(case)))
+    model = model.cuda().eval()
+    rng = np.random.default_rng(9)
+    vol = rng.integers(0, 256, size=(48, 32, 32)).astype(np.uint8)
+    patch = (16, 16, 16)
+    targets = {"sheet": {"channels": 1, "activation": "none"}, "normals": {"channels": 3, "activation": "none"}}
+    sw = inf.SlidingWindowInferer(model, targets, patch, overlap=0.5, batch_size=2, weight="uniform")
+    blender = sw.sweep(vol)
+    out, flt = blender.finalize(keep_float=True)
+    # replay: same patches through the same model, blended by the oracle loop
+    pos = inf.all_positions(vol.shape, patch, 0.5)
+    preds = {t: [] for t in targets}
+    dv = inf.DeviceVolume(vol, 0, vol.shape[0], "cuda")
+    with torch.no_grad():
+        for i in range(0, len(pos), 2):
+            batch = torch.empty((len(pos[i:i + 2]), 1, *patch), dtype=torch.float32, device="cuda")
+            for j, (z, y, x) in enumerate(pos[i:i + 2]):
+                dv.extract((z, y, x), patch, batch[j, 0], True)
+                p = O.standardize_patch(vol[z:z + 16, y:y + 16, x:x + 16].astype(np.float32) / np.float32(255))
+                assert np.allclose(batch[j, 0].cpu().numpy(), p, rtol=1e-4, atol=1e-5)
+            o = model(batch)
+            for t in targets:
+                preds[t].append(o[t].cpu().numpy())
+    preds = {t: np.concatenate(v) for t, v in preds.items()}
+    sums, cnt = O.blend_reference(preds, pos, vol.shape, targets)
+    exp = O.finalize_reference(sums, cnt, targets)
+    for t in targets:
+        # split-K / statistics atomics make two runs of the network differ in the last bf16 ulp of a
+        # few activations, so the replayed predictions are compared with a tolerance, not bit-wise
+        ref = sums[t].copy()
+        if t == "normals":
+            ref /= (np.sqrt((ref ** 2).sum(0)) + 1e-8)
+        else:
+            ref /= cnt[t]
+        assert np.abs(flt[t].cpu().numpy() - ref).max() < 3e-2, t
+        got = out[t].cpu().numpy().astype(np.int64)
+        lim = 8 if t == "sheet" else 1000
+        assert np.abs(got - exp[t].astype(np.int64)).max() <= lim, t
+    # z-slab sharding, two ranks emulated sequentially on one device
+    zs = inf.axis_positions(vol.shape, patch, 0.5)[0]
+    slabs = []
+    for r in range(2):
+        swr = inf.SlidingWindowInferer(model, targets, patch, overlap=0.5, batch_size=2, weight="uniform", rank=r,
+                                       world_size=2)
+        slabs.append(swr.sweep(vol))
+    pairs, own = inf.plan_slab_exchange(zs, patch[0], vol.shape[0], 2)
+    for src, dst, lo, hi in pairs:
+        s, d = slabs[src], slabs[dst]
+        for t in list(targets) + [None]:
+            a = s.wsum[lo - s.z_lo:hi - s.z_lo] if t is None else s.sums[t][:, lo - s.z_lo:hi - s.z_lo]
+            b = d.wsum[lo - d.z_lo:hi - d.z_lo] if t is None else d.sums[t][:, lo - d.z_lo:hi - d.z_lo]
+            b += a
+    merged = {t: torch.cat([slabs[r].finalize(*own[r])[t] for r in range(2)], dim=-3) for t in targets}
+    for t in targets:
+        diff = (merged[t].long() - out[t].long()).abs()
+        assert diff.max().item() <= (8 if t == "sheet" else 1000), t
+        assert merged[t].shape == out[t].shape

@@ -1,0 +1,259 @@
+"""GPU parity tests of the individual operators (through ops -> C ABI -> sm_100a kernels) against
+plain PyTorch fp32 references on the same bf16-rounded operands.
+
+Tolerances (stated here, relative L2 unless noted):
+  bf16 outputs (one rounding of an fp32 accumulator)      4e-3
+  fp32 outputs of bf16 x bf16 products (wgrad, heads)      2e-4
+Implementation under test is selected by RESENC_CONV_IMPL (auto | mma | tc5), default auto.
+"""
+import itertools
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL_BF16 = 4e-3
+TOL_F32 = 2e-4
+
+
+def q(t):
+    """bf16-round, keep fp32 (what the kernels see)."""
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.fixture(autouse=True)
+def _device_error_guard(rb):
+    yield
+    rb._lib.device_error_check()
+
+
+CONV_CASES = [
+    # n, cin, cout, dims, kernel, stride
+    (2, 32, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (2, 32, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2)),
+    (1, 64, 128, (8, 8, 8), (3, 3, 3), (1, 1, 1)),
+    (2, 64, 32, (8, 12, 20), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 64, (8, 16, 16), (1, 3, 3), (1, 2, 2)),
+    (1, 8, 16, (6, 10, 14), (3, 3, 3), (1, 1, 1)),
+    (2, 128, 128, (4, 4, 4), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 32, (10, 12, 18), (3, 3, 3), (2, 2, 2)),
+    (2, 512, 512, (4, 4, 4), (3, 3, 3), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"n{c[0]}_{c[1]}to{c[2]}_{'x'.join(map(str, c[3]))}_k{c[4][1]}s{c[5][1]}")
+def test_conv3d_fwd_bwd(rb, case):
+    n, cin, cout, dims, k, s = case
+    torch.manual_seed(0)
+    x = q(torch.randn(n, cin, *dims, device="cuda"))
+    w = (torch.randn(cout, cin, *k, device="cuda") / (cin * k[0] * k[1] * k[2]) ** 0.5).requires_grad_(True)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, q(w), None, s, pad)
+    xp = x.clone().requires_grad_(True)
+    y = rb.ops.conv3d(xp, w, s)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    assert rel_l2(y.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    gw_ref = torch.autograd.grad(F.conv3d(x, w, None, s, pad), w, g)[0]
+    y.backward(g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d))
+    assert rel_l2(xp.grad.float(), xr.grad) < TOL_BF16
+    assert rel_l2(w.grad, gw_ref) < TOL_F32
+
+
+def test_conv3d_two_sources_equals_cat(rb):
+    torch.manual_seed(1)
+    a = q(torch.randn(2, 32, 8, 8, 8, device="cuda"))
+    b = q(torch.randn(2, 32, 8, 8, 8, device="cuda"))
+    w = (torch.randn(32, 64, 3, 3, 3, device="cuda") / 40).requires_grad_(True)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv3d(torch.cat((ar, br), 1), q(w), None, 1, 1)
+    ap, bp = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = rb.ops.conv3d(ap, w, 1, x_cat=bp)
+    assert rel_l2(y.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    gw_ref = torch.autograd.grad(F.conv3d(torch.cat((a, b), 1), w, None, 1, 1), w, g)[0]
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(ap.grad.float(), ar.grad) < TOL_BF16
+    assert rel_l2(bp.grad.float(), br.grad) < TOL_BF16
+    assert rel_l2(w.grad, gw_ref) < TOL_F32
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("cin,cout", [(64, 32), (128, 64), (16, 8)])
+def test_conv_transpose3d(rb, stride, cin, cout):
+    torch.manual_seed(2)
+    x = q(torch.randn(2, cin, 4, 6, 8, device="cuda"))
+    w = (torch.randn(cin, cout, *stride, device="cuda") / cin ** 0.5).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, q(w), None, stride)
+    xp = x.clone().requires_grad_(True)
+    y = rb.ops.conv_transpose3d(xp, w, stride)
+    assert y.shape == ref.shape
+    assert rel_l2(y.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    gw_ref = torch.autograd.grad(F.conv_transpose3d(x, w, None, stride), w, g)[0]
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(xp.grad.float(), xr.grad) < TOL_BF16
+    assert rel_l2(w.grad, gw_ref) < TOL_F32
+
+
+@pytest.mark.parametrize("affine", [False, True])
+@pytest.mark.parametrize("with_res,act", [(False, True), (True, True), (False, False)])
+@pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 64, 4, 6, 10), (2, 512, 4, 4, 4), (1, 8, 16, 16, 16)])
+def test_instance_norm_act(rb, affine, with_res, act, shape):
+    torch.manual_seed(3)
+    n, c = shape[:2]
+    y = q(torch.randn(shape, device="cuda") * 2 + 0.5)
+    res = q(torch.randn(shape, device="cuda")) if with_res else None
+    gamma = (1 + 0.2 * torch.randn(c, device="cuda")).requires_grad_(True) if affine else None
+    beta = (0.1 * torch.randn(c, device="cuda")).requires_grad_(True) if affine else None
+
+    def reference(yy, rr, ga, be):
+        o = F.instance_norm(yy, None, None, ga, be, True, 0.0, 1e-5)
+        if rr is not None:
+            o = o + rr
+        return F.leaky_relu(o, 0.01) if act else o
+
+    yr = y.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if with_res else None
+    gr = gamma.detach().clone().requires_grad_(True) if affine else None
+    br = beta.detach().clone().requires_grad_(True) if affine else None
+    ref = reference(yr, rr, gr, br)
+    yp = y.clone().requires_grad_(True)
+    rp = res.clone().requires_grad_(True) if with_res else None
+    z = rb.ops.instance_norm_act(yp, rp, gamma, beta, 1e-5, act, 0.01)
+    assert rel_l2(z.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    z.backward(g.to(torch.bfloat16))
+    # the kernel's lrelu mask comes from the bf16-rounded output; elements within rounding of 0 may flip
+    assert rel_l2(yp.grad.float(), yr.grad) < 8e-3
+    if with_res:
+        assert rel_l2(rp.grad.float(), rr.grad) < 8e-3
+    if affine:
+        assert rel_l2(gamma.grad, gr.grad) < 5e-3
+        assert rel_l2(beta.grad, br.grad) < 5e-3
+
+
+@pytest.mark.parametrize("reduce_dims", ["all", (2, 3)])
+@pytest.mark.parametrize("affine", [False, True])
+def test_instance_norm_se_act(rb, reduce_dims, affine):
+    torch.manual_seed(4)
+    n, c, rd = 2, 32, 8
+    shape = (n, c, 6, 8, 10)
+    y = q(torch.randn(shape, device="cuda") * 1.5 + 0.3)
+    res = q(torch.randn(shape, device="cuda"))
+    params = [torch.randn(rd, c, 1, 1, 1, device="cuda") * 0.3, torch.randn(rd, device="cuda") * 0.1,
+              torch.randn(c, rd, 1, 1, 1, device="cuda") * 0.3, torch.randn(c, device="cuda") * 0.1]
+    gamma = (1 + 0.2 * torch.randn(c, device="cuda")) if affine else None
+    beta = (0.3 * torch.randn(c, device="cuda")) if affine else None
+
+    def reference(yy, rr, ga, be, w1, b1, w2, b2):
+        o = F.instance_norm(yy, None, None, ga, be, True, 0.0, 1e-5)
+        dims = (2, 3, 4) if reduce_dims == "all" else reduce_dims
+        s = o.mean(dims, keepdim=True)
+        s = F.conv3d(F.relu(F.conv3d(s, w1, b1)), w2, b2)
+        return F.leaky_relu(o * torch.sigmoid(s) + rr, 0.01)
+
+    leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)
+    ref_in = [leaf(t) for t in [y, res, gamma, beta] + params]
+    ref = reference(*ref_in)
+    prod_in = [leaf(t) for t in [y, res, gamma, beta] + params]
+    z = rb.ops.instance_norm_se_act(prod_in[0], prod_in[1], prod_in[2], prod_in[3], *prod_in[4:], eps=1e-5, act=True,
+                                    slope=0.01, reduce_dims=reduce_dims)
+    assert rel_l2(z.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    z.backward(g.to(torch.bfloat16))
+    names = ["y", "res", "gamma", "beta", "fc1.w", "fc1.b", "fc2.w", "fc2.b"]
+    for nm, a, b in zip(names, prod_in, ref_in):
+        if a is None:
+            continue
+        assert a.grad is not None, nm
+        assert rel_l2(a.grad.float(), b.grad) < 1e-2, nm
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+def test_avg_pool(rb, stride):
+    torch.manual_seed(5)
+    x = q(torch.randn(2, 32, 4, 8, 12, device="cuda"))
+    xr = x.clone().requires_grad_(True)
+    ref = F.avg_pool3d(xr, stride, stride)
+    xp = x.clone().requires_grad_(True)
+    out = rb.ops.avg_pool3d(xp, stride)
+    assert rel_l2(out.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    out.backward(g.to(torch.bfloat16))
+    assert rel_l2(xp.grad.float(), xr.grad) < TOL_BF16
+
+
+@pytest.mark.parametrize("k,act", [(1, None), (3, None), (1, "sigmoid"), (3, "softmax"), (2, "softmax")])
+def test_head(rb, k, act):
+    torch.manual_seed(6)
+    x = q(torch.randn(2, 32, 6, 8, 10, device="cuda"))
+    w = (torch.randn(k, 32, 1, 1, 1, device="cuda") * 0.2).requires_grad_(True)
+    b = (torch.randn(k, device="cuda") * 0.1).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ref = F.conv3d(xr, wr, br)
+    if act == "sigmoid":
+        ref = torch.sigmoid(ref)
+    elif act == "softmax":
+        ref = torch.softmax(ref, 1)
+    xp = x.clone().requires_grad_(True)
+    out = rb.ops.head_conv1x1(xp, w, b, act)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == ref.shape
+    assert rel_l2(out, ref) < 1e-5
+    if act is None:
+        g = torch.randn_like(ref)
+        ref.backward(g)
+        out.backward(g)
+        assert rel_l2(xp.grad.float(), xr.grad) < TOL_BF16
+        assert rel_l2(w.grad, wr.grad) < TOL_F32
+        assert rel_l2(b.grad, br.grad) < TOL_F32
+
+
+@pytest.mark.parametrize("cin", [1, 2, 4])
+def test_stem_conv(rb, cin):
+    torch.manual_seed(7)
+    x = q(torch.rand(2, cin, 8, 10, 12, device="cuda"))
+    w = (torch.randn(32, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5).requires_grad_(True)
+    ref = F.conv3d(x, q(w), None, 1, 1)
+    y = rb.ops.stem_conv3d(x, w)
+    assert rel_l2(y.float(), ref) < TOL_BF16
+    g = q(torch.randn_like(ref))
+    gw_ref = torch.autograd.grad(F.conv3d(x, w, None, 1, 1), w, g)[0]
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(w.grad, gw_ref) < TOL_F32
+
+
+def test_layout_roundtrip(rb):
+    x = q(torch.randn(2, 16, 3, 5, 7, device="cuda"))
+    cl = rb.ops.as_cl(x)
+    assert rb.ops.is_cl(cl) and torch.equal(cl.float(), x)
+    back = rb.ops.cl_to_ncdhw_f32(cl)
+    assert back.is_contiguous() and torch.equal(back, x)
+
+
+def test_conv_linearity_at_full_resolution(rb):
+    """Size-independent property at the headline layer shape (32 -> 32 @ 128^3): conv(2x) == 2 conv(x)
+    exactly in bf16 (scaling by a power of two commutes with every rounding)."""
+    torch.manual_seed(8)
+    x = rb.ops.as_cl(torch.randn(1, 32, 128, 128, 128, device="cuda"))
+    w = torch.randn(32, 32, 3, 3, 3, device="cuda") / 30
+    a = rb.ops.conv3d(x, w, 1)
+    b = rb.ops.conv3d((x.float() * 2).to(torch.bfloat16), w, 1)
+    assert torch.equal(b.float(), a.float() * 2)
+    # translation equivariance away from the border: shifting the input by one voxel along W
+    xs = torch.roll(x, 1, dims=4)
+    c = rb.ops.conv3d(xs, w, 1)
+    assert torch.equal(c[..., 2:-2].float(), torch.roll(a, 1, dims=4)[..., 2:-2].float())

