@@ -1,0 +1,128 @@
+"""The tcgen05 / TMEM / TMA gather-conv kernel against (a) PyTorch fp32 on bf16-rounded operands and
+(b) the shape-generic mma.sync kernel, on every geometry class the network uses: 3x3x3 stride 1 / 2,
+1x1x1, two K-segments (virtual concat), parity-class dgrad with strided stores, pixel-shuffle transposed
+conv and its k2s2 data gradient, ragged grids (TMA out-of-bounds fill), batch-folded tiles (tn > 1),
+N tiles of 32..256 and the fused InstanceNorm statistics epilogue."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 4e-3
+
+
+def q(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.fixture(autouse=True)
+def _device_error_guard(rb):
+    yield
+    rb._lib.device_error_check()
+
+
+CASES = [
+    (2, 32, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (1, 64, 64, (16, 16, 16), (3, 3, 3), (1, 1, 1)),
+    (2, 32, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2)),
+    (1, 128, 128, (8, 8, 8), (3, 3, 3), (1, 1, 1)),
+    (2, 64, 32, (8, 12, 20), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 64, (8, 16, 16), (1, 3, 3), (1, 2, 2)),
+    (1, 16, 32, (6, 10, 14), (3, 3, 3), (1, 1, 1)),
+    (2, 256, 256, (4, 4, 4), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 32, (10, 12, 18), (3, 3, 3), (2, 2, 2)),
+    (2, 256, 512, (8, 8, 8), (3, 3, 3), (2, 2, 2)),
+    (1, 48, 96, (8, 8, 24), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 32, (64, 64, 64), (3, 3, 3), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c[0]}_{c[1]}to{c[2]}_{'x'.join(map(str, c[3]))}_k{c[4][1]}s{c[5][1]}")
+def test_tc5_conv_fwd_bwd(rb, case):
+    n, cin, cout, dims, k, s = case
+    torch.manual_seed(0)
+    x = q(torch.randn(n, cin, *dims, device="cuda"))
+    w = (torch.randn(cout, cin, *k, device="cuda") / (cin * k[0] * k[1] * k[2]) ** 0.5).requires_grad_(True)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv3d(xr, q(w), None, s, pad)
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    outs = {}
+    for impl in ("tc5", "mma"):
+        xp = x.clone().requires_grad_(True)
+        y = rb.ops.conv3d(xp, w, s, impl=impl)
+        y.backward(g.to(torch.bfloat16))
+        outs[impl] = (y.detach().float(), xp.grad.float())
+        rb._lib.device_error_check()
+    e_f, e_b = rel_l2(outs["tc5"][0], ref), rel_l2(outs["tc5"][1], xr.grad)
+    print(f"tc5 fwd {e_f:.2e} bwd {e_b:.2e}; mma fwd {rel_l2(outs['mma'][0], ref):.2e}; "
+          f"tc5-vs-mma {rel_l2(outs['tc5'][0], outs['mma'][0]):.2e}")
+    assert e_f < TOL and e_b < TOL
+    assert rel_l2(outs["tc5"][0], outs["mma"][0]) < 3e-3
+
+
+def test_tc5_two_sources(rb):
+    torch.manual_seed(1)
+    a = q(torch.randn(2, 64, 8, 8, 8, device="cuda"))
+    b = q(torch.randn(2, 64, 8, 8, 8, device="cuda"))
+    w = torch.randn(64, 128, 3, 3, 3, device="cuda") / 58
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv3d(torch.cat((ar, br), 1), q(w), None, 1, 1)
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    ap, bp = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = rb.ops.conv3d(ap, w, 1, x_cat=bp, impl="tc5")
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(y.float(), ref) < TOL
+    assert rel_l2(ap.grad.float(), ar.grad) < TOL and rel_l2(bp.grad.float(), br.grad) < TOL
+
+
+@pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("cin,cout", [(64, 32), (512, 256)])
+def test_tc5_conv_transpose(rb, stride, cin, cout):
+    torch.manual_seed(2)
+    x = q(torch.randn(2, cin, 4, 6, 8, device="cuda"))
+    w = torch.randn(cin, cout, *stride, device="cuda") / cin ** 0.5
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, q(w), None, stride)
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    xp = x.clone().requires_grad_(True)
+    y = rb.ops.conv_transpose3d(xp, w, stride, impl="tc5")
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(y.float(), ref) < TOL
+    assert rel_l2(xp.grad.float(), xr.grad) < TOL
+
+
+def test_tc5_fused_statistics(rb):
+    """Sum / sum-of-squares epilogue == reductions of the fp32 accumulators (compared with the stored
+    bf16 output, so within bf16 rounding)."""
+    torch.manual_seed(3)
+    ops = rb.ops
+    for n, c, dims in [(2, 32, (16, 16, 16)), (2, 128, (4, 4, 4)), (1, 64, (10, 12, 14))]:
+        x = ops.as_cl(torch.randn(n, c, *dims, device="cuda"))
+        w = torch.randn(c, c, 3, 3, 3, device="cuda") / (27 * c) ** 0.5
+        y = ops.new_cl(n, c, *dims, "cuda")
+        ssum = torch.zeros(n, c, device="cuda")
+        ssq = torch.zeros(n, c, device="cuda")
+        ops._launch_gather(x, None, ops.pack_conv_fprop(w), y, None, in_dims=dims, taps=(3, 3, 3), off=(-1, -1, -1),
+                           istr=(1, 1, 1), out_grid=dims, nout=c, impl="tc5", stats=(ssum, ssq))
+        yf = y.float()
+        assert rel_l2(ssum, yf.sum((2, 3, 4))) < 5e-3
+        assert rel_l2(ssq, (yf * yf).sum((2, 3, 4))) < 5e-3
+
+
+def test_tc5_support_query(rb, built_lib):
+    d = rb._lib.ConvDesc()
+    for f, v in dict(nsrc=1, srcC0=8, NB=1, ID=4, IH=4, IW=4, tapD=3, tapH=3, tapW=3, offD=-1, offH=-1, offW=-1, istrD=1,
+                     istrH=1, istrW=1, OD=4, OH=4, OW=4, Nout=32, ostrD=1, ostrH=1, ostrW=1, FD=4, FH=4, FW=4, outC0=32,
+                     psD=1, psH=1, psW=1).items():
+        setattr(d, f, v)
+    assert built_lib.rb_conv_gather_tc5_supported(ctypes.byref(d)) == 0    # C % 16 != 0 -> mma.sync path
+    d.srcC0 = 32
+    assert built_lib.rb_conv_gather_tc5_supported(ctypes.byref(d)) == 1
