@@ -15,6 +15,7 @@ Reference arithmetic replaced (path:line under the reference tree):
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import itertools
 
@@ -24,6 +25,46 @@ from . import _lib as L
 
 BF16 = torch.bfloat16
 LRELU_SLOPE_DEFAULT = 0.01
+
+
+class _KernelTimer:
+    """Optional CUDA-event spans around kernel launches on the launching stream (bench.py's roofline
+    numbers: per-category device time and algorithmic FLOPs).  Disabled unless bench.py enables it."""
+
+    def __init__(self):
+        self.on = False
+        self.records = []
+
+    def enable(self, on=True):
+        self.on = bool(on)
+        if on:
+            self.records = []
+
+    @contextlib.contextmanager
+    def span(self, kind, flops=0.0):
+        if not self.on:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.records.append((kind, flops, a, b))
+
+    def summary(self):
+        if not self.records:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, a, b in self.records:
+            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += flops
+            d["launches"] += 1
+        return out
+
+
+KERNEL_TIMER = _KernelTimer()
 
 
 # ------------------------------------------------------------------------------------------
@@ -111,8 +152,10 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
     ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src0.device) if ws_bytes else None
     ssum, ssq = (None, None) if stats is None else stats
-    rc = lib.rb_conv_gather(C.byref(d), src0.data_ptr(), L.ptr(src1), wpk.data_ptr(), out0.data_ptr(), L.ptr(out1),
-                            L.ptr(ssum), L.ptr(ssq), L.ptr(ws), ws_bytes, L.stream_ptr())
+    flops = 2.0 * d.NB * d.OD * d.OH * d.OW * nout * (d.srcC0 + d.srcC1) * taps[0] * taps[1] * taps[2]
+    with KERNEL_TIMER.span("conv", flops):
+        rc = lib.rb_conv_gather(C.byref(d), src0.data_ptr(), L.ptr(src1), wpk.data_ptr(), out0.data_ptr(), L.ptr(out1),
+                                L.ptr(ssum), L.ptr(ssq), L.ptr(ws), ws_bytes, L.stream_ptr())
     L.check(rc, "rb_conv_gather")
 
 
@@ -132,8 +175,10 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr):
     d.splits = 0
     ntaps = taps[0] * taps[1] * taps[2]
     dw = torch.zeros((ntaps, d.PC, d.QC0 + d.QC1), dtype=torch.float32, device=P.device)
-    L.check(lib.rb_wgrad_gather(C.byref(d), P.data_ptr(), Q0.data_ptr(), L.ptr(Q1), dw.data_ptr(), L.stream_ptr()),
-            "rb_wgrad_gather")
+    flops = 2.0 * d.NB * d.GD * d.GH * d.GW * d.PC * (d.QC0 + d.QC1) * ntaps
+    with KERNEL_TIMER.span("wgrad", flops):
+        rc = lib.rb_wgrad_gather(C.byref(d), P.data_ptr(), Q0.data_ptr(), L.ptr(Q1), dw.data_ptr(), L.stream_ptr())
+    L.check(rc, "rb_wgrad_gather")
     return dw
 
 
@@ -339,8 +384,10 @@ def _plane_reduce(kind, y, dz, z, per_w, slope):
     n, c, d, h, w = y.shape
     g = w if per_w else 1
     out = torch.empty((n, g, c, 2), dtype=torch.float64, device=y.device)
-    L.check(L.load().rb_plane_reduce(kind, y.data_ptr(), L.ptr(dz), L.ptr(z), out.data_ptr(), n, d * h * w, c, w,
-                                     1 if per_w else 0, float(slope), L.stream_ptr()), "rb_plane_reduce")
+    with KERNEL_TIMER.span("norm_reduce"):
+        rc = L.load().rb_plane_reduce(kind, y.data_ptr(), L.ptr(dz), L.ptr(z), out.data_ptr(), n, d * h * w, c, w,
+                                      1 if per_w else 0, float(slope), L.stream_ptr())
+    L.check(rc, "rb_plane_reduce")
     return out
 
 
@@ -362,8 +409,10 @@ class _NormActFn(torch.autograd.Function):
                                        small[2].data_ptr(), small[3].data_ptr(), n, c, float(S), float(eps), st),
                 "rb_in_finalize_fwd")
         z = new_cl(n, c, d, h, w, y.device)
-        L.check(lib.rb_norm_act_fwd(y.data_ptr(), L.ptr(res), z.data_ptr(), small[2].data_ptr(), small[3].data_ptr(),
-                                    n, S, c, w, 0, 1 if act else 0, float(slope), st), "rb_norm_act_fwd")
+        with KERNEL_TIMER.span("norm_apply"):
+            rc = lib.rb_norm_act_fwd(y.data_ptr(), L.ptr(res), z.data_ptr(), small[2].data_ptr(), small[3].data_ptr(),
+                                     n, S, c, w, 0, 1 if act else 0, float(slope), st)
+        L.check(rc, "rb_norm_act_fwd")
         ctx.save_for_backward(y, z if act else None, small, gamma)
         ctx.act, ctx.slope, ctx.has_res, ctx.has_beta = act, slope, res is not None, beta is not None
         return z
@@ -385,9 +434,11 @@ class _NormActFn(torch.autograd.Function):
                                        n, c, float(S), st), "rb_in_finalize_bwd")
         dy = new_cl(n, c, d, h, w, y.device)
         dres = new_cl(n, c, d, h, w, y.device) if (ctx.has_res and ctx.needs_input_grad[1]) else None
-        L.check(lib.rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), dy.data_ptr(), L.ptr(dres), ks[0].data_ptr(),
-                                    ks[1].data_ptr(), ks[2].data_ptr(), n, S, c, w, 0, 1 if ctx.act else 0,
-                                    float(ctx.slope), st), "rb_norm_act_bwd")
+        with KERNEL_TIMER.span("norm_apply"):
+            rc = lib.rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), dy.data_ptr(), L.ptr(dres), ks[0].data_ptr(),
+                                     ks[1].data_ptr(), ks[2].data_ptr(), n, S, c, w, 0, 1 if ctx.act else 0,
+                                     float(ctx.slope), st)
+        L.check(rc, "rb_norm_act_bwd")
         return dy, dres, dgamma, dbeta, None, None, None
 
 
