@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - plain pointers and sizes, no torch types; all pointers are DEVICE pointers unless noted
- *   - activations: channels-last NDHWC bf16, C % 8 == 0, 16-byte aligned
+ *   - activations: channels-last NDHWC bf16, C % 8 == 0, 16-byte aligned; pre-norm conv outputs may be
+ *     NDHWC fp32 instead (y_f32 / outF32 flags)
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
  *   - every function returns 0 on success or a negative RbStatus; rb_last_error() gives the text
  *   - nothing is allocated persistently; workspaces are passed in by the caller
@@ -77,6 +78,7 @@ typedef struct RbConvDesc {
     int psC, psD, psH, psW;
     int impl;   /* RbConvImpl */
     int splitK; /* 0 = library heuristic, 1 = never, >1 = forced (mma.sync path only) */
+    int outF32; /* 1: destinations are fp32 (pre-norm conv outputs keep the accumulator precision) */
 } RbConvDesc;
 
 /* fp32 workspace bytes needed by rb_conv_gather for this descriptor (0 when no split-K). */
@@ -88,6 +90,9 @@ size_t rb_conv_gather_workspace(const RbConvDesc* d);
 int rb_conv_gather(const RbConvDesc* d, const void* src0, const void* src1, const void* w_packed,
                    void* out0, void* out1, float* stat_sum, float* stat_sq,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* Which implementation rb_conv_gather will run for this descriptor: RB_IMPL_MMA_SYNC or
+ * RB_IMPL_TCGEN05 (negative status if a forced implementation cannot run it). */
+int rb_conv_gather_plan(const RbConvDesc* d);
 /* 1 if the tcgen05 kernel can run this descriptor. */
 int rb_conv_gather_tc5_supported(const RbConvDesc* d);
 
@@ -117,16 +122,19 @@ int rb_wgrad_gather(const RbWgradDesc* d, const void* P, const void* Q0, const v
  * rb_norm_act_fwd   z = act(y * scale + shift + res)              one read of y (+res), one write
  * rb_norm_act_bwd   g = dz*act'(z); dres = g; dy = g*k1 + y*k2 + k3
  * ------------------------------------------------------------------------------------------ */
-int rb_plane_reduce(int kind, const void* y, const void* dz, const void* z, double* out,
+int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, double* out,
                     int NB, long long S, int C, int W, int perW, float slope, void* stream);
-int rb_in_finalize_fwd(const double* sums, const float* gamma, const float* beta, float* mean, float* rstd,
-                       float* scale, float* shift, int NB, int C, double S, double eps, void* stream);
+/* statistics either as double sums[NB][C][2] (rb_plane_reduce) or as the fp32 fsum/fsq[NB][C] the tcgen05
+ * conv epilogue accumulated */
+int rb_in_finalize_fwd(const double* sums, const float* fsum, const float* fsq, const float* gamma, const float* beta,
+                       float* mean, float* rstd, float* scale, float* shift, int NB, int C, double S, double eps,
+                       void* stream);
 int rb_in_finalize_bwd(const double* red, const float* mean, const float* rstd, const float* gamma,
                        float* k1, float* k2, float* k3, float* dgamma, float* dbeta,
                        int NB, int C, double S, void* stream);
-int rb_norm_act_fwd(const void* y, const void* res, void* z, const float* scale, const float* shift,
+int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const float* scale, const float* shift,
                     int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
-int rb_norm_act_bwd(const void* dz, const void* z, const void* y, void* dy, void* dres,
+int rb_norm_act_bwd(const void* dz, const void* z, const void* y, int y_f32, void* dy, void* dres,
                     const float* k1, const float* k2, const float* k3,
                     int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
 

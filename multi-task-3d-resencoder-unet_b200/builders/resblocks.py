@@ -5,9 +5,9 @@ call sites resblocks.py:9-11,79-87,109-112).
 
 Block forward on the B200 path (one kernel sequence, no elementwise pass of its own):
     r  = skip(x)                      identity | AvgPool [-> 1x1x1 conv -> IN]
-    y1 = conv1(x)  -> IN + LReLU      (ops.conv3d + ops.instance_norm_act)
-    y2 = conv2(.)                     pre-norm
-    out = LReLU( SE(IN(y2)) + r )     ONE fused pass: normalise, gate, residual add, activation
+    z1 = LReLU(IN(conv1(x)))          one fused unit (ops.conv_norm_act)
+    out = LReLU( SE(IN(conv2(z1))) + r )   one fused unit: the last conv's normalise pass also applies the
+                                      gate, the residual add and the activation
 """
 from __future__ import annotations
 
@@ -108,14 +108,13 @@ class _ResidualBlock(nn.Module):
             r = self.skip[self._proj_index](r)
         return r
 
-    def _tail(self, last, y, r):
-        """LReLU( [SE]( IN(y) ) + r ) in one pass."""
-        n = last.norm
+    def _tail(self, last, x, r):
+        """LReLU( [SE]( IN( last.conv(x) ) ) + r ): the block's last conv carries the whole tail."""
+        se, dims = None, "all"
         if self.apply_se:
-            se = self.squeeze_excitation
-            return ops.instance_norm_se_act(y, r, n.weight, n.bias, se.fc1.weight, se.fc1.bias, se.fc2.weight,
-                                            se.fc2.bias, n.eps, True, self._slope, se.dims())
-        return ops.instance_norm_act(y, r, n.weight, n.bias, n.eps, True, self._slope)
+            m = self.squeeze_excitation
+            se, dims = (m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias), m.dims()
+        return last(x, res=r, act=True, slope=self._slope, se=se, se_reduce_dims=dims)
 
 
 class BasicBlockD(_ResidualBlock):
@@ -142,8 +141,7 @@ class BasicBlockD(_ResidualBlock):
         if x_cat is not None:
             _unsupported("a residual block on a virtual concatenation")
         r = self._residual(x)
-        y = self.conv2.conv_only(self.conv1(x))
-        return self._tail(self.conv2, y, r)
+        return self._tail(self.conv2, self.conv1(x), r)
 
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == len(self.stride), "give the spatial size only, e.g. (x, y, z)"
@@ -184,8 +182,7 @@ class BottleneckD(_ResidualBlock):
         if x_cat is not None:
             _unsupported("a residual block on a virtual concatenation")
         r = self._residual(x)
-        y = self.conv3.conv_only(self.conv2(self.conv1(x)))
-        return self._tail(self.conv3, y, r)
+        return self._tail(self.conv3, self.conv2(self.conv1(x)), r)
 
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == len(self.stride), "give the spatial size only, e.g. (x, y, z)"

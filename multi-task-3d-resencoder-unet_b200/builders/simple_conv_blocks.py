@@ -65,19 +65,18 @@ class ConvDropoutNormReLU(nn.Module):
         self._act = nonlin is not None
         self._slope = float(self.nonlin.negative_slope) if self._act else 0.0
 
-    # -- pieces used by the fused block forwards ---------------------------------------------
-    def conv_only(self, x, x_cat=None):
-        """Pre-norm conv output.  A conv bias feeding InstanceNorm cancels exactly, so it is not
-        applied; its gradient is exactly zero (ops.attach_cancelled_bias)."""
-        y = ops.conv3d(x, self.conv.weight, self.stride, x_cat=x_cat)
-        return ops.attach_cancelled_bias(y, self.conv.bias)
+    _raw_input = False      # StemConv: consumes the raw NCDHW fp32 network input
 
-    def norm_act(self, y, res=None, act=None):
-        return ops.instance_norm_act(y, res, self.norm.weight, self.norm.bias, self.norm.eps,
-                                     self._act if act is None else act, self._slope or ops.LRELU_SLOPE_DEFAULT)
-
-    def forward(self, x, x_cat=None):
-        return self.norm_act(self.conv_only(x, x_cat))
+    def forward(self, x, x_cat=None, res=None, act=None, slope=None, se=None, se_reduce_dims="all"):
+        """act( [SE]( IN( conv(cat(x, x_cat)) ) ) + res ) as ONE fused unit (ops.conv_norm_act).  Called with
+        only `x` this is the reference's conv -> dropout(p=0) -> norm -> nonlin; residual blocks pass their
+        tail (`res`, `act`, `se`) so the block needs no elementwise pass of its own.  A conv bias feeding
+        InstanceNorm cancels exactly: it is not applied and receives the exact gradient, zero."""
+        act = self._act if act is None else act
+        slope = (self._slope or ops.LRELU_SLOPE_DEFAULT) if slope is None else slope
+        z = ops.conv_norm_act(x, self.conv.weight, self.stride, x_cat, res, self.norm.weight, self.norm.bias,
+                              self.norm.eps, act, slope, se, se_reduce_dims, stem=self._raw_input)
+        return ops.attach_cancelled_bias(z, self.conv.bias)
 
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == len(self.stride), "give the spatial size only, e.g. (x, y, z)"
@@ -86,11 +85,12 @@ class ConvDropoutNormReLU(nn.Module):
 
 class StemConv(ConvDropoutNormReLU):
     """First conv of the network: consumes the raw NCDHW fp32 input (any channel count)."""
+    _raw_input = True
 
-    def conv_only(self, x, x_cat=None):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
         if any(s != 1 for s in self.stride):
             _unsupported("a strided stem convolution")
-        return ops.attach_cancelled_bias(ops.stem_conv3d(x, self.conv.weight), self.conv.bias)
 
 
 class StackedConvBlocks(nn.Module):

@@ -93,6 +93,7 @@ struct Tc5Plan {
     size_t smem = 0;
     long long tiles = 0;
     int ksteps = 0;
+    bool statSmem = false;
 };
 
 Tc5Plan plan_tc5(const RbConvDesc& d) {
@@ -134,11 +135,15 @@ Tc5Plan plan_tc5(const RbConvDesc& d) {
     pl.tilesNB = (d.NB + pl.tn - 1) / pl.tn;
     pl.tiles = best * pl.nTilesN;
     const size_t stageBytes = (size_t)(128 + pl.Ntile) * pl.KW * 2;
-    int st = (int)((200 * 1024) / stageBytes);
+    // per-CTA statistics accumulators [2][NB][Nout] fp32 live behind the stages when they fit in 16 KB
+    const size_t statBytes = (size_t)2 * d.NB * d.Nout * sizeof(float);
+    pl.statSmem = statBytes <= 16 * 1024;
+    const size_t reserve = pl.statSmem ? statBytes : 0;
+    int st = (int)((200 * 1024 - reserve) / stageBytes);
     if (st > 8) st = 8;
     if (st < 2) return pl;
     pl.stages = st;
-    pl.smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)st * stageBytes;
+    pl.smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)st * stageBytes + reserve;
     const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
     pl.ksteps = d.tapD * d.tapH * d.tapW * (ctot / pl.KW);
     pl.ok = true;
@@ -242,10 +247,12 @@ int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const v
     p.mode = d.mode;
     p.ostrD = d.ostrD; p.ostrH = d.ostrH; p.ostrW = d.ostrW; p.ooffD = d.ooffD; p.ooffH = d.ooffH; p.ooffW = d.ooffW;
     p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
-    p.out0 = (rb::bf16*)out0; p.out1 = (rb::bf16*)out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
+    p.out0 = out0; p.out1 = out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
     p.psC = d.psC; p.psD = d.psD; p.psH = d.psH; p.psW = d.psW;
     p.stages = pl.stages;
     p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+    p.outF32 = d.outF32;
+    p.statSmem = pl.statSmem ? 1 : 0;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -280,6 +287,14 @@ int rb_device_error(void* stream) {
 int rb_conv_gather_tc5_supported(const RbConvDesc* d) {
     if (!d) return 0;
     return plan_tc5(*d).ok ? 1 : 0;
+}
+
+int rb_conv_gather_plan(const RbConvDesc* d) {
+    if (!d) return RB_ERR_INVALID;
+    if (d->impl == RB_IMPL_MMA_SYNC) return RB_IMPL_MMA_SYNC;
+    Tc5Plan pl = plan_tc5(*d);
+    if (d->impl == RB_IMPL_TCGEN05) return pl.ok ? RB_IMPL_TCGEN05 : RB_ERR_UNSUPPORTED;
+    return auto_prefers_tc5(*d, pl) ? RB_IMPL_TCGEN05 : RB_IMPL_MMA_SYNC;
 }
 
 size_t rb_conv_gather_workspace(const RbConvDesc* d) {
@@ -329,8 +344,9 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     p.OD = d.OD; p.OH = d.OH; p.OW = d.OW; p.Nout = d.Nout;
     p.mode = d.mode; p.ostrD = d.ostrD; p.ostrH = d.ostrH; p.ostrW = d.ostrW;
     p.ooffD = d.ooffD; p.ooffH = d.ooffH; p.ooffW = d.ooffW; p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
-    p.out0 = (rb::bf16*)out0; p.out1 = (rb::bf16*)out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
+    p.out0 = out0; p.out1 = out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
     p.psC = d.psC; p.psD = d.psD; p.psH = d.psH; p.psW = d.psW;
+    p.outF32 = d.outF32;
     const long long M = (long long)d.NB * d.OD * d.OH * d.OW;
     int sk = generic_splitk(d);
     const size_t need = (size_t)M * d.Nout * sizeof(float);
@@ -388,16 +404,16 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     return check_launch("gather_wgrad_mma_kernel");
 }
 
-int rb_plane_reduce(int kind, const void* y, const void* dz, const void* z, double* out, int NB, long long S, int C, int W,
-                    int perW, float slope, void* stream) {
+int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, double* out, int NB, long long S, int C,
+                    int W, int perW, float slope, void* stream) {
     if (!y || !out || (kind == 1 && !dz)) return fail(RB_ERR_INVALID, "plane_reduce: null pointer");
     if (C <= 0 || C % 8 != 0 || NB <= 0 || S <= 0) return fail(RB_ERR_INVALID, "plane_reduce: bad shape");
     if (perW && (W <= 0 || S % W != 0)) return fail(RB_ERR_INVALID, "plane_reduce: S must be a multiple of W");
     if (kind != 0 && kind != 1) return fail(RB_ERR_INVALID, "plane_reduce: kind must be 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
     rb::ReduceParams p;
-    p.y = (const rb::bf16*)y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out;
-    p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind;
+    p.y = y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out;
+    p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind; p.yF32 = y_f32 ? 1 : 0;
     const int cg = C / 8;
     const int rows = 256 / cg > 0 ? 256 / cg : 1;
     int gx;
@@ -415,10 +431,10 @@ int rb_plane_reduce(int kind, const void* y, const void* dz, const void* z, doub
     return check_launch("plane_reduce_kernel");
 }
 
-int rb_in_finalize_fwd(const double* sums, const float* gamma, const float* beta, float* mean, float* rstd, float* scale,
-                       float* shift, int NB, int C, double S, double eps, void* stream) {
-    if (!sums || !mean || !rstd || !scale || !shift) return fail(RB_ERR_INVALID, "in_finalize_fwd: null pointer");
-    rb::FinalizeParams p{sums, gamma, beta, mean, rstd, scale, shift, NB, C, S, eps};
+int rb_in_finalize_fwd(const double* sums, const float* fsum, const float* fsq, const float* gamma, const float* beta,
+                       float* mean, float* rstd, float* scale, float* shift, int NB, int C, double S, double eps, void* stream) {
+    if ((!sums && (!fsum || !fsq)) || !mean || !rstd || !scale || !shift) return fail(RB_ERR_INVALID, "in_finalize_fwd: null pointer");
+    rb::FinalizeParams p{sums, fsum, fsq, gamma, beta, mean, rstd, scale, shift, NB, C, S, eps};
     rb::in_finalize_fwd_kernel<<<(NB * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("in_finalize_fwd_kernel");
 }
@@ -438,25 +454,26 @@ static int check_apply_shape(const char* who, int NB, long long S, int C, int W,
     return RB_OK;
 }
 
-int rb_norm_act_fwd(const void* y, const void* res, void* z, const float* scale, const float* shift, int NB, long long S,
-                    int C, int W, int perW, int act, float slope, void* stream) {
+int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const float* scale, const float* shift, int NB,
+                    long long S, int C, int W, int perW, int act, float slope, void* stream) {
     if (!y || !z || !scale || !shift) return fail(RB_ERR_INVALID, "norm_act_fwd: null pointer");
     int rc = check_apply_shape("norm_act_fwd", NB, S, C, W, perW);
     if (rc) return rc;
-    rb::ApplyParams p{(const rb::bf16*)y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope};
+    rb::ApplyParams p{y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
     rb::norm_act_fwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_act_fwd_kernel");
 }
 
-int rb_norm_act_bwd(const void* dz, const void* z, const void* y, void* dy, void* dres, const float* k1, const float* k2,
-                    const float* k3, int NB, long long S, int C, int W, int perW, int act, float slope, void* stream) {
+int rb_norm_act_bwd(const void* dz, const void* z, const void* y, int y_f32, void* dy, void* dres, const float* k1,
+                    const float* k2, const float* k3, int NB, long long S, int C, int W, int perW, int act, float slope,
+                    void* stream) {
     if (!dz || !y || !dy || !k1 || !k2 || !k3 || (act && !z)) return fail(RB_ERR_INVALID, "norm_act_bwd: null pointer");
     int rc = check_apply_shape("norm_act_bwd", NB, S, C, W, perW);
     if (rc) return rc;
-    rb::ApplyBwdParams p{(const rb::bf16*)dz, (const rb::bf16*)z, (const rb::bf16*)y, (rb::bf16*)dy, (rb::bf16*)dres,
-                         k1, k2, k3, S, NB, C, W, perW, act, slope};
+    rb::ApplyBwdParams p{(const rb::bf16*)dz, (const rb::bf16*)z, y, (rb::bf16*)dy, (rb::bf16*)dres,
+                         k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
     rb::norm_act_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);

@@ -18,9 +18,10 @@ struct GConvParams {
     int OD, OH, OW;  // output class grid
     int Nout;
     int mode, ostrD, ostrH, ostrW, ooffD, ooffH, ooffW, FD, FH, FW;
-    bf16* out0;
-    bf16* out1;
+    void* out0;
+    void* out1;
     int outC0, outC1, psC, psD, psH, psW;
+    int outF32;  // destinations are fp32
     int splitK;  // > 1: blockIdx.z takes a contiguous slice of the (tap, k-chunk) loop and adds fp32
     float* ws;   //      partials into ws[m][Nout] (zeroed by the host); gather_finish_kernel stores
 };
@@ -186,8 +187,14 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
                     fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
                 }
                 const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
-                bf16* dst = (ch < p.outC0) ? p.out0 + vox * p.outC0 + ch : p.out1 + vox * p.outC1 + (ch - p.outC0);
-                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+                void* base = (ch < p.outC0) ? p.out0 : p.out1;
+                const size_t eoff = (ch < p.outC0) ? vox * p.outC0 + ch : vox * p.outC1 + (ch - p.outC0);
+                if (p.outF32)
+                    *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + eoff) =
+                        make_float2(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+                else
+                    *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(base) + eoff) =
+                        pack_bf16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
             }
         }
     }
@@ -217,8 +224,12 @@ __global__ void __launch_bounds__(256) gather_finish_kernel(const GConvParams p)
             fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
         }
         const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
-        bf16* dst = (ch < p.outC0) ? p.out0 + vox * p.outC0 + ch : p.out1 + vox * p.outC1 + (ch - p.outC0);
-        *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v.x, v.y);
+        void* base = (ch < p.outC0) ? p.out0 : p.out1;
+        const size_t eoff = (ch < p.outC0) ? vox * p.outC0 + ch : vox * p.outC1 + (ch - p.outC0);
+        if (p.outF32)
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + eoff) = v;
+        else
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(base) + eoff) = pack_bf16(v.x, v.y);
     }
 }
 

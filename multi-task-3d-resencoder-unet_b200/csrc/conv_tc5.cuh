@@ -40,15 +40,33 @@ struct Tc5ConvParams {
     int mode;  // 0 direct, 1 pixel shuffle (column = parity * psC + channel)
     int ostrD, ostrH, ostrW, ooffD, ooffH, ooffW;
     int FD, FH, FW;  // full output spatial dims
-    bf16* out0;
-    bf16* out1;
+    void* out0;
+    void* out1;
     int outC0, outC1;  // channel split of the destination (out1 may be null)
     int psC;
     int psD, psH, psW;  // pixel-shuffle factors per dim (1 or 2)
     int stages;
     float* stat_sum;  // optional [NB][Nout] per-(n,c) sum of outputs   (fp32, atomics)
     float* stat_sq;   // optional [NB][Nout] per-(n,c) sum of squares
+    int outF32;       // 1: destinations are fp32 (pre-norm activations keep the full accumulator)
+    int statSmem;     // 1: statistics are accumulated in shared memory per CTA and flushed once at the end
 };
+
+// Column sums over the 32 rows held by the lanes of a warp: v[j] (lane = row) -> lane j returns
+// sum_rows v[j].  Butterfly with halving: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
 
 static constexpr int TC5_THREADS = 192;
 
@@ -77,6 +95,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * p.Ntile) tmem_cols <<= 1;
+    // optional per-CTA statistics accumulators [2][NB][Nout] behind the pipeline stages
+    float* statS = reinterpret_cast<float*>(tiles + (size_t)S * stageBytes);
+    const int statN = p.NB * p.Nout;
+    if (p.stat_sum != nullptr && p.statSmem)
+        for (int i = threadIdx.x; i < 2 * statN; i += blockDim.x) statS[i] = 0.f;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.mapA[0]);
@@ -208,22 +231,43 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                 const int col0 = n0 + cg;
                 if (col0 < p.Nout) {
                     if (p.stat_sum != nullptr) {
-                        // per-(sample, channel) sum / sum of squares over the 32 rows of this warp;
-                        // rows of one warp may straddle samples only when tn > 1, handled per lane.
-#pragma unroll 4
-                        for (int j = 0; j < 32; ++j) {
-                            float x = valid ? __uint_as_float(v[j]) : 0.f;
-                            float s1, s2;
-                            if (p.tn == 1) {
-                                s1 = warp_sum(x);
-                                s2 = warp_sum(x * x);
-                                if (lane == 0 && col0 + j < p.Nout) {
-                                    atomicAdd(p.stat_sum + (size_t)nb * p.Nout + col0 + j, s1);
-                                    atomicAdd(p.stat_sq + (size_t)nb * p.Nout + col0 + j, s2);
+                        if (p.tn == 1) {
+                            // all 32 rows of this warp belong to sample nb: butterfly column sums, lane j ends up
+                            // with column col0 + j
+                            float a[32], b[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float x = valid ? __uint_as_float(v[j]) : 0.f;
+                                a[j] = x;
+                                b[j] = x * x;
+                            }
+                            const float s1 = warp_colsum32(a, lane);
+                            const float s2 = warp_colsum32(b, lane);
+                            if (col0 + lane < p.Nout && nb < p.NB) {
+                                const int idx = nb * p.Nout + col0 + lane;
+                                if (p.statSmem) {
+                                    atomicAdd(statS + idx, s1);
+                                    atomicAdd(statS + statN + idx, s2);
+                                } else {
+                                    atomicAdd(p.stat_sum + idx, s1);
+                                    atomicAdd(p.stat_sq + idx, s2);
                                 }
-                            } else if (valid && col0 + j < p.Nout) {
-                                atomicAdd(p.stat_sum + (size_t)nb * p.Nout + col0 + j, x);
-                                atomicAdd(p.stat_sq + (size_t)nb * p.Nout + col0 + j, x * x);
+                            }
+                        } else if (valid) {
+                            // batch-folded tiles (tiny grids): rows of a warp may belong to different samples
+#pragma unroll 4
+                            for (int j = 0; j < 32; ++j) {
+                                if (col0 + j < p.Nout) {
+                                    const float x = __uint_as_float(v[j]);
+                                    const int idx = nb * p.Nout + col0 + j;
+                                    if (p.statSmem) {
+                                        atomicAdd(statS + idx, x);
+                                        atomicAdd(statS + statN + idx, x * x);
+                                    } else {
+                                        atomicAdd(p.stat_sum + idx, x);
+                                        atomicAdd(p.stat_sq + idx, x * x);
+                                    }
+                                }
                             }
                         }
                     }
@@ -241,20 +285,31 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             fd = od * p.ostrD + p.ooffD; fh = oh * p.ostrH + p.ooffH; fw = ow * p.ostrW + p.ooffW;
                         }
                         const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
-                        bf16* dst;
-                        int lim;  // channels available from ch0 in the chosen destination
-                        if (ch0 < p.outC0) { dst = p.out0 + vox * p.outC0 + ch0; lim = p.outC0 - ch0; }
-                        else { dst = p.out1 + vox * p.outC1 + (ch0 - p.outC0); lim = p.outC1 - (ch0 - p.outC0); }
+                        int lim;      // channels available from ch0 in the chosen destination
+                        size_t eoff;  // element offset into it
+                        void* base;
+                        if (ch0 < p.outC0) { base = p.out0; eoff = vox * p.outC0 + ch0; lim = p.outC0 - ch0; }
+                        else { base = p.out1; eoff = vox * p.outC1 + (ch0 - p.outC0); lim = p.outC1 - (ch0 - p.outC0); }
                         if (p.mode == 1) lim = min(lim, p.psC - ch0);
+                        if (p.outF32) {
+                            float* dst = reinterpret_cast<float*>(base) + eoff;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (q * 8 < lim) {
-                                uint4 o;
-                                o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-                                o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-                                o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-                                o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-                                *reinterpret_cast<uint4*>(dst + q * 8) = o;
+                            for (int q = 0; q < 8; ++q) {
+                                if (q * 4 < lim)
+                                    *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                            }
+                        } else {
+                            bf16* dst = reinterpret_cast<bf16*>(base) + eoff;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (q * 8 < lim) {
+                                    uint4 o;
+                                    o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+                                    o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+                                    o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+                                    o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                                    *reinterpret_cast<uint4*>(dst + q * 8) = o;
+                                }
                             }
                         }
                     }
@@ -269,6 +324,15 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
 
     tc_fence_before();
     __syncthreads();
+    if (p.stat_sum != nullptr && p.statSmem) {
+        for (int i = threadIdx.x; i < statN; i += blockDim.x) {
+            const float a = statS[i], b = statS[statN + i];
+            if (a != 0.f || b != 0.f) {
+                atomicAdd(p.stat_sum + i, a);
+                atomicAdd(p.stat_sq + i, b);
+            }
+        }
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);

@@ -31,6 +31,19 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     return r;
 }
 
+// 8 consecutive channels of a pre-norm tensor that is either bf16 or fp32 (elem = element offset)
+__device__ __forceinline__ void load8_prenorm(const void* base, size_t elem, int f32, float (&f)[8]) {
+    if (f32) {
+        const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+        float4 a, b;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(q));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(q + 1));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+        unpack8(ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem)), f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Per-(sample, [w], channel) reductions.  out is double [NB][G][C][2] with G = 1 or W.
 //   kind 0: (sum y, sum y^2)                        -> InstanceNorm statistics / SE squeeze
@@ -38,7 +51,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 // grid = (blocks per sample, NB); a block strides over voxels, thread = (voxel row, 8 channels).
 // ---------------------------------------------------------------------------------------
 struct ReduceParams {
-    const bf16* y;   // [NB, S, C]
+    const void* y;   // [NB, S, C]  bf16 or fp32 (yF32)
     const bf16* dz;  // kind 1
     const bf16* z;   // kind 1 with act: sign source (may be null => g = dz)
     double* out;
@@ -46,6 +59,7 @@ struct ReduceParams {
     int C, W, perW;
     float slope;
     int kind;
+    int yF32;
 };
 
 __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p) {
@@ -67,7 +81,7 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
                 for (long long v = (long long)blockIdx.x * rows + myrow; v < p.S; v += (long long)gridDim.x * rows) {
                     const size_t off = (base + v) * p.C + (size_t)mycg * 8;
                     float a[8], b[8];
-                    unpack8(ld_stream(reinterpret_cast<const uint4*>(p.y + off)), a);
+                    load8_prenorm(p.y, off, p.yF32, a);
                     if (p.kind == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
@@ -113,7 +127,7 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
                 for (long long dh = myrow; dh < DH; dh += rows) {
                     const size_t off = ((size_t)nb * p.S + dh * p.W + w) * p.C + (size_t)mycg * 8;
                     float a[8], b[8];
-                    unpack8(ld_stream(reinterpret_cast<const uint4*>(p.y + off)), a);
+                    load8_prenorm(p.y, off, p.yF32, a);
                     if (p.kind == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
 // from the statistics; they are [NB][G][C] fp32 with G = 1 or W).
 // ---------------------------------------------------------------------------------------
 struct ApplyParams {
-    const bf16* y;
+    const void* y;    // bf16 or fp32 (yF32)
     const bf16* res;  // may be null
     bf16* z;
     const float* scale;
@@ -165,6 +179,7 @@ struct ApplyParams {
     long long S;
     int NB, C, W, perW, act;
     float slope;
+    int yF32;
 };
 
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) {
@@ -172,7 +187,6 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) 
     const uint32_t cg = (uint32_t)p.C >> 3;
     const uint32_t per = (uint32_t)p.S * cg;
     const int nb = blockIdx.y;
-    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + (size_t)nb * per;
     const uint4* rv = p.res ? reinterpret_cast<const uint4*>(p.res) + (size_t)nb * per : nullptr;
     uint4* zv = reinterpret_cast<uint4*>(p.z) + (size_t)nb * per;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) 
         const uint32_t v = i / cg;
         const size_t cidx = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
         float a[8], sc[8], sh[8];
-        unpack8(ld_stream(yv + i), a);
+        load8_prenorm(p.y, ((size_t)nb * per + i) * 8, p.yF32, a);
         *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx));
         *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx + 4));
         *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx));
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) 
 struct ApplyBwdParams {
     const bf16* dz;
     const bf16* z;
-    const bf16* y;
+    const void* y;    // bf16 or fp32 (yF32)
     bf16* dy;
     bf16* dres;
     const float* k1;
@@ -217,6 +231,7 @@ struct ApplyBwdParams {
     long long S;
     int NB, C, W, perW, act;
     float slope;
+    int yF32;
 };
 
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams p) {
@@ -226,7 +241,6 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
     const size_t base = (size_t)nb * per;
     const uint4* dzv = reinterpret_cast<const uint4*>(p.dz) + base;
     const uint4* zv = p.z ? reinterpret_cast<const uint4*>(p.z) + base : nullptr;
-    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + base;
     uint4* dyv = reinterpret_cast<uint4*>(p.dy) + base;
     uint4* drv = p.dres ? reinterpret_cast<uint4*>(p.dres) + base : nullptr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
@@ -243,7 +257,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
             for (int j = 0; j < 8; ++j) gd[j] = zz[j] > 0.f ? gd[j] : gd[j] * p.slope;
         }
         if (drv != nullptr) drv[i] = pack8(gd);
-        unpack8(ld_stream(yv + i), yy);
+        load8_prenorm(p.y, (base + i) * 8, p.yF32, yy);
         *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1));
         *reinterpret_cast<float4*>(a1 + 4) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1 + 4));
         *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(p.k2 + c2));
@@ -496,7 +510,9 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const Im2colParams p) 
 //        affine parameter gradients dgamma[c] = sum_n sum g*xhat, dbeta[c] = sum_n sum g.
 // ---------------------------------------------------------------------------------------
 struct FinalizeParams {
-    const double* sums;   // [NB][C][2]
+    const double* sums;   // [NB][C][2]  (or null when fsum/fsq are given)
+    const float* fsum;    // [NB][C] fp32 statistics from the conv epilogue
+    const float* fsq;
     const float* gamma;   // [C] or null
     const float* beta;    // [C] or null
     float* mean;          // [NB][C]
@@ -512,8 +528,10 @@ __global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const FinalizePara
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.NB * p.C) return;
     const int c = i % p.C;
-    const double m = p.sums[2 * (size_t)i] / p.S;
-    double var = p.sums[2 * (size_t)i + 1] / p.S - m * m;
+    const double s1 = p.sums ? p.sums[2 * (size_t)i] : (double)p.fsum[i];
+    const double s2 = p.sums ? p.sums[2 * (size_t)i + 1] : (double)p.fsq[i];
+    const double m = s1 / p.S;
+    double var = s2 / p.S - m * m;
     if (var < 0.0) var = 0.0;
     const double r = 1.0 / sqrt(var + p.eps);
     const double ga = p.gamma ? (double)p.gamma[c] : 1.0;

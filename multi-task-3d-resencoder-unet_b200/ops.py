@@ -120,10 +120,21 @@ def _triple(v):
 # ------------------------------------------------------------------------------------------
 # raw launches
 # ------------------------------------------------------------------------------------------
-def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode=0,
-                   ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0, impl=None, stats=None):
-    """One rb_conv_gather call.  src*/out* are NDHWC bf16 activations (logical NCDHW views)."""
-    lib = L.load()
+def new_cl_f32(n, c, d, h, w, device):
+    """Pre-norm conv output: logical [n, c, d, h, w], memory NDHWC fp32 (keeps the accumulator precision)."""
+    return torch.empty((n, d, h, w, c), dtype=torch.float32, device=device).permute(0, 4, 1, 2, 3)
+
+
+def is_cl_f32(x: torch.Tensor) -> bool:
+    return x.dim() == 5 and x.dtype == torch.float32 and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def as_prenorm(y: torch.Tensor) -> torch.Tensor:
+    """Pre-norm tensors are accepted as NDHWC fp32 (kept) or anything `as_cl` can turn into NDHWC bf16."""
+    return y if is_cl_f32(y) and y.shape[1] % 8 == 0 and y.is_cuda else as_cl(y)
+
+
+def _make_desc(src0, src1, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode, ostr, ooff, full, ps, psC, impl):
     d = L.ConvDesc()
     d.nsrc = 2 if src1 is not None else 1
     d.srcC0 = src0.shape[1]
@@ -149,6 +160,25 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
         d.psC = 0
     d.impl = L.default_impl() if impl is None else L.impl_code(impl)
     d.splitK = 0
+    d.outF32 = 1 if out0.dtype == torch.float32 else 0
+    return d
+
+
+def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode=0,
+                   ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0, impl=None, stats=None, want_stats=False):
+    """One rb_conv_gather call.  src* are NDHWC bf16 activations, out* NDHWC bf16 or fp32 (logical NCDHW views).
+    stats=(sum, sumsq) fp32 [NB, Nout] are filled by the tcgen05 epilogue; with want_stats=True they are
+    allocated here when (and only when) the library will run the tcgen05 kernel, and returned (else None)."""
+    lib = L.load()
+    d = _make_desc(src0, src1, out0, out1, in_dims=in_dims, taps=taps, off=off, istr=istr, out_grid=out_grid, nout=nout,
+                   mode=mode, ostr=ostr, ooff=ooff, full=full, ps=ps, psC=psC, impl=impl)
+    if want_stats and stats is None:
+        plan = lib.rb_conv_gather_plan(C.byref(d))
+        if plan < 0:
+            L.check(plan, "rb_conv_gather_plan")
+        if plan == L.IMPL_TCGEN05:
+            st = torch.zeros((2, d.NB, nout), dtype=torch.float32, device=src0.device)
+            stats = (st[0], st[1])
     ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src0.device) if ws_bytes else None
     ssum, ssq = (None, None) if stats is None else stats
@@ -157,6 +187,7 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
         rc = lib.rb_conv_gather(C.byref(d), src0.data_ptr(), L.ptr(src1), wpk.data_ptr(), out0.data_ptr(), L.ptr(out1),
                                 L.ptr(ssum), L.ptr(ssq), L.ptr(ws), ws_bytes, L.stream_ptr())
     L.check(rc, "rb_conv_gather")
+    return stats
 
 
 def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr):
@@ -227,38 +258,284 @@ def pack_conv_dgrad_class(weight, kds, khs, kws):
     """taps selected by kernel-index lists per axis -> [taps][Cin][Cout] bf16."""
     w = weight.detach()
     dev = w.device
-    w = w.index_select(2, torch.tensor(kds, device=dev)).index_select(3, torch.tensor(khs, device=dev)) \
-         .index_select(4, torch.tensor(kws, device=dev))
+    if len(kds) != w.shape[2] or list(kds) != list(range(w.shape[2])):
+        w = w.index_select(2, torch.tensor(kds, device=dev))
+    if len(khs) != w.shape[3] or list(khs) != list(range(w.shape[3])):
+        w = w.index_select(3, torch.tensor(khs, device=dev))
+    if len(kws) != w.shape[4] or list(kws) != list(range(w.shape[4])):
+        w = w.index_select(4, torch.tensor(kws, device=dev))
     co, ci = w.shape[:2]
     return w.permute(2, 3, 4, 1, 0).reshape(len(kds) * len(khs) * len(kws), ci, co).to(BF16).contiguous()
 
 
 # ------------------------------------------------------------------------------------------
-# Conv3d (k in {1,3} per axis, stride in {1,2} per axis, pad (k-1)//2, one or two concatenated inputs)
+# primitives (no autograd): convolution forward / backward
 # ------------------------------------------------------------------------------------------
 def _conv_out_dims(in_dims, k, s):
     return tuple((i + 2 * ((kk - 1) // 2) - kk) // ss + 1 for i, kk, ss in zip(in_dims, k, s))
 
 
+def _check_conv_args(weight, x0, x1):
+    co, ci, kd, kh, kw = weight.shape
+    c_in = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
+    if c_in != ci:
+        raise ValueError(f"conv3d: weight expects {ci} input channels, got {c_in}")
+    if any(kk not in (1, 3) for kk in (kd, kh, kw)):
+        raise NotImplementedError(f"conv3d: kernel sizes 1 and 3 are implemented, got {(kd, kh, kw)}")
+    if x1 is not None and tuple(x1.shape[2:]) != tuple(x0.shape[2:]):
+        raise ValueError("conv3d: concatenated inputs must share their spatial shape")
+
+
+def _conv_forward(weight, stride, impl, x0, x1, out_f32=False, want_stats=False):
+    _check_conv_args(weight, x0, x1)
+    co, ci, kd, kh, kw = weight.shape
+    k = (kd, kh, kw)
+    n = x0.shape[0]
+    in_dims = tuple(x0.shape[2:])
+    od = _conv_out_dims(in_dims, k, stride)
+    y = (new_cl_f32 if out_f32 else new_cl)(n, co, *od, x0.device)
+    stats = _launch_gather(x0, x1, pack_conv_fprop(weight), y, None, in_dims=in_dims, taps=k,
+                           off=tuple(-((kk - 1) // 2) for kk in k), istr=stride, out_grid=od, nout=co, impl=impl,
+                           want_stats=want_stats)
+    return y, stats
+
+
+def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
+    co, ci, kd, kh, kw = weight.shape
+    k = (kd, kh, kw)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    n = x0.shape[0]
+    in_dims = tuple(x0.shape[2:])
+    od = tuple(dy.shape[2:])
+    gw = gx0 = gx1 = None
+    if need_w:
+        dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride)
+        gw = dw.view(kd, kh, kw, co, ci).permute(3, 4, 0, 1, 2).contiguous()
+    need1 = need1 and x1 is not None
+    if need0 or need1:
+        c0 = x0.shape[1]
+        classes = [_axis_classes(k[a], stride[a], pad[a], in_dims[a]) for a in range(3)]
+        empty = any(len(cls[2]) == 0 for axis in classes for cls in axis)
+        mk = zeros_cl if empty else new_cl
+        gx0 = mk(n, c0, *in_dims, x0.device)
+        gx1 = mk(n, x1.shape[1], *in_dims, x0.device) if x1 is not None else None
+        for cd, ch, cw in itertools.product(*classes):
+            if not (cd[2] and ch[2] and cw[2]):
+                continue
+            wpk = pack_conv_dgrad_class(weight, cd[2], ch[2], cw[2])
+            _launch_gather(dy, None, wpk, gx0, gx1, in_dims=od, taps=(len(cd[2]), len(ch[2]), len(cw[2])),
+                           off=(cd[3], ch[3], cw[3]), istr=(1, 1, 1), out_grid=(cd[1], ch[1], cw[1]), nout=ci,
+                           ostr=stride, ooff=(cd[0], ch[0], cw[0]), full=in_dims, impl=impl)
+        if not need0:
+            gx0 = None
+        if not need1:
+            gx1 = None
+    return gw, gx0, gx1
+
+
+# stem: im2col of the raw NCDHW fp32 input, then a 1-tap GEMM over K = taps * Cin (padded to 16)
+def _stem_im2col(x, kshape):
+    L.require_cuda(x, "stem conv")
+    if x.requires_grad:
+        raise NotImplementedError("gradient w.r.t. the network input is not implemented")
+    x = x.detach().float().contiguous()
+    n, ci, d, h, w = x.shape
+    kd, kh, kw = kshape
+    K = kd * kh * kw * ci
+    if K > 1024:
+        raise NotImplementedError("stem im2col path supports up to 1024 (taps x input channels)")
+    kp = (K + 15) // 16 * 16
+    col = new_cl(n, kp, d, h, w, x.device)
+    with KERNEL_TIMER.span("stem_im2col"):
+        rc = L.load().rb_stem_im2col(x.data_ptr(), col.data_ptr(), n, ci, d, h, w, kd, kh, kw, kp, L.stream_ptr())
+    L.check(rc, "rb_stem_im2col")
+    return col
+
+
+def _stem_pack(weight, kp):
+    co, ci, kd, kh, kw = weight.shape
+    K = kd * kh * kw * ci
+
+    def pack():
+        wp = torch.zeros((1, co, kp), dtype=BF16, device=weight.device)
+        wp[0, :, :K] = weight.detach().permute(0, 2, 3, 4, 1).reshape(co, K).to(BF16)
+        return wp
+    return _cached_pack(weight, "s", pack)
+
+
+def _stem_forward(weight, impl, col, out_f32=False, want_stats=False):
+    co = weight.shape[0]
+    n, kp, d, h, w = col.shape
+    y = (new_cl_f32 if out_f32 else new_cl)(n, co, d, h, w, col.device)
+    stats = _launch_gather(col, None, _stem_pack(weight, kp), y, None, in_dims=(d, h, w), taps=(1, 1, 1), off=(0, 0, 0),
+                           istr=(1, 1, 1), out_grid=(d, h, w), nout=co, impl=impl, want_stats=want_stats)
+    return y, stats
+
+
+def _stem_backward(wshape, col, dy):
+    co, ci, kd, kh, kw = wshape
+    K = kd * kh * kw * ci
+    dims = tuple(dy.shape[2:])
+    dw = _launch_wgrad(dy, col, None, grid=dims, qdims=dims, taps=(1, 1, 1), off=(0, 0, 0), istr=(1, 1, 1))
+    return dw[0, :, :K].reshape(co, kd, kh, kw, ci).permute(0, 4, 1, 2, 3).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# primitives (no autograd): InstanceNorm (+affine, +SE gate) + residual + LeakyReLU
+# ------------------------------------------------------------------------------------------
+def _plane_reduce(kind, y, dz, z, per_w, slope):
+    n, c, d, h, w = y.shape
+    g = w if per_w else 1
+    out = torch.empty((n, g, c, 2), dtype=torch.float64, device=y.device)
+    with KERNEL_TIMER.span("norm_reduce"):
+        rc = L.load().rb_plane_reduce(kind, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(dz), L.ptr(z),
+                                      out.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, float(slope), L.stream_ptr())
+    L.check(rc, "rb_plane_reduce")
+    return out
+
+
+def _apply_fwd(y, res, A, B, per_w, act, slope):
+    n, c, d, h, w = y.shape
+    z = new_cl(n, c, d, h, w, y.device)
+    with KERNEL_TIMER.span("norm_apply"):
+        rc = L.load().rb_norm_act_fwd(y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(res), z.data_ptr(),
+                                      A.data_ptr(), B.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, 1 if act else 0,
+                                      float(slope), L.stream_ptr())
+    L.check(rc, "rb_norm_act_fwd")
+    return z
+
+
+def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres):
+    n, c, d, h, w = y.shape
+    dy = new_cl(n, c, d, h, w, y.device)
+    dres = new_cl(n, c, d, h, w, y.device) if want_dres else None
+    with KERNEL_TIMER.span("norm_apply"):
+        rc = L.load().rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), 1 if y.dtype == torch.float32 else 0,
+                                      dy.data_ptr(), L.ptr(dres), k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), n,
+                                      d * h * w, c, w, 1 if per_w else 0, 1 if act else 0, float(slope), L.stream_ptr())
+    L.check(rc, "rb_norm_act_bwd")
+    return dy, dres
+
+
+class _NormState:
+    """What the backward of a norm (+gate) + act needs besides y, z."""
+    __slots__ = ("small", "gamma", "has_beta", "act", "slope", "eps", "has_res", "gate", "per_w")
+
+
+def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, reduce_dims="all"):
+    """z = act( [gate *] (IN(y) [* gamma + beta]) + res ).  `stats` = fp32 (sum, sumsq) from the conv epilogue.
+    gate = (fc1_w, fc1_b, fc2_w, fc2_b) or None."""
+    n, c, d, h, w = y.shape
+    S = d * h * w
+    lib = L.load()
+    st = _NormState()
+    st.gamma, st.has_beta, st.act, st.slope, st.eps, st.has_res = gamma, beta is not None, act, slope, eps, res is not None
+    if gate is None:
+        st.gate, st.per_w = None, False
+        sums = None if stats is not None else _plane_reduce(0, y, None, None, False, slope)
+        small = torch.empty((4, n, c), dtype=torch.float32, device=y.device)     # mean, rstd, scale, shift
+        L.check(lib.rb_in_finalize_fwd(L.ptr(sums), L.ptr(stats[0]) if stats else None, L.ptr(stats[1]) if stats else None,
+                                       L.ptr(gamma), L.ptr(beta), small[0].data_ptr(), small[1].data_ptr(),
+                                       small[2].data_ptr(), small[3].data_ptr(), n, c, float(S), float(eps),
+                                       L.stream_ptr()), "rb_in_finalize_fwd")
+        st.small = small
+        z = _apply_fwd(y, res, small[2], small[3], False, act, slope)
+        return z, st
+    # gated (squeeze-excitation) path: the O(N*W*C) part is a small differentiable torch graph
+    per_w = _se_per_w(reduce_dims)
+    st.per_w = per_w
+    if stats is not None:
+        s1, s2 = stats[0].double(), stats[1].double()
+    else:
+        sums = _plane_reduce(0, y, None, None, False, slope)[:, 0]
+        s1, s2 = sums[..., 0], sums[..., 1]
+    pw = _plane_reduce(0, y, None, None, True, slope)[..., 0] if per_w else None      # [N, W, C]
+    params = [gamma, beta, *gate]
+    with torch.enable_grad():
+        leaves = [s1.detach().clone().requires_grad_(True), s2.detach().clone().requires_grad_(True),
+                  pw.detach().requires_grad_(True) if per_w else None]
+        pl = [p.detach().requires_grad_(True) if p is not None else None for p in params]
+        A, B = _gate_small_graph(leaves[0], leaves[1], leaves[2], float(S), float(d * h), pl[0], pl[1], eps,
+                                 pl[2], pl[3], pl[4], pl[5], per_w)
+    st.gate = (leaves, pl, A, B)
+    st.small = None
+    z = _apply_fwd(y, res, A, B, per_w, act, slope)
+    return z, st
+
+
+def _norm_backward(st, y, z, dz, want_dres):
+    """Returns dy, dres, dgamma, dbeta, gate parameter grads (4-tuple or None)."""
+    n, c, d, h, w = y.shape
+    S = d * h * w
+    lib = L.load()
+    if st.gate is None:
+        red = _plane_reduce(1, y, dz, z, False, st.slope)
+        ks = torch.empty((3, n, c), dtype=torch.float32, device=y.device)
+        dgamma = torch.zeros(c, dtype=torch.float32, device=y.device) if st.gamma is not None else None
+        dbeta = torch.zeros(c, dtype=torch.float32, device=y.device) if st.has_beta else None
+        L.check(lib.rb_in_finalize_bwd(red.data_ptr(), st.small[0].data_ptr(), st.small[1].data_ptr(), L.ptr(st.gamma),
+                                       ks[0].data_ptr(), ks[1].data_ptr(), ks[2].data_ptr(), L.ptr(dgamma), L.ptr(dbeta),
+                                       n, c, float(S), L.stream_ptr()), "rb_in_finalize_bwd")
+        dy, dres = _apply_bwd(dz, z, y, ks[0], ks[1], ks[2], False, st.act, st.slope, want_dres)
+        return dy, dres, dgamma, dbeta, None
+    leaves, pl, A, B = st.gate
+    per_w = st.per_w
+    red = _plane_reduce(1, y, dz, z, per_w, st.slope)          # [N, G, C, 2] = (sum g, sum g*y)
+    dB = red[..., 0].float()
+    dA = red[..., 1].float()
+    inputs = [t for t in leaves + pl if t is not None]
+    grads = torch.autograd.grad([A, B], inputs, [dA, dB], allow_unused=True)
+    it = iter(grads)
+    gl = [next(it) if t is not None else None for t in leaves]
+    gp = [next(it) if t is not None else None for t in pl]
+    g = A.shape[1]
+    zero = torch.zeros((n, c), dtype=torch.float64, device=y.device)
+    dS1 = gl[0] if gl[0] is not None else zero
+    dS2 = gl[1] if gl[1] is not None else zero
+    k2 = (2.0 * dS2).float().unsqueeze(1).expand(n, g, c).contiguous()
+    k3 = dS1.unsqueeze(1).expand(n, g, c)
+    if per_w and gl[2] is not None:
+        k3 = k3 + gl[2]
+    k3 = k3.float().contiguous()
+    dy, dres = _apply_bwd(dz, z, y, A, k2, k3, per_w, st.act, st.slope, want_dres)
+    return dy, dres, gp[0], gp[1], tuple(gp[2:6])
+
+
+def _se_per_w(reduce_dims):
+    if reduce_dims in ("all", (2, 3, 4), [2, 3, 4]):
+        return False
+    if tuple(reduce_dims) == (2, 3):
+        return True
+    raise NotImplementedError(f"SE squeeze over dims {reduce_dims} is not implemented (use 'all' or (2, 3))")
+
+
+def _gate_small_graph(S1, S2, Pw, count, plane, gamma, beta, eps, w1, b1, w2, b2, per_w):
+    mean = S1 / count
+    var = (S2 / count - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + eps)
+    a0 = rstd if gamma is None else rstd * gamma.double()
+    b0 = -mean * a0 if beta is None else beta.double() - mean * a0
+    if per_w:                                     # squeeze over (D, H): one value per (n, w, c)
+        sq = a0.unsqueeze(1) * (Pw / plane) + b0.unsqueeze(1)
+    else:                                         # global average pool of the normalised tensor
+        sq = (a0 * mean + b0).unsqueeze(1)
+    hid = torch.relu(torch.nn.functional.linear(sq.float(), w1.flatten(1), b1))
+    gate = torch.sigmoid(torch.nn.functional.linear(hid, w2.flatten(1), b2)).double()
+    A = (a0.unsqueeze(1) * gate).float()
+    B = (b0.unsqueeze(1) * gate).float()
+    return A.contiguous(), B.contiguous()          # [N, G, C]
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: stand-alone operators (public functional API, tests)
+# ------------------------------------------------------------------------------------------
 class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, stride, impl, x0, x1):
         x0 = as_cl(x0)
         x1 = as_cl(x1) if x1 is not None else None
         L.require_cuda(x0, "conv3d")
-        co, ci, kd, kh, kw = weight.shape
-        c_in = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
-        if c_in != ci:
-            raise ValueError(f"conv3d: weight expects {ci} input channels, got {c_in}")
-        k = (kd, kh, kw)
-        if any(kk not in (1, 3) for kk in k):
-            raise NotImplementedError(f"conv3d: kernel sizes 1 and 3 are implemented, got {k}")
-        n = x0.shape[0]
-        in_dims = tuple(x0.shape[2:])
-        od = _conv_out_dims(in_dims, k, stride)
-        y = new_cl(n, co, *od, x0.device)
-        _launch_gather(x0, x1, pack_conv_fprop(weight), y, None, in_dims=in_dims, taps=k,
-                       off=tuple(-((kk - 1) // 2) for kk in k), istr=stride, out_grid=od, nout=co, impl=impl)
+        y, _ = _conv_forward(weight, stride, impl, x0, x1)
         ctx.save_for_backward(weight, x0, x1)
         ctx.stride, ctx.impl = stride, impl
         return y
@@ -266,38 +543,8 @@ class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         weight, x0, x1 = ctx.saved_tensors
-        dy = as_cl(dy)
-        stride, impl = ctx.stride, ctx.impl
-        co, ci, kd, kh, kw = weight.shape
-        k = (kd, kh, kw)
-        pad = tuple((kk - 1) // 2 for kk in k)
-        n = x0.shape[0]
-        in_dims = tuple(x0.shape[2:])
-        od = tuple(dy.shape[2:])
-        gw = gx0 = gx1 = None
-        if ctx.needs_input_grad[0]:
-            dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride)
-            gw = dw.view(kd, kh, kw, co, ci).permute(3, 4, 0, 1, 2).contiguous()
-        need0 = ctx.needs_input_grad[3]
-        need1 = x1 is not None and ctx.needs_input_grad[4]
-        if need0 or need1:
-            c0 = x0.shape[1]
-            classes = [_axis_classes(k[a], stride[a], pad[a], in_dims[a]) for a in range(3)]
-            empty = any(len(cls[2]) == 0 for axis in classes for cls in axis)
-            mk = zeros_cl if empty else new_cl
-            gx0 = mk(n, c0, *in_dims, x0.device)
-            gx1 = mk(n, x1.shape[1], *in_dims, x0.device) if x1 is not None else None
-            for cd, ch, cw in itertools.product(*classes):
-                if not (cd[2] and ch[2] and cw[2]):
-                    continue
-                wpk = pack_conv_dgrad_class(weight, cd[2], ch[2], cw[2])
-                _launch_gather(dy, None, wpk, gx0, gx1, in_dims=od, taps=(len(cd[2]), len(ch[2]), len(cw[2])),
-                               off=(cd[3], ch[3], cw[3]), istr=(1, 1, 1), out_grid=(cd[1], ch[1], cw[1]), nout=ci,
-                               ostr=stride, ooff=(cd[0], ch[0], cw[0]), full=in_dims, impl=impl)
-            if not need0:
-                gx0 = None
-            if not need1:
-                gx1 = None
+        gw, gx0, gx1 = _conv_backward(weight, ctx.stride, ctx.impl, x0, x1, as_cl(dy), ctx.needs_input_grad[0],
+                                      ctx.needs_input_grad[3], ctx.needs_input_grad[4])
         return gw, None, None, gx0, gx1
 
 
@@ -305,6 +552,96 @@ def conv3d(x, weight, stride=1, x_cat=None, impl=None):
     """Pre-norm convolution output (bf16, channels-last).  `x_cat` is concatenated after `x`
     along channels without materialising the concatenation."""
     return _Conv3dFn.apply(weight, _triple(stride), impl, x, x_cat)
+
+
+class _NormActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, res, gamma, beta, eps, act, slope, gate_dims, *gate):
+        y = as_prenorm(y)
+        L.require_cuda(y, "instance_norm")
+        res = as_cl(res) if res is not None else None
+        if res is not None and res.shape != y.shape:
+            raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
+        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, None, gate if gate else None, gate_dims)
+        ctx.save_for_backward(y, z if act else None)
+        ctx.st = st
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, z = ctx.saved_tensors
+        st = ctx.st
+        dy, dres, dgamma, dbeta, ggate = _norm_backward(st, y, z, as_cl(dz), st.has_res and ctx.needs_input_grad[1])
+        if y.dtype == torch.float32:
+            dy = dy.float()      # autograd wants the gradient in the input's dtype (stand-alone use only)
+        ggate = ggate if ggate is not None else ()
+        return (dy, dres, dgamma, dbeta, None, None, None, None, *ggate)
+
+
+def instance_norm_act(y, res=None, gamma=None, beta=None, eps=1e-5, act=True, slope=LRELU_SLOPE_DEFAULT):
+    """z = [LeakyReLU]( InstanceNorm(y) [* gamma + beta] [+ res] )."""
+    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), "all")
+
+
+def instance_norm_se_act(y, res, gamma, beta, fc1_w, fc1_b, fc2_w, fc2_b, eps=1e-5, act=True,
+                         slope=LRELU_SLOPE_DEFAULT, reduce_dims="all"):
+    """z = [LeakyReLU]( SE(InstanceNorm(y)) + res ), SE(o) = o * sigmoid(fc2(relu(fc1(mean_dims(o)))))."""
+    _se_per_w(reduce_dims)
+    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), reduce_dims,
+                            fc1_w, fc1_b, fc2_w, fc2_b)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: the fused unit the network is built from
+#     z = act( [SE]( IN( conv(x [, x_cat]) ) ) + res )
+# The pre-norm conv output stays internal (fp32, accumulator precision; its statistics come from the
+# tcgen05 epilogue), so exactly one rounding to bf16 happens per stored activation.
+# ------------------------------------------------------------------------------------------
+class _ConvNormActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, cfg, x0, x1, res, gamma, beta, *gate):
+        stride, impl, eps, act, slope, gate_dims, stem = cfg
+        if stem:
+            src0, src1 = _stem_im2col(x0, tuple(weight.shape[2:])), None
+            y, stats = _stem_forward(weight, impl, src0, out_f32=True, want_stats=True)
+        else:
+            src0 = as_cl(x0)
+            src1 = as_cl(x1) if x1 is not None else None
+            L.require_cuda(src0, "conv3d")
+            y, stats = _conv_forward(weight, stride, impl, src0, src1, out_f32=True, want_stats=True)
+        res = as_cl(res) if res is not None else None
+        if res is not None and res.shape != y.shape:
+            raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
+        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, stats, gate if gate else None, gate_dims)
+        ctx.save_for_backward(weight, src0, src1, y, z if act else None)
+        ctx.st, ctx.cfg = st, cfg
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        weight, src0, src1, y, z = ctx.saved_tensors
+        stride, impl, eps, act, slope, gate_dims, stem = ctx.cfg
+        st = ctx.st
+        need = ctx.needs_input_grad
+        dy, dres, dgamma, dbeta, ggate = _norm_backward(st, y, z, as_cl(dz), st.has_res and need[4])
+        if stem:
+            gw = _stem_backward(tuple(weight.shape), src0, dy) if need[0] else None
+            gx0 = gx1 = None
+        else:
+            gw, gx0, gx1 = _conv_backward(weight, stride, impl, src0, src1, dy, need[0], need[2], need[3])
+        ggate = ggate if ggate is not None else ()
+        return (gw, None, gx0, gx1, dres, dgamma, dbeta, *ggate)
+
+
+def conv_norm_act(x, weight, stride=1, x_cat=None, res=None, gamma=None, beta=None, eps=1e-5, act=True,
+                  slope=LRELU_SLOPE_DEFAULT, se=None, se_reduce_dims="all", stem=False, impl=None):
+    """act( [SE]( InstanceNorm( conv3d(cat(x, x_cat), weight, stride) ) [*gamma + beta] ) + res ).
+    se = (fc1_w, fc1_b, fc2_w, fc2_b) enables the squeeze-excitation gate; stem=True reads the raw NCDHW
+    fp32 network input (any channel count)."""
+    if se is not None:
+        _se_per_w(se_reduce_dims)
+    cfg = (_triple(stride), impl, float(eps), bool(act), float(slope), se_reduce_dims, bool(stem))
+    return _ConvNormActFn.apply(weight, cfg, x, x_cat, res, gamma, beta, *(se or ()))
 
 
 class _ZeroGradParamFn(torch.autograd.Function):
@@ -375,174 +712,6 @@ class _ConvT3dFn(torch.autograd.Function):
 
 def conv_transpose3d(x, weight, stride, impl=None):
     return _ConvT3dFn.apply(weight, _triple(stride), impl, x)
-
-
-# ------------------------------------------------------------------------------------------
-# InstanceNorm (+affine) + residual + LeakyReLU, closed-form backward (no gate)
-# ------------------------------------------------------------------------------------------
-def _plane_reduce(kind, y, dz, z, per_w, slope):
-    n, c, d, h, w = y.shape
-    g = w if per_w else 1
-    out = torch.empty((n, g, c, 2), dtype=torch.float64, device=y.device)
-    with KERNEL_TIMER.span("norm_reduce"):
-        rc = L.load().rb_plane_reduce(kind, y.data_ptr(), L.ptr(dz), L.ptr(z), out.data_ptr(), n, d * h * w, c, w,
-                                      1 if per_w else 0, float(slope), L.stream_ptr())
-    L.check(rc, "rb_plane_reduce")
-    return out
-
-
-class _NormActFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, y, res, gamma, beta, eps, act, slope):
-        y = as_cl(y)
-        L.require_cuda(y, "instance_norm")
-        res = as_cl(res) if res is not None else None
-        if res is not None and res.shape != y.shape:
-            raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
-        n, c, d, h, w = y.shape
-        S = d * h * w
-        lib = L.load()
-        st = L.stream_ptr()
-        sums = _plane_reduce(0, y, None, None, False, slope)
-        small = torch.empty((4, n, c), dtype=torch.float32, device=y.device)  # mean, rstd, scale, shift
-        L.check(lib.rb_in_finalize_fwd(sums.data_ptr(), L.ptr(gamma), L.ptr(beta), small[0].data_ptr(), small[1].data_ptr(),
-                                       small[2].data_ptr(), small[3].data_ptr(), n, c, float(S), float(eps), st),
-                "rb_in_finalize_fwd")
-        z = new_cl(n, c, d, h, w, y.device)
-        with KERNEL_TIMER.span("norm_apply"):
-            rc = lib.rb_norm_act_fwd(y.data_ptr(), L.ptr(res), z.data_ptr(), small[2].data_ptr(), small[3].data_ptr(),
-                                     n, S, c, w, 0, 1 if act else 0, float(slope), st)
-        L.check(rc, "rb_norm_act_fwd")
-        ctx.save_for_backward(y, z if act else None, small, gamma)
-        ctx.act, ctx.slope, ctx.has_res, ctx.has_beta = act, slope, res is not None, beta is not None
-        return z
-
-    @staticmethod
-    def backward(ctx, dz):
-        y, z, small, gamma = ctx.saved_tensors
-        dz = as_cl(dz)
-        n, c, d, h, w = y.shape
-        S = d * h * w
-        lib = L.load()
-        st = L.stream_ptr()
-        red = _plane_reduce(1, y, dz, z, False, ctx.slope)
-        ks = torch.empty((3, n, c), dtype=torch.float32, device=y.device)
-        dgamma = torch.zeros(c, dtype=torch.float32, device=y.device) if gamma is not None else None
-        dbeta = torch.zeros(c, dtype=torch.float32, device=y.device) if ctx.has_beta else None
-        L.check(lib.rb_in_finalize_bwd(red.data_ptr(), small[0].data_ptr(), small[1].data_ptr(), L.ptr(gamma),
-                                       ks[0].data_ptr(), ks[1].data_ptr(), ks[2].data_ptr(), L.ptr(dgamma), L.ptr(dbeta),
-                                       n, c, float(S), st), "rb_in_finalize_bwd")
-        dy = new_cl(n, c, d, h, w, y.device)
-        dres = new_cl(n, c, d, h, w, y.device) if (ctx.has_res and ctx.needs_input_grad[1]) else None
-        with KERNEL_TIMER.span("norm_apply"):
-            rc = lib.rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), dy.data_ptr(), L.ptr(dres), ks[0].data_ptr(),
-                                     ks[1].data_ptr(), ks[2].data_ptr(), n, S, c, w, 0, 1 if ctx.act else 0,
-                                     float(ctx.slope), st)
-        L.check(rc, "rb_norm_act_bwd")
-        return dy, dres, dgamma, dbeta, None, None, None
-
-
-def instance_norm_act(y, res=None, gamma=None, beta=None, eps=1e-5, act=True, slope=LRELU_SLOPE_DEFAULT):
-    """z = [LeakyReLU]( InstanceNorm(y) [* gamma + beta] [+ res] )."""
-    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope))
-
-
-# ------------------------------------------------------------------------------------------
-# InstanceNorm + squeeze-excitation gate + residual + LeakyReLU.
-# The O(N*W*C) part (statistics -> scale/shift, the SE bottleneck MLP and its backward) is a small
-# differentiable torch graph; the two full-tensor passes per direction are the same kernels as above.
-# ------------------------------------------------------------------------------------------
-def _gate_small_graph(S1, S2, Pw, count, plane, gamma, beta, eps, w1, b1, w2, b2, per_w):
-    mean = S1 / count
-    var = (S2 / count - mean * mean).clamp_min(0.0)
-    rstd = torch.rsqrt(var + eps)
-    a0 = rstd if gamma is None else rstd * gamma.double()
-    b0 = -mean * a0 if beta is None else beta.double() - mean * a0
-    if per_w:                                     # squeeze over (D, H): one value per (n, w, c)
-        sq = a0.unsqueeze(1) * (Pw / plane) + b0.unsqueeze(1)
-    else:                                         # global average pool of the normalised tensor
-        sq = (a0 * mean + b0).unsqueeze(1)
-    hid = torch.relu(torch.nn.functional.linear(sq.float(), w1.flatten(1), b1))
-    gate = torch.sigmoid(torch.nn.functional.linear(hid, w2.flatten(1), b2)).double()
-    A = (a0.unsqueeze(1) * gate).float()
-    B = (b0.unsqueeze(1) * gate).float()
-    return A.contiguous(), B.contiguous()          # [N, G, C]
-
-
-class _NormGateActFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, y, res, gamma, beta, w1, b1, w2, b2, eps, act, slope, per_w):
-        y = as_cl(y)
-        L.require_cuda(y, "instance_norm_se")
-        res = as_cl(res) if res is not None else None
-        n, c, d, h, w = y.shape
-        S = d * h * w
-        lib = L.load()
-        st = L.stream_ptr()
-        sums = _plane_reduce(0, y, None, None, False, slope)[:, 0]          # [N, C, 2]
-        pw = _plane_reduce(0, y, None, None, True, slope)[..., 0] if per_w else None   # [N, W, C]
-        params = [gamma, beta, w1, b1, w2, b2]
-        with torch.enable_grad():
-            leaves = [sums[..., 0].detach().requires_grad_(True), sums[..., 1].detach().requires_grad_(True),
-                      pw.detach().requires_grad_(True) if per_w else None]
-            pl = [p.detach().requires_grad_(True) if p is not None else None for p in params]
-            A, B = _gate_small_graph(leaves[0], leaves[1], leaves[2], float(S), float(d * h), pl[0], pl[1], eps,
-                                     pl[2], pl[3], pl[4], pl[5], per_w)
-        z = new_cl(n, c, d, h, w, y.device)
-        L.check(lib.rb_norm_act_fwd(y.data_ptr(), L.ptr(res), z.data_ptr(), A.data_ptr(), B.data_ptr(), n, S, c, w,
-                                    1 if per_w else 0, 1 if act else 0, float(slope), st), "rb_norm_act_fwd")
-        ctx.save_for_backward(y, z if act else None)
-        ctx.graph = (leaves, pl, A, B)
-        ctx.cfg = (act, slope, per_w, res is not None)
-        return z
-
-    @staticmethod
-    def backward(ctx, dz):
-        y, z = ctx.saved_tensors
-        dz = as_cl(dz)
-        act, slope, per_w, has_res = ctx.cfg
-        leaves, pl, A, B = ctx.graph
-        n, c, d, h, w = y.shape
-        S = d * h * w
-        lib = L.load()
-        st = L.stream_ptr()
-        red = _plane_reduce(1, y, dz, z, per_w, slope)          # [N, G, C, 2] = (sum g, sum g*y)
-        dB = red[..., 0].float()
-        dA = red[..., 1].float()
-        inputs = [t for t in leaves + pl if t is not None]
-        grads = torch.autograd.grad([A, B], inputs, [dA, dB], allow_unused=True)
-        it = iter(grads)
-        gl = [next(it) if t is not None else None for t in leaves]
-        gp = [next(it) if t is not None else None for t in pl]
-        g = A.shape[1]
-        zero = torch.zeros((n, c), dtype=torch.float64, device=y.device)
-        dS1 = gl[0] if gl[0] is not None else zero
-        dS2 = gl[1] if gl[1] is not None else zero
-        k1 = A
-        k2 = (2.0 * dS2).float().unsqueeze(1).expand(n, g, c).contiguous()
-        k3 = dS1.unsqueeze(1).expand(n, g, c)
-        if per_w and gl[2] is not None:
-            k3 = k3 + gl[2]
-        k3 = k3.float().contiguous()
-        dy = new_cl(n, c, d, h, w, y.device)
-        dres = new_cl(n, c, d, h, w, y.device) if (has_res and ctx.needs_input_grad[1]) else None
-        L.check(lib.rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), dy.data_ptr(), L.ptr(dres), k1.data_ptr(),
-                                    k2.data_ptr(), k3.data_ptr(), n, S, c, w, 1 if per_w else 0, 1 if act else 0,
-                                    float(slope), st), "rb_norm_act_bwd")
-        gp = [None if v is None else v for v in gp]
-        return (dy, dres, gp[0], gp[1], gp[2], gp[3], gp[4], gp[5], None, None, None, None)
-
-
-def instance_norm_se_act(y, res, gamma, beta, fc1_w, fc1_b, fc2_w, fc2_b, eps=1e-5, act=True,
-                         slope=LRELU_SLOPE_DEFAULT, reduce_dims="all"):
-    """z = [LeakyReLU]( SE(InstanceNorm(y)) + res ), SE(o) = o * sigmoid(fc2(relu(fc1(mean_dims(o)))))."""
-    if reduce_dims in ("all", (2, 3, 4), [2, 3, 4]):
-        per_w = False
-    elif tuple(reduce_dims) == (2, 3):
-        per_w = True
-    else:
-        raise NotImplementedError(f"SE squeeze over dims {reduce_dims} is not implemented (use 'all' or (2, 3))")
-    return _NormGateActFn.apply(y, res, gamma, beta, fc1_w, fc1_b, fc2_w, fc2_b, float(eps), bool(act), float(slope), per_w)
 
 
 # ------------------------------------------------------------------------------------------
@@ -628,25 +797,8 @@ def head_conv1x1(x, weight, bias, activation=None):
 class _StemConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, impl):
-        L.require_cuda(x, "stem conv")
-        x = x.float().contiguous()
-        n, ci, d, h, w = x.shape
-        co, ci_w, kd, kh, kw = weight.shape
-        if ci != ci_w:
-            raise ValueError(f"stem conv: weight expects {ci_w} input channels, got {ci}")
-        K = kd * kh * kw * ci
-        kp = (K + 15) // 16 * 16
-        col = new_cl(n, kp, d, h, w, x.device)
-        L.check(L.load().rb_stem_im2col(x.data_ptr(), col.data_ptr(), n, ci, d, h, w, kd, kh, kw, kp, L.stream_ptr()),
-                "rb_stem_im2col")
-
-        def pack():
-            wp = torch.zeros((1, co, kp), dtype=BF16, device=x.device)
-            wp[0, :, :K] = weight.detach().permute(0, 2, 3, 4, 1).reshape(co, K).to(BF16)
-            return wp
-        y = new_cl(n, co, d, h, w, x.device)
-        _launch_gather(col, None, _cached_pack(weight, "s", pack), y, None, in_dims=(d, h, w), taps=(1, 1, 1),
-                       off=(0, 0, 0), istr=(1, 1, 1), out_grid=(d, h, w), nout=co, impl=impl)
+        col = _stem_im2col(x, tuple(weight.shape[2:]))
+        y, _ = _stem_forward(weight, impl, col)
         ctx.save_for_backward(col)
         ctx.wshape = tuple(weight.shape)
         return y
@@ -654,23 +806,12 @@ class _StemConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (col,) = ctx.saved_tensors
-        dy = as_cl(dy)
-        co, ci, kd, kh, kw = ctx.wshape
-        K = kd * kh * kw * ci
-        dims = tuple(dy.shape[2:])
-        gw = None
-        if ctx.needs_input_grad[1]:
-            dw = _launch_wgrad(dy, col, None, grid=dims, qdims=dims, taps=(1, 1, 1), off=(0, 0, 0), istr=(1, 1, 1))
-            gw = dw[0, :, :K].reshape(co, kd, kh, kw, ci).permute(0, 4, 1, 2, 3).contiguous()
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. the network input is not implemented")
+        gw = _stem_backward(ctx.wshape, col, as_cl(dy)) if ctx.needs_input_grad[1] else None
         return None, gw, None
 
 
 def stem_conv3d(x, weight, impl=None):
-    """Stride-1 'same' convolution of the raw network input (any Cin)."""
-    if x.dtype == BF16 and is_cl(x) and x.shape[1] % 8 == 0:
-        return conv3d(x, weight, 1, impl=impl)
-    if weight.shape[1] * weight.shape[2] * weight.shape[3] * weight.shape[4] > 1024:
-        raise NotImplementedError("stem im2col path supports up to 1024 (taps x input channels)")
+    """Stride-1 'same' convolution of the raw network input (any Cin); pre-norm bf16 output."""
+    if x.shape[1] != weight.shape[1]:
+        raise ValueError(f"stem conv: weight expects {weight.shape[1]} input channels, got {x.shape[1]}")
     return _StemConvFn.apply(x, weight, impl)

@@ -17,6 +17,9 @@ def pytest_configure(config):
 def _cuda_ok():
     try:
         import torch
+        # the PyTorch references in the GPU tests must be true fp32 (no TF32 convolutions / matmuls)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return torch.cuda.is_available()
     except Exception:
         return False

@@ -49,7 +49,7 @@ def test_tc5_conv_fwd_bwd(rb, case):
     w = (torch.randn(cout, cin, *k, device="cuda") / (cin * k[0] * k[1] * k[2]) ** 0.5).requires_grad_(True)
     pad = tuple((kk - 1) // 2 for kk in k)
     xr = x.clone().requires_grad_(True)
-    ref = F.conv3d(xr, q(w), None, s, pad)
+    ref = F.conv3d(xr, q(w.detach()), None, s, pad)
     g = q(torch.randn_like(ref))
     ref.backward(g)
     outs = {}
@@ -117,6 +117,14 @@ def test_tc5_fused_statistics(rb):
         yf = y.float()
         assert rel_l2(ssum, yf.sum((2, 3, 4))) < 5e-3
         assert rel_l2(ssq, (yf * yf).sum((2, 3, 4))) < 5e-3
+        # fp32 destination: same accumulators, no rounding; statistics then agree to fp32 summation error
+        y32 = ops.new_cl_f32(n, c, *dims, "cuda")
+        st = ops._launch_gather(x, None, ops.pack_conv_fprop(w), y32, None, in_dims=dims, taps=(3, 3, 3),
+                                off=(-1, -1, -1), istr=(1, 1, 1), out_grid=dims, nout=c, impl="tc5", want_stats=True)
+        assert st is not None
+        assert rel_l2(y32, yf) < 3e-3 and torch.equal(y32.to(torch.bfloat16), y)
+        assert rel_l2(st[0], y32.double().sum((2, 3, 4))) < 2e-5
+        assert rel_l2(st[1], (y32.double() ** 2).sum((2, 3, 4))) < 2e-5
 
 
 def test_tc5_support_query(rb, built_lib):
