@@ -135,8 +135,8 @@ Tc5Plan plan_tc5(const RbConvDesc& d) {
     pl.tilesNB = (d.NB + pl.tn - 1) / pl.tn;
     pl.tiles = best * pl.nTilesN;
     const size_t stageBytes = (size_t)(128 + pl.Ntile) * pl.KW * 2;
-    // per-CTA statistics accumulators [2][NB][Nout] fp32 live behind the stages when they fit in 16 KB
-    const size_t statBytes = (size_t)2 * d.NB * d.Nout * sizeof(float);
+    // per-epilogue-warp statistics accumulators 4 x [2][NB][Nout] fp32 live behind the stages when they fit in 16 KB
+    const size_t statBytes = (size_t)8 * d.NB * d.Nout * sizeof(float);
     pl.statSmem = statBytes <= 16 * 1024;
     const size_t reserve = pl.statSmem ? statBytes : 0;
     int st = (int)((200 * 1024 - reserve) / stageBytes);

@@ -95,11 +95,12 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * p.Ntile) tmem_cols <<= 1;
-    // optional per-CTA statistics accumulators [2][NB][Nout] behind the pipeline stages
+    // optional statistics accumulators behind the pipeline stages: one PRIVATE [2][NB][Nout] fp32 slot per
+    // epilogue warp (plain read-modify-write by the owning lane, no atomics), summed and flushed once at the end
     float* statS = reinterpret_cast<float*>(tiles + (size_t)S * stageBytes);
     const int statN = p.NB * p.Nout;
     if (p.stat_sum != nullptr && p.statSmem)
-        for (int i = threadIdx.x; i < 2 * statN; i += blockDim.x) statS[i] = 0.f;
+        for (int i = threadIdx.x; i < 8 * statN; i += blockDim.x) statS[i] = 0.f;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.mapA[0]);
@@ -246,8 +247,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             if (col0 + lane < p.Nout && nb < p.NB) {
                                 const int idx = nb * p.Nout + col0 + lane;
                                 if (p.statSmem) {
-                                    atomicAdd(statS + idx, s1);
-                                    atomicAdd(statS + statN + idx, s2);
+                                    float* slot = statS + (size_t)quad * 2 * statN + idx;
+                                    slot[0] += s1;
+                                    slot[statN] += s2;
                                 } else {
                                     atomicAdd(p.stat_sum + idx, s1);
                                     atomicAdd(p.stat_sq + idx, s2);
@@ -260,13 +262,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                                 if (col0 + j < p.Nout) {
                                     const float x = __uint_as_float(v[j]);
                                     const int idx = nb * p.Nout + col0 + j;
-                                    if (p.statSmem) {
-                                        atomicAdd(statS + idx, x);
-                                        atomicAdd(statS + statN + idx, x * x);
-                                    } else {
-                                        atomicAdd(p.stat_sum + idx, x);
-                                        atomicAdd(p.stat_sq + idx, x * x);
-                                    }
+                                    atomicAdd(p.stat_sum + idx, x);
+                                    atomicAdd(p.stat_sq + idx, x * x);
                                 }
                             }
                         }
@@ -326,7 +323,12 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
     __syncthreads();
     if (p.stat_sum != nullptr && p.statSmem) {
         for (int i = threadIdx.x; i < statN; i += blockDim.x) {
-            const float a = statS[i], b = statS[statN + i];
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                a += statS[(size_t)w * 2 * statN + i];
+                b += statS[(size_t)w * 2 * statN + statN + i];
+            }
             if (a != 0.f || b != 0.f) {
                 atomicAdd(p.stat_sum + i, a);
                 atomicAdd(p.stat_sq + i, b);

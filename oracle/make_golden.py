@@ -114,6 +114,11 @@ def make_net_case(case):
     model.eval()
     with torch.no_grad():
         ev = model(xt)
+    # calibration of the bf16 tolerance: PyTorch's own bf16 autocast of the UNMODIFIED reference vs its fp32 output
+    model.train()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ac = model(xt)
+    model.eval()
     rec = {"x": x, "loss_total": np.float64(float(total)), "grad_norms": gnorm, "has_grad": has_grad,
            "param_names": np.array([n for n, _ in names])}
     # a few full gradients (first conv, a deep conv, a transposed conv, a head)
@@ -129,6 +134,8 @@ def make_net_case(case):
         rec["train::" + t] = out[t].detach().numpy()
         rec["eval::" + t] = ev[t].numpy()
         rec["loss::" + t] = np.float64(per[t])
+        a, b = ac[t].float(), out[t].detach()
+        rec["autocast_bf16_rel::" + t] = np.float64(float((a - b).norm() / b.norm()))
     np.savez_compressed(os.path.join(GOLD, f"net_{case}.npz"), **rec)
     # state-dict key census (drop-in contract)
     keys = {k: list(v.shape) for k, v in model.state_dict().items()}
