@@ -122,8 +122,9 @@ Tc5Plan plan_tc5(const RbConvDesc& d) {
                 if ((tw - 1) * d.istrW + 1 > 256 || (th - 1) * d.istrH + 1 > 256 || (td - 1) * d.istrD + 1 > 256 || tn > 256) continue;
                 const long long t = (long long)((d.OW + tw - 1) / tw) * ((d.OH + th - 1) / th) * ((d.OD + td - 1) / td) *
                                     ((d.NB + tn - 1) / tn);
-                // ties: prefer the widest tw (longer contiguous runs for TMA and the epilogue stores)
-                if (best < 0 || t < best || (t == best && tw > pl.tw)) {
+                // ties: keep samples apart (tn == 1) first, then prefer the widest tw (longer contiguous runs
+                // for TMA and the epilogue stores)
+                if (best < 0 || t < best || (t == best && (tn < pl.tn || (tn == pl.tn && tw > pl.tw)))) {
                     best = t;
                     pl.tw = tw; pl.th = th; pl.td = td; pl.tn = tn;
                 }

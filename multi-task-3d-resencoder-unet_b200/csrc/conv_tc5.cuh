@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
         const int ih = (row / p.tw) % p.th;
         const int id = (row / (p.tw * p.th)) % p.td;
         const int in = row / (p.tw * p.th * p.td);
+        const bool warpUniformSample = ((p.tw * p.th * p.td) & 31) == 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
             const int nt = tile % p.nTilesN;
             int sp = tile / p.nTilesN;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                 const int col0 = n0 + cg;
                 if (col0 < p.Nout) {
                     if (p.stat_sum != nullptr) {
-                        if (p.tn == 1) {
+                        if (warpUniformSample) {
                             // all 32 rows of this warp belong to sample nb: butterfly column sums, lane j ends up
                             // with column col0 + j
                             float a[32], b[32];
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                                 }
                             }
                         } else if (valid) {
-                            // batch-folded tiles (tiny grids): rows of a warp may belong to different samples
-#pragma unroll 4
+                            // batch-folded tiles of tiny grids (< 32 voxels per sample): rows of a warp may belong to
+                            // different samples
+#pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if (col0 + j < p.Nout) {
                                     const float x = __uint_as_float(v[j]);

@@ -116,8 +116,17 @@ def make_net_case(case):
         ev = model(xt)
     # calibration of the bf16 tolerance: PyTorch's own bf16 autocast of the UNMODIFIED reference vs its fp32 output
     model.train()
-    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+    for p_ in model.parameters():
+        p_.grad = None
+    with torch.autocast("cpu", dtype=torch.bfloat16):
         ac = model(xt)
+    ac_total = 0.0
+    for t in tasks:
+        fn = losses_mod.MaskedCosineLoss() if t == "normals" else losses_mod.BCEDiceLoss(0.5, 0.5)
+        ac_total = ac_total + fn(ac[t].float(), torch.from_numpy(tgt[t]))
+    ac_total.backward()
+    ac_grads = {n: p_.grad for n, p_ in model.named_parameters()}
+    ac = {t: v.detach() for t, v in ac.items()}
     model.eval()
     rec = {"x": x, "loss_total": np.float64(float(total)), "grad_norms": gnorm, "has_grad": has_grad,
            "param_names": np.array([n for n, _ in names])}
@@ -129,6 +138,13 @@ def make_net_case(case):
     for n in picks:
         if grads[n] is not None and grads[n].numel() <= 200000:
             rec["grad::" + n] = grads[n].numpy()
+            if ac_grads[n] is not None:
+                rec["autocast_bf16_gradrel::" + n] = np.float64(
+                    float((ac_grads[n].float() - grads[n]).norm() / grads[n].norm()))
+    gmax = float(gnorm.max())
+    devs = [abs(float(ac_grads[n].double().norm()) - g) / g for (n, _), g in zip(names, gnorm)
+            if ac_grads[n] is not None and g >= 1e-4 * gmax]
+    rec["autocast_bf16_gradnorm_dev"] = np.float64(max(devs))
     for t in tasks:
         rec["target::" + t] = tgt[t]
         rec["train::" + t] = out[t].detach().numpy()
