@@ -110,6 +110,7 @@ typedef struct RbWgradDesc {
     int QD, QH, QW;
     int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
     int splits; /* 0 = heuristic */
+    int impl;   /* RbConvImpl: auto = tcgen05 when channel counts are multiples of 16 (and 32 in total for Q) */
 } RbWgradDesc;
 int rb_wgrad_gather(const RbWgradDesc* d, const void* P, const void* Q0, const void* Q1, float* dw, void* stream);
 

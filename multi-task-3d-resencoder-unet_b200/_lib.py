@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "PC", "nq", "QC0", "QC1", "NB", "GD", "GH", "GW", "QD", "QH", "QW", "tapD", "tapH", "tapW",
-        "offD", "offH", "offW", "istrD", "istrH", "istrW", "splits")]
+        "offD", "offH", "offW", "istrD", "istrH", "istrW", "splits", "impl")]
 
 
 _P, _I, _LL, _F, _D, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t

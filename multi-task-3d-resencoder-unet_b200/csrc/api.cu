@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "conv_tc5.cuh"
 #include "conv_generic.cuh"
+#include "wgrad_tc5.cuh"
 #include "elementwise.cuh"
 #include "blend.cuh"
 
@@ -265,6 +266,123 @@ int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const v
     return check_launch("tc5_gather_conv_kernel");
 }
 
+struct Tw5Plan {
+    bool ok = false;
+    int aw = 0, bw = 0, aAtoms = 0, bn = 0, aTiles = 0, bTiles = 0;
+    int cw = 0, ch = 0, cd = 0, cn = 0, chunksW = 0, chunksH = 0, chunksD = 0, chunksN = 0;
+    int splits = 1, chunksPerSplit = 0, stages = 0, accBufs = 1;
+    size_t smem = 0;
+};
+
+int atom_width(int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; }
+
+Tw5Plan plan_tw5(const RbWgradDesc& d) {
+    Tw5Plan pl;
+    const int qct = d.QC0 + (d.nq == 2 ? d.QC1 : 0);
+    if (d.PC % 16 != 0 || d.QC0 % 16 != 0 || (d.nq == 2 && d.QC1 % 16 != 0)) return pl;
+    if (qct % 32 != 0) return pl;
+    pl.aw = atom_width(d.PC);
+    pl.bw = atom_width(d.QC0);
+    if (d.nq == 2) { const int w1 = atom_width(d.QC1); if (w1 < pl.bw) pl.bw = w1; }
+    pl.aAtoms = 128 / pl.aw;
+    pl.aTiles = (d.PC + 127) / 128;
+    pl.bn = qct < 256 ? qct : 256;
+    if (qct > 256 && qct % 256 != 0) pl.bn = qct % 128 == 0 ? 128 : qct % 64 == 0 ? 64 : 32;
+    if (pl.bn % pl.bw != 0 || pl.bn % 32 != 0) return pl;
+    if (d.nq == 2 && d.QC0 % pl.bw != 0) return pl;
+    pl.bTiles = (qct + pl.bn - 1) / pl.bn;
+    long long best = -1;
+    for (int cw = 1; cw <= 64; cw <<= 1)
+        for (int ch = 1; cw * ch <= 64; ch <<= 1)
+            for (int cd = 1; cw * ch * cd <= 64; cd <<= 1) {
+                const int cn = 64 / (cw * ch * cd);
+                if ((cw - 1) * d.istrW + 1 > 256 || (ch - 1) * d.istrH + 1 > 256 || (cd - 1) * d.istrD + 1 > 256) continue;
+                const long long t = (long long)((d.GW + cw - 1) / cw) * ((d.GH + ch - 1) / ch) * ((d.GD + cd - 1) / cd) *
+                                    ((d.NB + cn - 1) / cn);
+                if (best < 0 || t < best || (t == best && cw > pl.cw)) {
+                    best = t;
+                    pl.cw = cw; pl.ch = ch; pl.cd = cd; pl.cn = cn;
+                }
+            }
+    if (best < 0 || best > 2000000000LL) return pl;
+    pl.chunksW = (d.GW + pl.cw - 1) / pl.cw;
+    pl.chunksH = (d.GH + pl.ch - 1) / pl.ch;
+    pl.chunksD = (d.GD + pl.cd - 1) / pl.cd;
+    pl.chunksN = (d.NB + pl.cn - 1) / pl.cn;
+    const int taps = d.tapD * d.tapH * d.tapW;
+    const long long base_items = (long long)pl.aTiles * pl.bTiles * taps;
+    long long splits = d.splits > 0 ? d.splits : (3LL * num_sms() + base_items - 1) / base_items;
+    long long maxs = (best + 3) / 4;      // at least 4 chunks (256 voxels) per item
+    if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+    pl.chunksPerSplit = (int)((best + splits - 1) / splits);
+    pl.splits = (int)((best + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
+    const size_t stageBytes = (size_t)rb::TW5_KBOX * 2 * (128 + pl.bn);
+    int st = (int)((200 * 1024) / stageBytes);
+    if (st > 8) st = 8;
+    if (st < 2) return pl;
+    pl.stages = st;
+    pl.accBufs = 2 * pl.bn <= 512 ? 2 : 1;
+    pl.smem = 1024 + 1024 + (size_t)st * stageBytes;
+    pl.ok = true;
+    return pl;
+}
+
+CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const void* Q0, const void* Q1, float* dw, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    rb::Tc5WgradParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        const cuuint64_t C = (cuuint64_t)d.PC;
+        cuuint64_t dims[5] = {C, (cuuint64_t)d.GW, (cuuint64_t)d.GH, (cuuint64_t)d.GD, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {C * 2, C * 2 * d.GW, C * 2 * d.GW * d.GH, C * 2 * d.GW * d.GH * d.GD};
+        cuuint32_t box[5] = {(cuuint32_t)pl.aw, (cuuint32_t)pl.cw, (cuuint32_t)pl.ch, (cuuint32_t)pl.cd, (cuuint32_t)pl.cn};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&p.mapP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(P), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(pl.aw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
+    }
+    const void* qs[2] = {Q0, Q1};
+    const int qc[2] = {d.QC0, d.QC1};
+    for (int s = 0; s < d.nq; ++s) {
+        const cuuint64_t C = (cuuint64_t)qc[s];
+        cuuint64_t dims[5] = {C, (cuuint64_t)d.QW, (cuuint64_t)d.QH, (cuuint64_t)d.QD, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {C * 2, C * 2 * d.QW, C * 2 * d.QW * d.QH, C * 2 * d.QW * d.QH * d.QD};
+        cuuint32_t box[5] = {(cuuint32_t)pl.bw, (cuuint32_t)((pl.cw - 1) * d.istrW + 1), (cuuint32_t)((pl.ch - 1) * d.istrH + 1),
+                             (cuuint32_t)((pl.cd - 1) * d.istrD + 1), (cuuint32_t)pl.cn};
+        cuuint32_t estr[5] = {1, (cuuint32_t)d.istrW, (cuuint32_t)d.istrH, (cuuint32_t)d.istrD, 1};
+        CUresult r = enc(&p.mapQ[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(qs[s]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(pl.bw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(Q%d) failed: %d", s, (int)r);
+    }
+    p.PC = d.PC; p.QC[0] = d.QC0; p.QC[1] = d.nq == 2 ? d.QC1 : 0; p.nq = d.nq;
+    p.aw = pl.aw; p.bw = pl.bw; p.aAtoms = pl.aAtoms; p.bn = pl.bn; p.aTiles = pl.aTiles; p.bTiles = pl.bTiles;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.istrD = d.istrD; p.istrH = d.istrH; p.istrW = d.istrW;
+    p.cw = pl.cw; p.ch = pl.ch; p.cd = pl.cd; p.cn = pl.cn;
+    p.chunksW = pl.chunksW; p.chunksH = pl.chunksH; p.chunksD = pl.chunksD; p.chunksN = pl.chunksN;
+    p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages; p.accBufs = pl.accBufs;
+    p.dw = dw;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(rb::tc5_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tw5): %s", cudaGetErrorString(attr_err));
+    const long long items = (long long)pl.aTiles * pl.bTiles * d.tapD * d.tapH * d.tapW * pl.splits;
+    const long long grid = items < num_sms() ? items : num_sms();
+    rb::tc5_wgrad_kernel<<<(int)grid, rb::TW5_THREADS, pl.smem, st>>>(p);
+    return check_launch("tc5_wgrad_kernel");
+}
+
 }  // namespace
 
 extern "C" {
@@ -376,6 +494,11 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     if (!P || !Q0 || !dw || (d.nq == 2 && !Q1)) return fail(RB_ERR_INVALID, "wgrad: null pointer");
     if (!aligned16(P) || !aligned16(Q0) || !aligned16(Q1)) return fail(RB_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
     if (d.NB <= 0 || d.GD <= 0 || d.GH <= 0 || d.GW <= 0 || d.QD <= 0 || d.QH <= 0 || d.QW <= 0) return fail(RB_ERR_INVALID, "wgrad: empty grid");
+    if (d.impl != RB_IMPL_MMA_SYNC) {
+        Tw5Plan pl = plan_tw5(d);
+        if (pl.ok) return launch_tw5(d, pl, P, Q0, Q1, dw, (cudaStream_t)stream);
+        if (d.impl == RB_IMPL_TCGEN05) return fail(RB_ERR_UNSUPPORTED, "wgrad: shape does not qualify for the tcgen05 kernel");
+    }
     rb::GWgradParams p;
     memset(&p, 0, sizeof(p));
     p.P = (const rb::bf16*)P; p.PC = d.PC;

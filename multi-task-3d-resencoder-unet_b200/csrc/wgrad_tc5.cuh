@@ -1,0 +1,227 @@
+// tcgen05 / TMEM / TMA weight-gradient kernel for sm_100a.
+//
+//   dW[tap][a][b] += sum_m P[m][a] * Q[gather(m, tap)][b]
+//
+// GEMM view: M = a (channels of P), N = b (channels of Q, one or two concatenated sources), K = voxels.
+// Both operands are channels-last, i.e. "MN-major" (the M / N index is the contiguous one), which
+// tcgen05.mma consumes directly: a TMA box [channels x 64 voxels] lands as 64 rows (K) of one swizzle
+// span (channels), exactly the canonical MN-major layout
+//     ((T, span/T, atoms), (8, k)) : ((1, T, LBO), (span, SBO))     T = 8 bf16 per 16 bytes
+// with SBO = 8 rows * span bytes and LBO = the distance between channel atoms (one TMA box each).
+//
+// Work item = (a tile of 128, b tile of <= 256, tap, voxel split); the K loop walks 64-voxel spatial
+// boxes (so the tap shift and the zero padding are TMA coordinates / out-of-bounds fill, as in the
+// forward kernel).  Accumulators sit in TMEM (double buffered when 2 * N <= 512 columns); the epilogue
+// adds the fp32 tile into dW with red.global (split-K over voxels and taps share nothing else).
+//
+// Replaces the weight half of aten::convolution_backward for Conv3d / ConvTranspose3d
+// (reference: train.py:224 backward of builders/simple_conv_blocks.py:43-51, builders/decoder.py:110-113).
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+struct Tc5WgradParams {
+    CUtensorMap mapP;      // rank 5 (C, W, H, D, N) over the P tensor, box (aw, cw, ch, cd, cn)
+    CUtensorMap mapQ[2];   // rank 5 over the Q tensor(s), box (bw, strided extents...)
+    int PC, QC[2], nq;
+    int aw, bw;            // channel atom widths (16 / 32 / 64) == swizzle span / 2
+    int aAtoms;            // 128 / aw
+    int bn;                // N tile (multiple of bw, <= 256)
+    int aTiles, bTiles;
+    int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
+    int cw, ch, cd, cn;    // voxel chunk box, product 64
+    int chunksW, chunksH, chunksD, chunksN;
+    int splits, chunksPerSplit;
+    int stages;
+    int accBufs;           // 1 or 2 TMEM accumulator buffers
+    float* dw;             // [taps][PC][QCtot]
+};
+
+static constexpr int TW5_THREADS = 192;
+static constexpr int TW5_KBOX = 64;
+
+__global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_constant__ Tc5WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + 192);
+    uint8_t* tiles = smem_al + 1024;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t atomA = (uint32_t)TW5_KBOX * p.aw * 2u;   // bytes of one A atom (64 rows x span)
+    const uint32_t atomB = (uint32_t)TW5_KBOX * p.bw * 2u;
+    const int bAtoms = p.bn / p.bw;
+    const uint32_t bytesA = atomA * p.aAtoms;
+    const uint32_t bytesB = atomB * bAtoms;
+    const uint32_t stageBytes = bytesA + bytesB;
+    const uint32_t tile_base = smem_u32(tiles);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(p.accBufs * p.bn)) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapP);
+        tma_prefetch_desc(&p.mapQ[0]);
+        if (p.nq > 1) tma_prefetch_desc(&p.mapQ[1]);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntaps = p.tapD * p.tapH * p.tapW;
+    const int nChunks = p.chunksW * p.chunksH * p.chunksD * p.chunksN;
+    const int totalItems = p.aTiles * p.bTiles * ntaps * p.splits;
+    const int QCtot = p.QC[0] + (p.nq > 1 ? p.QC[1] : 0);
+
+    // item -> (split, tap, bt, at); a-tile fastest so neighbouring CTAs share the Q boxes in L2
+    auto decode = [&](int item, int& at, int& bt, int& tap, int& sp) {
+        at = item % p.aTiles; item /= p.aTiles;
+        bt = item % p.bTiles; item /= p.bTiles;
+        tap = item % ntaps; item /= ntaps;
+        sp = item;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
+                int at, bt, tap, sp;
+                decode(item, at, bt, tap, sp);
+                const int kw = tap % p.tapW, kh = (tap / p.tapW) % p.tapH, kd = tap / (p.tapW * p.tapH);
+                const int c0 = sp * p.chunksPerSplit;
+                const int c1 = min(nChunks, c0 + p.chunksPerSplit);
+                for (int c = c0; c < c1; ++c) {
+                    int t = c;
+                    const int iw = t % p.chunksW; t /= p.chunksW;
+                    const int ih = t % p.chunksH; t /= p.chunksH;
+                    const int id = t % p.chunksD; t /= p.chunksD;
+                    const int in = t;
+                    const int gw0 = iw * p.cw, gh0 = ih * p.ch, gd0 = id * p.cd, n0 = in * p.cn;
+                    mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY);
+                    const uint32_t dstA = tile_base + stage * stageBytes;
+                    const uint32_t dstB = dstA + bytesA;
+                    mbar_expect_tx(full_bar(stage), stageBytes);
+                    for (int j = 0; j < p.aAtoms; ++j)
+                        tma_load_5d(dstA + j * atomA, &p.mapP, full_bar(stage), at * 128 + j * p.aw, gw0, gh0, gd0, n0);
+                    const int qx = gw0 * p.istrW + p.offW + kw, qy = gh0 * p.istrH + p.offH + kh,
+                              qz = gd0 * p.istrD + p.offD + kd;
+                    for (int j = 0; j < bAtoms; ++j) {
+                        const int cb = bt * p.bn + j * p.bw;   // channel in the concatenated Q
+                        if (p.nq > 1 && cb >= p.QC[0])
+                            tma_load_5d(dstB + j * atomB, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
+                        else
+                            tma_load_5d(dstB + j * atomB, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.bn, 1, 1);   // both operands MN-major
+            const uint32_t layA = swizzle_layout_code(p.aw * 2), layB = swizzle_layout_code(p.bw * 2);
+            const uint32_t sboA = 8u * p.aw * 2u, sboB = 8u * p.bw * 2u;   // 8 K rows of one span
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
+                int at, bt, tap, sp;
+                decode(item, at, bt, tap, sp);
+                const int c0 = sp * p.chunksPerSplit;
+                const int c1 = min(nChunks, c0 + p.chunksPerSplit);
+                if (c0 >= c1) continue;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+                for (int c = c0; c < c1; ++c) {
+                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL);
+                    tc_fence_after();
+                    const uint32_t aAddr = tile_base + stage * stageBytes;
+                    const uint32_t bAddr = aAddr + bytesA;
+#pragma unroll
+                    for (int k = 0; k < TW5_KBOX / 16; ++k) {
+                        // 16 voxels = two 8-row groups further down the K direction
+                        const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
+                        const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);
+                        umma_bf16(d_tmem, da, db, idesc, (c > c0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+                if (p.accBufs == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1u; } }
+                else acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): dW tile += TMEM =====================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
+            int at, bt, tap, sp;
+            decode(item, at, bt, tap, sp);
+            const int c0 = sp * p.chunksPerSplit;
+            const int c1 = min(nChunks, c0 + p.chunksPerSplit);
+            if (c0 >= c1) continue;
+            const int a = at * 128 + row;
+            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
+            float* drow = p.dw + ((size_t)tap * p.PC + a) * QCtot + (size_t)bt * p.bn;
+            for (int cg = 0; cg < p.bn; cg += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_addr + cg, v);
+                tmem_ld_wait();
+                if (a < p.PC) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int b = bt * p.bn + cg + j;
+                        if (b < QCtot) atomicAdd(drow + cg + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (p.accBufs == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1u; } }
+            else acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace rb

@@ -190,7 +190,7 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
     return stats
 
 
-def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr):
+def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
     lib = L.load()
     d = L.WgradDesc()
     d.PC = P.shape[1]
@@ -204,6 +204,7 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr):
     d.offD, d.offH, d.offW = off
     d.istrD, d.istrH, d.istrW = istr
     d.splits = 0
+    d.impl = L.default_impl() if impl is None else L.impl_code(impl)
     ntaps = taps[0] * taps[1] * taps[2]
     dw = torch.zeros((ntaps, d.PC, d.QC0 + d.QC1), dtype=torch.float32, device=P.device)
     flops = 2.0 * d.NB * d.GD * d.GH * d.GW * d.PC * (d.QC0 + d.QC1) * ntaps
@@ -309,7 +310,7 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
     od = tuple(dy.shape[2:])
     gw = gx0 = gx1 = None
     if need_w:
-        dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride)
+        dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride, impl=impl)
         gw = dw.view(kd, kh, kw, co, ci).permute(3, 4, 0, 1, 2).contiguous()
     need1 = need1 and x1 is not None
     if need0 or need1:
@@ -700,7 +701,7 @@ class _ConvT3dFn(torch.autograd.Function):
         npar = sd * sh * sw
         gw = gx = None
         if ctx.needs_input_grad[0]:
-            dw = _launch_wgrad(x, dy, None, grid=in_dims, qdims=full, taps=stride, off=(0, 0, 0), istr=stride)
+            dw = _launch_wgrad(x, dy, None, grid=in_dims, qdims=full, taps=stride, off=(0, 0, 0), istr=stride, impl=impl)
             gw = dw.view(sd, sh, sw, ci, co).permute(3, 4, 0, 1, 2).contiguous()
         if ctx.needs_input_grad[3]:
             gx = new_cl(n, ci, *in_dims, x.device)

@@ -136,3 +136,59 @@ def test_tc5_support_query(rb, built_lib):
     assert built_lib.rb_conv_gather_tc5_supported(ctypes.byref(d)) == 0    # C % 16 != 0 -> mma.sync path
     d.srcC0 = 32
     assert built_lib.rb_conv_gather_tc5_supported(ctypes.byref(d)) == 1
+
+
+WGRAD_CASES = [
+    # n, cin (per source), cout, dims, kernel, stride, two_sources
+    (2, 32, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1), False),
+    (1, 64, 64, (16, 16, 16), (3, 3, 3), (1, 1, 1), False),
+    (2, 32, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2), False),
+    (1, 128, 256, (8, 8, 8), (3, 3, 3), (2, 2, 2), False),
+    (2, 32, 32, (8, 12, 20), (3, 3, 3), (1, 1, 1), True),
+    (1, 64, 64, (10, 6, 12), (3, 3, 3), (1, 1, 1), True),
+    (2, 512, 512, (4, 4, 4), (3, 3, 3), (1, 1, 1), False),
+    (2, 64, 32, (8, 12, 20), (1, 1, 1), (1, 1, 1), False),
+    (1, 32, 64, (8, 16, 16), (1, 3, 3), (1, 2, 2), False),
+    (1, 48, 96, (6, 10, 14), (3, 3, 3), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: f"n{c[0]}_{c[1]}{'x2' if c[6] else ''}to{c[2]}_{'x'.join(map(str, c[3]))}_k{c[4][1]}s{c[5][1]}")
+def test_tc5_wgrad(rb, case):
+    """tcgen05 weight gradient (MN-major operands straight from the channels-last tensors) == torch fp32 on
+    the same bf16 operands, and == the mma.sync kernel."""
+    n, cin, cout, dims, k, s, two = case
+    torch.manual_seed(5)
+    ops = rb.ops
+    pad = tuple((kk - 1) // 2 for kk in k)
+    x0 = q(torch.randn(n, cin, *dims, device="cuda"))
+    x1 = q(torch.randn(n, cin, *dims, device="cuda")) if two else None
+    xin = torch.cat((x0, x1), 1) if two else x0
+    w = torch.randn(cout, xin.shape[1], *k, device="cuda", requires_grad=True)
+    y = F.conv3d(xin, w, None, s, pad)
+    g = q(torch.randn_like(y))
+    gw_ref = torch.autograd.grad(y, w, g)[0]
+    od = tuple(y.shape[2:])
+    got = {}
+    for impl in ("tc5", "mma"):
+        dw = ops._launch_wgrad(ops.as_cl(g), ops.as_cl(x0), ops.as_cl(x1) if two else None, grid=od, qdims=dims, taps=k,
+                               off=tuple(-p for p in pad), istr=s, impl=impl)
+        rb._lib.device_error_check()
+        got[impl] = dw.view(*k, cout, xin.shape[1]).permute(3, 4, 0, 1, 2)
+    e5, em = rel_l2(got["tc5"], gw_ref), rel_l2(got["mma"], gw_ref)
+    print(f"wgrad tc5 {e5:.2e} mma {em:.2e}")
+    assert e5 < 2e-4 and em < 2e-4
+
+
+@pytest.mark.parametrize("cin,cout,stride", [(64, 32, (2, 2, 2)), (512, 256, (2, 2, 2)), (128, 64, (1, 2, 2))])
+def test_tc5_wgrad_conv_transpose(rb, cin, cout, stride):
+    torch.manual_seed(6)
+    x = q(torch.randn(2, cin, 4, 6, 8, device="cuda"))
+    w = (torch.randn(cin, cout, *stride, device="cuda") / cin ** 0.5).requires_grad_(True)
+    gw_ref_in = w.detach().clone().requires_grad_(True)
+    ref = F.conv_transpose3d(x, gw_ref_in, None, stride)
+    g = q(torch.randn_like(ref))
+    gw_ref = torch.autograd.grad(ref, gw_ref_in, g)[0]
+    y = rb.ops.conv_transpose3d(x.clone().requires_grad_(True), w, stride, impl="tc5")
+    y.backward(g.to(torch.bfloat16))
+    assert rel_l2(w.grad, gw_ref) < 2e-4
