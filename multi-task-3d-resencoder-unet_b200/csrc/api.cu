@@ -272,6 +272,8 @@ struct Tw5Plan {
     int cw = 0, ch = 0, cd = 0, cn = 0, chunksW = 0, chunksH = 0, chunksD = 0, chunksN = 0;
     int splits = 1, chunksPerSplit = 0, stages = 0, accBufs = 1;
     size_t smem = 0;
+    bool swap = false;
+    int tpi = 1, tapGroups = 1;
 };
 
 int atom_width(int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; }
@@ -281,16 +283,31 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
     const int qct = d.QC0 + (d.nq == 2 ? d.QC1 : 0);
     if (d.PC % 16 != 0 || d.QC0 % 16 != 0 || (d.nq == 2 && d.QC1 % 16 != 0)) return pl;
     if (qct % 32 != 0) return pl;
-    pl.aw = atom_width(d.PC);
-    pl.bw = atom_width(d.QC0);
-    if (d.nq == 2) { const int w1 = atom_width(d.QC1); if (w1 < pl.bw) pl.bw = w1; }
-    pl.aAtoms = 128 / pl.aw;
-    pl.aTiles = (d.PC + 127) / 128;
-    pl.bn = qct < 256 ? qct : 256;
-    if (qct > 256 && qct % 256 != 0) pl.bn = qct % 128 == 0 ? 128 : qct % 64 == 0 ? 64 : 32;
-    if (pl.bn % pl.bw != 0 || pl.bn % 32 != 0) return pl;
-    if (d.nq == 2 && d.QC0 % pl.bw != 0) return pl;
-    pl.bTiles = (qct + pl.bn - 1) / pl.bn;
+    int qw = atom_width(d.QC0);
+    if (d.nq == 2) { const int w1 = atom_width(d.QC1); if (w1 < qw) qw = w1; }
+    if (d.nq == 2 && d.QC0 % qw != 0) return pl;
+    const int taps_all = d.tapD * d.tapH * d.tapW;
+    pl.swap = (qct == 32 || qct == 64) && d.PC % 32 == 0 && d.PC <= 256 && taps_all > 1;
+    if (pl.swap) {
+        // tap stacking: M = tpi taps x qct Q channels, N = PC
+        pl.tpi = 128 / qct;
+        pl.tapGroups = (taps_all + pl.tpi - 1) / pl.tpi;
+        pl.aw = qw;                 // A atoms come from Q
+        pl.aAtoms = 128 / qw;
+        pl.bw = atom_width(d.PC);   // B atoms come from P
+        pl.bn = d.PC;
+        pl.aTiles = 1;
+        pl.bTiles = 1;
+    } else {
+        pl.aw = atom_width(d.PC);
+        pl.bw = qw;
+        pl.aAtoms = 128 / pl.aw;
+        pl.aTiles = (d.PC + 127) / 128;
+        pl.bn = qct < 256 ? qct : 256;
+        if (qct > 256 && qct % 256 != 0) pl.bn = qct % 128 == 0 ? 128 : qct % 64 == 0 ? 64 : 32;
+        if (pl.bn % pl.bw != 0 || pl.bn % 32 != 0) return pl;
+        pl.bTiles = (qct + pl.bn - 1) / pl.bn;
+    }
     long long best = -1;
     for (int cw = 1; cw <= 64; cw <<= 1)
         for (int ch = 1; cw * ch <= 64; ch <<= 1)
@@ -309,7 +326,7 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
     pl.chunksH = (d.GH + pl.ch - 1) / pl.ch;
     pl.chunksD = (d.GD + pl.cd - 1) / pl.cd;
     pl.chunksN = (d.NB + pl.cn - 1) / pl.cn;
-    const int taps = d.tapD * d.tapH * d.tapW;
+    const int taps = pl.swap ? pl.tapGroups : taps_all;
     const long long base_items = (long long)pl.aTiles * pl.bTiles * taps;
     long long splits = d.splits > 0 ? d.splits : (3LL * num_sms() + base_items - 1) / base_items;
     long long maxs = (best + 3) / 4;      // at least 4 chunks (256 voxels) per item
@@ -342,10 +359,11 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
         const cuuint64_t C = (cuuint64_t)d.PC;
         cuuint64_t dims[5] = {C, (cuuint64_t)d.GW, (cuuint64_t)d.GH, (cuuint64_t)d.GD, (cuuint64_t)d.NB};
         cuuint64_t strides[4] = {C * 2, C * 2 * d.GW, C * 2 * d.GW * d.GH, C * 2 * d.GW * d.GH * d.GD};
-        cuuint32_t box[5] = {(cuuint32_t)pl.aw, (cuuint32_t)pl.cw, (cuuint32_t)pl.ch, (cuuint32_t)pl.cd, (cuuint32_t)pl.cn};
+        const int pw = pl.swap ? pl.bw : pl.aw;
+        cuuint32_t box[5] = {(cuuint32_t)pw, (cuuint32_t)pl.cw, (cuuint32_t)pl.ch, (cuuint32_t)pl.cd, (cuuint32_t)pl.cn};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&p.mapP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(P), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(pl.aw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(pw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
     }
@@ -355,11 +373,12 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
         const cuuint64_t C = (cuuint64_t)qc[s];
         cuuint64_t dims[5] = {C, (cuuint64_t)d.QW, (cuuint64_t)d.QH, (cuuint64_t)d.QD, (cuuint64_t)d.NB};
         cuuint64_t strides[4] = {C * 2, C * 2 * d.QW, C * 2 * d.QW * d.QH, C * 2 * d.QW * d.QH * d.QD};
-        cuuint32_t box[5] = {(cuuint32_t)pl.bw, (cuuint32_t)((pl.cw - 1) * d.istrW + 1), (cuuint32_t)((pl.ch - 1) * d.istrH + 1),
+        const int qw = pl.swap ? pl.aw : pl.bw;
+        cuuint32_t box[5] = {(cuuint32_t)qw, (cuuint32_t)((pl.cw - 1) * d.istrW + 1), (cuuint32_t)((pl.ch - 1) * d.istrH + 1),
                              (cuuint32_t)((pl.cd - 1) * d.istrD + 1), (cuuint32_t)pl.cn};
         cuuint32_t estr[5] = {1, (cuuint32_t)d.istrW, (cuuint32_t)d.istrH, (cuuint32_t)d.istrD, 1};
         CUresult r = enc(&p.mapQ[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(qs[s]), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(pl.bw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(qw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(Q%d) failed: %d", s, (int)r);
     }
@@ -371,13 +390,14 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
     p.chunksW = pl.chunksW; p.chunksH = pl.chunksH; p.chunksD = pl.chunksD; p.chunksN = pl.chunksN;
     p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages; p.accBufs = pl.accBufs;
     p.dw = dw;
+    p.swap = pl.swap ? 1 : 0; p.tpi = pl.tpi; p.tapGroups = pl.tapGroups;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(rb::tc5_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tw5): %s", cudaGetErrorString(attr_err));
-    const long long items = (long long)pl.aTiles * pl.bTiles * d.tapD * d.tapH * d.tapW * pl.splits;
+    const long long items = (long long)pl.aTiles * pl.bTiles * (pl.swap ? pl.tapGroups : d.tapD * d.tapH * d.tapW) * pl.splits;
     const long long grid = items < num_sms() ? items : num_sms();
     rb::tc5_wgrad_kernel<<<(int)grid, rb::TW5_THREADS, pl.smem, st>>>(p);
     return check_launch("tc5_wgrad_kernel");

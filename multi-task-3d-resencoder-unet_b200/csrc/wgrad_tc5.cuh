@@ -36,6 +36,12 @@ struct Tc5WgradParams {
     int stages;
     int accBufs;           // 1 or 2 TMEM accumulator buffers
     float* dw;             // [taps][PC][QCtot]
+    // Narrow layers (QCtot in {32, 64}): "tap stacking".  The roles are swapped: the 128 MMA rows are
+    // tpi = 128 / QCtot taps x QCtot channels of Q (one TMA box per tap and channel atom), the N side is P
+    // (N = PC <= 256).  One P box then serves tpi taps and no MMA row is padding.
+    int swap;
+    int tpi;               // taps per item (swap mode)
+    int tapGroups;         // ceil(ntaps / tpi)
 };
 
 static constexpr int TW5_THREADS = 192;
@@ -53,7 +59,7 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
     const int S = p.stages;
     const uint32_t atomA = (uint32_t)TW5_KBOX * p.aw * 2u;   // bytes of one A atom (64 rows x span)
     const uint32_t atomB = (uint32_t)TW5_KBOX * p.bw * 2u;
-    const int bAtoms = p.bn / p.bw;
+    const int bAtoms = p.bn / p.bw;   // swap mode: aw = Q atom width, bw = P atom width, bn = PC
     const uint32_t bytesA = atomA * p.aAtoms;
     const uint32_t bytesB = atomB * bAtoms;
     const uint32_t stageBytes = bytesA + bytesB;
@@ -92,14 +98,16 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
 
     const int ntaps = p.tapD * p.tapH * p.tapW;
     const int nChunks = p.chunksW * p.chunksH * p.chunksD * p.chunksN;
-    const int totalItems = p.aTiles * p.bTiles * ntaps * p.splits;
+    const int tapSlots = p.swap ? p.tapGroups : ntaps;
+    const int totalItems = p.aTiles * p.bTiles * tapSlots * p.splits;
     const int QCtot = p.QC[0] + (p.nq > 1 ? p.QC[1] : 0);
+    const int qAtomsPerTap = p.swap ? QCtot / p.aw : 0;
 
     // item -> (split, tap, bt, at); a-tile fastest so neighbouring CTAs share the Q boxes in L2
     auto decode = [&](int item, int& at, int& bt, int& tap, int& sp) {
         at = item % p.aTiles; item /= p.aTiles;
         bt = item % p.bTiles; item /= p.bTiles;
-        tap = item % ntaps; item /= ntaps;
+        tap = item % tapSlots; item /= tapSlots;   // swap mode: tap group index
         sp = item;
     };
 
@@ -125,16 +133,35 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     const uint32_t dstA = tile_base + stage * stageBytes;
                     const uint32_t dstB = dstA + bytesA;
                     mbar_expect_tx(full_bar(stage), stageBytes);
-                    for (int j = 0; j < p.aAtoms; ++j)
-                        tma_load_5d(dstA + j * atomA, &p.mapP, full_bar(stage), at * 128 + j * p.aw, gw0, gh0, gd0, n0);
-                    const int qx = gw0 * p.istrW + p.offW + kw, qy = gh0 * p.istrH + p.offH + kh,
-                              qz = gd0 * p.istrD + p.offD + kd;
-                    for (int j = 0; j < bAtoms; ++j) {
-                        const int cb = bt * p.bn + j * p.bw;   // channel in the concatenated Q
-                        if (p.nq > 1 && cb >= p.QC[0])
-                            tma_load_5d(dstB + j * atomB, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
-                        else
-                            tma_load_5d(dstB + j * atomB, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
+                    if (!p.swap) {
+                        for (int j = 0; j < p.aAtoms; ++j)
+                            tma_load_5d(dstA + j * atomA, &p.mapP, full_bar(stage), at * 128 + j * p.aw, gw0, gh0, gd0, n0);
+                        const int qx = gw0 * p.istrW + p.offW + kw, qy = gh0 * p.istrH + p.offH + kh,
+                                  qz = gd0 * p.istrD + p.offD + kd;
+                        for (int j = 0; j < bAtoms; ++j) {
+                            const int cb = bt * p.bn + j * p.bw;   // channel in the concatenated Q
+                            if (p.nq > 1 && cb >= p.QC[0])
+                                tma_load_5d(dstB + j * atomB, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
+                            else
+                                tma_load_5d(dstB + j * atomB, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
+                        }
+                    } else {
+                        // A side: tpi taps x Q channel atoms (taps beyond the kernel re-read the last tap; their
+                        // rows are ignored by the epilogue); B side: P
+                        for (int j = 0; j < p.aAtoms; ++j) {
+                            int tt = tap * p.tpi + j / qAtomsPerTap;
+                            if (tt >= ntaps) tt = ntaps - 1;
+                            const int tw_ = tt % p.tapW, th_ = (tt / p.tapW) % p.tapH, td_ = tt / (p.tapW * p.tapH);
+                            const int qx = gw0 * p.istrW + p.offW + tw_, qy = gh0 * p.istrH + p.offH + th_,
+                                      qz = gd0 * p.istrD + p.offD + td_;
+                            const int cb = (j % qAtomsPerTap) * p.aw;
+                            if (p.nq > 1 && cb >= p.QC[0])
+                                tma_load_5d(dstA + j * atomA, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
+                            else
+                                tma_load_5d(dstA + j * atomA, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
+                        }
+                        for (int j = 0; j < bAtoms; ++j)
+                            tma_load_5d(dstB + j * atomB, &p.mapP, full_bar(stage), j * p.bw, gw0, gh0, gd0, n0);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
@@ -191,20 +218,39 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
             const int c0 = sp * p.chunksPerSplit;
             const int c1 = min(nChunks, c0 + p.chunksPerSplit);
             if (c0 >= c1) continue;
-            const int a = at * 128 + row;
             mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
-            float* drow = p.dw + ((size_t)tap * p.PC + a) * QCtot + (size_t)bt * p.bn;
-            for (int cg = 0; cg < p.bn; cg += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_addr + cg, v);
-                tmem_ld_wait();
-                if (a < p.PC) {
+            if (!p.swap) {
+                const int a = at * 128 + row;
+                float* drow = p.dw + ((size_t)tap * p.PC + a) * QCtot + (size_t)bt * p.bn;
+                for (int cg = 0; cg < p.bn; cg += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_addr + cg, v);
+                    tmem_ld_wait();
+                    if (a < p.PC) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int b = bt * p.bn + cg + j;
-                        if (b < QCtot) atomicAdd(drow + cg + j, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) {
+                            const int b = bt * p.bn + cg + j;
+                            if (b < QCtot) atomicAdd(drow + cg + j, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            } else {
+                // row = (tap within the group, Q channel b); column = P channel a
+                const int tt = tap * p.tpi + row / QCtot;
+                const int b = row % QCtot;
+                float* dcol = p.dw + (size_t)tt * p.PC * QCtot + b;
+                for (int cg = 0; cg < p.bn; cg += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_addr + cg, v);
+                    tmem_ld_wait();
+                    if (tt < ntaps) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int a = cg + j;
+                            if (a < p.PC) atomicAdd(dcol + (size_t)a * QCtot, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
