@@ -68,17 +68,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait (about 0.5 s at 2 GHz).  Returns false and records `code` on timeout; once any
-// wait in the grid has timed out every later wait gives up at once, so a broken pipeline drains in
-// well under a second instead of hanging the GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int code) {
+// Bounded wait (about 0.5 s at 2 GHz).  Returns false and records `code` on timeout.  The spin loop touches
+// nothing but the mbarrier, the SM clock and (rarely) a CTA-local flag in shared memory: a global-memory poll
+// here would put an L2 round trip on every producer/consumer hand-off.  Once one wait of a CTA has timed out
+// the flag makes that CTA's later waits give up at once, so a broken pipeline drains in about the timeout.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int code, uint32_t err_flag_smem) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 63u) == 0) {
-            if (*reinterpret_cast<volatile int*>(&g_dev_error) != 0) return false;
+        if ((++spins & 255u) == 0) {
+            uint32_t flag;
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(flag) : "r"(err_flag_smem));
+            if (flag != 0) return false;
             if (clock64() - t0 > 1000000000LL) {
+                asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(err_flag_smem), "r"(1u) : "memory");
                 atomicCAS(&g_dev_error, 0, code);
                 return false;
             }

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
     // full[8], empty[8], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + 192);
+    const uint32_t err_flag = smem_u32(smem_al + 200);   // CTA-local "a wait timed out" flag
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_al + 200) = 0u;
     uint8_t* tiles = smem_al + 1024;
 
     const int warp = threadIdx.x >> 5;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                     int cbase = 0;
                     for (int s = 0; s < p.nsrc; ++s) {
                         for (int c = 0; c < p.srcC[s]; c += p.KW) {
-                            mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY);
+                            mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
                             const uint32_t dstA = tile_base + stage * stageBytes;
                             const uint32_t dstB = dstA + bytesA;
                             mbar_expect_tx(full_bar(stage), stageBytes);
@@ -181,11 +183,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
                 for (int ks = 0; ks < stepsPerTile; ++ks) {
-                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL);
+                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             const bool valid = (ow < p.OW) && (oh < p.OH) && (od < p.OD) && (nb < p.NB);
             const int n0 = nt * p.Ntile;
 
-            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL);
+            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.Ntile);
             for (int cg = 0; cg < p.Ntile; cg += 32) {

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
     uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + 192);
+    const uint32_t err_flag = smem_u32(smem_al + 200);   // CTA-local "a wait timed out" flag
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_al + 200) = 0u;
     uint8_t* tiles = smem_al + 1024;
 
     const int warp = threadIdx.x >> 5;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     const int id = t % p.chunksD; t /= p.chunksD;
                     const int in = t;
                     const int gw0 = iw * p.cw, gh0 = ih * p.ch, gd0 = id * p.cd, n0 = in * p.cn;
-                    mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY);
+                    mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
                     const uint32_t dstA = tile_base + stage * stageBytes;
                     const uint32_t dstB = dstA + bytesA;
                     mbar_expect_tx(full_bar(stage), stageBytes);
@@ -183,11 +185,11 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                 const int c0 = sp * p.chunksPerSplit;
                 const int c1 = min(nChunks, c0 + p.chunksPerSplit);
                 if (c0 >= c1) continue;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
                 for (int c = c0; c < c1; ++c) {
-                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL);
+                    mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
             const int c0 = sp * p.chunksPerSplit;
             const int c1 = min(nChunks, c0 + p.chunksPerSplit);
             if (c0 >= c1) continue;
-            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL);
+            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
             if (!p.swap) {
