@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/resenc_b200.h"
@@ -255,6 +256,13 @@ int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const v
     p.stat_sum = stat_sum; p.stat_sq = stat_sq;
     p.outF32 = d.outF32;
     p.statSmem = pl.statSmem ? 1 : 0;
+    p.fdTilesN = rb::make_fastdiv(pl.nTilesN); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
+    p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
+    p.fdTw = rb::make_fastdiv(pl.tw); p.fdTwTh = rb::make_fastdiv(pl.tw * pl.th); p.fdTwThTd = rb::make_fastdiv(pl.tw * pl.th * pl.td);
+    {
+        static const int dbg = getenv("RESENC_TC5_DEBUG") ? atoi(getenv("RESENC_TC5_DEBUG")) : 0;
+        p.debug = dbg;
+    }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -305,6 +313,7 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
         pl.aTiles = (d.PC + 127) / 128;
         pl.bn = qct < 256 ? qct : 256;
         if (qct > 256 && qct % 256 != 0) pl.bn = qct % 128 == 0 ? 128 : qct % 64 == 0 ? 64 : 32;
+        if (pl.bn / pl.bw > 8) pl.bn = 8 * pl.bw;   // the producer keeps an 8-entry atom table
         if (pl.bn % pl.bw != 0 || pl.bn % 32 != 0) return pl;
         pl.bTiles = (qct + pl.bn - 1) / pl.bn;
     }
@@ -391,6 +400,7 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
     p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages; p.accBufs = pl.accBufs;
     p.dw = dw;
     p.swap = pl.swap ? 1 : 0; p.tpi = pl.tpi; p.tapGroups = pl.tapGroups;
+    p.fdChunksW = rb::make_fastdiv(pl.chunksW); p.fdChunksH = rb::make_fastdiv(pl.chunksH); p.fdChunksD = rb::make_fastdiv(pl.chunksD);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {

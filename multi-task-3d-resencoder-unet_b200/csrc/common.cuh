@@ -182,6 +182,32 @@ __host__ __device__ constexpr uint32_t swizzle_layout_code(int swizzle_bytes) {
     return swizzle_bytes == 128 ? 2u : swizzle_bytes == 64 ? 4u : swizzle_bytes == 32 ? 6u : 0u;
 }
 
+// ------------------------------- fast division ----------------------------------------
+// Division by a run-time constant as multiply-high + shift (valid for n < 2^31).  Integer division on
+// the GPU is a ~30-instruction dependent sequence; the single producer / issuer threads of the
+// tcgen05 kernels must not execute one per pipeline stage.
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(int d_) {
+    FastDiv f;
+    f.d = (uint32_t)d_;
+    if (d_ <= 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t lg = 0;
+    while ((1u << lg) < (uint32_t)d_) ++lg;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint32_t)d_ - 1) / (uint32_t)d_);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+    return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+    q = fdiv(n, f);
+    r = n - q * f.d;
+}
+
 // ------------------------------- misc --------------------------------------------------
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

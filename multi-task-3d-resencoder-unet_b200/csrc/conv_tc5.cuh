@@ -50,6 +50,9 @@ struct Tc5ConvParams {
     float* stat_sq;   // optional [NB][Nout] per-(n,c) sum of squares
     int outF32;       // 1: destinations are fp32 (pre-norm activations keep the full accumulator)
     int statSmem;     // 1: statistics are accumulated in shared memory per CTA and flushed once at the end
+    FastDiv fdTilesN, fdTilesW, fdTilesH, fdTilesD;   // tile index decode without integer division
+    FastDiv fdTw, fdTwTh, fdTwThTd;                    // row -> (iw, ih, id, in) inside a tile
+    int debug;        // profiling experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
 
 // Column sums over the 32 rows held by the lanes of a warp: v[j] (lane = row) -> lane j returns
@@ -139,33 +142,38 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
                 // n-tile fastest so CTAs that share an activation tile run close in time (L2 reuse)
-                const int nt = tile % p.nTilesN;
-                int sp = tile / p.nTilesN;
-                const int tiw = sp % p.tilesW; sp /= p.tilesW;
-                const int tih = sp % p.tilesH; sp /= p.tilesH;
-                const int tid = sp % p.tilesD; sp /= p.tilesD;
-                const int tib = sp;
+                uint32_t sp, nt, tiw, tih, tid, tib;
+                fdivmod((uint32_t)tile, p.fdTilesN, sp, nt);
+                fdivmod(sp, p.fdTilesW, sp, tiw);
+                fdivmod(sp, p.fdTilesH, sp, tih);
+                fdivmod(sp, p.fdTilesD, tib, tid);
                 const int ow0 = tiw * p.tw, oh0 = tih * p.th, od0 = tid * p.td, nb0 = tib * p.tn;
                 const int n0 = nt * p.Ntile;
-                for (int t = 0; t < ntaps; ++t) {
-                    const int kw = t % p.tapW;
-                    const int kh = (t / p.tapW) % p.tapH;
-                    const int kd = t / (p.tapW * p.tapH);
-                    const int ix = ow0 * p.istrW + p.offW + kw;
-                    const int iy = oh0 * p.istrH + p.offH + kh;
+                int t = 0;
+                for (int kd = 0; kd < p.tapD; ++kd) {
                     const int iz = od0 * p.istrD + p.offD + kd;
-                    int cbase = 0;
-                    for (int s = 0; s < p.nsrc; ++s) {
-                        for (int c = 0; c < p.srcC[s]; c += p.KW) {
-                            mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
-                            const uint32_t dstA = tile_base + stage * stageBytes;
-                            const uint32_t dstB = dstA + bytesA;
-                            mbar_expect_tx(full_bar(stage), stageBytes);
-                            tma_load_5d(dstA, &p.mapA[s], full_bar(stage), c, ix, iy, iz, nb0);
-                            tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);
-                            if (++stage == S) { stage = 0; phase ^= 1u; }
+                    for (int kh = 0; kh < p.tapH; ++kh) {
+                        const int iy = oh0 * p.istrH + p.offH + kh;
+                        for (int kw = 0; kw < p.tapW; ++kw, ++t) {
+                            const int ix = ow0 * p.istrW + p.offW + kw;
+                            int cbase = 0;
+                            for (int s = 0; s < p.nsrc; ++s) {
+                                for (int c = 0; c < p.srcC[s]; c += p.KW) {
+                                    mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
+                                    const uint32_t dstA = tile_base + stage * stageBytes;
+                                    const uint32_t dstB = dstA + bytesA;
+                                    if (p.debug == 2) {
+                                        mbar_arrive(full_bar(stage));
+                                    } else {
+                                        mbar_expect_tx(full_bar(stage), stageBytes);
+                                        tma_load_5d(dstA, &p.mapA[s], full_bar(stage), c, ix, iy, iz, nb0);
+                                        tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);
+                                    }
+                                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                                }
+                                cbase += p.srcC[s];
+                            }
                         }
-                        cbase += p.srcC[s];
                     }
                 }
             }
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA;
-                    for (int k = 0; k < kPerStep; ++k) {
+                    for (int k = 0; k < kPerStep && p.debug != 1; ++k) {
                         const uint64_t da = make_smem_desc(aAddr + k * 32u, 16u, sbo, lay);
                         const uint64_t db = make_smem_desc(bAddr + k * 32u, 16u, sbo, lay);
                         umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
@@ -212,18 +220,17 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
         const int iw = row % p.tw;
         const int ih = (row / p.tw) % p.th;
         const int id = (row / (p.tw * p.th)) % p.td;
-        const int in = row / (p.tw * p.th * p.td);
+        const int in = row / (p.tw * p.th * p.td);   // once per kernel
         const bool warpUniformSample = ((p.tw * p.th * p.td) & 31) == 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-            const int nt = tile % p.nTilesN;
-            int sp = tile / p.nTilesN;
-            const int tiw = sp % p.tilesW; sp /= p.tilesW;
-            const int tih = sp % p.tilesH; sp /= p.tilesH;
-            const int tid = sp % p.tilesD; sp /= p.tilesD;
-            const int tib = sp;
-            const int ow = tiw * p.tw + iw, oh = tih * p.th + ih, od = tid * p.td + id, nb = tib * p.tn + in;
+            uint32_t sp, nt, tiw, tih, tid, tib;
+            fdivmod((uint32_t)tile, p.fdTilesN, sp, nt);
+            fdivmod(sp, p.fdTilesW, sp, tiw);
+            fdivmod(sp, p.fdTilesH, sp, tih);
+            fdivmod(sp, p.fdTilesD, tib, tid);
+            const int ow = (int)tiw * p.tw + iw, oh = (int)tih * p.th + ih, od = (int)tid * p.td + id, nb = (int)tib * p.tn + in;
             const bool valid = (ow < p.OW) && (oh < p.OH) && (od < p.OD) && (nb < p.NB);
-            const int n0 = nt * p.Ntile;
+            const int n0 = (int)nt * p.Ntile;
 
             mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
             tc_fence_after();

@@ -42,6 +42,7 @@ struct Tc5WgradParams {
     int swap;
     int tpi;               // taps per item (swap mode)
     int tapGroups;         // ceil(ntaps / tpi)
+    FastDiv fdChunksW, fdChunksH, fdChunksD;   // chunk index decode without integer division
 };
 
 static constexpr int TW5_THREADS = 192;
@@ -121,47 +122,57 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
             for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
                 int at, bt, tap, sp;
                 decode(item, at, bt, tap, sp);
-                const int kw = tap % p.tapW, kh = (tap / p.tapW) % p.tapH, kd = tap / (p.tapW * p.tapH);
                 const int c0 = sp * p.chunksPerSplit;
                 const int c1 = min(nChunks, c0 + p.chunksPerSplit);
+                // per-item atom table (once per item: divisions are fine here, not per chunk)
+                int atX[8], atY[8], atZ[8], atC[8], atSrc[8];
+                const int nA = p.aAtoms;
+                if (!p.swap) {
+                    const int kw = tap % p.tapW, kh = (tap / p.tapW) % p.tapH, kd = tap / (p.tapW * p.tapH);
+                    for (int j = 0; j < 8; ++j) {     // B side (Q) atoms
+                        const int cb = bt * p.bn + j * p.bw;
+                        const bool second = p.nq > 1 && cb >= p.QC[0];
+                        atX[j] = p.offW + kw; atY[j] = p.offH + kh; atZ[j] = p.offD + kd;
+                        atC[j] = second ? cb - p.QC[0] : cb;
+                        atSrc[j] = second ? 1 : 0;
+                    }
+                } else {
+                    for (int j = 0; j < 8; ++j) {     // A side (Q) atoms: tap-major, then channel atoms
+                        int tt = tap * p.tpi + j / qAtomsPerTap;
+                        if (tt >= ntaps) tt = ntaps - 1;   // rows of taps beyond the kernel are ignored by the epilogue
+                        const int tw_ = tt % p.tapW, th_ = (tt / p.tapW) % p.tapH, td_ = tt / (p.tapW * p.tapH);
+                        const int cb = (j % qAtomsPerTap) * p.aw;
+                        const bool second = p.nq > 1 && cb >= p.QC[0];
+                        atX[j] = p.offW + tw_; atY[j] = p.offH + th_; atZ[j] = p.offD + td_;
+                        atC[j] = second ? cb - p.QC[0] : cb;
+                        atSrc[j] = second ? 1 : 0;
+                    }
+                }
                 for (int c = c0; c < c1; ++c) {
-                    int t = c;
-                    const int iw = t % p.chunksW; t /= p.chunksW;
-                    const int ih = t % p.chunksH; t /= p.chunksH;
-                    const int id = t % p.chunksD; t /= p.chunksD;
-                    const int in = t;
+                    uint32_t t, iw, ih, id, in;
+                    fdivmod((uint32_t)c, p.fdChunksW, t, iw);
+                    fdivmod(t, p.fdChunksH, t, ih);
+                    fdivmod(t, p.fdChunksD, in, id);
                     const int gw0 = iw * p.cw, gh0 = ih * p.ch, gd0 = id * p.cd, n0 = in * p.cn;
+                    const int qx0 = gw0 * p.istrW, qy0 = gh0 * p.istrH, qz0 = gd0 * p.istrD;
                     mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
                     const uint32_t dstA = tile_base + stage * stageBytes;
                     const uint32_t dstB = dstA + bytesA;
                     mbar_expect_tx(full_bar(stage), stageBytes);
                     if (!p.swap) {
-                        for (int j = 0; j < p.aAtoms; ++j)
+                        for (int j = 0; j < nA; ++j)
                             tma_load_5d(dstA + j * atomA, &p.mapP, full_bar(stage), at * 128 + j * p.aw, gw0, gh0, gd0, n0);
-                        const int qx = gw0 * p.istrW + p.offW + kw, qy = gh0 * p.istrH + p.offH + kh,
-                                  qz = gd0 * p.istrD + p.offD + kd;
-                        for (int j = 0; j < bAtoms; ++j) {
-                            const int cb = bt * p.bn + j * p.bw;   // channel in the concatenated Q
-                            if (p.nq > 1 && cb >= p.QC[0])
-                                tma_load_5d(dstB + j * atomB, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
-                            else
-                                tma_load_5d(dstB + j * atomB, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
-                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < bAtoms)
+                                tma_load_5d(dstB + j * atomB, &p.mapQ[atSrc[j]], full_bar(stage), atC[j], qx0 + atX[j],
+                                            qy0 + atY[j], qz0 + atZ[j], n0);
                     } else {
-                        // A side: tpi taps x Q channel atoms (taps beyond the kernel re-read the last tap; their
-                        // rows are ignored by the epilogue); B side: P
-                        for (int j = 0; j < p.aAtoms; ++j) {
-                            int tt = tap * p.tpi + j / qAtomsPerTap;
-                            if (tt >= ntaps) tt = ntaps - 1;
-                            const int tw_ = tt % p.tapW, th_ = (tt / p.tapW) % p.tapH, td_ = tt / (p.tapW * p.tapH);
-                            const int qx = gw0 * p.istrW + p.offW + tw_, qy = gh0 * p.istrH + p.offH + th_,
-                                      qz = gd0 * p.istrD + p.offD + td_;
-                            const int cb = (j % qAtomsPerTap) * p.aw;
-                            if (p.nq > 1 && cb >= p.QC[0])
-                                tma_load_5d(dstA + j * atomA, &p.mapQ[1], full_bar(stage), cb - p.QC[0], qx, qy, qz, n0);
-                            else
-                                tma_load_5d(dstA + j * atomA, &p.mapQ[0], full_bar(stage), cb, qx, qy, qz, n0);
-                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nA)
+                                tma_load_5d(dstA + j * atomA, &p.mapQ[atSrc[j]], full_bar(stage), atC[j], qx0 + atX[j],
+                                            qy0 + atY[j], qz0 + atZ[j], n0);
                         for (int j = 0; j < bAtoms; ++j)
                             tma_load_5d(dstB + j * atomB, &p.mapP, full_bar(stage), j * p.bw, gw0, gh0, gd0, n0);
                     }
