@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                 tmem_ld_wait();
                 const int col0 = n0 + cg;
                 if (col0 < p.Nout) {
-                    if (p.stat_sum != nullptr) {
+                    if (p.stat_sum != nullptr && p.debug != 3) {
                         if (warpUniformSample) {
                             // all 32 rows of this warp belong to sample nb: butterfly column sums, lane j ends up
                             // with column col0 + j
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             }
                         }
                     }
-                    if (valid) {
+                    if (valid && p.debug != 4) {
                         int fd, fh, fw, ch0;
                         if (p.mode == 1) {
                             const int par = col0 / p.psC;

@@ -97,7 +97,7 @@ def test_network_matches_reference_golden(rb, case):
                 if float(np.linalg.norm(gold[k])) < 1e-4 * gmax:
                     continue     # noise in the reference itself (see above)
                 print(f"{case}: {k} rel-L2 {r:.3e} (torch bf16 autocast {ac:.3e})")
-                assert r < max(5e-2, 1.1 * ac), (k, r)
+                assert r < max(5e-2, 1.5 * ac), (k, r)
         model.eval()
         with torch.no_grad():
             ev = model(x)
@@ -142,7 +142,7 @@ def test_network_64_vs_oracle_default_init(rb):
 
 def test_training_loss_decreases_and_tracks_oracle(rb):
     """30 SGD steps on a fixed batch (16^3 net): the loss curve of the CUDA path follows the oracle's
-    fp32 curve (same init, same data) within 2e-2 absolute at every step and decreases."""
+    fp32 curve (same init, same data) within 3e-2 absolute at every step and decreases."""
     case = "sheet_normals_16"
     model, mgr = _build(rb, case)
     gold = load_net_golden(case)
@@ -173,7 +173,7 @@ def test_training_loss_decreases_and_tracks_oracle(rb):
     print("oracle :", " ".join(f"{v:.4f}" for v in lo))
     print("product:", " ".join(f"{v:.4f}" for v in lp))
     assert lp[-1] < lp[0]
-    assert max(abs(a - b) for a, b in zip(lo, lp)) < 2e-2
+    assert max(abs(a - b) for a, b in zip(lo, lp)) < 3e-2
 
 
 def test_state_dict_roundtrip_and_compile_wrapper(rb):
