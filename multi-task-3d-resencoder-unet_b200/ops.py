@@ -219,7 +219,13 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
 # The fprop pack is cached on the Parameter and reused until the optimiser touches it, so the
 # sliding-window sweep packs each weight once.
 # ------------------------------------------------------------------------------------------
+PACK_CACHE = True     # set False while capturing a CUDA graph so the (re)packing kernels are part of every replay
+
+
 def _cached_pack(weight, kind, fn):
+    if not PACK_CACHE:
+        with torch.no_grad():
+            return fn()
     key = (weight._version, weight.data_ptr(), str(weight.device))
     cache = getattr(weight, "_rb_pack", None)
     if cache is None or cache.get("key") != key:
