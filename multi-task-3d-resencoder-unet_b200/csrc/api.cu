@@ -96,6 +96,7 @@ struct Tc5Plan {
     long long tiles = 0;
     int ksteps = 0;
     bool statSmem = false;
+    int tps = 1;
 };
 
 Tc5Plan plan_tc5(const RbConvDesc& d) {
@@ -137,7 +138,9 @@ Tc5Plan plan_tc5(const RbConvDesc& d) {
     pl.tilesD = (d.OD + pl.td - 1) / pl.td;
     pl.tilesNB = (d.NB + pl.tn - 1) / pl.tn;
     pl.tiles = best * pl.nTilesN;
-    const size_t stageBytes = (size_t)(128 + pl.Ntile) * pl.KW * 2;
+    // narrow-K layers (K chunk <= 32 channels): put all tapW taps of a row into one pipeline stage
+    pl.tps = (pl.KW <= 32 && d.tapW == 3) ? 3 : 1;
+    const size_t stageBytes = (size_t)(128 + pl.Ntile) * pl.KW * 2 * pl.tps;
     // per-epilogue-warp statistics accumulators 4 x [2][NB][Nout] fp32 live behind the stages when they fit in 16 KB
     const size_t statBytes = (size_t)8 * d.NB * d.Nout * sizeof(float);
     pl.statSmem = statBytes <= 16 * 1024;
@@ -231,7 +234,7 @@ int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const v
         const int ntaps = d.tapD * d.tapH * d.tapW;
         cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, (cuuint64_t)ntaps};
         cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
-        cuuint32_t box[3] = {(cuuint32_t)pl.KW, (cuuint32_t)pl.Ntile, 1};
+        cuuint32_t box[3] = {(cuuint32_t)pl.KW, (cuuint32_t)pl.Ntile, (cuuint32_t)pl.tps};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -256,6 +259,7 @@ int launch_tc5(const RbConvDesc& d, const Tc5Plan& pl, const void* src0, const v
     p.stat_sum = stat_sum; p.stat_sq = stat_sq;
     p.outF32 = d.outF32;
     p.statSmem = pl.statSmem ? 1 : 0;
+    p.tps = pl.tps;
     p.fdTilesN = rb::make_fastdiv(pl.nTilesN); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
     p.fdTw = rb::make_fastdiv(pl.tw); p.fdTwTh = rb::make_fastdiv(pl.tw * pl.th); p.fdTwThTd = rb::make_fastdiv(pl.tw * pl.th * pl.td);
@@ -282,6 +286,7 @@ struct Tw5Plan {
     size_t smem = 0;
     bool swap = false;
     int tpi = 1, tapGroups = 1;
+    int kbox = 64;
 };
 
 int atom_width(int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; }
@@ -317,11 +322,14 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
         if (pl.bn % pl.bw != 0 || pl.bn % 32 != 0) return pl;
         pl.bTiles = (qct + pl.bn - 1) / pl.bn;
     }
+    // narrow tiles are issue-latency bound: give every mbarrier round trip 128 voxels (8 MMAs) instead of 64
+    const long long gvox = (long long)d.NB * d.GD * d.GH * d.GW;
+    pl.kbox = (pl.swap && gvox >= (1 << 16)) ? 128 : 64;
     long long best = -1;
-    for (int cw = 1; cw <= 64; cw <<= 1)
-        for (int ch = 1; cw * ch <= 64; ch <<= 1)
-            for (int cd = 1; cw * ch * cd <= 64; cd <<= 1) {
-                const int cn = 64 / (cw * ch * cd);
+    for (int cw = 1; cw <= pl.kbox; cw <<= 1)
+        for (int ch = 1; cw * ch <= pl.kbox; ch <<= 1)
+            for (int cd = 1; cw * ch * cd <= pl.kbox; cd <<= 1) {
+                const int cn = pl.kbox / (cw * ch * cd);
                 if ((cw - 1) * d.istrW + 1 > 256 || (ch - 1) * d.istrH + 1 > 256 || (cd - 1) * d.istrD + 1 > 256) continue;
                 const long long t = (long long)((d.GW + cw - 1) / cw) * ((d.GH + ch - 1) / ch) * ((d.GD + cd - 1) / cd) *
                                     ((d.NB + cn - 1) / cn);
@@ -344,7 +352,7 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
     if (splits < 1) splits = 1;
     pl.chunksPerSplit = (int)((best + splits - 1) / splits);
     pl.splits = (int)((best + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
-    const size_t stageBytes = (size_t)rb::TW5_KBOX * 2 * (128 + pl.bn);
+    const size_t stageBytes = (size_t)pl.kbox * 2 * (128 + pl.bn);
     int st = (int)((200 * 1024) / stageBytes);
     if (st > 8) st = 8;
     if (st < 2) return pl;
@@ -400,6 +408,7 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
     p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages; p.accBufs = pl.accBufs;
     p.dw = dw;
     p.swap = pl.swap ? 1 : 0; p.tpi = pl.tpi; p.tapGroups = pl.tapGroups;
+    p.kbox = pl.kbox;
     p.fdChunksW = rb::make_fastdiv(pl.chunksW); p.fdChunksH = rb::make_fastdiv(pl.chunksH); p.fdChunksD = rb::make_fastdiv(pl.chunksD);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;

@@ -52,6 +52,8 @@ struct Tc5ConvParams {
     int statSmem;     // 1: statistics are accumulated in shared memory per CTA and flushed once at the end
     FastDiv fdTilesN, fdTilesW, fdTilesH, fdTilesD;   // tile index decode without integer division
     FastDiv fdTw, fdTwTh, fdTwThTd;                    // row -> (iw, ih, id, in) inside a tile
+    int tps;          // taps (along W) per pipeline stage: 1, or tapW for narrow-K layers so that one mbarrier round
+                      // trip feeds tps * KW/16 MMAs instead of KW/16
     int debug;        // profiling experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
 
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
     const int S = p.stages;
     const uint32_t bytesA = 128u * p.KW * 2u;
     const uint32_t bytesB = (uint32_t)p.Ntile * p.KW * 2u;
-    const uint32_t stageBytes = bytesA + bytesB;
+    const uint32_t stageBytes = (bytesA + bytesB) * (uint32_t)p.tps;   // [A tap 0 .. tps-1][B tap 0 .. tps-1]
     const uint32_t tile_base = smem_u32(tiles);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -154,20 +156,21 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                     const int iz = od0 * p.istrD + p.offD + kd;
                     for (int kh = 0; kh < p.tapH; ++kh) {
                         const int iy = oh0 * p.istrH + p.offH + kh;
-                        for (int kw = 0; kw < p.tapW; ++kw, ++t) {
+                        for (int kw = 0; kw < p.tapW; kw += p.tps, t += p.tps) {
                             const int ix = ow0 * p.istrW + p.offW + kw;
                             int cbase = 0;
                             for (int s = 0; s < p.nsrc; ++s) {
                                 for (int c = 0; c < p.srcC[s]; c += p.KW) {
                                     mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
                                     const uint32_t dstA = tile_base + stage * stageBytes;
-                                    const uint32_t dstB = dstA + bytesA;
+                                    const uint32_t dstB = dstA + bytesA * p.tps;
                                     if (p.debug == 2) {
                                         mbar_arrive(full_bar(stage));
                                     } else {
                                         mbar_expect_tx(full_bar(stage), stageBytes);
-                                        tma_load_5d(dstA, &p.mapA[s], full_bar(stage), c, ix, iy, iz, nb0);
-                                        tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);
+                                        for (int j = 0; j < p.tps; ++j)
+                                            tma_load_5d(dstA + j * bytesA, &p.mapA[s], full_bar(stage), c, ix + j, iy, iz, nb0);
+                                        tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);   // box depth = tps taps
                                     }
                                     if (++stage == S) { stage = 0; phase ^= 1u; }
                                 }
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             const uint32_t lay = swizzle_layout_code(p.KW * 2);
             const uint32_t sbo = 8u * p.KW * 2u;  // 8 rows of one swizzle span
             const int kPerStep = p.KW / 16;
-            const int stepsPerTile = ntaps * (Ctot / p.KW);
+            const int stepsPerTile = (ntaps / p.tps) * (Ctot / p.KW);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -198,11 +201,13 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                     mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
-                    const uint32_t bAddr = aAddr + bytesA;
-                    for (int k = 0; k < kPerStep && p.debug != 1; ++k) {
-                        const uint64_t da = make_smem_desc(aAddr + k * 32u, 16u, sbo, lay);
-                        const uint64_t db = make_smem_desc(bAddr + k * 32u, 16u, sbo, lay);
-                        umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
+                    const uint32_t bAddr = aAddr + bytesA * p.tps;
+                    for (int j = 0; j < p.tps && p.debug != 1; ++j) {
+                        for (int k = 0; k < kPerStep; ++k) {
+                            const uint64_t da = make_smem_desc(aAddr + j * bytesA + k * 32u, 16u, sbo, lay);
+                            const uint64_t db = make_smem_desc(bAddr + j * bytesB + k * 32u, 16u, sbo, lay);
+                            umma_bf16(d_tmem, da, db, idesc, (ks | j | k) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
                     if (++stage == S) { stage = 0; phase ^= 1u; }

@@ -43,6 +43,7 @@ struct Tc5WgradParams {
     int tpi;               // taps per item (swap mode)
     int tapGroups;         // ceil(ntaps / tpi)
     FastDiv fdChunksW, fdChunksH, fdChunksD;   // chunk index decode without integer division
+    int kbox;              // voxels per pipeline stage (64 or 128)
 };
 
 static constexpr int TW5_THREADS = 192;
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int S = p.stages;
-    const uint32_t atomA = (uint32_t)TW5_KBOX * p.aw * 2u;   // bytes of one A atom (64 rows x span)
-    const uint32_t atomB = (uint32_t)TW5_KBOX * p.bw * 2u;
+    const uint32_t atomA = (uint32_t)p.kbox * p.aw * 2u;   // bytes of one A atom (kbox rows x span)
+    const uint32_t atomB = (uint32_t)p.kbox * p.bw * 2u;
     const int bAtoms = p.bn / p.bw;   // swap mode: aw = Q atom width, bw = P atom width, bn = PC
     const uint32_t bytesA = atomA * p.aAtoms;
     const uint32_t bytesB = atomB * bAtoms;
@@ -204,8 +205,7 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA;
-#pragma unroll
-                    for (int k = 0; k < TW5_KBOX / 16; ++k) {
+                    for (int k = 0; k < p.kbox / 16; ++k) {
                         // 16 voxels = two 8-row groups further down the K direction
                         const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
                         const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);

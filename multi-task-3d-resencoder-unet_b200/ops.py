@@ -261,16 +261,25 @@ def _axis_classes(K, s, pad, I):
     return out
 
 
-def pack_conv_dgrad_class(weight, kds, khs, kws):
-    """taps selected by kernel-index lists per axis -> [taps][Cin][Cout] bf16."""
-    w = weight.detach()
-    dev = w.device
-    if len(kds) != w.shape[2] or list(kds) != list(range(w.shape[2])):
-        w = w.index_select(2, torch.tensor(kds, device=dev))
-    if len(khs) != w.shape[3] or list(khs) != list(range(w.shape[3])):
-        w = w.index_select(3, torch.tensor(khs, device=dev))
-    if len(kws) != w.shape[4] or list(kws) != list(range(w.shape[4])):
-        w = w.index_select(4, torch.tensor(kws, device=dev))
+def _flipped(weight):
+    """w[..., ::-1, ::-1, ::-1]: every data-gradient class is a strided slice of this one tensor."""
+    return _cached_pack(weight, "flip", lambda: weight.detach().flip(2, 3, 4))
+
+
+def pack_conv_dgrad_class(weight, kds, khs, kws, strides=None):
+    """taps selected by kernel-index lists per axis -> [taps][Cin][Cout] bf16.  The lists produced by
+    `_axis_classes` are descending arithmetic progressions, i.e. strided slices of the flipped kernel."""
+    wf = _flipped(weight)
+    K = weight.shape[2:]
+
+    def sl(ks, k):
+        if len(ks) == 1:
+            a = k - 1 - ks[0]
+            return slice(a, a + 1)
+        step = ks[0] - ks[1]
+        return slice(k - 1 - ks[0], None, step)
+    w = wf[:, :, sl(kds, K[0]), sl(khs, K[1]), sl(kws, K[2])]
+    assert w.shape[2:] == (len(kds), len(khs), len(kws))
     co, ci = w.shape[:2]
     return w.permute(2, 3, 4, 1, 0).reshape(len(kds) * len(khs) * len(kws), ci, co).to(BF16).contiguous()
 
