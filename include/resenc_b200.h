@@ -46,6 +46,9 @@ int rb_device_error(void* stream);
 /* Number of kernel launches issued through this library by the calling process (bench.py's
  * gpu_launches). */
 long long rb_launch_count(void);
+/* Pipeline cycle counters of CTA 0 of the last tcgen05 conv launch (only filled when the environment variable
+ * RESENC_TC5_DEBUG has bit 3 set; profiling experiments, see profiles/). out16: host array of 16 u64. */
+int rb_debug_counters(unsigned long long* out16);
 
 /* ------------------------------------------------------------------------------------------
  * Gather convolution: one implicit GEMM covers every dense contraction of the network.

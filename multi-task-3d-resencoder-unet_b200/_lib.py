@@ -45,6 +45,7 @@ SIGNATURES = {
     "rb_version": (_I, []),
     "rb_device_error": (_I, [_P]),
     "rb_launch_count": (_LL, []),
+    "rb_debug_counters": (_I, [_P]),
     "rb_conv_gather_workspace": (_SZ, [C.POINTER(ConvDesc)]),
     "rb_conv_gather": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "rb_conv_gather_tc5_supported": (_I, [C.POINTER(ConvDesc)]),

@@ -442,6 +442,13 @@ int rb_device_error(void* stream) {
     return RB_OK;
 }
 
+int rb_debug_counters(unsigned long long* out16) {
+    if (!out16) return fail(RB_ERR_INVALID, "debug_counters: null pointer");
+    RB_CUDA(cudaDeviceSynchronize());
+    RB_CUDA(cudaMemcpyFromSymbol(out16, rb::g_dbg, 16 * sizeof(unsigned long long)));
+    return RB_OK;
+}
+
 int rb_conv_gather_tc5_supported(const RbConvDesc* d) {
     if (!d) return 0;
     return plan_tc5(*d).ok ? 1 : 0;

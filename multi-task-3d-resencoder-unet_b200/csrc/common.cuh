@@ -15,7 +15,9 @@ typedef __nv_bfloat16 bf16;
 // timeout they record a code here and fall through so the launch drains.  The host API reads
 // it back after synchronising (rb_check_device_error).
 // ---------------------------------------------------------------------------------------
-static __device__ int g_dev_error = 0;  // single translation unit (api.cu)
+static __device__ int g_dev_error = 0;
+// cycle counters of CTA 0 for pipeline experiments (RESENC_TC5_DEBUG & 8): see rb_debug_counters
+static __device__ unsigned long long g_dbg[16];  // single translation unit (api.cu)
 
 enum DevErr : int {
     DEVERR_NONE = 0,

@@ -139,9 +139,14 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform control flow lets ptxas keep the pipeline state in uniform
+        // registers); one elected lane issues.  Issuing from inside an `if (lane == 0)` region instead costs
+        // ~230 cycles per TMA / MMA instruction (measured, profiles/r1_bottleneck_experiments.md).
+        {
             int stage = 0;
             uint32_t phase = 0;
+            const bool dbgT = (p.debug & 8) && blockIdx.x == 0;
+            long long tWait = 0, tAll0 = clock64();
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
                 // n-tile fastest so CTAs that share an activation tile run close in time (L2 reuse)
                 uint32_t sp, nt, tiw, tih, tid, tib;
@@ -161,17 +166,22 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             int cbase = 0;
                             for (int s = 0; s < p.nsrc; ++s) {
                                 for (int c = 0; c < p.srcC[s]; c += p.KW) {
+                                    const long long w0 = dbgT ? clock64() : 0;
                                     mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
+                                    if (dbgT) tWait += clock64() - w0;
                                     const uint32_t dstA = tile_base + stage * stageBytes;
                                     const uint32_t dstB = dstA + bytesA * p.tps;
-                                    if (p.debug == 2) {
-                                        mbar_arrive(full_bar(stage));
-                                    } else {
-                                        mbar_expect_tx(full_bar(stage), stageBytes);
-                                        for (int j = 0; j < p.tps; ++j)
-                                            tma_load_5d(dstA + j * bytesA, &p.mapA[s], full_bar(stage), c, ix + j, iy, iz, nb0);
-                                        tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);   // box depth = tps taps
+                                    if (elect_one()) {
+                                        if ((p.debug & 7) == 2) {
+                                            mbar_arrive(full_bar(stage));
+                                        } else {
+                                            mbar_expect_tx(full_bar(stage), stageBytes);
+                                            for (int j = 0; j < p.tps; ++j)
+                                                tma_load_5d(dstA + j * bytesA, &p.mapA[s], full_bar(stage), c, ix + j, iy, iz, nb0);
+                                            tma_load_3d(dstB, &p.mapB, full_bar(stage), cbase + c, n0, t);   // box depth = tps taps
+                                        }
                                     }
+                                    __syncwarp();
                                     if (++stage == S) { stage = 0; phase ^= 1u; }
                                 }
                                 cbase += p.srcC[s];
@@ -180,10 +190,13 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                     }
                 }
             }
+            if (dbgT && lane == 0) { g_dbg[0] = (unsigned long long)tWait; g_dbg[1] = (unsigned long long)(clock64() - tAll0); }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        {
+            const bool dbgT = (p.debug & 8) && blockIdx.x == 0;
+            long long tWaitFull = 0, tWaitAcc = 0, tAll0 = clock64();
             const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
             const uint32_t lay = swizzle_layout_code(p.KW * 2);
             const uint32_t sbo = 8u * p.KW * 2u;  // 8 rows of one swizzle span
@@ -194,26 +207,38 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+                long long w0 = dbgT ? clock64() : 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
+                if (dbgT) tWaitAcc += clock64() - w0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
                 for (int ks = 0; ks < stepsPerTile; ++ks) {
+                    w0 = dbgT ? clock64() : 0;
                     mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
+                    if (dbgT) tWaitFull += clock64() - w0;
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA * p.tps;
-                    for (int j = 0; j < p.tps && p.debug != 1; ++j) {
-                        for (int k = 0; k < kPerStep; ++k) {
-                            const uint64_t da = make_smem_desc(aAddr + j * bytesA + k * 32u, 16u, sbo, lay);
-                            const uint64_t db = make_smem_desc(bAddr + j * bytesB + k * 32u, 16u, sbo, lay);
-                            umma_bf16(d_tmem, da, db, idesc, (ks | j | k) ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int j = 0; j < p.tps && (p.debug & 7) != 1; ++j) {
+                            for (int k = 0; k < kPerStep; ++k) {
+                                const uint64_t da = make_smem_desc(aAddr + j * bytesA + k * 32u, 16u, sbo, lay);
+                                const uint64_t db = make_smem_desc(bAddr + j * bytesB + k * 32u, 16u, sbo, lay);
+                                umma_bf16(d_tmem, da, db, idesc, (ks | j | k) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (dbgT && lane == 0) {
+                g_dbg[2] = (unsigned long long)tWaitFull; g_dbg[3] = (unsigned long long)tWaitAcc;
+                g_dbg[4] = (unsigned long long)(clock64() - tAll0);
             }
         }
     } else {
@@ -227,6 +252,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
         const int id = (row / (p.tw * p.th)) % p.td;
         const int in = row / (p.tw * p.th * p.td);   // once per kernel
         const bool warpUniformSample = ((p.tw * p.th * p.td) & 31) == 0;
+        const bool dbgT = (p.debug & 8) && blockIdx.x == 0 && warp == 2 && lane == 0;
+        long long tWaitE = 0, tAllE0 = clock64();
+        int nTilesE = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
             uint32_t sp, nt, tiw, tih, tid, tib;
             fdivmod((uint32_t)tile, p.fdTilesN, sp, nt);
@@ -237,7 +265,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             const bool valid = (ow < p.OW) && (oh < p.OH) && (od < p.OD) && (nb < p.NB);
             const int n0 = (int)nt * p.Ntile;
 
+            const long long we0 = dbgT ? clock64() : 0;
             mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
+            if (dbgT) { tWaitE += clock64() - we0; ++nTilesE; }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.Ntile);
             for (int cg = 0; cg < p.Ntile; cg += 32) {
@@ -246,7 +276,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                 tmem_ld_wait();
                 const int col0 = n0 + cg;
                 if (col0 < p.Nout) {
-                    if (p.stat_sum != nullptr && p.debug != 3) {
+                    if (p.stat_sum != nullptr && (p.debug & 7) != 3) {
                         if (warpUniformSample) {
                             // all 32 rows of this warp belong to sample nb: butterfly column sums, lane j ends up
                             // with column col0 + j
@@ -284,7 +314,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             }
                         }
                     }
-                    if (valid && p.debug != 4) {
+                    if (valid && (p.debug & 7) != 4) {
                         int fd, fh, fw, ch0;
                         if (p.mode == 1) {
                             const int par = col0 / p.psC;
@@ -332,6 +362,10 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (dbgT) {
+            g_dbg[5] = (unsigned long long)tWaitE; g_dbg[6] = (unsigned long long)(clock64() - tAllE0);
+            g_dbg[7] = (unsigned long long)nTilesE;
         }
     }
 

@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
     };
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
                     const uint32_t dstA = tile_base + stage * stageBytes;
                     const uint32_t dstB = dstA + bytesA;
+                    if (elect_one()) {
                     mbar_expect_tx(full_bar(stage), stageBytes);
                     if (!p.swap) {
                         for (int j = 0; j < nA; ++j)
@@ -177,13 +178,15 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                         for (int j = 0; j < bAtoms; ++j)
                             tma_load_5d(dstB + j * atomB, &p.mapP, full_bar(stage), j * p.bw, gw0, gh0, gd0, n0);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        {
             const uint32_t idesc = make_idesc_bf16(128, p.bn, 1, 1);   // both operands MN-major
             const uint32_t layA = swizzle_layout_code(p.aw * 2), layB = swizzle_layout_code(p.bw * 2);
             const uint32_t sboA = 8u * p.aw * 2u, sboB = 8u * p.bw * 2u;   // 8 K rows of one span
@@ -205,16 +208,20 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     tc_fence_after();
                     const uint32_t aAddr = tile_base + stage * stageBytes;
                     const uint32_t bAddr = aAddr + bytesA;
-                    for (int k = 0; k < p.kbox / 16; ++k) {
-                        // 16 voxels = two 8-row groups further down the K direction
-                        const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
-                        const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);
-                        umma_bf16(d_tmem, da, db, idesc, (c > c0 || k > 0) ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int k = 0; k < p.kbox / 16; ++k) {
+                            // 16 voxels = two 8-row groups further down the K direction
+                            const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
+                            const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);
+                            umma_bf16(d_tmem, da, db, idesc, (c > c0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(empty_bar(stage));
                     }
-                    umma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));
+                if (elect_one()) umma_commit(tfull_bar(acc));
+                __syncwarp();
                 if (p.accBufs == 2) { if (++acc == 2) { acc = 0; acc_phase ^= 1u; } }
                 else acc_phase ^= 1u;
             }
