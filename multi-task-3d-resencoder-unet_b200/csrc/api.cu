@@ -11,6 +11,7 @@
 #include "../../include/resenc_b200.h"
 #include "common.cuh"
 #include "conv_tc5.cuh"
+#include "conv_tc5t.cuh"
 #include "conv_generic.cuh"
 #include "wgrad_tc5.cuh"
 #include "elementwise.cuh"
@@ -154,6 +155,118 @@ Tc5Plan plan_tc5(const RbConvDesc& d) {
     pl.ksteps = d.tapD * d.tapH * d.tapW * (ctot / pl.KW);
     pl.ok = true;
     return pl;
+}
+
+// ---- "weights on M, 256 voxels on N" orientation (conv_tc5t.cuh): mode 0, Nout <= 128 -----------------------
+struct Tc5tPlan {
+    bool ok = false;
+    int KW = 0, lw = 0, lh = 0, ld = 0, tn = 0, tilesW = 0, tilesH = 0, tilesD = 0, tilesNB = 0, tilesM = 0, stages = 0;
+    long long tiles = 0;
+    size_t smem = 0;
+    bool statSmem = false;
+};
+
+Tc5tPlan plan_tc5t(const RbConvDesc& d) {
+    Tc5tPlan pl;
+    if (d.mode != 0 || d.nsrc < 1 || d.nsrc > 2) return pl;
+    if (d.srcC0 % 16 != 0 || (d.nsrc == 2 && d.srcC1 % 16 != 0)) return pl;
+    if (d.Nout % 8 != 0 || d.Nout > 128) return pl;
+    int kw = 64;
+    while (kw > 16 && (d.srcC0 % kw != 0 || (d.nsrc == 2 && d.srcC1 % kw != 0))) kw >>= 1;
+    pl.KW = kw;
+    pl.tilesM = (d.Nout + 127) / 128;
+    long long best = -1;
+    int btn = 0, btw = 0;
+    for (int lw = 0; lw <= 8; ++lw)
+        for (int lh = 0; lw + lh <= 8; ++lh)
+            for (int ld = 0; lw + lh + ld <= 8; ++ld) {
+                const int tw = 1 << lw, th = 1 << lh, td = 1 << ld, tn = 256 >> (lw + lh + ld);
+                if ((tw - 1) * d.istrW + 1 > 256 || (th - 1) * d.istrH + 1 > 256 || (td - 1) * d.istrD + 1 > 256) continue;
+                const long long t = (long long)((d.OW + tw - 1) / tw) * ((d.OH + th - 1) / th) * ((d.OD + td - 1) / td) *
+                                    ((d.NB + tn - 1) / tn);
+                if (best < 0 || t < best || (t == best && (tn < btn || (tn == btn && tw > btw)))) {
+                    best = t; btn = tn; btw = tw;
+                    pl.lw = lw; pl.lh = lh; pl.ld = ld; pl.tn = tn;
+                }
+            }
+    if (best < 0) return pl;
+    const int tw = 1 << pl.lw, th = 1 << pl.lh, td = 1 << pl.ld;
+    pl.tilesW = (d.OW + tw - 1) / tw; pl.tilesH = (d.OH + th - 1) / th; pl.tilesD = (d.OD + td - 1) / td;
+    pl.tilesNB = (d.NB + pl.tn - 1) / pl.tn;
+    pl.tiles = best * pl.tilesM;
+    const size_t stageBytes = (size_t)(256 + 128) * pl.KW * 2;
+    const size_t statBytes = (size_t)8 * d.NB * d.Nout * sizeof(float);
+    pl.statSmem = statBytes <= 16 * 1024;
+    const size_t reserve = pl.statSmem ? statBytes : 0;
+    int st = (int)((200 * 1024 - reserve) / stageBytes);
+    if (st > 8) st = 8;
+    if (st < 2) return pl;
+    pl.stages = st;
+    pl.smem = 1024 + 1024 + (size_t)st * stageBytes + reserve;
+    pl.ok = true;
+    return pl;
+}
+
+bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
+    static const bool off = getenv("RESENC_NO_TC5T") != nullptr;
+    return pl.ok && !off && pl.tiles >= 64;
+}
+
+int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const void* src1, const void* w, void* out0,
+                void* out1, float* stat_sum, float* stat_sq, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    rb::Tc5tConvParams p;
+    memset(&p, 0, sizeof(p));
+    const int tw = 1 << pl.lw, th = 1 << pl.lh, td = 1 << pl.ld;
+    const void* srcs[2] = {src0, src1};
+    const int srcC[2] = {d.srcC0, d.srcC1};
+    for (int s = 0; s < d.nsrc; ++s) {
+        const cuuint64_t C = (cuuint64_t)srcC[s];
+        cuuint64_t dims[5] = {C, (cuuint64_t)d.IW, (cuuint64_t)d.IH, (cuuint64_t)d.ID, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {C * 2, C * 2 * d.IW, C * 2 * d.IW * d.IH, C * 2 * d.IW * d.IH * d.ID};
+        cuuint32_t box[5] = {(cuuint32_t)pl.KW, (cuuint32_t)((tw - 1) * d.istrW + 1), (cuuint32_t)((th - 1) * d.istrH + 1),
+                             (cuuint32_t)((td - 1) * d.istrD + 1), (cuuint32_t)pl.tn};
+        cuuint32_t estr[5] = {1, (cuuint32_t)d.istrW, (cuuint32_t)d.istrH, (cuuint32_t)d.istrD, 1};
+        CUresult r = enc(&p.mapX[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(X%d) failed: %d", s, (int)r);
+    }
+    {
+        const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+        const int ntaps = d.tapD * d.tapH * d.tapW;
+        cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, (cuuint64_t)ntaps};
+        cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
+        cuuint32_t box[3] = {(cuuint32_t)pl.KW, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    }
+    p.nsrc = d.nsrc; p.srcC[0] = d.srcC0; p.srcC[1] = d.nsrc == 2 ? d.srcC1 : 0;
+    p.KW = pl.KW;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.istrD = d.istrD; p.istrH = d.istrH; p.istrW = d.istrW;
+    p.lw = pl.lw; p.lh = pl.lh; p.ld = pl.ld;
+    p.tilesW = pl.tilesW; p.tilesH = pl.tilesH; p.tilesD = pl.tilesD; p.tilesNB = pl.tilesNB; p.tilesM = pl.tilesM;
+    p.OW = d.OW; p.OH = d.OH; p.OD = d.OD; p.NB = d.NB; p.Nout = d.Nout;
+    p.ostrD = d.ostrD; p.ostrH = d.ostrH; p.ostrW = d.ostrW; p.ooffD = d.ooffD; p.ooffH = d.ooffH; p.ooffW = d.ooffW;
+    p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
+    p.out0 = out0; p.out1 = out1; p.outC0 = d.outC0; p.outC1 = d.outC1; p.outF32 = d.outF32;
+    p.stages = pl.stages; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.statSmem = pl.statSmem ? 1 : 0;
+    p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
+    p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(rb::tc5t_gather_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tc5t): %s", cudaGetErrorString(attr_err));
+    long long grid = pl.tiles < num_sms() ? pl.tiles : num_sms();
+    rb::tc5t_gather_conv_kernel<<<(int)grid, rb::TC5T_THREADS, pl.smem, st>>>(p);
+    return check_launch("tc5t_gather_conv_kernel");
 }
 
 int validate_conv(const RbConvDesc& d) {
@@ -495,7 +608,13 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     } else if (d.impl != RB_IMPL_MMA_SYNC) {
         return fail(RB_ERR_INVALID, "conv: unknown impl %d", d.impl);
     }
-    if (use_tc5) return launch_tc5(d, pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
+    if (use_tc5) {
+        if (d.impl == RB_IMPL_AUTO || d.impl == RB_IMPL_TCGEN05) {
+            Tc5tPlan plt = plan_tc5t(d);
+            if (auto_prefers_tc5t(d, plt)) return launch_tc5t(d, plt, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
+        }
+        return launch_tc5(d, pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
+    }
     if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");
 
     rb::GConvParams p;

@@ -1,0 +1,324 @@
+// tcgen05 gather convolution, "weights-stationary-on-M" orientation, for layers with few output channels.
+//
+//   D^T[co][v] = sum_{tap, c} W[tap][co][c] * X[src(v, tap)][c]        M = co (padded to 128), N = 256 voxels
+//
+// Why a second orientation: an SS-mode tcgen05.mma reads its A operand from shared memory at about one
+// 32-byte row per cycle, so an M=128 instruction costs >= ~128 cycles whatever N is (measured on this path:
+// ~170 cycles per M=128,N=32,K=16 MMA, profiles/r1_bottleneck_experiments.md).  With the voxels on M and
+// Cout = 32 on N the tensor pipe can therefore never exceed 12 % of its peak.  Putting the (zero padded)
+// weights on M and 256 voxels on N makes every MMA a full-rate N=256 instruction: 32/64/128 output channels
+// reach 25/50/100 % of the MMA rate instead of 12/25/50 %.
+//
+// Side effects that help: TMEM lane = output channel, column = voxel, so the epilogue's stores of one column
+// are 32 consecutive channels (perfectly coalesced) and the InstanceNorm statistics are plain per-thread sums
+// over columns (no shuffles).
+//
+// Same operand conventions, geometry parameters and fusions as conv_tc5.cuh (mode 0 only).
+#pragma once
+#include "common.cuh"
+
+namespace rb {
+
+struct Tc5tConvParams {
+    CUtensorMap mapX[2];  // rank 5 (C, W, H, D, N), box (KW, tw.., tn) covering 256 output voxels
+    CUtensorMap mapW;     // rank 3 (Ctot, Nout, taps), box (KW, 128, 1): rows >= Nout are zero filled
+    int nsrc, srcC[2];
+    int KW;
+    int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
+    int lw, lh, ld;       // log2 of the tile box extents (tw, th, td); tn = 256 >> (lw + lh + ld)
+    int tilesW, tilesH, tilesD, tilesNB, tilesM;
+    int OW, OH, OD, NB;
+    int Nout;
+    int ostrD, ostrH, ostrW, ooffD, ooffH, ooffW;
+    int FD, FH, FW;
+    void* out0;
+    void* out1;
+    int outC0, outC1;
+    int outF32;
+    int stages;
+    float* stat_sum;
+    float* stat_sq;
+    int statSmem;
+    FastDiv fdTilesM, fdTilesW, fdTilesH, fdTilesD;
+};
+
+static constexpr int TC5T_THREADS = 192;
+static constexpr int TC5T_VOX = 256;
+
+__global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const __grid_constant__ Tc5tConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + 192);
+    const uint32_t err_flag = smem_u32(smem_al + 200);
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem_al + 200) = 0u;
+    uint8_t* tiles = smem_al + 1024;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t bytesX = (uint32_t)TC5T_VOX * p.KW * 2u;
+    const uint32_t bytesW = 128u * p.KW * 2u;
+    const uint32_t stageBytes = bytesX + bytesW;
+    const uint32_t tile_base = smem_u32(tiles);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+
+    // per-epilogue-warp statistics slots behind the stages: [quad][2][NB][128 channels of this M tile]... indexed
+    // by the global channel: [quad][2][NB * Nout]
+    float* statS = reinterpret_cast<float*>(tiles + (size_t)S * stageBytes);
+    const int statN = p.NB * p.Nout;
+    if (p.stat_sum != nullptr && p.statSmem)
+        for (int i = threadIdx.x; i < 8 * statN; i += blockDim.x) statS[i] = 0.f;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapX[0]);
+        if (p.nsrc > 1) tma_prefetch_desc(&p.mapX[1]);
+        tma_prefetch_desc(&p.mapW);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), 512);   // two 256-column fp32 accumulators
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tw = 1 << p.lw, th = 1 << p.lh, td = 1 << p.ld;
+    const int tn = TC5T_VOX >> (p.lw + p.lh + p.ld);
+    const int totalTiles = p.tilesW * p.tilesH * p.tilesD * p.tilesNB * p.tilesM;
+    const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
+    const int ntaps = p.tapD * p.tapH * p.tapW;
+
+    auto decode = [&](int tile, uint32_t& mt, uint32_t& tiw, uint32_t& tih, uint32_t& tid, uint32_t& tib) {
+        uint32_t sp;
+        fdivmod((uint32_t)tile, p.fdTilesM, sp, mt);   // M tile fastest: CTAs sharing a voxel tile run together
+        fdivmod(sp, p.fdTilesW, sp, tiw);
+        fdivmod(sp, p.fdTilesH, sp, tih);
+        fdivmod(sp, p.fdTilesD, tib, tid);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            uint32_t mt, tiw, tih, tid, tib;
+            decode(tile, mt, tiw, tih, tid, tib);
+            const int ow0 = tiw * tw, oh0 = tih * th, od0 = tid * td, nb0 = tib * tn;
+            const int m0 = mt * 128;
+            int t = 0;
+            for (int kd = 0; kd < p.tapD; ++kd) {
+                const int iz = od0 * p.istrD + p.offD + kd;
+                for (int kh = 0; kh < p.tapH; ++kh) {
+                    const int iy = oh0 * p.istrH + p.offH + kh;
+                    for (int kw = 0; kw < p.tapW; ++kw, ++t) {
+                        const int ix = ow0 * p.istrW + p.offW + kw;
+                        int cbase = 0;
+                        for (int s = 0; s < p.nsrc; ++s) {
+                            for (int c = 0; c < p.srcC[s]; c += p.KW) {
+                                mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
+                                if (elect_one()) {
+                                    const uint32_t dstX = tile_base + stage * stageBytes;
+                                    const uint32_t dstW = dstX + bytesX;
+                                    mbar_expect_tx(full_bar(stage), stageBytes);
+                                    tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, ix, iy, iz, nb0);
+                                    tma_load_3d(dstW, &p.mapW, full_bar(stage), cbase + c, m0, t);
+                                }
+                                __syncwarp();
+                                if (++stage == S) { stage = 0; phase ^= 1u; }
+                            }
+                            cbase += p.srcC[s];
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: A = weights (M = 128), B = voxels (N = 256) =====================
+        const uint32_t idesc = make_idesc_bf16(128, TC5T_VOX, 0, 0);
+        const uint32_t lay = swizzle_layout_code(p.KW * 2);
+        const uint32_t sbo = 8u * p.KW * 2u;
+        const int kPerStep = p.KW / 16;
+        const int stepsPerTile = ntaps * (Ctot / p.KW);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC5T_VOX);
+            for (int ks = 0; ks < stepsPerTile; ++ks) {
+                mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t xAddr = tile_base + stage * stageBytes;
+                    const uint32_t wAddr = xAddr + bytesX;
+                    for (int k = 0; k < kPerStep; ++k) {
+                        const uint64_t da = make_smem_desc(wAddr + k * 32u, 16u, sbo, lay);
+                        const uint64_t db = make_smem_desc(xAddr + k * 32u, 16u, sbo, lay);
+                        umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+            if (elect_one()) umma_commit(tfull_bar(acc));
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): lane = output channel, column = voxel =====================
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int spatial = tw * th * td;   // voxels of one sample inside a tile (a multiple of 32 or < 32)
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            uint32_t mt, tiw, tih, tid, tib;
+            decode(tile, mt, tiw, tih, tid, tib);
+            const int co = (int)mt * 128 + quad * 32 + lane;
+            const bool rowValid = co < p.Nout;
+            const bool warpHasRows = (int)mt * 128 + quad * 32 < p.Nout;
+            mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
+            tc_fence_after();
+            if (warpHasRows) {
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC5T_VOX);
+                // destination of this lane's channel
+                const bool first = co < p.outC0;
+                const int cdst = first ? co : co - p.outC0;
+                const int cpitch = first ? p.outC0 : p.outC1;
+                void* const base = first ? p.out0 : p.out1;
+                for (int cg = 0; cg < TC5T_VOX; cg += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_addr + cg, v);
+                    tmem_ld_wait();
+                    float s1 = 0.f, s2 = 0.f;
+                    int nbStat = -1;
+                    if (p.lw >= 5) {
+                        // the 32 columns of this group are 32 consecutive voxels of one W row: one address
+                        // computation per group, then a constant stride per column
+                        const int r0 = cg;
+                        const int iw0 = r0 & (tw - 1);
+                        const int ih = (r0 >> p.lw) & (th - 1);
+                        const int id = (r0 >> (p.lw + p.lh)) & (td - 1);
+                        const int in = r0 >> (p.lw + p.lh + p.ld);
+                        const int ow0 = (int)tiw * tw + iw0, oh = (int)tih * th + ih, od = (int)tid * td + id,
+                                  nb = (int)tib * tn + in;
+                        const bool gvalid = (oh < p.OH) && (od < p.OD) && (nb < p.NB);
+                        if (gvalid) {
+                            nbStat = nb;
+                            const int fd = od * p.ostrD + p.ooffD, fh = oh * p.ostrH + p.ooffH, fw0 = ow0 * p.ostrW + p.ooffW;
+                            const size_t vox0 = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw0;
+                            const size_t e0 = vox0 * cpitch + cdst;
+                            const size_t estep = (size_t)p.ostrW * cpitch;
+                            const int nvalid = min(32, p.OW - ow0);   // columns beyond the row end are padding
+                            if (p.outF32) {
+                                float* dst = reinterpret_cast<float*>(base) + e0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (j < nvalid) {
+                                        const float x = __uint_as_float(v[j]);
+                                        s1 += x; s2 += x * x;
+                                        if (rowValid) dst[j * estep] = x;
+                                    }
+                                }
+                            } else {
+                                bf16* dst = reinterpret_cast<bf16*>(base) + e0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (j < nvalid) {
+                                        const float x = __uint_as_float(v[j]);
+                                        s1 += x; s2 += x * x;
+                                        if (rowValid) dst[j * estep] = __float2bfloat16_rn(x);
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int r = cg + j;                       // voxel row inside the tile
+                        const int iw = r & (tw - 1);
+                        const int ih = (r >> p.lw) & (th - 1);
+                        const int id = (r >> (p.lw + p.lh)) & (td - 1);
+                        const int in = r >> (p.lw + p.lh + p.ld);
+                        const int ow = (int)tiw * tw + iw, oh = (int)tih * th + ih, od = (int)tid * td + id,
+                                  nb = (int)tib * tn + in;
+                        const bool valid = (ow < p.OW) && (oh < p.OH) && (od < p.OD) && (nb < p.NB);
+                        const float x = __uint_as_float(v[j]);
+                        if (valid) {
+                            if (p.stat_sum != nullptr) {
+                                if (spatial >= 32) {               // the 32 columns of this group share one sample
+                                    s1 += x; s2 += x * x; nbStat = nb;
+                                } else if (rowValid) {
+                                    atomicAdd(p.stat_sum + nb * p.Nout + co, x);
+                                    atomicAdd(p.stat_sq + nb * p.Nout + co, x * x);
+                                }
+                            }
+                            if (rowValid) {
+                                const int fd = od * p.ostrD + p.ooffD, fh = oh * p.ostrH + p.ooffH, fw = ow * p.ostrW + p.ooffW;
+                                const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
+                                if (p.outF32) reinterpret_cast<float*>(base)[vox * cpitch + cdst] = x;
+                                else reinterpret_cast<bf16*>(base)[vox * cpitch + cdst] = __float2bfloat16_rn(x);
+                            }
+                        }
+                    }
+                    }
+                    if (p.stat_sum != nullptr && spatial >= 32 && nbStat >= 0 && rowValid) {
+                        const int idx = nbStat * p.Nout + co;
+                        if (p.statSmem) {
+                            float* slot = statS + (size_t)quad * 2 * statN + idx;
+                            slot[0] += s1;
+                            slot[statN] += s2;
+                        } else {
+                            atomicAdd(p.stat_sum + idx, s1);
+                            atomicAdd(p.stat_sq + idx, s2);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (p.stat_sum != nullptr && p.statSmem) {
+        for (int i = threadIdx.x; i < statN; i += blockDim.x) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                a += statS[(size_t)w * 2 * statN + i];
+                b += statS[(size_t)w * 2 * statN + statN + i];
+            }
+            if (a != 0.f || b != 0.f) {
+                atomicAdd(p.stat_sum + i, a);
+                atomicAdd(p.stat_sq + i, b);
+            }
+        }
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace rb

@@ -38,6 +38,13 @@ CASES = [
     (2, 256, 512, (8, 8, 8), (3, 3, 3), (2, 2, 2)),
     (1, 48, 96, (8, 8, 24), (3, 3, 3), (1, 1, 1)),
     (1, 32, 32, (64, 64, 64), (3, 3, 3), (1, 1, 1)),
+    # >= 64 tiles of 256 voxels with <= 128 output channels: the weights-on-M orientation (conv_tc5t.cuh)
+    (1, 64, 64, (32, 32, 32), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 64, (64, 64, 64), (3, 3, 3), (2, 2, 2)),
+    (2, 128, 128, (16, 32, 32), (3, 3, 3), (1, 1, 1)),
+    (1, 32, 32, (40, 36, 44), (3, 3, 3), (1, 1, 1)),
+    (1, 64, 32, (24, 40, 72), (1, 1, 1), (1, 1, 1)),
+    (1, 32, 64, (16, 64, 64), (1, 3, 3), (1, 2, 2)),
 ]
 
 
@@ -68,11 +75,12 @@ def test_tc5_conv_fwd_bwd(rb, case):
     assert rel_l2(outs["tc5"][0], outs["mma"][0]) < 3e-3
 
 
-def test_tc5_two_sources(rb):
+@pytest.mark.parametrize("dims,c,co", [((8, 8, 8), 64, 64), ((32, 32, 32), 32, 32), ((16, 48, 40), 64, 64)])
+def test_tc5_two_sources(rb, dims, c, co):
     torch.manual_seed(1)
-    a = q(torch.randn(2, 64, 8, 8, 8, device="cuda"))
-    b = q(torch.randn(2, 64, 8, 8, 8, device="cuda"))
-    w = torch.randn(64, 128, 3, 3, 3, device="cuda") / 58
+    a = q(torch.randn(2, c, *dims, device="cuda"))
+    b = q(torch.randn(2, c, *dims, device="cuda"))
+    w = torch.randn(co, 2 * c, 3, 3, 3, device="cuda") / (54 * c) ** 0.5
     ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
     ref = F.conv3d(torch.cat((ar, br), 1), q(w), None, 1, 1)
     g = q(torch.randn_like(ref))
@@ -106,7 +114,8 @@ def test_tc5_fused_statistics(rb):
     bf16 output, so within bf16 rounding)."""
     torch.manual_seed(3)
     ops = rb.ops
-    for n, c, dims in [(2, 32, (16, 16, 16)), (2, 128, (4, 4, 4)), (1, 64, (10, 12, 14))]:
+    for n, c, dims in [(2, 32, (16, 16, 16)), (2, 128, (4, 4, 4)), (1, 64, (10, 12, 14)), (2, 32, (32, 32, 32)),
+                       (1, 64, (20, 36, 40))]:
         x = ops.as_cl(torch.randn(n, c, *dims, device="cuda"))
         w = torch.randn(c, c, 3, 3, 3, device="cuda") / (27 * c) ** 0.5
         y = ops.new_cl(n, c, *dims, "cuda")
