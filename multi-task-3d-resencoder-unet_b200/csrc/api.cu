@@ -209,7 +209,13 @@ Tc5tPlan plan_tc5t(const RbConvDesc& d) {
 
 bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
     static const bool off = getenv("RESENC_NO_TC5T") != nullptr;
-    return pl.ok && !off && pl.tiles >= 64;
+    if (!pl.ok || off || pl.tiles < 64) return false;
+    // Measured (profiles/r1_convbench.json): the N = 256 orientation wins when a tile carries enough MMA work to
+    // hide its epilogue (one warp per 32 output channels) and the K chunks are >= 128-byte TMA rows; 32-channel
+    // inputs (64-byte rows, TMA row-rate bound) and few-tap data-gradient classes stay on the voxels-on-M kernel.
+    const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+    const int ntaps = d.tapD * d.tapH * d.tapW;
+    return ntaps * ctot >= 864 && ctot >= 64;
 }
 
 int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const void* src1, const void* w, void* out0,
