@@ -196,7 +196,7 @@ def main():
     n_stages = model.num_stages
     model.train()
     use_graph = (world == 1) and not args.no_graph
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
     buckets = par.GradientBuckets(model) if world > 1 else None
     params = [p for p in model.parameters()]
 

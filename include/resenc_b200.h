@@ -157,6 +157,13 @@ int rb_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, f
  * col [NB,D,H,W,Kp] bf16, column = tap*Cin + ci, zero padded to Kp (multiple of 16). */
 int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream);
 
+/* Weight (un)packing between the canonical parameter layout w[Cout][Cin][taps] fp32 (the reference's nn.Conv3d
+ * weight, builders/simple_conv_blocks.py:43-51) and the kernels' operand layouts, tiled through shared memory:
+ *   out_f[t][Cout][Cin] bf16 (fprop operand), out_d[taps-1-t][Cin][Cout] bf16 (stride-1 data-gradient operand);
+ *   grad[A][B][taps] = dwp[taps][A][B] (rb_wgrad_gather result -> canonical gradient). Either output may be NULL. */
+int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int Cin, int taps, void* stream);
+int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int taps, void* stream);
+
 /* Layout conversion at module boundaries: NCDHW fp32 <-> NDHWC bf16 (C % 8 == 0). */
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream);
 int rb_cl_to_ncdhw(const void* src, float* dst, int NB, int C, long long S, void* stream);

@@ -830,6 +830,30 @@ int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int
     return check_launch("stem_im2col_kernel");
 }
 
+int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int Cin, int T, void* stream) {
+    if (!w || (!out_f && !out_d)) return fail(RB_ERR_INVALID, "pack_conv_weights: null pointer");
+    if (Cout <= 0 || Cin <= 0 || T <= 0 || T > 27) return fail(RB_ERR_INVALID, "pack_conv_weights: need 1 <= taps <= 27");
+    rb::WPackParams p{w, (rb::bf16*)out_f, (rb::bf16*)out_d, Cout, Cin, T};
+    const size_t smem = (size_t)32 * (32 * T + 2) * sizeof(rb::bf16);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(rb::pack_conv_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+    rb::pack_conv_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("pack_conv_weights_kernel");
+}
+
+int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int T, void* stream) {
+    if (!dwp || !grad) return fail(RB_ERR_INVALID, "unpack_wgrad: null pointer");
+    if (A <= 0 || B <= 0 || T <= 0 || T > 27) return fail(RB_ERR_INVALID, "unpack_wgrad: need 1 <= taps <= 27");
+    rb::WUnpackParams p{dwp, grad, A, B, T};
+    const size_t smem = (size_t)32 * (32 * T + 1) * sizeof(float);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(rb::unpack_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
+    dim3 grid((B + 31) / 32, (A + 31) / 32);
+    rb::unpack_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("unpack_wgrad_kernel");
+}
+
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream) {
     if (!src || !dst || C <= 0 || C % 8 != 0) return fail(RB_ERR_INVALID, "ncdhw_to_cl: bad arguments");
     rb::LayoutParams p{src, (rb::bf16*)dst, S, NB, C};

@@ -625,4 +625,79 @@ __global__ void __launch_bounds__(256) cl_to_ncdhw_kernel(const LayoutBackParams
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Weight (un)packing between the canonical parameter layout and the kernels' layouts, as tiled transposes
+// through shared memory (both sides coalesced).  T = taps (kd*kh*kw), canonical w[co][ci][t] fp32.
+//   pack  : out_f[t][co][ci] = bf16(w[co][ci][t])                       (fprop operand)
+//           out_d[T-1-t][ci][co] = bf16(w[co][ci][t])                   (stride-1 data-gradient operand: flipped taps)
+//   unpack: grad[co][ci][t] = dwp[t][co][ci]                            (weight-gradient result -> canonical)
+// One block = a 32 x 32 (co, ci) tile with all taps (T <= 27).
+// ---------------------------------------------------------------------------------------
+struct WPackParams {
+    const float* w;   // [Cout][Cin][T]
+    bf16* out_f;      // [T][Cout][Cin] or null
+    bf16* out_d;      // [T][Cin][Cout] (taps flipped) or null
+    int Cout, Cin, T;
+};
+
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const WPackParams p) {
+    extern __shared__ bf16 tileW[];   // [32 co][32 ci][T] (+1 padding on the ci stride)
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int T = p.T;
+    const int pitch = 32 * T + 2;     // elements per co row of the tile (padding breaks bank alignment)
+    // load: for each co of the tile, 32 ci x T floats are contiguous in the canonical layout
+    for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+        const int co = co0 + r;
+        if (co >= p.Cout) continue;
+        const int nci = min(32, p.Cin - ci0);
+        const float* src = p.w + ((size_t)co * p.Cin + ci0) * T;
+        for (int i = threadIdx.x & 31; i < nci * T; i += 32) tileW[r * pitch + i] = __float2bfloat16_rn(__ldg(src + i));
+    }
+    __syncthreads();
+    // fprop pack: [t][co][ci]: 32 consecutive ci per (t, co)
+    if (p.out_f != nullptr) {
+        for (int j = threadIdx.x >> 5; j < 32 * T; j += 8) {
+            const int t = j / 32, r = j - t * 32;
+            const int co = co0 + r, ci = ci0 + (threadIdx.x & 31);
+            if (co < p.Cout && ci < p.Cin)
+                p.out_f[((size_t)t * p.Cout + co) * p.Cin + ci] = tileW[r * pitch + (threadIdx.x & 31) * T + t];
+        }
+    }
+    // dgrad pack: [T-1-t][ci][co]: 32 consecutive co per (t, ci)
+    if (p.out_d != nullptr) {
+        for (int j = threadIdx.x >> 5; j < 32 * T; j += 8) {
+            const int t = j / 32, c = j - t * 32;
+            const int ci = ci0 + c, co = co0 + (threadIdx.x & 31);
+            if (co < p.Cout && ci < p.Cin)
+                p.out_d[((size_t)(T - 1 - t) * p.Cin + ci) * p.Cout + co] = tileW[(threadIdx.x & 31) * pitch + c * T + t];
+        }
+    }
+}
+
+struct WUnpackParams {
+    const float* dwp;  // [T][A][B]
+    float* grad;       // [A][B][T]
+    int A, B, T;
+};
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const WUnpackParams p) {
+    extern __shared__ float tileG[];  // [32 a][32 b][T] (+1)
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    const int T = p.T;
+    const int pitch = 32 * T + 1;
+    for (int j = threadIdx.x >> 5; j < 32 * T; j += 8) {
+        const int t = j / 32, r = j - t * 32;
+        const int a = a0 + r, b = b0 + (threadIdx.x & 31);
+        if (a < p.A && b < p.B) tileG[r * pitch + (threadIdx.x & 31) * T + t] = __ldg(p.dwp + ((size_t)t * p.A + a) * p.B + b);
+    }
+    __syncthreads();
+    for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+        const int a = a0 + r;
+        if (a >= p.A) continue;
+        const int nb = min(32, p.B - b0);
+        float* dst = p.grad + ((size_t)a * p.B + b0) * T;
+        for (int i = threadIdx.x & 31; i < nb * T; i += 32) dst[i] = tileG[r * pitch + i];
+    }
+}
+
 }  // namespace rb

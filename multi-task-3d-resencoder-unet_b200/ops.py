@@ -240,11 +240,46 @@ def _cached_pack(weight, kind, fn):
     return cache[kind]
 
 
+def _pack_kernel(weight, want_f, want_d):
+    """rb_pack_conv_weights: canonical fp32 [Cout, Cin, kd, kh, kw] -> bf16 [taps][Cout][Cin] (fprop operand) and /
+    or [taps, flipped][Cin][Cout] (stride-1 data-gradient operand), one coalesced pass."""
+    co, ci, kd, kh, kw = weight.shape
+    T = kd * kh * kw
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    f = torch.empty((T, co, ci), dtype=BF16, device=w.device) if want_f else None
+    d = torch.empty((T, ci, co), dtype=BF16, device=w.device) if want_d else None
+    L.check(L.load().rb_pack_conv_weights(w.data_ptr(), L.ptr(f), L.ptr(d), co, ci, T, L.stream_ptr()),
+            "rb_pack_conv_weights")
+    return f, d
+
+
 def pack_conv_fprop(weight):
     """[Cout, Cin, kd, kh, kw] -> [taps][Cout][Cin] bf16."""
-    co, ci, kd, kh, kw = weight.shape
-    return _cached_pack(weight, "f", lambda: weight.detach().permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci)
-                        .to(BF16).contiguous())
+    if not weight.is_cuda or weight.dtype != torch.float32:
+        co, ci, kd, kh, kw = weight.shape
+        return _cached_pack(weight, "f", lambda: weight.detach().permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci)
+                            .to(BF16).contiguous())
+    if not PACK_CACHE:
+        return _pack_kernel(weight, True, False)[0]
+    both = _cached_pack(weight, "fd", lambda: _pack_kernel(weight, True, True))
+    return both[0]
+
+
+def pack_conv_dgrad_full(weight):
+    """Stride-1 data-gradient operand: all taps, flipped, [taps][Cin][Cout] bf16."""
+    if not PACK_CACHE:
+        return _pack_kernel(weight, False, True)[1]
+    return _cached_pack(weight, "fd", lambda: _pack_kernel(weight, True, True))[1]
+
+
+def unpack_wgrad(dw, a, b, kshape):
+    """[taps][A][B] fp32 (kernel result) -> canonical [A, B, kd, kh, kw] fp32."""
+    T = kshape[0] * kshape[1] * kshape[2]
+    out = torch.empty((a, b, *kshape), dtype=torch.float32, device=dw.device)
+    L.check(L.load().rb_unpack_wgrad(dw.data_ptr(), out.data_ptr(), a, b, T, L.stream_ptr()), "rb_unpack_wgrad")
+    return out
 
 
 def _axis_classes(K, s, pad, I):
@@ -326,7 +361,7 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
     gw = gx0 = gx1 = None
     if need_w:
         dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride, impl=impl)
-        gw = dw.view(kd, kh, kw, co, ci).permute(3, 4, 0, 1, 2).contiguous()
+        gw = unpack_wgrad(dw, co, ci, k)
     need1 = need1 and x1 is not None
     if need0 or need1:
         c0 = x0.shape[1]
@@ -338,7 +373,9 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
         for cd, ch, cw in itertools.product(*classes):
             if not (cd[2] and ch[2] and cw[2]):
                 continue
-            wpk = pack_conv_dgrad_class(weight, cd[2], ch[2], cw[2])
+            full = all(len(c[2]) == kk and stride[a] == 1 for a, (c, kk) in enumerate(zip((cd, ch, cw), k)))
+            wpk = pack_conv_dgrad_full(weight) if (full and weight.is_cuda and weight.dtype == torch.float32) \
+                else pack_conv_dgrad_class(weight, cd[2], ch[2], cw[2])
             _launch_gather(dy, None, wpk, gx0, gx1, in_dims=od, taps=(len(cd[2]), len(ch[2]), len(cw[2])),
                            off=(cd[3], ch[3], cw[3]), istr=(1, 1, 1), out_grid=(cd[1], ch[1], cw[1]), nout=ci,
                            ostr=stride, ooff=(cd[0], ch[0], cw[0]), full=in_dims, impl=impl)
@@ -717,7 +754,7 @@ class _ConvT3dFn(torch.autograd.Function):
         gw = gx = None
         if ctx.needs_input_grad[0]:
             dw = _launch_wgrad(x, dy, None, grid=in_dims, qdims=full, taps=stride, off=(0, 0, 0), istr=stride, impl=impl)
-            gw = dw.view(sd, sh, sw, ci, co).permute(3, 4, 0, 1, 2).contiguous()
+            gw = unpack_wgrad(dw, ci, co, (sd, sh, sw))
         if ctx.needs_input_grad[3]:
             gx = new_cl(n, ci, *in_dims, x.device)
             wpk = weight.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(BF16).contiguous()

@@ -294,3 +294,19 @@ def test_fused_conv_norm_act_unit(rb, case):
     assert rel_l2(gamma.grad, gr.grad) < 1e-2 and rel_l2(beta.grad, br.grad) < 1e-2
     if with_res:
         assert rel_l2(rp.grad.float(), rr.grad) < 8e-3
+
+
+@pytest.mark.parametrize("co,ci,k", [(32, 32, (3, 3, 3)), (64, 128, (3, 3, 3)), (40, 24, (1, 3, 3)), (512, 1024, (3, 3, 3)),
+                                     (64, 32, (1, 1, 1))])
+def test_weight_pack_unpack_kernels(rb, co, ci, k):
+    """Tiled pack / unpack kernels == the torch permutes they replace (bit-exact)."""
+    ops = rb.ops
+    torch.manual_seed(11)
+    w = torch.randn(co, ci, *k, device="cuda")
+    T = k[0] * k[1] * k[2]
+    f, d = ops._pack_kernel(w, True, True)
+    assert torch.equal(f, w.permute(2, 3, 4, 0, 1).reshape(T, co, ci).to(torch.bfloat16))
+    assert torch.equal(d, w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(T, ci, co).to(torch.bfloat16))
+    dw = torch.randn(T, co, ci, device="cuda")
+    g = ops.unpack_wgrad(dw, co, ci, k)
+    assert torch.equal(g, dw.view(*k, co, ci).permute(3, 4, 0, 1, 2))
