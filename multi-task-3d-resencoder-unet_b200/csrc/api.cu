@@ -164,13 +164,14 @@ struct Tc5tPlan {
     long long tiles = 0;
     size_t smem = 0;
     bool statSmem = false;
+    int splitK = 1, tapsPer = 27;
 };
 
 Tc5tPlan plan_tc5t(const RbConvDesc& d) {
     Tc5tPlan pl;
     if (d.mode != 0 || d.nsrc < 1 || d.nsrc > 2) return pl;
     if (d.srcC0 % 16 != 0 || (d.nsrc == 2 && d.srcC1 % 16 != 0)) return pl;
-    if (d.Nout % 8 != 0 || d.Nout > 128) return pl;
+    if (d.Nout % 8 != 0) return pl;
     int kw = 64;
     while (kw > 16 && (d.srcC0 % kw != 0 || (d.nsrc == 2 && d.srcC1 % kw != 0))) kw >>= 1;
     pl.KW = kw;
@@ -203,13 +204,26 @@ Tc5tPlan plan_tc5t(const RbConvDesc& d) {
     if (st < 2) return pl;
     pl.stages = st;
     pl.smem = 1024 + 1024 + (size_t)st * stageBytes + reserve;
+    // deep layers: a handful of voxel tiles with a very long K loop -> split the taps over the chip
+    const int ntaps = d.tapD * d.tapH * d.tapW;
+    const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+    pl.tapsPer = ntaps;
+    pl.splitK = 1;
+    if (pl.tiles < 48 && ntaps >= 8 && ctot >= 256 && d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1) {
+        long long want = (2LL * num_sms() + pl.tiles - 1) / pl.tiles;
+        if (want > ntaps) want = ntaps;
+        pl.tapsPer = (int)((ntaps + want - 1) / want);
+        pl.splitK = (ntaps + pl.tapsPer - 1) / pl.tapsPer;
+    }
     pl.ok = true;
     return pl;
 }
 
 bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
     static const bool off = getenv("RESENC_NO_TC5T") != nullptr;
-    if (!pl.ok || off || pl.tiles < 64) return false;
+    if (!pl.ok || off) return false;
+    if (pl.splitK > 1) return true;           // deep layers: tap-split tcgen05 instead of split-K mma.sync
+    if (pl.tiles < 64 || d.Nout > 128) return false;
     // Measured (profiles/r1_convbench.json): the N = 256 orientation wins when a tile carries enough MMA work to
     // hide its epilogue (one warp per 32 output channels) and the K chunks are >= 128-byte TMA rows; 32-channel
     // inputs (64-byte rows, TMA row-rate bound) and few-tap data-gradient classes stay on the voxels-on-M kernel.
@@ -219,7 +233,7 @@ bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
 }
 
 int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const void* src1, const void* w, void* out0,
-                void* out1, float* stat_sum, float* stat_sq, cudaStream_t st) {
+                void* out1, float* stat_sum, float* stat_sq, float* ws, cudaStream_t st) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     rb::Tc5tConvParams p;
@@ -264,13 +278,15 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     p.stages = pl.stages; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.statSmem = pl.statSmem ? 1 : 0;
     p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
+    p.splitK = pl.splitK; p.tapsPer = pl.tapsPer; p.fdSplitK = rb::make_fastdiv(pl.splitK); p.ws = ws;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(rb::tc5t_gather_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tc5t): %s", cudaGetErrorString(attr_err));
-    long long grid = pl.tiles < num_sms() ? pl.tiles : num_sms();
+    const long long items = pl.tiles * pl.splitK;
+    long long grid = items < num_sms() ? items : num_sms();
     rb::tc5t_gather_conv_kernel<<<(int)grid, rb::TC5T_THREADS, pl.smem, st>>>(p);
     return check_launch("tc5t_gather_conv_kernel");
 }
@@ -573,57 +589,53 @@ int rb_conv_gather_tc5_supported(const RbConvDesc* d) {
     return plan_tc5(*d).ok ? 1 : 0;
 }
 
+enum ConvChoice { CH_UNSUPPORTED = 0, CH_MMA = 1, CH_TC5 = 2, CH_TC5T = 3, CH_TC5T_SPLIT = 4 };
+struct ConvDecision {
+    int choice = CH_MMA;
+    Tc5Plan pl;
+    Tc5tPlan plt;
+};
+
+// One place decides which kernel runs a descriptor (used by the plan / workspace queries and by the launch).
+ConvDecision decide_conv(const RbConvDesc& d, bool stats_requested) {
+    ConvDecision r;
+    if (d.impl == RB_IMPL_MMA_SYNC) return r;
+    r.pl = plan_tc5(d);
+    r.plt = plan_tc5t(d);
+    static const bool no_t = getenv("RESENC_NO_TC5T") != nullptr;
+    const bool split_ok = r.plt.ok && r.plt.splitK > 1 && !no_t && !stats_requested;
+    if (split_ok) { r.choice = CH_TC5T_SPLIT; return r; }
+    const bool tc5 = d.impl == RB_IMPL_TCGEN05 ? r.pl.ok : auto_prefers_tc5(d, r.pl);
+    if (tc5) {
+        r.choice = auto_prefers_tc5t(d, r.plt) ? CH_TC5T : CH_TC5;
+        return r;
+    }
+    if (d.impl == RB_IMPL_TCGEN05) r.choice = CH_UNSUPPORTED;
+    return r;
+}
+
 int rb_conv_gather_plan(const RbConvDesc* d) {
     if (!d) return RB_ERR_INVALID;
-    if (d->impl == RB_IMPL_MMA_SYNC) return RB_IMPL_MMA_SYNC;
-    Tc5Plan pl = plan_tc5(*d);
-    if (d->impl == RB_IMPL_TCGEN05) return pl.ok ? RB_IMPL_TCGEN05 : RB_ERR_UNSUPPORTED;
-    return auto_prefers_tc5(*d, pl) ? RB_IMPL_TCGEN05 : RB_IMPL_MMA_SYNC;
+    const ConvDecision r = decide_conv(*d, false);
+    switch (r.choice) {
+        case CH_MMA: return RB_IMPL_MMA_SYNC;
+        case CH_TC5: case CH_TC5T: return RB_IMPL_TCGEN05;
+        case CH_TC5T_SPLIT: return RB_IMPL_TCGEN05_SPLITK;
+        default: return RB_ERR_UNSUPPORTED;
+    }
 }
 
 size_t rb_conv_gather_workspace(const RbConvDesc* d) {
     if (!d) return 0;
-    if (d->impl == RB_IMPL_TCGEN05) return 0;
-    if (d->impl == RB_IMPL_AUTO && auto_prefers_tc5(*d, plan_tc5(*d))) return 0;
-    if (generic_splitk(*d) <= 1) return 0;
-    return (size_t)d->NB * d->OD * d->OH * d->OW * d->Nout * sizeof(float);
+    const ConvDecision r = decide_conv(*d, false);
+    const size_t full = (size_t)d->NB * d->OD * d->OH * d->OW * d->Nout * sizeof(float);
+    if (r.choice == CH_TC5T_SPLIT) return full;
+    if (r.choice == CH_MMA && generic_splitk(*d) > 1) return full;
+    return 0;
 }
 
-int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, const void* w, void* out0, void* out1,
-                   float* stat_sum, float* stat_sq, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!dp) return fail(RB_ERR_INVALID, "conv: null descriptor");
-    const RbConvDesc& d = *dp;
-    int rc = validate_conv(d);
-    if (rc) return rc;
-    if (!src0 || !w || !out0 || (d.nsrc == 2 && !src1) || (d.outC1 > 0 && !out1)) return fail(RB_ERR_INVALID, "conv: null pointer");
-    if (!aligned16(src0) || !aligned16(src1) || !aligned16(w) || !aligned16(out0) || !aligned16(out1))
-        return fail(RB_ERR_INVALID, "conv: pointers must be 16-byte aligned");
-    if ((stat_sum == nullptr) != (stat_sq == nullptr)) return fail(RB_ERR_INVALID, "conv: stat_sum and stat_sq go together");
-    cudaStream_t st = (cudaStream_t)stream;
-
-    bool use_tc5 = false;
-    Tc5Plan pl;
-    if (d.impl == RB_IMPL_TCGEN05 || d.impl == RB_IMPL_AUTO) {
-        pl = plan_tc5(d);
-        if (d.impl == RB_IMPL_TCGEN05) {
-            if (!pl.ok) return fail(RB_ERR_UNSUPPORTED, "conv: shape does not qualify for the tcgen05 kernel");
-            use_tc5 = true;
-        } else {
-            use_tc5 = auto_prefers_tc5(d, pl);
-        }
-    } else if (d.impl != RB_IMPL_MMA_SYNC) {
-        return fail(RB_ERR_INVALID, "conv: unknown impl %d", d.impl);
-    }
-    if (use_tc5) {
-        if (d.impl == RB_IMPL_AUTO || d.impl == RB_IMPL_TCGEN05) {
-            Tc5tPlan plt = plan_tc5t(d);
-            if (auto_prefers_tc5t(d, plt)) return launch_tc5t(d, plt, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
-        }
-        return launch_tc5(d, pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
-    }
-    if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");
-
-    rb::GConvParams p;
+static void fill_generic_params(const RbConvDesc& d, const void* src0, const void* src1, const void* w, void* out0, void* out1,
+                                rb::GConvParams& p) {
     memset(&p, 0, sizeof(p));
     p.src[0] = (const rb::bf16*)src0; p.src[1] = (const rb::bf16*)src1;
     p.srcC[0] = d.srcC0; p.srcC[1] = d.nsrc == 2 ? d.srcC1 : 0; p.nsrc = d.nsrc;
@@ -637,9 +649,48 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     p.out0 = out0; p.out1 = out1; p.outC0 = d.outC0; p.outC1 = d.outC1;
     p.psC = d.psC; p.psD = d.psD; p.psH = d.psH; p.psW = d.psW;
     p.outF32 = d.outF32;
+}
+
+int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, const void* w, void* out0, void* out1,
+                   float* stat_sum, float* stat_sq, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!dp) return fail(RB_ERR_INVALID, "conv: null descriptor");
+    const RbConvDesc& d = *dp;
+    int rc = validate_conv(d);
+    if (rc) return rc;
+    if (!src0 || !w || !out0 || (d.nsrc == 2 && !src1) || (d.outC1 > 0 && !out1)) return fail(RB_ERR_INVALID, "conv: null pointer");
+    if (!aligned16(src0) || !aligned16(src1) || !aligned16(w) || !aligned16(out0) || !aligned16(out1))
+        return fail(RB_ERR_INVALID, "conv: pointers must be 16-byte aligned");
+    if ((stat_sum == nullptr) != (stat_sq == nullptr)) return fail(RB_ERR_INVALID, "conv: stat_sum and stat_sq go together");
+    if (d.impl != RB_IMPL_AUTO && d.impl != RB_IMPL_MMA_SYNC && d.impl != RB_IMPL_TCGEN05) return fail(RB_ERR_INVALID, "conv: unknown impl %d", d.impl);
+    cudaStream_t st = (cudaStream_t)stream;
     const long long M = (long long)d.NB * d.OD * d.OH * d.OW;
-    int sk = generic_splitk(d);
     const size_t need = (size_t)M * d.Nout * sizeof(float);
+
+    ConvDecision dec = decide_conv(d, stat_sum != nullptr);
+    if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need)) dec = decide_conv(d, true);  // no room: unsplit
+    if (dec.choice == CH_UNSUPPORTED) return fail(RB_ERR_UNSUPPORTED, "conv: shape does not qualify for the tcgen05 kernel");
+    if (dec.choice == CH_TC5) return launch_tc5(d, dec.pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
+    if (dec.choice == CH_TC5T) {
+        Tc5tPlan plt = dec.plt;
+        plt.splitK = 1; plt.tapsPer = d.tapD * d.tapH * d.tapW;
+        return launch_tc5t(d, plt, src0, src1, w, out0, out1, stat_sum, stat_sq, nullptr, st);
+    }
+    if (dec.choice == CH_TC5T_SPLIT) {
+        RB_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+        rc = launch_tc5t(d, dec.plt, src0, src1, w, out0, out1, nullptr, nullptr, (float*)workspace, st);
+        if (rc) return rc;
+        rb::GConvParams p;
+        fill_generic_params(d, src0, src1, w, out0, out1, p);
+        p.splitK = dec.plt.splitK;
+        p.ws = (float*)workspace;
+        rb::gather_finish_kernel<<<grid_for(M * (d.Nout / 2), 256), 256, 0, st>>>(p);
+        return check_launch("gather_finish_kernel");
+    }
+    if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");
+
+    rb::GConvParams p;
+    fill_generic_params(d, src0, src1, w, out0, out1, p);
+    int sk = generic_splitk(d);
     if (sk > 1 && (workspace == nullptr || workspace_bytes < need)) sk = 1;
     p.splitK = sk;
     p.ws = sk > 1 ? (float*)workspace : nullptr;

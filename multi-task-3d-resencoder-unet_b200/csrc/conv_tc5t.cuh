@@ -40,6 +40,11 @@ struct Tc5tConvParams {
     float* stat_sq;
     int statSmem;
     FastDiv fdTilesM, fdTilesW, fdTilesH, fdTilesD;
+    // split-K over taps for the deep layers (few voxels, huge K): each work item takes `tapsPer` consecutive taps and
+    // adds its fp32 partial tile into ws[voxel][Nout] with red.global; gather_finish_kernel stores the result
+    int splitK, tapsPer;
+    FastDiv fdSplitK;
+    float* ws;
 };
 
 static constexpr int TC5T_THREADS = 192;
@@ -99,13 +104,14 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
 
     const int tw = 1 << p.lw, th = 1 << p.lh, td = 1 << p.ld;
     const int tn = TC5T_VOX >> (p.lw + p.lh + p.ld);
-    const int totalTiles = p.tilesW * p.tilesH * p.tilesD * p.tilesNB * p.tilesM;
+    const int totalTiles = p.tilesW * p.tilesH * p.tilesD * p.tilesNB * p.tilesM * p.splitK;
     const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
     const int ntaps = p.tapD * p.tapH * p.tapW;
 
-    auto decode = [&](int tile, uint32_t& mt, uint32_t& tiw, uint32_t& tih, uint32_t& tid, uint32_t& tib) {
+    auto decode = [&](int tile, uint32_t& mt, uint32_t& tiw, uint32_t& tih, uint32_t& tid, uint32_t& tib, uint32_t& sk) {
         uint32_t sp;
-        fdivmod((uint32_t)tile, p.fdTilesM, sp, mt);   // M tile fastest: CTAs sharing a voxel tile run together
+        fdivmod((uint32_t)tile, p.fdSplitK, sp, sk);   // tap slice fastest
+        fdivmod(sp, p.fdTilesM, sp, mt);   // M tile fastest: CTAs sharing a voxel tile run together
         fdivmod(sp, p.fdTilesW, sp, tiw);
         fdivmod(sp, p.fdTilesH, sp, tih);
         fdivmod(sp, p.fdTilesD, tib, tid);
@@ -116,16 +122,18 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-            uint32_t mt, tiw, tih, tid, tib;
-            decode(tile, mt, tiw, tih, tid, tib);
+            uint32_t mt, tiw, tih, tid, tib, sk;
+            decode(tile, mt, tiw, tih, tid, tib, sk);
             const int ow0 = tiw * tw, oh0 = tih * th, od0 = tid * td, nb0 = tib * tn;
             const int m0 = mt * 128;
+            const int t0 = (int)sk * p.tapsPer, t1 = min(ntaps, t0 + p.tapsPer);
             int t = 0;
             for (int kd = 0; kd < p.tapD; ++kd) {
                 const int iz = od0 * p.istrD + p.offD + kd;
                 for (int kh = 0; kh < p.tapH; ++kh) {
                     const int iy = oh0 * p.istrH + p.offH + kh;
                     for (int kw = 0; kw < p.tapW; ++kw, ++t) {
+                        if (t < t0 || t >= t1) continue;
                         const int ix = ow0 * p.istrW + p.offW + kw;
                         int cbase = 0;
                         for (int s = 0; s < p.nsrc; ++s) {
@@ -153,12 +161,15 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
         const uint32_t lay = swizzle_layout_code(p.KW * 2);
         const uint32_t sbo = 8u * p.KW * 2u;
         const int kPerStep = p.KW / 16;
-        const int stepsPerTile = ntaps * (Ctot / p.KW);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            uint32_t mt_, tiw_, tih_, tid_, tib_, sk;
+            decode(tile, mt_, tiw_, tih_, tid_, tib_, sk);
+            const int t0 = (int)sk * p.tapsPer, t1 = min(ntaps, t0 + p.tapsPer);
+            const int stepsPerTile = (t1 - t0) * (Ctot / p.KW);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC5T_VOX);
@@ -189,8 +200,8 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
         uint32_t acc_phase = 0;
         const int spatial = tw * th * td;   // voxels of one sample inside a tile (a multiple of 32 or < 32)
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-            uint32_t mt, tiw, tih, tid, tib;
-            decode(tile, mt, tiw, tih, tid, tib);
+            uint32_t mt, tiw, tih, tid, tib, sk;
+            decode(tile, mt, tiw, tih, tid, tib, sk);
             const int co = (int)mt * 128 + quad * 32 + lane;
             const bool rowValid = co < p.Nout;
             const bool warpHasRows = (int)mt * 128 + quad * 32 < p.Nout;
@@ -209,7 +220,23 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                     tmem_ld_wait();
                     float s1 = 0.f, s2 = 0.f;
                     int nbStat = -1;
-                    if (p.lw >= 5) {
+                    if (p.splitK > 1) {
+                        // partial tile of one tap slice: fp32 adds into ws[m][Nout], m = linear output-grid voxel
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int r = cg + j;
+                            const int iw = r & (tw - 1);
+                            const int ih = (r >> p.lw) & (th - 1);
+                            const int id = (r >> (p.lw + p.lh)) & (td - 1);
+                            const int in = r >> (p.lw + p.lh + p.ld);
+                            const int ow = (int)tiw * tw + iw, oh = (int)tih * th + ih, od = (int)tid * td + id,
+                                      nb = (int)tib * tn + in;
+                            if (rowValid && ow < p.OW && oh < p.OH && od < p.OD && nb < p.NB) {
+                                const size_t m = (((size_t)nb * p.OD + od) * p.OH + oh) * p.OW + ow;
+                                atomicAdd(p.ws + m * p.Nout + co, __uint_as_float(v[j]));
+                            }
+                        }
+                    } else if (p.lw >= 5) {
                         // the 32 columns of this group are 32 consecutive voxels of one W row: one address
                         // computation per group, then a constant stride per column
                         const int r0 = cg;
