@@ -107,7 +107,8 @@ int rb_conv_gather_tc5_supported(const RbConvDesc* d);
  *   conv  wgrad: P = dy on the output grid (a = Cout), Q = x (b = Cin; two sources allowed)
  *   convT wgrad: P = x on the input grid (a = Cin), Q = dy gathered at 2i + p (b = Cout)
  * Replaces the weight half of aten::convolution_backward for the call sites listed above
- * (train.py:224 `scaler.scale(loss).backward()`).  dw must be zeroed by the caller.
+ * (train.py:224 `scaler.scale(loss).backward()`).  dw ([taps][PC][QC0+QC1] fp32) is fully initialised by the
+ * call ("+=" describes the internal split accumulation; the caller need not zero it).
  * ------------------------------------------------------------------------------------------ */
 typedef struct RbWgradDesc {
     int PC;

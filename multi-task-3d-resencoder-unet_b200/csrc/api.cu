@@ -716,9 +716,14 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     if (!P || !Q0 || !dw || (d.nq == 2 && !Q1)) return fail(RB_ERR_INVALID, "wgrad: null pointer");
     if (!aligned16(P) || !aligned16(Q0) || !aligned16(Q1)) return fail(RB_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
     if (d.NB <= 0 || d.GD <= 0 || d.GH <= 0 || d.GW <= 0 || d.QD <= 0 || d.QH <= 0 || d.QW <= 0) return fail(RB_ERR_INVALID, "wgrad: empty grid");
+    const size_t dw_bytes = (size_t)d.tapD * d.tapH * d.tapW * d.PC * (d.QC0 + (d.nq == 2 ? d.QC1 : 0)) * sizeof(float);
     if (d.impl != RB_IMPL_MMA_SYNC) {
         Tw5Plan pl = plan_tw5(d);
-        if (pl.ok) return launch_tw5(d, pl, P, Q0, Q1, dw, (cudaStream_t)stream);
+        if (pl.ok) {
+            // every element has exactly one writer when nothing is split: no zero-fill, plain stores
+            if (pl.swap || pl.splits > 1) RB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, (cudaStream_t)stream));
+            return launch_tw5(d, pl, P, Q0, Q1, dw, (cudaStream_t)stream);
+        }
         if (d.impl == RB_IMPL_TCGEN05) return fail(RB_ERR_UNSUPPORTED, "wgrad: shape does not qualify for the tcgen05 kernel");
     }
     rb::GWgradParams p;
@@ -746,6 +751,7 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     splits = (M + per - 1) / per;
     p.mPerSplit = (int)per;
     dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)splits);
+    RB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, (cudaStream_t)stream));
     rb::gather_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("gather_wgrad_mma_kernel");
 }
@@ -897,10 +903,8 @@ int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int T, void* st
     if (!dwp || !grad) return fail(RB_ERR_INVALID, "unpack_wgrad: null pointer");
     if (A <= 0 || B <= 0 || T <= 0 || T > 27) return fail(RB_ERR_INVALID, "unpack_wgrad: need 1 <= taps <= 27");
     rb::WUnpackParams p{dwp, grad, A, B, T};
-    const size_t smem = (size_t)32 * (32 * T + 1) * sizeof(float);
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(rb::unpack_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); });
-    dim3 grid((B + 31) / 32, (A + 31) / 32);
+    const size_t smem = (size_t)8 * (32 * T + 1) * sizeof(float);
+    dim3 grid((B + 31) / 32, (A + 7) / 8);
     rb::unpack_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("unpack_wgrad_kernel");
 }

@@ -681,17 +681,17 @@ struct WUnpackParams {
 };
 
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const WUnpackParams p) {
-    extern __shared__ float tileG[];  // [32 a][32 b][T] (+1)
-    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    extern __shared__ float tileG[];  // [8 a][32 b][T] (+1): small tiles, many resident blocks (latency bound otherwise)
+    const int a0 = blockIdx.y * 8, b0 = blockIdx.x * 32;
     const int T = p.T;
     const int pitch = 32 * T + 1;
-    for (int j = threadIdx.x >> 5; j < 32 * T; j += 8) {
-        const int t = j / 32, r = j - t * 32;
+    for (int j = threadIdx.x >> 5; j < 8 * T; j += 8) {
+        const int t = j / 8, r = j - t * 8;
         const int a = a0 + r, b = b0 + (threadIdx.x & 31);
         if (a < p.A && b < p.B) tileG[r * pitch + (threadIdx.x & 31) * T + t] = __ldg(p.dwp + ((size_t)t * p.A + a) * p.B + b);
     }
     __syncthreads();
-    for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+    for (int r = threadIdx.x >> 5; r < 8; r += 8) {
         const int a = a0 + r;
         if (a >= p.A) continue;
         const int nb = min(32, p.B - b0);

@@ -249,10 +249,22 @@ __global__ void __launch_bounds__(TW5_THREADS, 1) tc5_wgrad_kernel(const __grid_
                     tmem_ld_32x32b_x32(t_addr + cg, v);
                     tmem_ld_wait();
                     if (a < p.PC) {
+                        if (p.splits == 1 && bt * p.bn + cg + 32 <= QCtot) {
+                            // the only writer of these elements: plain 16-byte stores, no zero-fill needed
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int b = bt * p.bn + cg + j;
-                            if (b < QCtot) atomicAdd(drow + cg + j, __uint_as_float(v[j]));
+                            for (int q4 = 0; q4 < 8; ++q4)
+                                *reinterpret_cast<uint4*>(drow + cg + q4 * 4) =
+                                    make_uint4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+                        } else if (p.splits == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (bt * p.bn + cg + j < QCtot) drow[cg + j] = __uint_as_float(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int b = bt * p.bn + cg + j;
+                                if (b < QCtot) atomicAdd(drow + cg + j, __uint_as_float(v[j]));
+                            }
                         }
                     }
                 }

@@ -248,7 +248,7 @@ class SlidingWindowInferer:
 
     def __init__(self, model, targets: Dict[str, dict], patch_size, overlap: float = 0.5, batch_size: int = 1,
                  weight: str = "uniform", standardize: bool = True, in_channels: int = 1, rank: int = 0,
-                 world_size: int = 1, device=None):
+                 world_size: int = 1, device=None, use_cuda_graph: bool = True):
         self.model = model
         self.targets = targets
         self.patch = tuple(int(p) for p in patch_size)
@@ -259,6 +259,8 @@ class SlidingWindowInferer:
         self.in_channels = in_channels
         self.rank, self.world = int(rank), int(world_size)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
         if in_channels != 1:
             raise NotImplementedError("the reference's InferenceDataset yields single-channel patches "
                                       "(inference_dataset.py:73); multi-channel sweeps are not implemented")
@@ -273,6 +275,24 @@ class SlidingWindowInferer:
             z_lo = z_hi = 0
         return positions, z_lo, z_hi, (zs, ys, xs)
 
+    def _graphed_forward(self, batch: torch.Tensor):
+        """Capture model(batch) once for full batches (static shapes, ~350 launches per forward): replaying the
+        graph removes the host launch latency of the deep, tiny layers.  `batch` is the static input buffer."""
+        if self._graph is not None:
+            return self._graph
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                     # warm-up outside capture (weight packs, kernel attributes)
+                self.model(batch)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.model(batch)
+        self._graph = (g, out)
+        return self._graph
+
     @torch.no_grad()
     def sweep(self, volume):
         """Accumulate this rank's patches.  Returns the SlabBlender (un-finalised)."""
@@ -286,13 +306,30 @@ class SlidingWindowInferer:
         was_training = self.model.training
         self.model.eval()
         B = self.batch_size
+        static = torch.empty((B, 1, *self.patch), dtype=torch.float32, device=self.device)
         try:
+            graph = None
+            if self.use_cuda_graph and len(positions) >= 2 * B:
+                try:
+                    static.zero_()
+                    graph = self._graphed_forward(static)
+                except Exception as e:      # capture is an optimisation; eager launches are the contract
+                    import warnings
+                    warnings.warn(f"CUDA graph capture of the inference forward failed, running eagerly: {e!r}")
+                    self._graph, graph = None, None
+                    torch.cuda.synchronize(self.device)
             for i in range(0, len(positions), B):
                 chunk = positions[i:i + B]
-                batch = torch.empty((len(chunk), 1, *self.patch), dtype=torch.float32, device=self.device)
+                full = len(chunk) == B
+                batch = static if full else torch.empty((len(chunk), 1, *self.patch), dtype=torch.float32,
+                                                        device=self.device)
                 for j, pos in enumerate(chunk):
                     dvol.extract(pos, self.patch, batch[j, 0], self.standardize)
-                preds = self.model(batch)
+                if graph is not None and full:
+                    graph[0].replay()
+                    preds = graph[1]
+                else:
+                    preds = self.model(batch)
                 for j, pos in enumerate(chunk):
                     blender.add(preds, j, pos, apply_activation=True)
         finally:

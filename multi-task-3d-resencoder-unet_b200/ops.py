@@ -206,7 +206,7 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
     d.splits = 0
     d.impl = L.default_impl() if impl is None else L.impl_code(impl)
     ntaps = taps[0] * taps[1] * taps[2]
-    dw = torch.zeros((ntaps, d.PC, d.QC0 + d.QC1), dtype=torch.float32, device=P.device)
+    dw = torch.empty((ntaps, d.PC, d.QC0 + d.QC1), dtype=torch.float32, device=P.device)   # initialised by the library
     flops = 2.0 * d.NB * d.GD * d.GH * d.GW * d.PC * (d.QC0 + d.QC1) * ntaps
     with KERNEL_TIMER.span("wgrad", flops):
         rc = lib.rb_wgrad_gather(C.byref(d), P.data_ptr(), Q0.data_ptr(), L.ptr(Q1), dw.data_ptr(), L.stream_ptr())
