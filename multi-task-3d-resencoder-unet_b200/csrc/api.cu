@@ -14,6 +14,7 @@
 #include "conv_tc5t.cuh"
 #include "conv_generic.cuh"
 #include "wgrad_tc5.cuh"
+#include "wgrad2_tc5.cuh"
 #include "elementwise.cuh"
 #include "blend.cuh"
 
@@ -498,6 +499,73 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
     return pl;
 }
 
+// ---- two-sided tap stacking (wgrad2_tc5.cuh): stride-1 convs, channel counts multiples of 32 ----------------------
+struct Tw52Plan {
+    bool ok = false;
+    int pw = 0, qw = 0, mAtomsTotal = 0, nAtomsTotal = 0, mPerGroup = 0, nPerGroup = 0, mGroups = 0, nGroups = 0;
+    int kbox = 64, cw = 0, ch = 0, cd = 0, cn = 0, chunksW = 0, chunksH = 0, chunksD = 0, chunksN = 0;
+    int splits = 1, chunksPerSplit = 0, stages = 0;
+    size_t smem = 0;
+};
+
+Tw52Plan plan_tw52(const RbWgradDesc& d) {
+    Tw52Plan pl;
+    static const bool off = getenv("RESENC_NO_WGRAD2") != nullptr;
+    if (off) return pl;
+    if (d.istrD != 1 || d.istrH != 1 || d.istrW != 1) return pl;
+    if (d.GD != d.QD || d.GH != d.QH || d.GW != d.QW) return pl;
+    const int taps = d.tapD * d.tapH * d.tapW;
+    if (taps < 9 || d.tapW > 3) return pl;
+    const int qct = d.QC0 + (d.nq == 2 ? d.QC1 : 0);
+    if (d.PC % 32 != 0 || d.QC0 % 32 != 0 || (d.nq == 2 && d.QC1 % 32 != 0)) return pl;
+    pl.pw = d.PC % 64 == 0 ? 64 : 32;
+    pl.qw = d.QC0 % 64 == 0 ? 64 : 32;
+    if (d.nq == 2 && d.QC1 % 64 != 0) pl.qw = 32;
+    pl.mPerGroup = 128 / pl.qw;
+    pl.nPerGroup = 256 / pl.pw;
+    pl.mAtomsTotal = d.tapW * (qct / pl.qw);
+    pl.nAtomsTotal = d.tapD * d.tapH * (d.PC / pl.pw);
+    pl.mGroups = (pl.mAtomsTotal + pl.mPerGroup - 1) / pl.mPerGroup;
+    pl.nGroups = (pl.nAtomsTotal + pl.nPerGroup - 1) / pl.nPerGroup;
+    long long best = -1;
+    for (int cw = 1; cw <= pl.kbox; cw <<= 1)
+        for (int ch = 1; cw * ch <= pl.kbox; ch <<= 1)
+            for (int cd = 1; cw * ch * cd <= pl.kbox; cd <<= 1) {
+                const int cn = pl.kbox / (cw * ch * cd);
+                const long long t = (long long)((d.GW + cw - 1) / cw) * ((d.GH + ch - 1) / ch) * ((d.GD + cd - 1) / cd) *
+                                    ((d.NB + cn - 1) / cn);
+                if (best < 0 || t < best || (t == best && cw > pl.cw)) {
+                    best = t;
+                    pl.cw = cw; pl.ch = ch; pl.cd = cd; pl.cn = cn;
+                }
+            }
+    if (best < 0 || best > 2000000000LL) return pl;
+    pl.chunksW = (d.GW + pl.cw - 1) / pl.cw; pl.chunksH = (d.GH + pl.ch - 1) / pl.ch;
+    pl.chunksD = (d.GD + pl.cd - 1) / pl.cd; pl.chunksN = (d.NB + pl.cn - 1) / pl.cn;
+    const long long base_items = (long long)pl.mGroups * pl.nGroups;
+    long long splits = d.splits > 0 ? d.splits : (3LL * num_sms() + base_items - 1) / base_items;
+    long long maxs = (best + 7) / 8;      // at least 8 chunks (512 voxels) per item
+    if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+    pl.chunksPerSplit = (int)((best + splits - 1) / splits);
+    pl.splits = (int)((best + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
+    const size_t stageBytes = (size_t)pl.kbox * 2 * (128 + 256);
+    int st = (int)((200 * 1024) / stageBytes);
+    if (st > 8) st = 8;
+    if (st < 2) return pl;
+    pl.stages = st;
+    pl.smem = 1024 + 1024 + (size_t)st * stageBytes;
+    pl.ok = true;
+    return pl;
+}
+
+bool prefers_tw52(const RbWgradDesc& d, const Tw52Plan& pl) {
+    if (!pl.ok) return false;
+    // enough voxels to amortise the 288-column epilogue of every item
+    return (long long)d.NB * d.GD * d.GH * d.GW >= 4096;
+}
+
 CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
     return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
@@ -555,6 +623,51 @@ int launch_tw5(const RbWgradDesc& d, const Tw5Plan& pl, const void* P, const voi
     const long long grid = items < num_sms() ? items : num_sms();
     rb::tc5_wgrad_kernel<<<(int)grid, rb::TW5_THREADS, pl.smem, st>>>(p);
     return check_launch("tc5_wgrad_kernel");
+}
+
+int launch_tw52(const RbWgradDesc& d, const Tw52Plan& pl, const void* P, const void* Q0, const void* Q1, float* dw, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    rb::Tc5Wgrad2Params p;
+    memset(&p, 0, sizeof(p));
+    auto encode = [&](CUtensorMap* m, const void* ptr, int C, int W, int H, int D, int width) -> CUresult {
+        const cuuint64_t c = (cuuint64_t)C;
+        cuuint64_t dims[5] = {c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {c * 2, c * 2 * W, c * 2 * W * H, c * 2 * W * H * D};
+        cuuint32_t box[5] = {(cuuint32_t)width, (cuuint32_t)pl.cw, (cuuint32_t)pl.ch, (cuuint32_t)pl.cd, (cuuint32_t)pl.cn};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(width * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = encode(&p.mapP, P, d.PC, d.GW, d.GH, d.GD, pl.pw);
+    if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
+    r = encode(&p.mapQ[0], Q0, d.QC0, d.QW, d.QH, d.QD, pl.qw);
+    if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(Q0) failed: %d", (int)r);
+    if (d.nq == 2) {
+        r = encode(&p.mapQ[1], Q1, d.QC1, d.QW, d.QH, d.QD, pl.qw);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(Q1) failed: %d", (int)r);
+    }
+    p.PC = d.PC; p.QC[0] = d.QC0; p.QC[1] = d.nq == 2 ? d.QC1 : 0; p.nq = d.nq;
+    p.pw = pl.pw; p.qw = pl.qw; p.mAtomsTotal = pl.mAtomsTotal; p.nAtomsTotal = pl.nAtomsTotal;
+    p.mPerGroup = pl.mPerGroup; p.nPerGroup = pl.nPerGroup; p.mGroups = pl.mGroups; p.nGroups = pl.nGroups;
+    p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
+    p.kbox = pl.kbox; p.cw = pl.cw; p.ch = pl.ch; p.cd = pl.cd; p.cn = pl.cn;
+    p.chunksW = pl.chunksW; p.chunksH = pl.chunksH; p.chunksD = pl.chunksD; p.chunksN = pl.chunksN;
+    p.fdChunksW = rb::make_fastdiv(pl.chunksW); p.fdChunksH = rb::make_fastdiv(pl.chunksH); p.fdChunksD = rb::make_fastdiv(pl.chunksD);
+    p.fdMGroups = rb::make_fastdiv(pl.mGroups); p.fdNGroups = rb::make_fastdiv(pl.nGroups);
+    p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages;
+    p.dw = dw;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(rb::tc5_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tw52): %s", cudaGetErrorString(attr_err));
+    const long long items = (long long)pl.mGroups * pl.nGroups * pl.splits;
+    const long long grid = items < num_sms() ? items : num_sms();
+    rb::tc5_wgrad2_kernel<<<(int)grid, rb::TW52_THREADS, pl.smem, st>>>(p);
+    return check_launch("tc5_wgrad2_kernel");
 }
 
 }  // namespace
@@ -718,6 +831,11 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     if (d.NB <= 0 || d.GD <= 0 || d.GH <= 0 || d.GW <= 0 || d.QD <= 0 || d.QH <= 0 || d.QW <= 0) return fail(RB_ERR_INVALID, "wgrad: empty grid");
     const size_t dw_bytes = (size_t)d.tapD * d.tapH * d.tapW * d.PC * (d.QC0 + (d.nq == 2 ? d.QC1 : 0)) * sizeof(float);
     if (d.impl != RB_IMPL_MMA_SYNC) {
+        Tw52Plan pl2 = plan_tw52(d);
+        if (prefers_tw52(d, pl2)) {
+            RB_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, (cudaStream_t)stream));
+            return launch_tw52(d, pl2, P, Q0, Q1, dw, (cudaStream_t)stream);
+        }
         Tw5Plan pl = plan_tw5(d);
         if (pl.ok) {
             // every element has exactly one writer when nothing is split: no zero-fill, plain stores

@@ -159,6 +159,14 @@ WGRAD_CASES = [
     (2, 64, 32, (8, 12, 20), (1, 1, 1), (1, 1, 1), False),
     (1, 32, 64, (8, 16, 16), (1, 3, 3), (1, 2, 2), False),
     (1, 48, 96, (6, 10, 14), (3, 3, 3), (1, 1, 1), False),
+    # stride 1, channels % 32 == 0, >= 4096 voxels: two-sided tap stacking (wgrad2_tc5.cuh)
+    (1, 32, 32, (32, 32, 32), (3, 3, 3), (1, 1, 1), False),
+    (1, 32, 32, (16, 32, 32), (3, 3, 3), (1, 1, 1), True),
+    (1, 64, 128, (16, 16, 16), (3, 3, 3), (1, 1, 1), False),
+    (1, 128, 64, (12, 20, 24), (3, 3, 3), (1, 1, 1), False),
+    (2, 64, 64, (10, 18, 22), (3, 3, 3), (1, 1, 1), True),
+    (1, 32, 64, (8, 32, 32), (1, 3, 3), (1, 1, 1), False),
+    (1, 96, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1), False),
 ]
 
 
