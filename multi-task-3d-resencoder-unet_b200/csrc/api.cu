@@ -74,6 +74,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn encode_tiled_fn() {
+    // cuTensorMapEncodeTiled is a driver call: the calling thread (e.g. an autograd worker that has not touched the
+    // runtime yet) must have the primary context bound, which any runtime call does
+    thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
