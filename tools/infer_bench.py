@@ -67,7 +67,16 @@ def main():
             model(x)
     torch.cuda.synchronize()
     if world > 1:
+        # establish the point-to-point connections the slab exchange uses (one-time NCCL setup, not part of a sweep)
+        pairs, _ = inf.plan_slab_exchange(zs, P, V, world)
+        one = torch.zeros(1, device=dev)
+        for src, dst, _, _ in pairs:
+            if rank == src:
+                dist.send(one, dst)
+            elif rank == dst:
+                dist.recv(one, src)
         dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
