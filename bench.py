@@ -66,16 +66,19 @@ def losses(out, tgt, O):
 # ------------------------------------------------------------------------------------------
 # CPU arms (the oracle port of the reference's PyTorch path, timed on the host cores)
 # ------------------------------------------------------------------------------------------
-def cpu_step_rate(patch, batch, steps, warmup):
-    """voxels/s of fwd + loss + bwd + AdamW with the oracle's functional network on the CPU."""
+def cpu_step_rate(patch, batch, steps, warmup, topology_patch=None):
+    """voxels/s of fwd + loss + bwd + AdamW with the oracle's functional network on the CPU.  `topology_patch`
+    selects the network (the 128^3 autoconfiguration: 6 stages, 235.5 M parameters) independently of the size of
+    the sample that is pushed through it."""
+    topology_patch = topology_patch or patch
     from oracle import resenc_oracle as O
     import resenc_b200 as rb
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
-        shell = rb.NetworkFromConfig(make_mgr(patch, batch))        # parameter container only (CPU)
+        shell = rb.NetworkFromConfig(make_mgr(topology_patch, batch))        # parameter container only (CPU)
     params = {n: p.detach().clone().requires_grad_(True) for n, p in shell.named_parameters()}
-    topo = O.autoconfig([patch] * 3)
+    topo = O.autoconfig([topology_patch] * 3)
     opt = torch.optim.AdamW(list(params.values()), lr=1e-3, weight_decay=1e-4)
     x, tgt = synthetic_batch(batch, patch, "cpu", 0)
     times = []
@@ -98,9 +101,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     p = args.cpu_sample_patch
-    rate, sec = cpu_step_rate(p, 1, args.steps, args.warmup)
+    rate, sec = cpu_step_rate(p, 1, args.steps, args.warmup, topology_patch=args.patch)
     cores = os.cpu_count()
-    sample = f"{p}^3 x1 sub-batch of the {args.patch}^3 x{args.batch} step per timed step (same topology family, fp32 eager)"
+    sample = (f"{p}^3 x1 crop per timed step through the same {args.patch}^3-autoconfigured network "
+              f"(6 stages, 235.5 M parameters), fwd+loss+bwd+clip+AdamW, fp32 eager, all host threads")
     line = {
         "impl": "reference", "metric": "train voxels/s", "value": rate, "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -359,10 +363,11 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             p = args.cpu_sample_patch
-            rate, sec = cpu_step_rate(p, 1, 3, 1)
+            rate, sec = cpu_step_rate(p, 1, 3, 1, topology_patch=P)
             line["cpu_baseline"] = {"value": rate, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{p}^3 x1 train step (fwd+loss+bwd+AdamW), oracle port of the reference, "
-                                              f"fp32 eager, 1 warm-up + 3 timed, {sec:.2f} s/step"}
+                                    "sample": f"{p}^3 x1 crop through the same {P}^3-autoconfigured network (fwd+loss+bwd+"
+                                              f"clip+AdamW), oracle port of the reference, fp32 eager, 1 warm-up + 3 "
+                                              f"timed, {sec:.2f} s/step"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
