@@ -36,8 +36,10 @@ enum RbConvImpl {
     RB_IMPL_AUTO = 0,     /* tcgen05 when the shape qualifies, else mma.sync */
     RB_IMPL_MMA_SYNC = 1, /* shape-generic warp-level tensor path (cross-check + odd shapes) */
     RB_IMPL_TCGEN05 = 2,  /* TMA + tcgen05.mma + TMEM; RB_ERR_UNSUPPORTED if the shape does not qualify */
-    RB_IMPL_TCGEN05_SPLITK = 3 /* only returned by rb_conv_gather_plan: tcgen05 with taps split over the chip
-                                  (needs the workspace, produces no fused statistics) */
+    RB_IMPL_TCGEN05_SPLITK = 3, /* only returned by rb_conv_gather_plan: tcgen05 with taps split over the chip
+                                   (needs the workspace, produces no fused statistics) */
+    RB_IMPL_TCGEN05_SLAB = 4    /* only returned by rb_conv_gather_plan: the z-marching tcgen05 kernel for 3x3x3
+                                   stride-1 convolutions between 32-channel tensors (fused statistics available) */
 };
 
 const char* rb_last_error(void);
@@ -96,8 +98,8 @@ int rb_conv_gather(const RbConvDesc* d, const void* src0, const void* src1, cons
                    void* out0, void* out1, float* stat_sum, float* stat_sq,
                    void* workspace, size_t workspace_bytes, void* stream);
 /* Which implementation rb_conv_gather will run for this descriptor: RB_IMPL_MMA_SYNC, RB_IMPL_TCGEN05 or
- * RB_IMPL_TCGEN05_SPLITK (negative status if a forced implementation cannot run it).  Fused statistics are
- * produced only for RB_IMPL_TCGEN05. */
+ * RB_IMPL_TCGEN05_SPLITK / RB_IMPL_TCGEN05_SLAB (negative status if a forced implementation cannot run it).
+ * Fused statistics are produced only for RB_IMPL_TCGEN05 and RB_IMPL_TCGEN05_SLAB. */
 int rb_conv_gather_plan(const RbConvDesc* d);
 /* 1 if the tcgen05 kernel can run this descriptor. */
 int rb_conv_gather_tc5_supported(const RbConvDesc* d);

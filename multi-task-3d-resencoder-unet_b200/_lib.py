@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libresenc_b200.so")
 
-IMPL_AUTO, IMPL_MMA_SYNC, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_MMA_SYNC, IMPL_TCGEN05, IMPL_TCGEN05_SPLITK, IMPL_TCGEN05_SLAB = 0, 1, 2, 3, 4
 _IMPL_NAMES = {"auto": IMPL_AUTO, "mma": IMPL_MMA_SYNC, "mma_sync": IMPL_MMA_SYNC, "tc5": IMPL_TCGEN05,
                "tcgen05": IMPL_TCGEN05}
 

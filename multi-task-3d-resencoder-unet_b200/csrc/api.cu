@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "conv_tc5.cuh"
 #include "conv_tc5t.cuh"
+#include "conv_slab.cuh"
 #include "conv_generic.cuh"
 #include "wgrad_tc5.cuh"
 #include "wgrad2_tc5.cuh"
@@ -237,6 +238,8 @@ bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
     // inputs (64-byte rows, TMA row-rate bound) and few-tap data-gradient classes stay on the voxels-on-M kernel.
     const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
     const int ntaps = d.tapD * d.tapH * d.tapW;
+    static const bool force = getenv("RESENC_FORCE_TC5T") != nullptr;   // experiments
+    if (force) return true;
     return ntaps * ctot >= 864 && ctot >= 64;
 }
 
@@ -287,6 +290,10 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
     p.splitK = pl.splitK; p.tapsPer = pl.tapsPer; p.fdSplitK = rb::make_fastdiv(pl.splitK); p.ws = ws;
+    {
+        static const int dbg = getenv("RESENC_TC5_DEBUG") ? atoi(getenv("RESENC_TC5_DEBUG")) : 0;
+        p.debug = dbg & 7;
+    }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -297,6 +304,116 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     long long grid = items < num_sms() ? items : num_sms();
     rb::tc5t_gather_conv_kernel<<<(int)grid, rb::TC5T_THREADS, pl.smem, st>>>(p);
     return check_launch("tc5t_gather_conv_kernel");
+}
+
+// ---- slab kernel (conv_slab.cuh): 3x3x3 stride-1 pad-1 convolutions between 32-channel tensors at W in {32,64,128} ----
+struct SlabPlan {
+    bool ok = false;
+    int R = 0, lw = 0, DC = 0, hTiles = 0, dChunks = 0;
+    long long items = 0;
+    size_t smem = 0;
+};
+
+SlabPlan plan_slab(const RbConvDesc& d) {
+    SlabPlan pl;
+    static const bool off = getenv("RESENC_NO_SLAB") != nullptr;
+    if (off || d.mode != 0) return pl;
+    if (d.tapD != 3 || d.tapH != 3 || d.tapW != 3 || d.offD != -1 || d.offH != -1 || d.offW != -1) return pl;
+    if (d.istrD != 1 || d.istrH != 1 || d.istrW != 1 || d.ostrD != 1 || d.ostrH != 1 || d.ostrW != 1) return pl;
+    if (d.ooffD != 0 || d.ooffH != 0 || d.ooffW != 0) return pl;
+    if (d.OD != d.ID || d.OH != d.IH || d.OW != d.IW || d.FD != d.OD || d.FH != d.OH || d.FW != d.OW) return pl;
+    if (d.srcC0 != 32 || (d.nsrc == 2 && d.srcC1 != 32)) return pl;
+    if (!((d.Nout == 32 && d.outC0 == 32 && d.outC1 == 0) || (d.Nout == 64 && d.outC0 == 32 && d.outC1 == 32))) return pl;
+    if (d.nsrc == 2 && !d.outF32) return pl;   // the second source accumulates into an fp32 destination
+    if (d.IW != 32 && d.IW != 64 && d.IW != 128) return pl;
+    pl.R = 256 / d.IW;
+    if (d.IH % pl.R != 0) return pl;
+    pl.lw = d.IW == 32 ? 5 : d.IW == 64 ? 6 : 7;
+    pl.hTiles = d.IH / pl.R;
+    // output planes per work item: whole waves of CTAs first, then fewer halo re-loads
+    double bestScore = -1.0;
+    for (int dc = 4; dc <= 32; dc <<= 1) {
+        const int chunks = (d.OD + dc - 1) / dc;
+        const long long items = (long long)d.NB * pl.hTiles * chunks;
+        const long long waves = (items + num_sms() - 1) / num_sms();
+        const double eff = (double)items / (double)(waves * num_sms()) * ((double)dc / (dc + 0.5));
+        if (eff > bestScore) { bestScore = eff; pl.DC = dc; pl.dChunks = chunks; pl.items = items; }
+    }
+    if ((long long)d.NB * pl.hTiles * d.OD < 2LL * num_sms()) return pl;   // too little work for a z-marching CTA per SM
+    const size_t slot = (size_t)(pl.R + 2) * d.IW * 64;
+    pl.smem = 1024 + 1024 + rb::SLAB_WBYTES + 4 * slot + rb::SLAB_OBYTES;
+    if (pl.smem > 227 * 1024) return pl;
+    pl.ok = true;
+    return pl;
+}
+
+int launch_slab_one(const RbConvDesc& d, const SlabPlan& pl, const void* src, int c0, int m0, const void* w, void* out, int accumulate,
+                    float* stat_sum, float* stat_sq, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    rb::SlabConvParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        cuuint64_t dims[5] = {32, (cuuint64_t)d.IW, (cuuint64_t)d.IH, (cuuint64_t)d.ID, (cuuint64_t)d.NB};
+        cuuint64_t strides[4] = {64, (cuuint64_t)64 * d.IW, (cuuint64_t)64 * d.IW * d.IH, (cuuint64_t)64 * d.IW * d.IH * d.ID};
+        cuuint32_t box[5] = {32, (cuuint32_t)d.IW, (cuuint32_t)(pl.R + 2), 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(src), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(slab X) failed: %d", (int)r);
+    }
+    {
+        const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
+        cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, 27};
+        cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
+        cuuint32_t box[3] = {32, 32, 27};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RB_ERR_CUDA, "cuTensorMapEncodeTiled(slab W) failed: %d", (int)r);
+    }
+    p.c0 = c0; p.m0 = m0;
+    p.W = d.IW; p.H = d.IH; p.D = d.ID; p.NB = d.NB; p.lw = pl.lw; p.R = pl.R; p.DC = pl.DC;
+    p.hTiles = pl.hTiles; p.dChunks = pl.dChunks;
+    p.fdH = rb::make_fastdiv(pl.hTiles); p.fdDC = rb::make_fastdiv(pl.dChunks);
+    p.out = out;
+    p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.statPitch = d.Nout; p.statC0 = m0;
+    {
+        static const int dbg = getenv("RESENC_SLAB_DEBUG") ? atoi(getenv("RESENC_SLAB_DEBUG")) : 0;
+        p.debug = dbg;
+    }
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(slab): %s", cudaGetErrorString(attr_err));
+    const long long grid = pl.items < num_sms() ? pl.items : num_sms();
+    if (!d.outF32) rb::slab_conv_kernel<0><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
+    else if (!accumulate) rb::slab_conv_kernel<1><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
+    else rb::slab_conv_kernel<2><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
+    return check_launch("slab_conv_kernel");
+}
+
+// one launch per (destination half, source): the second source of a virtual concat adds into the fp32 destination
+int launch_slab(const RbConvDesc& d, const SlabPlan& pl, const void* src0, const void* src1, const void* w, void* out0, void* out1,
+                float* stat_sum, float* stat_sq, cudaStream_t st) {
+    const void* srcs[2] = {src0, src1};
+    void* outs[2] = {out0, out1};
+    for (int o = 0; o < d.Nout / 32; ++o)
+        for (int s = 0; s < d.nsrc; ++s) {
+            const bool last = s == d.nsrc - 1;
+            int rc = launch_slab_one(d, pl, srcs[s], s * 32, o * 32, w, outs[o], s > 0 ? 1 : 0, last ? stat_sum : nullptr,
+                                     last ? stat_sq : nullptr, st);
+            if (rc) return rc;
+        }
+    return RB_OK;
 }
 
 int validate_conv(const RbConvDesc& d) {
@@ -709,17 +826,20 @@ int rb_conv_gather_tc5_supported(const RbConvDesc* d) {
     return plan_tc5(*d).ok ? 1 : 0;
 }
 
-enum ConvChoice { CH_UNSUPPORTED = 0, CH_MMA = 1, CH_TC5 = 2, CH_TC5T = 3, CH_TC5T_SPLIT = 4 };
+enum ConvChoice { CH_UNSUPPORTED = 0, CH_MMA = 1, CH_TC5 = 2, CH_TC5T = 3, CH_TC5T_SPLIT = 4, CH_SLAB = 5 };
 struct ConvDecision {
     int choice = CH_MMA;
     Tc5Plan pl;
     Tc5tPlan plt;
+    SlabPlan pls;
 };
 
 // One place decides which kernel runs a descriptor (used by the plan / workspace queries and by the launch).
 ConvDecision decide_conv(const RbConvDesc& d, bool stats_requested) {
     ConvDecision r;
     if (d.impl == RB_IMPL_MMA_SYNC) return r;
+    r.pls = plan_slab(d);
+    if (r.pls.ok) { r.choice = CH_SLAB; return r; }
     r.pl = plan_tc5(d);
     r.plt = plan_tc5t(d);
     static const bool no_t = getenv("RESENC_NO_TC5T") != nullptr;
@@ -740,6 +860,7 @@ int rb_conv_gather_plan(const RbConvDesc* d) {
     switch (r.choice) {
         case CH_MMA: return RB_IMPL_MMA_SYNC;
         case CH_TC5: case CH_TC5T: return RB_IMPL_TCGEN05;
+        case CH_SLAB: return RB_IMPL_TCGEN05_SLAB;
         case CH_TC5T_SPLIT: return RB_IMPL_TCGEN05_SPLITK;
         default: return RB_ERR_UNSUPPORTED;
     }
@@ -789,6 +910,7 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     ConvDecision dec = decide_conv(d, stat_sum != nullptr);
     if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need)) dec = decide_conv(d, true);  // no room: unsplit
     if (dec.choice == CH_UNSUPPORTED) return fail(RB_ERR_UNSUPPORTED, "conv: shape does not qualify for the tcgen05 kernel");
+    if (dec.choice == CH_SLAB) return launch_slab(d, dec.pls, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
     if (dec.choice == CH_TC5) return launch_tc5(d, dec.pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
     if (dec.choice == CH_TC5T) {
         Tc5tPlan plt = dec.plt;

@@ -159,6 +159,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         : "memory");
 }
 
+// 32 lanes x 1 fp32 column.
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t (&v)[1]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr) : "memory");
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1").  Addresses/offsets are in bytes and
 // must be multiples of 16.  layout: 0 none, 2 = 128B swizzle, 4 = 64B, 6 = 32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,

@@ -45,6 +45,7 @@ struct Tc5tConvParams {
     int splitK, tapsPer;
     FastDiv fdSplitK;
     float* ws;
+    int debug;   // profiling experiments only (RESENC_TC5_DEBUG): 1 skip MMAs, 2 skip TMA loads, 4 skip the epilogue body
 };
 
 static constexpr int TC5T_THREADS = 192;
@@ -142,9 +143,13 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                                 if (elect_one()) {
                                     const uint32_t dstX = tile_base + stage * stageBytes;
                                     const uint32_t dstW = dstX + bytesX;
-                                    mbar_expect_tx(full_bar(stage), stageBytes);
-                                    tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, ix, iy, iz, nb0);
-                                    tma_load_3d(dstW, &p.mapW, full_bar(stage), cbase + c, m0, t);
+                                    if (p.debug == 2) {
+                                        mbar_arrive(full_bar(stage));
+                                    } else {
+                                        mbar_expect_tx(full_bar(stage), stageBytes);
+                                        tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, ix, iy, iz, nb0);
+                                        tma_load_3d(dstW, &p.mapW, full_bar(stage), cbase + c, m0, t);
+                                    }
                                 }
                                 __syncwarp();
                                 if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                 if (elect_one()) {
                     const uint32_t xAddr = tile_base + stage * stageBytes;
                     const uint32_t wAddr = xAddr + bytesX;
-                    for (int k = 0; k < kPerStep; ++k) {
+                    for (int k = 0; k < kPerStep && p.debug != 1; ++k) {
                         const uint64_t da = make_smem_desc(wAddr + k * 32u, 16u, sbo, lay);
                         const uint64_t db = make_smem_desc(xAddr + k * 32u, 16u, sbo, lay);
                         umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
             const bool warpHasRows = (int)mt * 128 + quad * 32 < p.Nout;
             mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
             tc_fence_after();
-            if (warpHasRows) {
+            if (warpHasRows && p.debug != 4) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC5T_VOX);
                 // destination of this lane's channel
                 const bool first = co < p.outC0;

@@ -176,7 +176,7 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
         plan = lib.rb_conv_gather_plan(C.byref(d))
         if plan < 0:
             L.check(plan, "rb_conv_gather_plan")
-        if plan == L.IMPL_TCGEN05:
+        if plan in (L.IMPL_TCGEN05, L.IMPL_TCGEN05_SLAB):
             st = torch.zeros((2, d.NB, nout), dtype=torch.float32, device=src0.device)
             stats = (st[0], st[1])
     ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))

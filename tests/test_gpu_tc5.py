@@ -136,6 +136,62 @@ def test_tc5_fused_statistics(rb):
         assert rel_l2(st[1], (y32.double() ** 2).sum((2, 3, 4))) < 2e-5
 
 
+SLAB_CASES = [(1, (64, 64, 64)), (1, (24, 32, 128)), (2, (40, 32, 32)), (2, (10, 64, 64))]
+
+
+@pytest.mark.parametrize("n,dims", SLAB_CASES, ids=lambda v: str(v).replace(" ", ""))
+def test_slab_conv(rb, n, dims):
+    """conv_slab.cuh (z-marching CTAs, kw taps stacked on M and shifted in the epilogue) against the shape-generic
+    mma.sync kernel and PyTorch: bf16 and fp32 destinations, fused statistics, the two-source accumulate pass
+    (virtual concat) and the two-destination data gradient.  Ragged z chunks included (D = 40, 10, 24)."""
+    ops, L = rb.ops, rb._lib
+    torch.manual_seed(11)
+    a = q(torch.randn(n, 32, *dims, device="cuda"))
+    b = q(torch.randn(n, 32, *dims, device="cuda"))
+    w1 = torch.randn(32, 32, 3, 3, 3, device="cuda") / (27 * 32) ** 0.5
+    w2 = torch.randn(32, 64, 3, 3, 3, device="cuda") / (27 * 64) ** 0.5
+    kw = dict(in_dims=dims, taps=(3, 3, 3), off=(-1, -1, -1), istr=(1, 1, 1), out_grid=dims)
+    acl, bcl = ops.as_cl(a), ops.as_cl(b)
+
+    # the library really picks the slab kernel for these shapes
+    y16 = ops.new_cl(n, 32, *dims, "cuda")
+    d = ops._make_desc(acl, None, y16, None, nout=32, mode=0, ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0,
+                       impl=None, **kw)
+    assert L.load().rb_conv_gather_plan(ctypes.byref(d)) == L.IMPL_TCGEN05_SLAB
+
+    # one source, bf16 destination
+    ref1 = F.conv3d(a, q(w1), None, 1, 1)
+    ops._launch_gather(acl, None, ops.pack_conv_fprop(w1), y16, None, nout=32, **kw)
+    ym = ops.new_cl(n, 32, *dims, "cuda")
+    ops._launch_gather(acl, None, ops.pack_conv_fprop(w1), ym, None, nout=32, impl="mma", **kw)
+    assert rel_l2(y16.float(), ref1) < TOL and rel_l2(y16.float(), ym.float()) < 3e-3
+
+    # one source, fp32 destination + statistics
+    y32 = ops.new_cl_f32(n, 32, *dims, "cuda")
+    st = ops._launch_gather(acl, None, ops.pack_conv_fprop(w1), y32, None, nout=32, want_stats=True, **kw)
+    assert st is not None
+    assert rel_l2(y32, ref1) < 1e-4
+    assert rel_l2(st[0], y32.double().sum((2, 3, 4))) < 2e-5
+    assert rel_l2(st[1], (y32.double() ** 2).sum((2, 3, 4))) < 2e-5
+
+    # two sources (virtual concat): second launch accumulates into the fp32 destination, statistics of the sum
+    ref2 = F.conv3d(torch.cat((a, b), 1), q(w2), None, 1, 1)
+    z32 = ops.new_cl_f32(n, 32, *dims, "cuda")
+    st2 = ops._launch_gather(acl, bcl, ops.pack_conv_fprop(w2), z32, None, nout=32, want_stats=True, **kw)
+    assert st2 is not None
+    assert rel_l2(z32, ref2) < 1e-4
+    assert rel_l2(st2[0], z32.double().sum((2, 3, 4))) < 2e-5
+    assert rel_l2(st2[1], (z32.double() ** 2).sum((2, 3, 4))) < 2e-5
+
+    # data gradient of the two-source conv: one 32-channel source, two 32-channel destinations
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    g = q(torch.randn_like(ref2))
+    F.conv3d(torch.cat((ar, br), 1), q(w2), None, 1, 1).backward(g)
+    ap, bp = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ops.conv3d(ap, w2, 1, x_cat=bp).backward(g.to(torch.bfloat16))
+    assert rel_l2(ap.grad.float(), ar.grad) < TOL and rel_l2(bp.grad.float(), br.grad) < TOL
+
+
 def test_tc5_support_query(rb, built_lib):
     d = rb._lib.ConvDesc()
     for f, v in dict(nsrc=1, srcC0=8, NB=1, ID=4, IH=4, IW=4, tapD=3, tapH=3, tapW=3, offD=-1, offH=-1, offW=-1, istrD=1,
