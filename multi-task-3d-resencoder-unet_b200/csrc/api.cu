@@ -1129,6 +1129,10 @@ int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int
     if (!x || !col) return fail(RB_ERR_INVALID, "stem_im2col: null pointer");
     if (Kp % 8 != 0 || Kp < kd * kh * kw * Cin) return fail(RB_ERR_INVALID, "stem_im2col: Kp must be a multiple of 8 covering taps*Cin");
     rb::Im2colParams p{x, (rb::bf16*)col, NB, Cin, D, H, W, kd, kh, kw, Kp};
+    if (Cin == 1 && kd == 3 && kh == 3 && kw == 3 && Kp == 32) {
+        rb::stem_im2col_fixed_kernel<3, 3, 3, 1, 32><<<grid_for((long long)NB * D * H * W, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("stem_im2col_fixed_kernel");
+    }
     const long long total = (long long)NB * D * H * W * (Kp / 8);
     rb::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("stem_im2col_kernel");

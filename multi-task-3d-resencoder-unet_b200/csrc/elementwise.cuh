@@ -423,9 +423,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdParams p) {
     // multiple of cg, so round the stride
     const long long stride = ((long long)gridDim.x * blockDim.x / cg) * cg;
     const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % cg);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long v = i / cg;
-        const long long nb = v / p.S, s = v % p.S;
+    // (sample, voxel) of this thread's element: divided once, then advanced by the loop stride (64-bit divisions in the
+    // loop body used to dominate this kernel)
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long vstep = stride / cg;
+    long long nb = (i0 / cg) / p.S, s = (i0 / cg) % p.S;
+    for (long long i = i0; i < total; i += stride, s += vstep) {
+        while (s >= p.S) { s -= p.S; ++nb; }
         float f[8], o[8];
         unpack8(ld_stream(reinterpret_cast<const uint4*>(p.x) + i), f);
 #pragma unroll
@@ -498,6 +502,53 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const Im2colParams p) 
             f[j] = val;
         }
         reinterpret_cast<uint4*>(p.col)[i] = pack8(f);
+    }
+}
+
+// Fixed-shape fast path (the reference stem: 3x3x3 taps on a 1-channel volume): one thread per voxel, all taps unrolled,
+// the thread writes its whole Kp-wide row (coalesced 16-byte stores); the shape-generic kernel above spends its time in
+// run-time divisions.
+template <int KD, int KH, int KW, int CIN, int KP>
+__global__ void __launch_bounds__(256) stem_im2col_fixed_kernel(const Im2colParams p) {
+    const long long S = (long long)p.D * p.H * p.W;
+    const long long total = (long long)p.NB * S;
+    const size_t HW = (size_t)p.H * p.W;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+        long long r = v;
+        const int w = (int)(r % p.W); r /= p.W;
+        const int h = (int)(r % p.H); r /= p.H;
+        const int d = (int)(r % p.D); r /= p.D;
+        const int nb = (int)r;
+        float f[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) f[k] = 0.f;
+#pragma unroll
+        for (int td = 0; td < KD; ++td) {
+            const int z = d + td - (KD - 1) / 2;
+#pragma unroll
+            for (int th = 0; th < KH; ++th) {
+                const int y = h + th - (KH - 1) / 2;
+                const bool rowOk = z >= 0 && z < p.D && y >= 0 && y < p.H;
+#pragma unroll
+                for (int tw = 0; tw < KW; ++tw) {
+                    const int x = w + tw - (KW - 1) / 2;
+                    if (rowOk && x >= 0 && x < p.W) {
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci)
+                            f[((td * KH + th) * KW + tw) * CIN + ci] =
+                                __ldg(p.x + (((size_t)nb * CIN + ci) * p.D + z) * HW + (size_t)y * p.W + x);
+                    }
+                }
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.col) + v * (KP / 8);
+#pragma unroll
+        for (int g = 0; g < KP / 8; ++g) {
+            float q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = f[g * 8 + j];
+            dst[g] = pack8(q);
+        }
     }
 }
 
