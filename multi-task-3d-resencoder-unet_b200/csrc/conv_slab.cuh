@@ -60,9 +60,17 @@ static constexpr int SLAB_SGROUP = 2 * 2 * SLAB_SBUF;         // per column grou
 // as [channel = lane][voxel] rows with 16-byte stores into side buffer Q/2 of staging set (cnt & 1).
 template <int Q>
 __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, int lane, int Wm, uint32_t sfull0,
-                                            uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait) {
+                                            uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait, const float* yrow) {
     uint32_t v0[32], v1[32], ex[1];
     ex[0] = 0u;
+    // accumulate mode (second source of a virtual concat): this side warp also adds the existing fp32 output of half of
+    // its 64 voxels (Q = 0: the first 32, Q = 2: the last 32) - the loads overlap the TMEM loads, and the side warps
+    // have the slack the centre warp lacks
+    float y[32];
+    if (yrow != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __ldcs(yrow + (size_t)((Q == 0 ? 0 : 32) + i) * 32);
+    }
     tmem_ld_32x32b_x32(t_addr + a, v0);
     tmem_ld_32x32b_x32(t_addr + a + 32, v1);
     if (Q == 0 && a > 0) tmem_ld_32x32b_x1(t_addr + a - 1, ex);
@@ -89,6 +97,7 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
                     // only the first / last voxel of a W row can be padding, and rows start at multiples of 32
                     if (Q == 0 && ii == 0 && ((a + i) & Wm) == 0) f[k] = 0.f;
                     if (Q == 2 && ii == 31 && ((a + i) & Wm) == Wm) f[k] = 0.f;
+                    if (yrow != nullptr && half == (Q == 0 ? 0 : 1)) f[k] += y[ii];
                 }
                 *reinterpret_cast<float4*>(dst + vec * 4) = make_float4(f[0], f[1], f[2], f[3]);
             }
@@ -278,13 +287,16 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                 if (dbgT) { tWT += clock64() - w0; ++nT; }
                 tc_fence_after();
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+                const size_t voxT = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;   // voxel of tile column 0
                 if (p.debug & 4) {
                 } else if (q == 0) {
                     for (int a = g * 128; a < g * 128 + 128; a += 64)
-                        slab_side64<0>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr);
+                        slab_side64<0>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                                       MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
                 } else if (q == 2) {
                     for (int a = g * 128; a < g * 128 + 128; a += 64)
-                        slab_side64<2>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr);
+                        slab_side64<2>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                                       MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
                 } else {
                     const size_t vox0 = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;
                     for (int a = g * 128; a < g * 128 + 128; a += 64) {
@@ -320,13 +332,6 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                                     for (int ii = 0; ii < 32; ++ii) gp[ii * 32] = __float2bfloat16_rn(x[ii]);
                                 } else {
                                     float* gp = reinterpret_cast<float*>(p.out) + e0;
-                                    if (MODE == 2) {
-                                        float y[32];
-#pragma unroll
-                                        for (int ii = 0; ii < 32; ++ii) y[ii] = gp[ii * 32];
-#pragma unroll
-                                        for (int ii = 0; ii < 32; ++ii) x[ii] += y[ii];
-                                    }
 #pragma unroll
                                     for (int ii = 0; ii < 32; ++ii) gp[ii * 32] = x[ii];
                                 }

@@ -35,3 +35,16 @@ tot = sum(r[1] for r in rows)
 print(f"total device time per step: {tot:.2f} ms")
 for k, ms, n in rows[:40]:
     print(f"{ms:8.3f} ms {100*ms/tot:5.1f}% {n:5d}  {k[:110]}")
+
+# per-launch durations of the conv kernels in launch order (second profiled step), to spot the slow geometry classes
+if os.environ.get("STEP_PROFILE_LAUNCHES"):
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and
+           any(k in e.name for k in ("gather_conv", "slab_conv", "wgrad"))]
+    evs.sort(key=lambda e: e.time_range.start)
+    half = evs[len(evs) // 2:]
+    out = []
+    for e in half:
+        short = "tc5t" if "tc5t" in e.name else "slab" if "slab" in e.name else "wgrad2" if "wgrad2" in e.name else \
+            "wgrad" if "wgrad" in e.name else "tc5" if "tc5_gather" in e.name else "mma"
+        out.append(f"{short}:{e.device_time:.0f}")
+    print("launch order (us):", " ".join(out))
