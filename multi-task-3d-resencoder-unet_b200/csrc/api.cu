@@ -367,7 +367,7 @@ int launch_slab_one(const RbConvDesc& d, const SlabPlan& pl, const void* src, in
         const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
         cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, 27};
         cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
-        cuuint32_t box[3] = {32, 32, 27};
+        cuuint32_t box[3] = {32, 32, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&p.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

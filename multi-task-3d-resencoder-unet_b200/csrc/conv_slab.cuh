@@ -12,10 +12,9 @@
 //     plus all 27 x 32 x 32 weights (55 KB, loaded once);
 //   * B operand of an MMA = 256 consecutive voxels (R full rows) of plane d+kd-1 starting at row kh: a plain
 //     K-major SW64 tile whose start is a multiple of W*64 bytes - no halo columns, no sub-row shifts;
-//   * A operand = the weights of the three kw taps of (kd, kh) stacked on M: row kw*32 + co (that is simply the
-//     [tap][co][ci] weight pack viewed as [9][96][32]; rows 96..127 of the M = 128 instruction read whatever
-//     follows in shared memory and only pollute TMEM lanes nobody reads).  So 18 MMAs (9 (kd,kh) x 2 K steps) of
-//     M=128 x N=256 cover all 27 taps: TMEM lanes [32kw, 32kw+32) hold
+//   * A operand = the weights of the three kw taps of (kd, kh) stacked on M: row kw*32 + co, and the centre tap
+//     (kw = 1) once more in rows 96..127.  So 18 MMAs (9 (kd,kh) x 2 K steps) of M=128 x N=256 cover all 27
+//     taps: TMEM lanes [32kw, 32kw+32) (and lanes 96..127 again for kw = 1) hold
 //         P_kw[co][v] = sum_{kd,kh,ci} W[kd,kh,kw][co][ci] * X[d+kd-1][h+kh-1][w(v)][ci]
 //   * the kw shift is applied where it is free, in the epilogue: out[co][(h,w)] = P_0[(h,w-1)] + P_1[(h,w)] +
 //     P_2[(h,w+1)], terms with w-1 < 0 or w+1 >= W dropped (that IS the zero padding in W).  Epilogue warp q
@@ -33,7 +32,7 @@ namespace rb {
 
 struct SlabConvParams {
     CUtensorMap mapX;   // rank 5 (32, W, H, D, N), box (32, W, R+2, 1, 1), SWIZZLE_64B
-    CUtensorMap mapW;   // rank 3 (Ctot, Mtot, 27), box (32, 32, 27), SWIZZLE_64B
+    CUtensorMap mapW;   // rank 3 (Ctot, Mtot, 27), box (32, 32, 1), SWIZZLE_64B
     int c0, m0;         // weight box origin: input-channel offset (source), output-row offset (destination half)
     int W, H, D, NB, lw;
     int R;              // output rows per tile (256 / W)
@@ -47,17 +46,19 @@ struct SlabConvParams {
     int debug;   // profiling experiments (RESENC_SLAB_DEBUG bit mask): 1 skip MMAs, 2 skip plane loads, 4 skip epilogue, 8 skip staging, 16 skip output
 };
 
-static constexpr int SLAB_THREADS = 320;   // warps: 0 TMA, 1 MMA, {4,5,2} and {8,9,6} epilogue (TMEM lane quarters 0,1,2), 3 and 7 idle
-static constexpr int SLAB_WBYTES = 27 * 32 * 64;       // all taps, SW64 rows of 32 bf16
-static constexpr int SLAB_OBYTES = 2 * 2 * 2 * 32 * 36 * 4;   // 2 column groups x 2 sets x 2 sides x [32 ch][32 voxels + 4 pad] fp32
+static constexpr int SLAB_THREADS = 320;   // warps: 0 TMA, 1 MMA, 2..5 and 6..9 epilogue (TMEM lane quarter = warp & 3)
+static constexpr int SLAB_WBYTES = 9 * 128 * 64;       // per (kd,kh): rows kw0, kw1, kw2, kw1 again (32 co each), SW64 rows of 32 bf16
 
-static constexpr int SLAB_SPITCH = 36;                       // floats per channel row of a staging buffer (32 + 4 pad)
-static constexpr int SLAB_SBUF = 32 * SLAB_SPITCH;            // one buffer: [32 channels][32 voxels (+pad)]
+static constexpr int SLAB_CHUNK = 16;                        // voxels per staging hand-off
+static constexpr int SLAB_SPITCH = SLAB_CHUNK + 4;           // floats per channel row of a staging buffer (+4 pad: conflict-free 16-byte accesses)
+static constexpr int SLAB_SBUF = 32 * SLAB_SPITCH;            // one buffer: [32 channels][16 voxels (+pad)]
 static constexpr int SLAB_SGROUP = 2 * 2 * SLAB_SBUF;         // per column group: 2 sets x 2 sides
+static constexpr int SLAB_OBYTES = 2 * SLAB_SGROUP * 4;   // 2 column groups x 2 sets x 2 sides x [32 ch][16 voxels + 4 pad] fp32
 
-// Side warps of the epilogue (TMEM lane quarter Q = kw = 0 or 2), 64 columns = two 32-voxel chunks per call:
+// Side warps of the epilogue (TMEM lane quarter Q = kw = 0 or 2), 64 columns = four 16-voxel chunks per call:
 // voxel a + i receives column a + i + Q - 1 of this warp's partial sums (zero where that column is W padding), written
-// as [channel = lane][voxel] rows with 16-byte stores into side buffer Q/2 of staging set (cnt & 1).
+// as [channel = lane][voxel] rows with 16-byte stores into side buffer Q/2 of staging set (cnt & 1).  Even chunks
+// (set 0) are consumed by the centre warp of lane quarter 1, odd chunks (set 1) by the one of quarter 3.
 template <int Q>
 __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, int lane, int Wm, uint32_t sfull0,
                                             uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait, const float* yrow) {
@@ -65,7 +66,7 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
     ex[0] = 0u;
     // accumulate mode (second source of a virtual concat): this side warp also adds the existing fp32 output of half of
     // its 64 voxels (Q = 0: the first 32, Q = 2: the last 32) - the loads overlap the TMEM loads, and the side warps
-    // have the slack the centre warp lacks
+    // have the slack the centre warps lack
     float y[32];
     if (yrow != nullptr) {
 #pragma unroll
@@ -77,7 +78,7 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
     if (Q == 2 && a < 192) tmem_ld_32x32b_x1(t_addr + a + 64, ex);
     tmem_ld_wait();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int ch = 0; ch < 4; ++ch) {
         const uint32_t b = cnt & 1u;
         const long long w0 = tWait ? clock64() : 0;
         mbar_wait(sempty0 + 8u * b, ((cnt >> 1) & 1u) ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
@@ -85,19 +86,18 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
         float* dst = stg + b * (2 * SLAB_SBUF) + (Q / 2) * SLAB_SBUF + lane * SLAB_SPITCH;
         if (!skip) {
 #pragma unroll
-            for (int vec = 0; vec < 8; ++vec) {
+            for (int vec = 0; vec < SLAB_CHUNK / 4; ++vec) {
                 float f[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int ii = vec * 4 + k;
-                    const int i = half * 32 + ii;
+                    const int i = ch * SLAB_CHUNK + vec * 4 + k;
                     const int c = i + Q - 1;   // column relative to a
                     const uint32_t x = c < 0 ? ex[0] : c < 32 ? v0[c & 31] : c < 64 ? v1[c & 31] : ex[0];
                     f[k] = __uint_as_float(x);
                     // only the first / last voxel of a W row can be padding, and rows start at multiples of 32
-                    if (Q == 0 && ii == 0 && ((a + i) & Wm) == 0) f[k] = 0.f;
-                    if (Q == 2 && ii == 31 && ((a + i) & Wm) == Wm) f[k] = 0.f;
-                    if (yrow != nullptr && half == (Q == 0 ? 0 : 1)) f[k] += y[ii];
+                    if (Q == 0 && (i & 31) == 0 && ((a + i) & Wm) == 0) f[k] = 0.f;
+                    if (Q == 2 && (i & 31) == 31 && ((a + i) & Wm) == Wm) f[k] = 0.f;
+                    if (yrow != nullptr && (i >> 5) == (Q == 0 ? 0 : 1)) f[k] += y[i & 31];
                 }
                 *reinterpret_cast<float4*>(dst + vec * 4) = make_float4(f[0], f[1], f[2], f[3]);
             }
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 6);
+            mbar_init(tempty_bar(a), 8);
         }
         for (uint32_t gb = 0; gb < 2; ++gb)
             for (uint32_t b = 0; b < 2; ++b) {
@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
         // ===================== TMA producer: the weights once, then one plane per ring slot =====================
         if (elect_one()) {
             mbar_expect_tx(w_bar, SLAB_WBYTES);
-            tma_load_3d(w_base, &p.mapW, w_bar, p.c0, p.m0, 0);
+            for (int gk = 0; gk < 9; ++gk) {   // rows of group gk: taps 3gk, 3gk+1, 3gk+2, then 3gk+1 (centre) again
+                for (int r = 0; r < 4; ++r)
+                    tma_load_3d(w_base + (uint32_t)(gk * 128 + r * 32) * 64u, &p.mapW, w_bar, p.c0, p.m0, gk * 3 + (r == 3 ? 1 : r));
+            }
         }
         __syncwarp();
         uint32_t idx = 0;   // planes issued so far
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                         const uint32_t plane = ring_base + ((kbase + (uint32_t)(j + kd)) & 3u) * slotBytes;
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
-                            const uint32_t aAddr = w_base + (uint32_t)(kd * 3 + kh) * (96u * 64u);
+                            const uint32_t aAddr = w_base + (uint32_t)(kd * 3 + kh) * (128u * 64u);
                             const uint32_t bAddr = plane + (uint32_t)kh * rowBytes;
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
@@ -262,13 +265,14 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
         if (dbgT && lane == 0) {
             g_dbg[2] = (unsigned long long)tWF; g_dbg[3] = (unsigned long long)tWT; g_dbg[4] = (unsigned long long)(clock64() - tA);
         }
-    } else if ((warp & 3) != 3) {
-        // ===================== epilogue: warps {4,5,2} own columns 0..127 of a tile, warps {8,9,6} columns 128..255 ==========
+    } else {
+        // ===================== epilogue: warps 2..5 own columns 0..127 of a tile, warps 6..9 columns 128..255 ==========
         // out[(h,w)] = P_0[(h,w-1)] + P_1[(h,w)] + P_2[(h,w+1)].  TMEM lane quarter q = warp & 3 = kw.  The two side warps
-        // (q = 0, 2) hand their shifted columns to the centre warp (q = 1) through a double-buffered staging set in shared
-        // memory; the centre warp adds its own columns (lane = output channel), accumulates the statistics and stores.
+        // (q = 0, 2) hand their shifted columns, 16 voxels at a time, to the centre warps (q = 1 and, through the second copy
+        // of the centre weights, q = 3) through one staging set each; a centre warp adds its own columns (lane = output
+        // channel), accumulates the statistics and stores.  Two centre quarters = two warp schedulers for the store work.
         const int q = warp & 3;
-        const int g = warp >= 6 ? 1 : 0;
+        const int g = warp >= 6 ? 1 : 0;   // warps 2..5 / 6..9
         const int Wm = p.W - 1;
         float* const stg = O + g * SLAB_SGROUP;
         const uint32_t sfull0 = bar_base + 104u + 32u * g, sempty0 = sfull0 + 16u;
@@ -298,46 +302,48 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                         slab_side64<2>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
                                        MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
                 } else {
-                    const size_t vox0 = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;
+                    // centre warp of lane quarter 1 (even chunks, staging set 0) or 3 (odd chunks, set 1): both quarters hold
+                    // the kw = 1 partial sums because the centre weights sit in M rows 32..63 and again in rows 96..127
+                    const uint32_t b = q == 1 ? 0u : 1u;
                     for (int a = g * 128; a < g * 128 + 128; a += 64) {
-                        uint32_t v0[32], v1[32];
+                        uint32_t va[16], vb[16];
                         const long long l0 = dbgT ? clock64() : 0;
-                        tmem_ld_32x32b_x32(t_addr + a, v0);
-                        tmem_ld_32x32b_x32(t_addr + a + 32, v1);
+                        tmem_ld_32x32b_x16(t_addr + a + (int)b * SLAB_CHUNK, va);
+                        tmem_ld_32x32b_x16(t_addr + a + (int)b * SLAB_CHUNK + 32, vb);
                         tmem_ld_wait();
                         if (dbgT) tLd += clock64() - l0;
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
-                            const uint32_t b = cnt & 1u;
                             const long long w1 = dbgT ? clock64() : 0;
-                            mbar_wait(sfull0 + 8u * b, (cnt >> 1) & 1u, DEVERR_WAIT_FULL, err_flag);
+                            mbar_wait(sfull0 + 8u * b, cnt & 1u, DEVERR_WAIT_FULL, err_flag);
                             if (dbgT) tWS += clock64() - w1;
                             const float* L = stg + b * (2 * SLAB_SBUF) + lane * SLAB_SPITCH;
-                            const size_t e0 = (vox0 + a + half * 32) * 32 + lane;   // destinations are 32-channel tensors
+                            // destinations are 32-channel tensors: voxel (a + half*32 + b*16 + k), channel lane
+                            const size_t e0 = (voxT + a + half * 32 + (int)b * SLAB_CHUNK) * 32 + lane;
                             const long long c0 = dbgT ? clock64() : 0;
                             if (!(p.debug & 16)) {
-                                float x[32];
+                                float x[SLAB_CHUNK];
 #pragma unroll
-                                for (int vec = 0; vec < 8; ++vec) {
+                                for (int vec = 0; vec < SLAB_CHUNK / 4; ++vec) {
                                     const float4 l = *reinterpret_cast<const float4*>(L + vec * 4);
                                     const float4 r = *reinterpret_cast<const float4*>(L + SLAB_SBUF + vec * 4);
-                                    x[vec * 4 + 0] = __uint_as_float(half ? v1[vec * 4 + 0] : v0[vec * 4 + 0]) + (l.x + r.x);
-                                    x[vec * 4 + 1] = __uint_as_float(half ? v1[vec * 4 + 1] : v0[vec * 4 + 1]) + (l.y + r.y);
-                                    x[vec * 4 + 2] = __uint_as_float(half ? v1[vec * 4 + 2] : v0[vec * 4 + 2]) + (l.z + r.z);
-                                    x[vec * 4 + 3] = __uint_as_float(half ? v1[vec * 4 + 3] : v0[vec * 4 + 3]) + (l.w + r.w);
+                                    x[vec * 4 + 0] = __uint_as_float(half ? vb[vec * 4 + 0] : va[vec * 4 + 0]) + (l.x + r.x);
+                                    x[vec * 4 + 1] = __uint_as_float(half ? vb[vec * 4 + 1] : va[vec * 4 + 1]) + (l.y + r.y);
+                                    x[vec * 4 + 2] = __uint_as_float(half ? vb[vec * 4 + 2] : va[vec * 4 + 2]) + (l.z + r.z);
+                                    x[vec * 4 + 3] = __uint_as_float(half ? vb[vec * 4 + 3] : va[vec * 4 + 3]) + (l.w + r.w);
                                 }
                                 if (MODE == 0) {
                                     bf16* gp = reinterpret_cast<bf16*>(p.out) + e0;
 #pragma unroll
-                                    for (int ii = 0; ii < 32; ++ii) gp[ii * 32] = __float2bfloat16_rn(x[ii]);
+                                    for (int ii = 0; ii < SLAB_CHUNK; ++ii) gp[ii * 32] = __float2bfloat16_rn(x[ii]);
                                 } else {
                                     float* gp = reinterpret_cast<float*>(p.out) + e0;
 #pragma unroll
-                                    for (int ii = 0; ii < 32; ++ii) gp[ii * 32] = x[ii];
+                                    for (int ii = 0; ii < SLAB_CHUNK; ++ii) gp[ii * 32] = x[ii];
                                 }
                                 float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                                for (int ii = 0; ii < 32; ++ii) {
+                                for (int ii = 0; ii < SLAB_CHUNK; ++ii) {
                                     a1[ii & 3] += x[ii];
                                     a2[ii & 3] += x[ii] * x[ii];
                                 }
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                             if (dbgT) tSt += clock64() - c0;
                             __syncwarp();
                             if (lane == 0) mbar_arrive(sempty0 + 8u * b);
-                            ++cnt;
+                            ++cnt;   // uses of this warp's staging set
                         }
                     }
                 }
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (q == 1 && p.stat_sum != nullptr) {
+            if ((q & 1) && p.stat_sum != nullptr) {
                 const int idx = n * p.statPitch + p.statC0 + lane;
                 atomicAdd(p.stat_sum + idx, s1);
                 atomicAdd(p.stat_sq + idx, s2);
