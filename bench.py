@@ -190,7 +190,19 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment: route fd 1 to stderr
+        # while the communicator comes up so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     rb._lib.load()
 
     P, B = args.patch, args.batch
@@ -199,7 +211,7 @@ def main():
         model = rb.NetworkFromConfig(make_mgr(P, B)).to(dev)
     n_stages = model.num_stages
     model.train()
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph   # N > 1: the bucketed NCCL all-reduces on the side stream are captured with the step
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
     buckets = par.GradientBuckets(model) if world > 1 else None
     params = [p for p in model.parameters()]
@@ -234,8 +246,9 @@ def main():
         step(x_d, tgt_d)
     barrier()
 
-    # ---- whole-step CUDA graph (single GPU): the step is ~700 of our launches plus torch glue; replaying it as
-    # one graph removes the host launch latency that otherwise dominates the deep 4^3 / 8^3 layers ----
+    # ---- whole-step CUDA graph: the step is ~700 of our launches plus torch glue; replaying it as one graph removes
+    # the host launch latency that otherwise dominates the deep 4^3 / 8^3 layers.  Under torchrun the gradient
+    # all-reduces (NCCL, side stream, overlapped with backward) are part of the captured graph ----
     graph, g_loss, graph_note = None, None, "eager"
     if use_graph:
         try:
@@ -253,7 +266,8 @@ def main():
             graph.replay()
             torch.cuda.synchronize()
             rb._lib.device_error_check()
-            graph_note = "cuda-graph replay of the whole step (fwd + loss + bwd + clip + AdamW)"
+            graph_note = ("cuda-graph replay of the whole step (fwd + loss + bwd + clip + AdamW)" if world == 1 else
+                          "cuda-graph replay of the whole step (fwd + loss + bwd + bucketed NCCL all-reduce + clip + AdamW)")
         except Exception as e:   # pragma: no cover - capture is an optimisation, eager is the contract
             print(f"[bench] CUDA graph capture failed, timing eager launches: {e!r}", file=sys.stderr)
             graph, g_loss = None, None
@@ -370,6 +384,16 @@ def main():
                                               f"timed, {sec:.2f} s/step"}
         print(json.dumps(line))
     if world > 1:
+        # a communicator whose collectives were captured into a CUDA graph can block in destroy_process_group():
+        # drop the graph first, and never let tear-down outlive the measurement (the line above is already printed)
+        sys.stdout.flush()
+        if graph is not None:
+            graph.reset()
+        torch.cuda.synchronize()
+        dist.barrier()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
 
 
