@@ -1121,7 +1121,11 @@ int rb_head_bwd(const void* x, const float* w, const float* dl, void* dx, float*
     if (K < 1 || K > rb::HEAD_MAXK || C <= 0 || C % 8 != 0 || C > 1024) return fail(RB_ERR_INVALID, "head_bwd: need 1 <= K <= 8, C %% 8 == 0, C <= 1024");
     rb::HeadBwdParams p{(const rb::bf16*)x, w, dl, (rb::bf16*)dx, dw, db, S, NB, C, K};
     const size_t smem = (size_t)(2 * K * C + K) * sizeof(float);
-    rb::head_bwd_kernel<<<grid_for((long long)NB * S * (C / 8), 256, 4), 256, smem, (cudaStream_t)stream>>>(p);
+    const int grid = grid_for((long long)NB * S * (C / 8), 256, 4);
+    if (K == 1) rb::head_bwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else if (K == 2) rb::head_bwd_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else if (K <= 4) rb::head_bwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else rb::head_bwd_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("head_bwd_kernel");
 }
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import itertools
+import os
 
 import torch
 
@@ -220,6 +221,8 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
 # sliding-window sweep packs each weight once.
 # ------------------------------------------------------------------------------------------
 PACK_CACHE = True     # set False while capturing a CUDA graph so the (re)packing kernels are part of every replay
+# strided data gradients as one pixel-shuffle launch (False: one launch per parity class, the cross-check path)
+MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
 
 
 def _cached_pack(weight, kind, fn):
@@ -319,6 +322,47 @@ def pack_conv_dgrad_class(weight, kds, khs, kws, strides=None):
     return w.permute(2, 3, 4, 1, 0).reshape(len(kds) * len(khs) * len(kws), ci, co).to(BF16).contiguous()
 
 
+def _merged_dgrad_plan(k, stride, pad, in_dims, od):
+    """Strided data gradient as ONE pixel-shuffle gather conv over dy (instead of one launch per parity class):
+    every input voxel i = s*j + r of an axis receives from outputs j + off .. through a class-specific tap subset, so
+    all prod(s) classes of a dy neighbourhood are the N columns [(rd, rh, rw), ci] of one GEMM whose weight blocks
+    are zero where a (class, window tap) pair has no kernel index.  Returns per-axis (ntap, off, [(r, u0, ks)]) or
+    None when the geometry does not tile exactly."""
+    if all(s == 1 for s in stride) or any(s > 2 for s in stride):
+        return None
+    axes = []
+    for a in range(3):
+        cls = _axis_classes(k[a], stride[a], pad[a], in_dims[a])
+        if len(cls) != stride[a] or any(c[1] != od[a] for c in cls):
+            return None
+        live = [c for c in cls if c[2]]
+        if not live:
+            return None
+        lo = min(c[3] for c in live)
+        hi = max(c[3] + len(c[2]) - 1 for c in live)
+        axes.append((hi - lo + 1, lo, [(c[0], c[3] - lo, c[2]) for c in cls]))
+    return axes
+
+
+def pack_conv_dgrad_merged(weight, axes, stride):
+    """[window taps][(rd, rh, rw, ci)][co] bf16 for `_merged_dgrad_plan` (zero blocks included)."""
+    def pack():
+        co, ci = weight.shape[:2]
+        nt = [a[0] for a in axes]
+        wp = torch.zeros((nt[0], nt[1], nt[2], stride[0], stride[1], stride[2], ci, co), dtype=BF16, device=weight.device)
+        w = weight.detach()
+        for rd, ud, kd in axes[0][2]:
+            for rh, uh, kh in axes[1][2]:
+                for rw, uw, kw in axes[2][2]:
+                    if not (kd and kh and kw):
+                        continue
+                    blk = w[:, :, kd][:, :, :, kh][:, :, :, :, kw]            # [co, ci, |kd|, |kh|, |kw|]
+                    wp[ud:ud + len(kd), uh:uh + len(kh), uw:uw + len(kw), rd, rh, rw] = blk.permute(2, 3, 4, 1, 0).to(BF16)
+        return wp.reshape(nt[0] * nt[1] * nt[2], stride[0] * stride[1] * stride[2] * ci, co)
+    return _cached_pack(weight, "dmerge", pack)
+
+
+
 # ------------------------------------------------------------------------------------------
 # primitives (no autograd): convolution forward / backward
 # ------------------------------------------------------------------------------------------
@@ -365,6 +409,15 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
     need1 = need1 and x1 is not None
     if need0 or need1:
         c0 = x0.shape[1]
+        merged = _merged_dgrad_plan(k, stride, pad, in_dims, od) if MERGED_STRIDED_DGRAD else None
+        if merged is not None and ci % 32 == 0 and co % 16 == 0 and c0 % 8 == 0:
+            gx0 = new_cl(n, c0, *in_dims, x0.device)
+            gx1 = new_cl(n, x1.shape[1], *in_dims, x0.device) if x1 is not None else None
+            npar = stride[0] * stride[1] * stride[2]
+            _launch_gather(dy, None, pack_conv_dgrad_merged(weight, merged, stride), gx0, gx1, in_dims=od,
+                           taps=tuple(a[0] for a in merged), off=tuple(a[1] for a in merged), istr=(1, 1, 1), out_grid=od,
+                           nout=npar * ci, mode=1, ostr=stride, full=in_dims, ps=stride, psC=ci, impl=impl)
+            return gw, (gx0 if need0 else None), (gx1 if need1 else None)
         classes = [_axis_classes(k[a], stride[a], pad[a], in_dims[a]) for a in range(3)]
         empty = any(len(cls[2]) == 0 for axis in classes for cls in axis)
         mk = zeros_cl if empty else new_cl

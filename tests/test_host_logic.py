@@ -158,3 +158,43 @@ def test_slab_exchange_plan(rb):
     # more ranks than z-starts: empty ranks own nothing and exchange nothing
     pairs2, own2 = inf.plan_slab_exchange([0, 64], 128, 192, 4)
     assert own2[2] == (0, 0) and own2[3] == (0, 0) and all(d < 2 for _, d, _, _ in pairs2)
+
+
+@pytest.mark.parametrize("k,stride,dims", [((3, 3, 3), (2, 2, 2), (8, 8, 8)), ((1, 3, 3), (1, 2, 2), (4, 8, 8)),
+                                           ((3, 3, 3), (1, 2, 2), (5, 4, 10)), ((1, 1, 1), (2, 2, 2), (4, 4, 4))])
+def test_merged_strided_dgrad_pack(rb, k, stride, dims):
+    """Host side of the one-launch strided data gradient (ops._merged_dgrad_plan / pack_conv_dgrad_merged): the
+    zero-padded [window tap][(parity, ci)][co] weights, applied as a stride-1 gather over dy followed by a pixel
+    shuffle, reproduce autograd's data gradient of the strided convolution (pure torch emulation, bf16 weights)."""
+    import torch.nn.functional as F
+    ops = rb.ops
+    torch.manual_seed(0)
+    co, ci = 16, 32
+    w = torch.randn(co, ci, *k)
+    x = torch.randn(2, ci, *dims, requires_grad=True)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    y = F.conv3d(x, w.to(torch.bfloat16).float(), None, stride, pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    od = tuple(y.shape[2:])
+    axes = ops._merged_dgrad_plan(k, stride, pad, dims, od)
+    assert axes is not None
+    wp = ops.pack_conv_dgrad_merged(w, axes, stride).float()
+    nt, off = [a[0] for a in axes], [a[1] for a in axes]
+    lo = [max(0, -o) for o in off]
+    dyp = F.pad(dy, (lo[2], nt[2], lo[1], nt[1], lo[0], nt[0]))
+    out = torch.zeros(2, wp.shape[1], *od)
+    t = 0
+    for ud in range(nt[0]):
+        for uh in range(nt[1]):
+            for uw in range(nt[2]):
+                s0 = [u + o + l for u, o, l in zip((ud, uh, uw), off, lo)]
+                sl = dyp[:, :, s0[0]:s0[0] + od[0], s0[1]:s0[1] + od[1], s0[2]:s0[2] + od[2]]
+                out += torch.einsum("bcdhw,nc->bndhw", sl, wp[t])
+                t += 1
+    o6 = out.view(2, stride[0], stride[1], stride[2], ci, *od)
+    dx = o6.permute(0, 4, 5, 1, 6, 2, 7, 3).reshape(2, ci, *[o * s for o, s in zip(od, stride)])
+    assert float((dx - x.grad).norm() / x.grad.norm()) < 1e-5
+    # geometries that do not tile exactly keep the per-class path
+    assert ops._merged_dgrad_plan((3, 3, 3), (2, 2, 2), (1, 1, 1), (7, 8, 8), (4, 4, 4)) is None
+    assert ops._merged_dgrad_plan((3, 3, 3), (1, 1, 1), (1, 1, 1), (8, 8, 8), (8, 8, 8)) is None
