@@ -350,13 +350,18 @@ def pack_conv_dgrad_merged(weight, axes, stride):
         co, ci = weight.shape[:2]
         nt = [a[0] for a in axes]
         wp = torch.zeros((nt[0], nt[1], nt[2], stride[0], stride[1], stride[2], ci, co), dtype=BF16, device=weight.device)
-        w = weight.detach()
+        wf = _flipped(weight)
+        K = weight.shape[2:]
+
+        def sl(ks, kk):   # descending kernel-index progression -> slice of the flipped kernel (no index tensors:
+            a = kk - 1 - ks[0]   # nothing here may copy from the host, this runs inside CUDA graph capture)
+            return slice(a, a + 1) if len(ks) == 1 else slice(a, a + (len(ks) - 1) * (ks[0] - ks[1]) + 1, ks[0] - ks[1])
         for rd, ud, kd in axes[0][2]:
             for rh, uh, kh in axes[1][2]:
                 for rw, uw, kw in axes[2][2]:
                     if not (kd and kh and kw):
                         continue
-                    blk = w[:, :, kd][:, :, :, kh][:, :, :, :, kw]            # [co, ci, |kd|, |kh|, |kw|]
+                    blk = wf[:, :, sl(kd, K[0]), sl(kh, K[1]), sl(kw, K[2])]   # [co, ci, |kd|, |kh|, |kw|]
                     wp[ud:ud + len(kd), uh:uh + len(kh), uw:uw + len(kw), rd, rh, rw] = blk.permute(2, 3, 4, 1, 0).to(BF16)
         return wp.reshape(nt[0] * nt[1] * nt[2], stride[0] * stride[1] * stride[2] * ci, co)
     return _cached_pack(weight, "dmerge", pack)

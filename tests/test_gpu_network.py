@@ -218,3 +218,48 @@ def test_eval_activation_semantics(rb):
     # two forward passes differ by atomics-order rounding (a few bf16 ulps on a few activations)
     assert rel_l2(act, torch.softmax(raw, 1)) < 5e-3
     assert torch.allclose(act.sum(1), torch.ones_like(act.sum(1)), atol=1e-5)
+
+
+def test_training_step_is_cuda_graph_capturable(rb):
+    """bench.py replays the whole step (fwd + loss + bwd + clip + AdamW) as one CUDA graph: nothing on the path may
+    synchronise, copy from pageable host memory or allocate index tensors on the host (weight packs included, which are
+    rebuilt inside the graph when ops.PACK_CACHE is off).  Strided convs (merged data gradient) and the 32-channel
+    full-resolution layers are part of this 32^3 network."""
+    tasks = {"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}}
+    torch.manual_seed(0)
+    model = quiet_build(rb.NetworkFromConfig, make_mgr([32, 32, 32], tasks)).cuda().train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, fused=True)
+    x = torch.rand(2, 1, 32, 32, 32, device="cuda")
+    tg = {"sheet": (torch.rand(2, 1, 32, 32, 32, device="cuda") > 0.5).float(),
+          "normals": torch.nn.functional.normalize(torch.randn(2, 3, 32, 32, 32, device="cuda"), dim=1)}
+    params = [p for p in model.parameters()]
+
+    def step():
+        out = model(x)
+        loss = sum(_loss(t, out[t], tg[t]) for t in tasks)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 3.0)
+        opt.step()
+        return loss
+
+    rb.ops.PACK_CACHE = False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eager = float(step())
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gl = step()
+        losses = []
+        for _ in range(3):
+            g.replay()
+            torch.cuda.synchronize()
+            losses.append(float(gl))
+    finally:
+        rb.ops.PACK_CACHE = True
+    print("eager", eager, "graph replays", losses)
+    assert all(np.isfinite(losses)) and losses[0] <= eager + 1e-2 and losses[-1] < losses[0]
