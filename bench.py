@@ -60,7 +60,13 @@ def synthetic_batch(batch, patch, device, seed):
 
 
 def losses(out, tgt, O):
+    """CPU arm: the oracle's restatement of the reference losses."""
     return O.bce_dice_loss(out["sheet"], tgt["sheet"]) + O.masked_cosine_loss(out["normals"], tgt["normals"])
+
+
+def gpu_losses(out, tgt, crit):
+    """GPU arm: the package's own loss modules (training/losses/losses.py mirrors); nothing under oracle/ runs here."""
+    return sum(crit[t](out[t], tgt[t]) for t in out)
 
 
 # ------------------------------------------------------------------------------------------
@@ -177,9 +183,9 @@ def main():
 
     import torch.distributed as dist
     import resenc_b200 as rb
-    from oracle import resenc_oracle as O      # losses only (glue around the measured path) + cpu_baseline leg
     import importlib
     par = importlib.import_module(rb._pkg.__name__ + ".parallel")
+    loss_mod = importlib.import_module(rb._pkg.__name__ + ".losses")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,6 +216,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         model = rb.NetworkFromConfig(make_mgr(P, B)).to(dev)
     n_stages = model.num_stages
+    crit = loss_mod.task_losses(make_mgr(P, B).tasks)
     model.train()
     use_graph = not args.no_graph   # N > 1: the bucketed NCCL all-reduces on the side stream are captured with the step
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
@@ -225,7 +232,7 @@ def main():
 
     def step(x, tgt):
         out = model(x)
-        loss = losses(out, tgt, O)
+        loss = gpu_losses(out, tgt, crit)
         if buckets is not None:
             buckets.zero_grad()
         else:

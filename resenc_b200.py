@@ -16,6 +16,8 @@ NetworkFromConfig = _pkg.NetworkFromConfig
 builders = _pkg.builders
 inference = _pkg.inference
 ops = _pkg.ops
+losses = importlib.import_module(_pkg.__name__ + ".losses")
+parallel = importlib.import_module(_pkg.__name__ + ".parallel")
 _lib = _pkg._lib
 
 

@@ -198,3 +198,31 @@ def test_merged_strided_dgrad_pack(rb, k, stride, dims):
     # geometries that do not tile exactly keep the per-class path
     assert ops._merged_dgrad_plan((3, 3, 3), (2, 2, 2), (1, 1, 1), (7, 8, 8), (4, 4, 4)) is None
     assert ops._merged_dgrad_plan((3, 3, 3), (1, 1, 1), (1, 1, 1), (8, 8, 8), (8, 8, 8)) is None
+
+
+def test_package_losses_match_oracle(rb):
+    """losses.py of the package (what bench.py's GPU arm calls) against the oracle's restatement of
+    training/losses/losses.py on random logits / targets, values and gradients."""
+    import importlib
+    from oracle import resenc_oracle as O   # checker only
+    L = importlib.import_module(rb._pkg.__name__ + ".losses")
+    torch.manual_seed(0)
+    z = torch.randn(2, 1, 6, 7, 8, requires_grad=True)
+    t = (torch.rand(2, 1, 6, 7, 8) > 0.8).float()
+    a = L.BCEDiceLoss(0.5, 0.5)(z, t)
+    a.backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    b = O.bce_dice_loss(z2, t)
+    b.backward()
+    assert abs(float(a) - float(b)) < 1e-6 and torch.allclose(z.grad, z2.grad, atol=1e-8)
+    n = torch.randn(2, 3, 6, 7, 8, requires_grad=True)
+    tn = torch.nn.functional.normalize(torch.randn(2, 3, 6, 7, 8), dim=1)
+    tn[:, :, :2] = 0          # masked-out voxels
+    c = L.MaskedCosineLoss()(n, tn)
+    c.backward()
+    n2 = n.detach().clone().requires_grad_(True)
+    d = O.masked_cosine_loss(n2, tn)
+    d.backward()
+    assert abs(float(c) - float(d)) < 1e-6 and torch.allclose(n.grad, n2.grad, atol=1e-8)
+    crit = L.task_losses({"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}})
+    assert isinstance(crit["sheet"], L.BCEDiceLoss) and isinstance(crit["normals"], L.MaskedCosineLoss)

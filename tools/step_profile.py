@@ -6,17 +6,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import resenc_b200 as rb
 import bench
-from oracle import resenc_oracle as O
+import importlib
 P, B = 128, 2
 torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     model = rb.NetworkFromConfig(bench.make_mgr(P, B)).cuda().train()
+crit = importlib.import_module(rb._pkg.__name__ + ".losses").task_losses(bench.make_mgr(P, B).tasks)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
 x, tgt = bench.synthetic_batch(B, P, "cpu", 0)
 x = x.cuda(); tgt = {k: v.cuda() for k, v in tgt.items()}
 def step():
     out = model(x)
-    loss = bench.losses(out, tgt, O)
+    loss = bench.gpu_losses(out, tgt, crit)
     opt.zero_grad(set_to_none=True)
     loss.backward()
     torch.nn.utils.clip_grad_norm_(list(model.parameters()), 3.0)
