@@ -194,6 +194,22 @@ int rb_blend_add(float* dst, const float* src, long long n, void* stream);
 int rb_extract_patch(const void* vol, int is_u16, int VZ, int VY, int VX, int z0, int y0, int x0,
                      int PZ, int PY, int PX, int standardize, double* stats, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused task losses on the fp32 NCDHW logits (training/losses/losses.py): BCEDiceLoss :307-318 (label-smoothed
+ * BCE-with-logits :217-238 + DiceLoss :105-126 / compute_per_channel_dice :17-43) and MaskedCosineLoss :187-215.
+ * *_reduce accumulates into `stats` (device double, zeroed by the caller): BCEDice [C][4] = sum bce, sum p*t,
+ * sum p*p, sum t*t; cosine [2] = sum mask*cos, sum mask.  *_grad writes d(loss)/d(x) scaled by the device scalar
+ * `grad_out`, using the same stats.
+ * ------------------------------------------------------------------------------------------ */
+int rb_loss_bce_dice_reduce(const float* logits, const float* target, double* stats, int NB, int C, long long S,
+                            float smoothing, void* stream);
+int rb_loss_bce_dice_grad(const float* logits, const float* target, const double* stats, const float* grad_out,
+                          float* dlogits, int NB, int C, long long S, float alpha, float beta, float eps,
+                          float smoothing, void* stream);
+int rb_loss_cosine_reduce(const float* pred, const float* target, double* stats, int NB, long long S, void* stream);
+int rb_loss_cosine_grad(const float* pred, const float* target, const double* stats, const float* grad_out,
+                        float* dpred, int NB, long long S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

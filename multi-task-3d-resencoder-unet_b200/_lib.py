@@ -69,6 +69,10 @@ SIGNATURES = {
     "rb_blend_finalize_cast": (_I, [_P, _P, _P, _P, _LL, _I, _I, _P]),
     "rb_blend_add": (_I, [_P, _P, _LL, _P]),
     "rb_extract_patch": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "rb_loss_bce_dice_reduce": (_I, [_P, _P, _P, _I, _I, _LL, _F, _P]),
+    "rb_loss_bce_dice_grad": (_I, [_P, _P, _P, _P, _P, _I, _I, _LL, _F, _F, _F, _F, _P]),
+    "rb_loss_cosine_reduce": (_I, [_P, _P, _P, _I, _LL, _P]),
+    "rb_loss_cosine_grad": (_I, [_P, _P, _P, _P, _P, _I, _LL, _P]),
 }
 
 _lib = None

@@ -13,6 +13,7 @@
 #include "conv_tc5.cuh"
 #include "conv_tc5t.cuh"
 #include "conv_slab.cuh"
+#include "loss.cuh"
 #include "conv_generic.cuh"
 #include "wgrad_tc5.cuh"
 #include "wgrad2_tc5.cuh"
@@ -1092,7 +1093,8 @@ int rb_avgpool_fwd(const void* in, void* out, int NB, int D, int H, int W, int C
     if (rc) return rc;
     rb::PoolParams p{(const rb::bf16*)in, (rb::bf16*)out, NB, D, H, W, C, sd, sh, sw};
     const long long total = (long long)NB * (D / sd) * (H / sh) * (W / sw) * (C / 8);
-    rb::avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    if (total < (1LL << 31) - (1LL << 22)) rb::avgpool_fwd_kernel<unsigned><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    else rb::avgpool_fwd_kernel<long long><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("avgpool_fwd_kernel");
 }
 
@@ -1102,7 +1104,8 @@ int rb_avgpool_bwd(const void* dout, void* din, int NB, int D, int H, int W, int
     if (rc) return rc;
     rb::PoolParams p{(const rb::bf16*)dout, (rb::bf16*)din, NB, D, H, W, C, sd, sh, sw};
     const long long total = (long long)NB * D * H * W * (C / 8);
-    rb::avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    if (total < (1LL << 31) - (1LL << 22)) rb::avgpool_bwd_kernel<unsigned><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    else rb::avgpool_bwd_kernel<long long><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("avgpool_bwd_kernel");
 }
 
@@ -1219,6 +1222,49 @@ int rb_extract_patch(const void* vol, int is_u16, int VZ, int VY, int VX, int z0
     }
     rb::patch_write_kernel<<<grid_for(PS, 256), 256, 0, st>>>(p);
     return check_launch("patch_write_kernel");
+}
+
+
+static dim3 loss_grid(long long S, int C, int NB) {
+    long long bx = (S + 256 * 8 - 1) / (256 * 8);
+    if (bx < 1) bx = 1;
+    if (bx > 4096) bx = 4096;
+    return dim3((unsigned)bx, (unsigned)C, (unsigned)NB);
+}
+
+int rb_loss_bce_dice_reduce(const float* logits, const float* target, double* stats, int NB, int C, long long S, float smoothing,
+                            void* stream) {
+    if (!logits || !target || !stats) return fail(RB_ERR_INVALID, "loss_bce_dice_reduce: null pointer");
+    if (NB <= 0 || C <= 0 || C > 65535 || NB > 65535 || S <= 0) return fail(RB_ERR_INVALID, "loss_bce_dice_reduce: bad shape");
+    rb::LossParams p{logits, target, stats, nullptr, nullptr, S, NB, C, 0.f, 0.f, 0.f, smoothing};
+    rb::loss_bce_dice_reduce_kernel<<<loss_grid(S, C, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("loss_bce_dice_reduce_kernel");
+}
+
+int rb_loss_bce_dice_grad(const float* logits, const float* target, const double* stats, const float* grad_out, float* dlogits,
+                          int NB, int C, long long S, float alpha, float beta, float eps, float smoothing, void* stream) {
+    if (!logits || !target || !stats || !grad_out || !dlogits) return fail(RB_ERR_INVALID, "loss_bce_dice_grad: null pointer");
+    if (NB <= 0 || C <= 0 || C > 65535 || NB > 65535 || S <= 0) return fail(RB_ERR_INVALID, "loss_bce_dice_grad: bad shape");
+    rb::LossParams p{logits, target, const_cast<double*>(stats), dlogits, grad_out, S, NB, C, alpha, beta, eps, smoothing};
+    rb::loss_bce_dice_grad_kernel<<<loss_grid(S, C, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("loss_bce_dice_grad_kernel");
+}
+
+int rb_loss_cosine_reduce(const float* pred, const float* target, double* stats, int NB, long long S, void* stream) {
+    if (!pred || !target || !stats) return fail(RB_ERR_INVALID, "loss_cosine_reduce: null pointer");
+    if (NB <= 0 || NB > 65535 || S <= 0) return fail(RB_ERR_INVALID, "loss_cosine_reduce: bad shape");
+    rb::LossParams p{pred, target, stats, nullptr, nullptr, S, NB, 3, 0.f, 0.f, 0.f, 0.f};
+    rb::loss_cosine_reduce_kernel<<<loss_grid(S, 1, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("loss_cosine_reduce_kernel");
+}
+
+int rb_loss_cosine_grad(const float* pred, const float* target, const double* stats, const float* grad_out, float* dpred, int NB,
+                        long long S, void* stream) {
+    if (!pred || !target || !stats || !grad_out || !dpred) return fail(RB_ERR_INVALID, "loss_cosine_grad: null pointer");
+    if (NB <= 0 || NB > 65535 || S <= 0) return fail(RB_ERR_INVALID, "loss_cosine_grad: bad shape");
+    rb::LossParams p{pred, target, const_cast<double*>(stats), dpred, grad_out, S, NB, 3, 0.f, 0.f, 0.f, 0.f};
+    rb::loss_cosine_grad_kernel<<<loss_grid(S, 1, NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("loss_cosine_grad_kernel");
 }
 
 }  // extern "C"

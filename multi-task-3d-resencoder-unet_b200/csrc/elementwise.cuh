@@ -281,13 +281,15 @@ struct PoolParams {
     int sd, sh, sw;
 };
 
+// IDX: unsigned int when the element count fits 31 bits (64-bit div/mod chains made the pooling kernels run at 1 TB/s)
+template <typename IDX>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const PoolParams p) {
     const int cg = p.C >> 3;
     const int OD = p.D / p.sd, OH = p.H / p.sh, OW = p.W / p.sw;
-    const long long total = (long long)p.NB * OD * OH * OW * cg;
+    const IDX total = (IDX)p.NB * OD * OH * OW * cg;
     const float inv = 1.f / (float)(p.sd * p.sh * p.sw);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        IDX t = i;
         const int g = (int)(t % cg); t /= cg;
         const int ow = (int)(t % OW); t /= OW;
         const int oh = (int)(t % OH); t /= OH;
@@ -312,13 +314,14 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const PoolParams p) {
 }
 
 // in = d(pooled) [NB, D/sd, H/sh, W/sw, C]; out = d(full) [NB, D, H, W, C]
+template <typename IDX>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const PoolParams p) {
     const int cg = p.C >> 3;
     const int OD = p.D / p.sd, OH = p.H / p.sh, OW = p.W / p.sw;
-    const long long total = (long long)p.NB * p.D * p.H * p.W * cg;
+    const IDX total = (IDX)p.NB * p.D * p.H * p.W * cg;
     const float inv = 1.f / (float)(p.sd * p.sh * p.sw);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        IDX t = i;
         const int g = (int)(t % cg); t /= cg;
         const int w = (int)(t % p.W); t /= p.W;
         const int h = (int)(t % p.H); t /= p.H;

@@ -70,8 +70,89 @@ class MaskedCosineLoss(nn.Module):
         return 1.0 - cos.sum() / (mask.sum() + 1e-8)
 
 
-def task_losses(tasks):
+# ------------------------------------------------------------------------------------------
+# Fused CUDA versions (csrc/loss.cuh): one reduction pass + a few scalar ops forward, one pass that writes
+# d(loss)/d(logits) backward.  Same values as the compositions above (tests/test_gpu_ops.py).
+# ------------------------------------------------------------------------------------------
+def _fused_ok(x, t):
+    return x.is_cuda and t.is_cuda and x.dtype == torch.float32 and t.dtype == torch.float32 and x.dim() >= 3 \
+        and x.shape == t.shape
+
+
+class _BCEDiceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, alpha, beta, eps, smoothing):
+        from . import _lib as L
+        x, t = logits.contiguous(), target.contiguous()
+        nb, c = x.shape[:2]
+        s = x[0, 0].numel()
+        stats = torch.zeros((c, 4), dtype=torch.float64, device=x.device)
+        L.check(L.load().rb_loss_bce_dice_reduce(x.data_ptr(), t.data_ptr(), stats.data_ptr(), nb, c, s, smoothing,
+                                                 L.stream_ptr()), "rb_loss_bce_dice_reduce")
+        bce = stats[:, 0].sum() / float(nb * c * s)
+        dice = 2.0 * stats[:, 1] / (stats[:, 2] + stats[:, 3]).clamp(min=eps)
+        ctx.save_for_backward(x, t, stats)
+        ctx.cfg = (alpha, beta, eps, smoothing)
+        return (alpha * bce + beta * (1.0 - dice.mean())).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib as L
+        x, t, stats = ctx.saved_tensors
+        alpha, beta, eps, smoothing = ctx.cfg
+        nb, c = x.shape[:2]
+        dx = torch.empty_like(x)
+        g = g.detach().float().contiguous()
+        L.check(L.load().rb_loss_bce_dice_grad(x.data_ptr(), t.data_ptr(), stats.data_ptr(), g.data_ptr(), dx.data_ptr(), nb,
+                                               c, x[0, 0].numel(), alpha, beta, eps, smoothing, L.stream_ptr()),
+                "rb_loss_bce_dice_grad")
+        return dx, None, None, None, None, None
+
+
+class _MaskedCosineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        from . import _lib as L
+        x, t = pred.contiguous(), target.contiguous()
+        nb = x.shape[0]
+        s = x[0, 0].numel()
+        stats = torch.zeros(2, dtype=torch.float64, device=x.device)
+        L.check(L.load().rb_loss_cosine_reduce(x.data_ptr(), t.data_ptr(), stats.data_ptr(), nb, s, L.stream_ptr()),
+                "rb_loss_cosine_reduce")
+        ctx.save_for_backward(x, t, stats)
+        return (1.0 - stats[0] / (stats[1] + 1e-8)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib as L
+        x, t, stats = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        g = g.detach().float().contiguous()
+        L.check(L.load().rb_loss_cosine_grad(x.data_ptr(), t.data_ptr(), stats.data_ptr(), g.data_ptr(), dx.data_ptr(),
+                                             x.shape[0], x[0, 0].numel(), L.stream_ptr()), "rb_loss_cosine_grad")
+        return dx, None
+
+
+class FusedBCEDiceLoss(BCEDiceLoss):
+    """BCEDiceLoss through csrc/loss.cuh when logits and target are fp32 CUDA tensors (else the composition)."""
+
+    def forward(self, input, target):
+        if _fused_ok(input, target):
+            return _BCEDiceFn.apply(input, target, float(self.alpha), float(self.beta), float(self.dice.epsilon),
+                                    float(self.bce.smoothing))
+        return super().forward(input, target)
+
+
+class FusedMaskedCosineLoss(MaskedCosineLoss):
+    def forward(self, pred, target):
+        if _fused_ok(pred, target) and pred.shape[1] == 3:
+            return _MaskedCosineFn.apply(pred, target)
+        return super().forward(pred, target)
+
+
+def task_losses(tasks, fused: bool = True):
     """name -> loss module, the pairing `bench.py` uses: MaskedCosineLoss for a 3-channel task called "normals",
-    BCEDiceLoss(0.5, 0.5) otherwise."""
-    return {t: (MaskedCosineLoss() if t == "normals" and info.get("channels") == 3 else BCEDiceLoss(0.5, 0.5))
-            for t, info in tasks.items()}
+    BCEDiceLoss(0.5, 0.5) otherwise; `fused` selects the CUDA kernels (same values)."""
+    cos = FusedMaskedCosineLoss if fused else MaskedCosineLoss
+    bd = FusedBCEDiceLoss if fused else BCEDiceLoss
+    return {t: (cos() if t == "normals" and info.get("channels") == 3 else bd(0.5, 0.5)) for t, info in tasks.items()}

@@ -310,3 +310,36 @@ def test_weight_pack_unpack_kernels(rb, co, ci, k):
     dw = torch.randn(T, co, ci, device="cuda")
     g = ops.unpack_wgrad(dw, co, ci, k)
     assert torch.equal(g, dw.view(*k, co, ci).permute(3, 4, 0, 1, 2))
+
+
+def test_fused_losses_match_compositions(rb):
+    """csrc/loss.cuh (one reduction pass + one gradient pass) against the PyTorch compositions of
+    training/losses/losses.py in the package and against the oracle: loss values to 1e-6, gradients to rel-L2 1e-5.
+    Includes masked-out normals, saturated logits, several channels and a grad_out != 1."""
+    from oracle import resenc_oracle as O   # checker only
+    L = rb.losses
+    torch.manual_seed(5)
+    for shape in [(2, 1, 16, 24, 40), (1, 3, 8, 8, 8), (2, 2, 5, 7, 9)]:
+        z = (torch.randn(*shape, device="cuda") * 4).requires_grad_(True)
+        t = (torch.rand(*shape, device="cuda") > 0.8).float()
+        a = L.FusedBCEDiceLoss(0.5, 0.5)(z, t)
+        (a * 1.7).backward()
+        z2 = z.detach().clone().requires_grad_(True)
+        b = L.BCEDiceLoss(0.5, 0.5)(z2, t)
+        (b * 1.7).backward()
+        assert abs(float(a) - float(b)) < 2e-6 and abs(float(a) - float(O.bce_dice_loss(z.detach().cpu(), t.cpu()))) < 2e-6
+        assert rel_l2(z.grad, z2.grad) < 1e-5
+    for shape in [(2, 3, 16, 24, 40), (1, 3, 7, 9, 11)]:
+        p = torch.randn(*shape, device="cuda", requires_grad=True)
+        tn = torch.nn.functional.normalize(torch.randn(*shape, device="cuda"), dim=1)
+        tn[:, :, :3] = 0
+        a = L.FusedMaskedCosineLoss()(p, tn)
+        (a * 0.6).backward()
+        p2 = p.detach().clone().requires_grad_(True)
+        b = L.MaskedCosineLoss()(p2, tn)
+        (b * 0.6).backward()
+        assert abs(float(a) - float(b)) < 2e-6 and abs(float(a) - float(O.masked_cosine_loss(p.detach().cpu(), tn.cpu()))) < 2e-6
+        assert rel_l2(p.grad, p2.grad) < 1e-5
+    # CPU tensors keep the composition (the fused kernels are CUDA only)
+    zc = torch.randn(1, 1, 4, 4, 4)
+    assert torch.isfinite(L.FusedBCEDiceLoss(0.5, 0.5)(zc, (zc > 0).float()))
