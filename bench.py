@@ -323,6 +323,8 @@ def main():
     rb.ops.KERNEL_TIMER.enable(False)
 
     # ---- timed region 2: end to end (pinned host batch in, loss out, every step) -----------------
+    # (a prefetching variant - next batch copied on a side stream during the step, loss read one step late - measured
+    # slower here, 38.9 vs 33.5 ms per step, so the plain in-order loop stays)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -128,12 +128,16 @@ int rb_wgrad_gather(const RbWgradDesc* d, const void* P, const void* Q0, const v
  *   builders/simple_conv_blocks.py:58-64, builders/resblocks.py:106-114, DNA SqueezeExcite
  * rb_plane_reduce   per-(n,[w],c) reductions in double: kind 0 (sum y, sum y^2); kind 1
  *                   (sum g, sum g*y) with g = dz * lrelu'(z).  out: [NB][G][C][2], G = 1 or W.
+ *                   The sign of z comes either from the stored activation `z` or, when z == NULL and
+ *                   sign_scale / sign_shift ([NB][C], the forward's folded scale / shift) are given, from
+ *                   fmaf(y, scale, shift) > 0 - layers without residual then never re-read z in backward.
  * rb_in_finalize_*  tiny: statistics -> folded scale/shift (fwd) or backward coefficients.
  * rb_norm_act_fwd   z = act(y * scale + shift + res)              one read of y (+res), one write
  * rb_norm_act_bwd   g = dz*act'(z); dres = g; dy = g*k1 + y*k2 + k3
  * ------------------------------------------------------------------------------------------ */
-int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, double* out,
-                    int NB, long long S, int C, int W, int perW, float slope, void* stream);
+int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, const float* sign_scale,
+                    const float* sign_shift, double* out, int NB, long long S, int C, int W, int perW, float slope,
+                    void* stream);
 /* statistics either as double sums[NB][C][2] (rb_plane_reduce) or as the fp32 fsum/fsq[NB][C] the tcgen05
  * conv epilogue accumulated */
 int rb_in_finalize_fwd(const double* sums, const float* fsum, const float* fsq, const float* gamma, const float* beta,
@@ -144,8 +148,8 @@ int rb_in_finalize_bwd(const double* red, const float* mean, const float* rstd, 
                        int NB, int C, double S, void* stream);
 int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const float* scale, const float* shift,
                     int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
-int rb_norm_act_bwd(const void* dz, const void* z, const void* y, int y_f32, void* dy, void* dres,
-                    const float* k1, const float* k2, const float* k3,
+int rb_norm_act_bwd(const void* dz, const void* z, const float* sign_scale, const float* sign_shift, const void* y,
+                    int y_f32, void* dy, void* dres, const float* k1, const float* k2, const float* k3,
                     int NB, long long S, int C, int W, int perW, int act, float slope, void* stream);
 
 /* AvgPool3d(stride, stride) of the ResNet-D skip, builders/resblocks.py:92-95.  D,H,W = full-res dims. */

@@ -51,11 +51,11 @@ SIGNATURES = {
     "rb_conv_gather_tc5_supported": (_I, [C.POINTER(ConvDesc)]),
     "rb_conv_gather_plan": (_I, [C.POINTER(ConvDesc)]),
     "rb_wgrad_gather": (_I, [C.POINTER(WgradDesc), _P, _P, _P, _P, _P]),
-    "rb_plane_reduce": (_I, [_I, _P, _I, _P, _P, _P, _I, _LL, _I, _I, _I, _F, _P]),
+    "rb_plane_reduce": (_I, [_I, _P, _I, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _F, _P]),
     "rb_in_finalize_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _P]),
     "rb_in_finalize_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "rb_norm_act_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _F, _P]),
-    "rb_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _F, _P]),
+    "rb_norm_act_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _F, _P]),
     "rb_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_head_fwd": (_I, [_P, _P, _P, _P, _I, _LL, _I, _I, _I, _P]),

@@ -1004,15 +1004,17 @@ int rb_wgrad_gather(const RbWgradDesc* dp, const void* P, const void* Q0, const 
     return check_launch("gather_wgrad_mma_kernel");
 }
 
-int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, double* out, int NB, long long S, int C,
-                    int W, int perW, float slope, void* stream) {
+int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const void* z, const float* sign_scale,
+                    const float* sign_shift, double* out, int NB, long long S, int C, int W, int perW, float slope, void* stream) {
     if (!y || !out || (kind == 1 && !dz)) return fail(RB_ERR_INVALID, "plane_reduce: null pointer");
+    if ((sign_scale == nullptr) != (sign_shift == nullptr) || (sign_scale && (z || perW || kind != 1)))
+        return fail(RB_ERR_INVALID, "plane_reduce: sign_scale/sign_shift go together, kind 1 only, without z and per-w");
     if (C <= 0 || C % 8 != 0 || NB <= 0 || S <= 0) return fail(RB_ERR_INVALID, "plane_reduce: bad shape");
     if (perW && (W <= 0 || S % W != 0)) return fail(RB_ERR_INVALID, "plane_reduce: S must be a multiple of W");
     if (kind != 0 && kind != 1) return fail(RB_ERR_INVALID, "plane_reduce: kind must be 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
     rb::ReduceParams p;
-    p.y = y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out;
+    p.y = y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out; p.sgnA = sign_scale; p.sgnB = sign_shift;
     p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind; p.yF32 = y_f32 ? 1 : 0;
     const int cg = C / 8;
     const int rows = 256 / cg > 0 ? 256 / cg : 1;
@@ -1066,14 +1068,15 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
     return check_launch("norm_act_fwd_kernel");
 }
 
-int rb_norm_act_bwd(const void* dz, const void* z, const void* y, int y_f32, void* dy, void* dres, const float* k1,
-                    const float* k2, const float* k3, int NB, long long S, int C, int W, int perW, int act, float slope,
-                    void* stream) {
-    if (!dz || !y || !dy || !k1 || !k2 || !k3 || (act && !z)) return fail(RB_ERR_INVALID, "norm_act_bwd: null pointer");
+int rb_norm_act_bwd(const void* dz, const void* z, const float* sign_scale, const float* sign_shift, const void* y, int y_f32,
+                    void* dy, void* dres, const float* k1, const float* k2, const float* k3, int NB, long long S, int C, int W,
+                    int perW, int act, float slope, void* stream) {
+    if (!dz || !y || !dy || !k1 || !k2 || !k3) return fail(RB_ERR_INVALID, "norm_act_bwd: null pointer");
+    if (act && !z && !(sign_scale && sign_shift)) return fail(RB_ERR_INVALID, "norm_act_bwd: the activation needs z or sign_scale/sign_shift");
     int rc = check_apply_shape("norm_act_bwd", NB, S, C, W, perW);
     if (rc) return rc;
     rb::ApplyBwdParams p{(const rb::bf16*)dz, (const rb::bf16*)z, y, (rb::bf16*)dy, (rb::bf16*)dres,
-                         k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0};
+                         k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0, sign_scale, sign_shift};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
     rb::norm_act_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);

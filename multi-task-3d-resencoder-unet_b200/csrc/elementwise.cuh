@@ -53,7 +53,9 @@ __device__ __forceinline__ void load8_prenorm(const void* base, size_t elem, int
 struct ReduceParams {
     const void* y;   // [NB, S, C]  bf16 or fp32 (yF32)
     const bf16* dz;  // kind 1
-    const bf16* z;   // kind 1 with act: sign source (may be null => g = dz)
+    const bf16* z;   // kind 1 with act: sign source (may be null => g = dz, or the sign is recomputed from y)
+    const float* sgnA;   // kind 1, z == null: lrelu'(z) from sign(fmaf(y, sgnA[n][c], sgnB[n][c])) - the expression the
+    const float* sgnB;   // forward pass rounded to z, so the stored activation need not be read again
     double* out;
     long long S;
     int C, W, perW;
@@ -76,6 +78,14 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
             float s1[8], s2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            float sA[8], sB[8];
+            if (active && p.sgnA != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sA[j] = __ldg(p.sgnA + (size_t)nb * p.C + (size_t)mycg * 8 + j);
+                    sB[j] = __ldg(p.sgnB + (size_t)nb * p.C + (size_t)mycg * 8 + j);
+                }
+            }
             if (active) {
                 const size_t base = (size_t)nb * p.S;
                 for (long long v = (long long)blockIdx.x * rows + myrow; v < p.S; v += (long long)gridDim.x * rows) {
@@ -92,6 +102,9 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
                             unpack8(ld_stream(reinterpret_cast<const uint4*>(p.z + off)), zz);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) b[j] = zz[j] > 0.f ? b[j] : b[j] * p.slope;
+                        } else if (p.sgnA != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) b[j] = fmaf(a[j], sA[j], sB[j]) > 0.f ? b[j] : b[j] * p.slope;
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { s1[j] += b[j]; s2[j] += b[j] * a[j]; }
@@ -232,6 +245,8 @@ struct ApplyBwdParams {
     int NB, C, W, perW, act;
     float slope;
     int yF32;
+    const float* sgnA;   // act && z == null: sign of the activation input recomputed as fmaf(y, sgnA, sgnB) > 0
+    const float* sgnB;
 };
 
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams p) {
@@ -250,14 +265,23 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
         const size_t c2 = c1;
         float gd[8], yy[8], a1[8], a2[8], a3[8];
         unpack8(ld_stream(dzv + i), gd);
-        if (p.act) {
+        load8_prenorm(p.y, (base + i) * 8, p.yF32, yy);
+        if (p.act && zv != nullptr) {
             float zz[8];
             unpack8(ld_stream(zv + i), zz);
 #pragma unroll
             for (int j = 0; j < 8; ++j) gd[j] = zz[j] > 0.f ? gd[j] : gd[j] * p.slope;
+        } else if (p.act) {
+            const size_t cs = (size_t)nb * p.C + g * 8;
+            float sa[8], sb[8];
+            *reinterpret_cast<float4*>(sa) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs));
+            *reinterpret_cast<float4*>(sa + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs + 4));
+            *reinterpret_cast<float4*>(sb) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs));
+            *reinterpret_cast<float4*>(sb + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd[j] = fmaf(yy[j], sa[j], sb[j]) > 0.f ? gd[j] : gd[j] * p.slope;
         }
         if (drv != nullptr) drv[i] = pack8(gd);
-        load8_prenorm(p.y, (base + i) * 8, p.yF32, yy);
         *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1));
         *reinterpret_cast<float4*>(a1 + 4) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1 + 4));
         *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(p.k2 + c2));

@@ -223,6 +223,10 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
 PACK_CACHE = True     # set False while capturing a CUDA graph so the (re)packing kernels are part of every replay
 # strided data gradients as one pixel-shuffle launch (False: one launch per parity class, the cross-check path)
 MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
+# InstanceNorm+LeakyReLU backward without re-reading the stored activation (sign recomputed from the fp32 pre-norm).
+# Opt-in: it removes 2 of 8-10 bytes per element from the two backward passes but measured no faster on B200 (the
+# passes run at ~5 TB/s with or without the extra stream), so the default keeps the simpler read of z.
+SIGN_FROM_PRENORM = os.environ.get("RESENC_SIGN_FROM_PRENORM") is not None
 
 
 def _cached_pack(weight, kind, fn):
@@ -494,12 +498,15 @@ def _stem_backward(wshape, col, dy):
 # ------------------------------------------------------------------------------------------
 # primitives (no autograd): InstanceNorm (+affine, +SE gate) + residual + LeakyReLU
 # ------------------------------------------------------------------------------------------
-def _plane_reduce(kind, y, dz, z, per_w, slope):
+def _plane_reduce(kind, y, dz, z, per_w, slope, sign=None):
+    """`sign` = (scale, shift) [N, C] fp32 of the forward pass: the activation's sign is recomputed from y instead of
+    being read from the stored z (layers without residual / gate)."""
     n, c, d, h, w = y.shape
     g = w if per_w else 1
     out = torch.empty((n, g, c, 2), dtype=torch.float64, device=y.device)
     with KERNEL_TIMER.span("norm_reduce"):
         rc = L.load().rb_plane_reduce(kind, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(dz), L.ptr(z),
+                                      L.ptr(sign[0]) if sign else None, L.ptr(sign[1]) if sign else None,
                                       out.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, float(slope), L.stream_ptr())
     L.check(rc, "rb_plane_reduce")
     return out
@@ -516,12 +523,13 @@ def _apply_fwd(y, res, A, B, per_w, act, slope):
     return z
 
 
-def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres):
+def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres, sign=None):
     n, c, d, h, w = y.shape
     dy = new_cl(n, c, d, h, w, y.device)
     dres = new_cl(n, c, d, h, w, y.device) if want_dres else None
     with KERNEL_TIMER.span("norm_apply"):
-        rc = L.load().rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), y.data_ptr(), 1 if y.dtype == torch.float32 else 0,
+        rc = L.load().rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), L.ptr(sign[0]) if sign else None,
+                                      L.ptr(sign[1]) if sign else None, y.data_ptr(), 1 if y.dtype == torch.float32 else 0,
                                       dy.data_ptr(), L.ptr(dres), k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), n,
                                       d * h * w, c, w, 1 if per_w else 0, 1 if act else 0, float(slope), L.stream_ptr())
     L.check(rc, "rb_norm_act_bwd")
@@ -580,14 +588,17 @@ def _norm_backward(st, y, z, dz, want_dres):
     S = d * h * w
     lib = L.load()
     if st.gate is None:
-        red = _plane_reduce(1, y, dz, z, False, st.slope)
+        # no residual, no gate: z = lrelu(fmaf(y, scale, shift)), so lrelu'(z) follows from y and the stored z is not read
+        sign = (st.small[2], st.small[3]) if (st.act and not st.has_res and SIGN_FROM_PRENORM) else None
+        zs = None if (sign is not None or not st.act) else z
+        red = _plane_reduce(1, y, dz, zs, False, st.slope, sign)
         ks = torch.empty((3, n, c), dtype=torch.float32, device=y.device)
         dgamma = torch.zeros(c, dtype=torch.float32, device=y.device) if st.gamma is not None else None
         dbeta = torch.zeros(c, dtype=torch.float32, device=y.device) if st.has_beta else None
         L.check(lib.rb_in_finalize_bwd(red.data_ptr(), st.small[0].data_ptr(), st.small[1].data_ptr(), L.ptr(st.gamma),
                                        ks[0].data_ptr(), ks[1].data_ptr(), ks[2].data_ptr(), L.ptr(dgamma), L.ptr(dbeta),
                                        n, c, float(S), L.stream_ptr()), "rb_in_finalize_bwd")
-        dy, dres = _apply_bwd(dz, z, y, ks[0], ks[1], ks[2], False, st.act, st.slope, want_dres)
+        dy, dres = _apply_bwd(dz, zs, y, ks[0], ks[1], ks[2], False, st.act, st.slope, want_dres, sign)
         return dy, dres, dgamma, dbeta, None
     leaves, pl, A, B = st.gate
     per_w = st.per_w

@@ -343,3 +343,26 @@ def test_fused_losses_match_compositions(rb):
     # CPU tensors keep the composition (the fused kernels are CUDA only)
     zc = torch.randn(1, 1, 4, 4, 4)
     assert torch.isfinite(L.FusedBCEDiceLoss(0.5, 0.5)(zc, (zc > 0).float()))
+
+
+def test_norm_backward_sign_from_prenorm(rb):
+    """Opt-in backward of conv + InstanceNorm + LeakyReLU that recomputes lrelu'(z) from the fp32 pre-norm tensor and
+    the forward's folded scale / shift instead of reading the stored activation: same gradients."""
+    ops = rb.ops
+    torch.manual_seed(9)
+    x = q(torch.randn(2, 32, 12, 16, 16, device="cuda"))
+    w = (torch.randn(32, 32, 3, 3, 3, device="cuda") / 30).requires_grad_(True)
+    g = q(torch.randn(2, 32, 12, 16, 16, device="cuda")).to(torch.bfloat16)
+    outs = []
+    for flag in (False, True):
+        ops.SIGN_FROM_PRENORM = flag
+        try:
+            xp = x.clone().requires_grad_(True)
+            w.grad = None
+            z = ops.conv_norm_act(xp, w, (1, 1, 1), None, None, None, None, 1e-5, True, 0.01)
+            z.backward(g)
+            outs.append((z.detach().float(), xp.grad.float(), w.grad.clone()))
+        finally:
+            ops.SIGN_FROM_PRENORM = False
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-3
+    assert rel_l2(outs[1][1], outs[0][1]) < 5e-3 and rel_l2(outs[1][2], outs[0][2]) < 5e-3

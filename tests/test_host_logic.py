@@ -139,7 +139,7 @@ def test_c_abi_rejects_bad_descriptors_without_gpu(rb, built_lib):
     d = rb._lib.ConvDesc()
     rc = built_lib.rb_conv_gather(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"nsrc" in built_lib.rb_last_error()
-    assert built_lib.rb_plane_reduce(0, None, 0, None, None, None, 1, 8, 8, 1, 0, 0.01, None) == -1
+    assert built_lib.rb_plane_reduce(0, None, 0, None, None, None, None, None, 1, 8, 8, 1, 0, 0.01, None) == -1
     assert built_lib.rb_blend_finalize_cast(None, None, None, None, 8, 1, 0, None) == -1
 
 
