@@ -1029,7 +1029,8 @@ int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const vo
         gx = (int)(want < 1 ? 1 : want);
     }
     const size_t smem = (size_t)256 * 16 * sizeof(float);
-    rb::plane_reduce_kernel<<<dim3(gx, NB), 256, smem, st>>>(p);
+    if (sign_scale) rb::plane_reduce_kernel<true><<<dim3(gx, NB), 256, smem, st>>>(p);
+    else rb::plane_reduce_kernel<false><<<dim3(gx, NB), 256, smem, st>>>(p);
     return check_launch("plane_reduce_kernel");
 }
 

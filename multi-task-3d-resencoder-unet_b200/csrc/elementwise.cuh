@@ -64,6 +64,9 @@ struct ReduceParams {
     int yF32;
 };
 
+// SGN: the sign-from-pre-norm variant (separate instantiation: its 16 extra registers would cost the default
+// path one resident block per SM)
+template <bool SGN>
 __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p) {
     extern __shared__ float red[];  // [rows][cg*16]
     const int cg = p.C >> 3;
@@ -78,14 +81,6 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
             float s1[8], s2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-            float sA[8], sB[8];
-            if (active && p.sgnA != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sA[j] = __ldg(p.sgnA + (size_t)nb * p.C + (size_t)mycg * 8 + j);
-                    sB[j] = __ldg(p.sgnB + (size_t)nb * p.C + (size_t)mycg * 8 + j);
-                }
-            }
             if (active) {
                 const size_t base = (size_t)nb * p.S;
                 for (long long v = (long long)blockIdx.x * rows + myrow; v < p.S; v += (long long)gridDim.x * rows) {
@@ -102,7 +97,14 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
                             unpack8(ld_stream(reinterpret_cast<const uint4*>(p.z + off)), zz);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) b[j] = zz[j] > 0.f ? b[j] : b[j] * p.slope;
-                        } else if (p.sgnA != nullptr) {
+                        } else if (SGN) {
+                            // scale / shift re-read per row (L1 hits) instead of 16 live registers per thread
+                            const size_t cs = (size_t)nb * p.C + (size_t)mycg * 8;
+                            float sA[8], sB[8];
+                            *reinterpret_cast<float4*>(sA) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs));
+                            *reinterpret_cast<float4*>(sA + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs + 4));
+                            *reinterpret_cast<float4*>(sB) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs));
+                            *reinterpret_cast<float4*>(sB + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs + 4));
 #pragma unroll
                             for (int j = 0; j < 8; ++j) b[j] = fmaf(a[j], sA[j], sB[j]) > 0.f ? b[j] : b[j] * p.slope;
                         }

@@ -223,10 +223,10 @@ def _launch_wgrad(P, Q0, Q1, *, grid, qdims, taps, off, istr, impl=None):
 PACK_CACHE = True     # set False while capturing a CUDA graph so the (re)packing kernels are part of every replay
 # strided data gradients as one pixel-shuffle launch (False: one launch per parity class, the cross-check path)
 MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
-# InstanceNorm+LeakyReLU backward without re-reading the stored activation (sign recomputed from the fp32 pre-norm).
-# Opt-in: it removes 2 of 8-10 bytes per element from the two backward passes but measured no faster on B200 (the
-# passes run at ~5 TB/s with or without the extra stream), so the default keeps the simpler read of z.
-SIGN_FROM_PRENORM = os.environ.get("RESENC_SIGN_FROM_PRENORM") is not None
+# InstanceNorm+LeakyReLU backward without re-reading the stored activation: layers without residual / gate recompute
+# lrelu'(z) from the fp32 pre-norm tensor and the forward's folded scale / shift (2 of 8-10 bytes per element less in
+# both backward passes; 32.5 -> 32.1 ms per step).  RESENC_NO_SIGN_FROM_PRENORM=1 restores the read of z.
+SIGN_FROM_PRENORM = os.environ.get("RESENC_NO_SIGN_FROM_PRENORM") is None
 
 
 def _cached_pack(weight, kind, fn):

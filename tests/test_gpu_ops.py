@@ -346,7 +346,7 @@ def test_fused_losses_match_compositions(rb):
 
 
 def test_norm_backward_sign_from_prenorm(rb):
-    """Opt-in backward of conv + InstanceNorm + LeakyReLU that recomputes lrelu'(z) from the fp32 pre-norm tensor and
+    """Backward of conv + InstanceNorm + LeakyReLU that recomputes lrelu'(z) from the fp32 pre-norm tensor and
     the forward's folded scale / shift instead of reading the stored activation: same gradients."""
     ops = rb.ops
     torch.manual_seed(9)
@@ -363,6 +363,6 @@ def test_norm_backward_sign_from_prenorm(rb):
             z.backward(g)
             outs.append((z.detach().float(), xp.grad.float(), w.grad.clone()))
         finally:
-            ops.SIGN_FROM_PRENORM = False
+            ops.SIGN_FROM_PRENORM = True
     assert rel_l2(outs[1][0], outs[0][0]) < 1e-3
     assert rel_l2(outs[1][1], outs[0][1]) < 5e-3 and rel_l2(outs[1][2], outs[0][2]) < 5e-3
