@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-parameter gradient comparison of the CUDA path against the oracle's fp32 autograd on one golden case
-(diagnostic; prints rel-L2 of every parameter gradient in registration order)."""
+(diagnostic script, not collected by pytest; it lives under tests/ because it calls the oracle; prints rel-L2 of every
+parameter gradient in registration order)."""
 import importlib
 import sys
 import os
