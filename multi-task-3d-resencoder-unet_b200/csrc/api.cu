@@ -175,6 +175,7 @@ struct Tc5tPlan {
     size_t smem = 0;
     bool statSmem = false;
     int splitK = 1, tapsPer = 27;
+    bool hm = false;   // h-major 32 x 8 tile: one X load per (kd, kh) serves the three kw taps (conv_tc5t.cuh)
 };
 
 Tc5tPlan plan_tc5t(const RbConvDesc& d) {
@@ -225,6 +226,26 @@ Tc5tPlan plan_tc5t(const RbConvDesc& d) {
         pl.tapsPer = (int)((ntaps + want - 1) / want);
         pl.splitK = (ntaps + pl.tapsPer - 1) / pl.tapsPer;
     }
+    // h-major tile for plain 3-tap-wide stride-1 convolutions on rows that are whole multiples of 32 voxels: the per-tap
+    // gather is TMA-row-rate bound at 64/128-byte channel rows (cycle counters: 18.6 k cycles of loads against 13.5 k of
+    // MMAs per 64->64 tile), this layout loads 9 boxes of 272 rows per tile instead of 27 boxes of 256
+    static const bool no_hm = getenv("RESENC_NO_TC5T_HM") != nullptr;
+    if (!no_hm && pl.splitK == 1 && d.mode == 0 && d.tapW == 3 && d.offW == -1 && d.istrD == 1 && d.istrH == 1 && d.istrW == 1 &&
+        d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1 && d.ooffD == 0 && d.ooffH == 0 && d.ooffW == 0 && d.FD == d.OD &&
+        d.FH == d.OH && d.FW == d.OW && d.OW % 32 == 0 && d.OW == d.IW && d.Nout <= 128 && pl.KW >= 32) {
+        const int wRows = d.Nout;
+        const size_t sb = ((size_t)34 * 8 + 2 * wRows + 128) * pl.KW * 2;
+        int sth = (int)((200 * 1024 - reserve) / sb);
+        if (sth > 6) sth = 6;
+        if (sth >= 2 && sb % 1024 == 0) {
+            pl.hm = true;
+            pl.lw = 5; pl.lh = 3; pl.ld = 0; pl.tn = 1;
+            pl.tilesW = d.OW / 32; pl.tilesH = (d.OH + 7) / 8; pl.tilesD = d.OD; pl.tilesNB = d.NB;
+            pl.tiles = (long long)pl.tilesW * pl.tilesH * pl.tilesD * pl.tilesNB * pl.tilesM;
+            pl.stages = sth;
+            pl.smem = 1024 + 1024 + (size_t)sth * sb + reserve;
+        }
+    }
     pl.ok = true;
     return pl;
 }
@@ -260,6 +281,12 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
         cuuint32_t box[5] = {(cuuint32_t)pl.KW, (cuuint32_t)((tw - 1) * d.istrW + 1), (cuuint32_t)((th - 1) * d.istrH + 1),
                              (cuuint32_t)((td - 1) * d.istrD + 1), (cuuint32_t)pl.tn};
         cuuint32_t estr[5] = {1, (cuuint32_t)d.istrW, (cuuint32_t)d.istrH, (cuuint32_t)d.istrD, 1};
+        if (pl.hm) {   // dimension order (c, h, w, d, n): the box lands in shared memory as [w][h][c]
+            dims[1] = (cuuint64_t)d.IH; dims[2] = (cuuint64_t)d.IW;
+            strides[0] = C * 2 * d.IW; strides[1] = C * 2;
+            box[1] = 8; box[2] = 34; box[3] = 1; box[4] = 1;
+            estr[1] = estr[2] = estr[3] = 1;
+        }
         CUresult r = enc(&p.mapX[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(srcs[s]), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -270,7 +297,7 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
         const int ntaps = d.tapD * d.tapH * d.tapW;
         cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d.Nout, (cuuint64_t)ntaps};
         cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)ctot * 2 * d.Nout};
-        cuuint32_t box[3] = {(cuuint32_t)pl.KW, 128, 1};
+        cuuint32_t box[3] = {(cuuint32_t)pl.KW, (cuuint32_t)(d.Nout < 128 ? d.Nout : 128), (cuuint32_t)(pl.hm ? 3 : 1)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&p.mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.KW), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -288,12 +315,14 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     p.FD = d.FD; p.FH = d.FH; p.FW = d.FW;
     p.out0 = out0; p.out1 = out1; p.outC0 = d.outC0; p.outC1 = d.outC1; p.outF32 = d.outF32;
     p.stages = pl.stages; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.statSmem = pl.statSmem ? 1 : 0;
+    p.wRows = d.Nout < 128 ? d.Nout : 128;
+    p.hm = pl.hm ? 1 : 0;
     p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
     p.splitK = pl.splitK; p.tapsPer = pl.tapsPer; p.fdSplitK = rb::make_fastdiv(pl.splitK); p.ws = ws;
     {
-        static const int dbg = getenv("RESENC_TC5_DEBUG") ? atoi(getenv("RESENC_TC5_DEBUG")) : 0;
-        p.debug = dbg & 7;
+        static const int dbg = getenv("RESENC_TC5T_DEBUG") ? atoi(getenv("RESENC_TC5T_DEBUG")) : 0;
+        p.debug = dbg & 15;
     }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;

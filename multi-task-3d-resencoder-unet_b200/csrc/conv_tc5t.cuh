@@ -21,7 +21,7 @@ namespace rb {
 
 struct Tc5tConvParams {
     CUtensorMap mapX[2];  // rank 5 (C, W, H, D, N), box (KW, tw.., tn) covering 256 output voxels
-    CUtensorMap mapW;     // rank 3 (Ctot, Nout, taps), box (KW, 128, 1): rows >= Nout are zero filled
+    CUtensorMap mapW;     // rank 3 (Ctot, Nout, taps), box (KW, wRows, 1); with several M tiles rows >= Nout are zero filled
     int nsrc, srcC[2];
     int KW;
     int tapD, tapH, tapW, offD, offH, offW, istrD, istrH, istrW;
@@ -36,6 +36,10 @@ struct Tc5tConvParams {
     int outC0, outC1;
     int outF32;
     int stages;
+    int hm;               // 1 = h-major tile (32 w x 8 h): X box (KW, 8 h, 34 w), smem rows ordered [w][h], so a kw shift is 8
+                          // rows = one swizzle atom and the three kw taps of a (kd, kh) share ONE X load (1/3 of the TMA rows)
+    int wRows;            // rows of the weight box (= min(128, Nout)): rows beyond it are never loaded - the MMA reads
+                          // stale shared memory there and fills TMEM lanes no epilogue warp reads
     float* stat_sum;
     float* stat_sq;
     int statSmem;
@@ -45,7 +49,7 @@ struct Tc5tConvParams {
     int splitK, tapsPer;
     FastDiv fdSplitK;
     float* ws;
-    int debug;   // profiling experiments only (RESENC_TC5_DEBUG): 1 skip MMAs, 2 skip TMA loads, 4 skip the epilogue body
+    int debug;   // profiling experiments only (RESENC_TC5T_DEBUG bit mask): 1 skip MMAs, 2 skip TMA loads, 4 skip the epilogue body
 };
 
 static constexpr int TC5T_THREADS = 192;
@@ -63,8 +67,11 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int S = p.stages;
-    const uint32_t bytesX = (uint32_t)TC5T_VOX * p.KW * 2u;
-    const uint32_t bytesW = 128u * p.KW * 2u;
+    const uint32_t rowB = (uint32_t)p.KW * 2u;
+    const uint32_t bytesX = (p.hm ? 34u * 8u : (uint32_t)TC5T_VOX) * rowB;
+    // hm: three weight tiles of wRows rows; the MMA of the last one reads 128 rows, so the region is 2*wRows + 128 rows
+    const uint32_t bytesW = (p.hm ? (2u * (uint32_t)p.wRows + 128u) : 128u) * rowB;
+    const uint32_t txBytes = bytesX + (p.hm ? 3u : 1u) * (uint32_t)p.wRows * rowB;
     const uint32_t stageBytes = bytesX + bytesW;
     const uint32_t tile_base = smem_u32(tiles);
     const uint32_t bar_base = smem_u32(bars);
@@ -108,6 +115,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
     const int totalTiles = p.tilesW * p.tilesH * p.tilesD * p.tilesNB * p.tilesM * p.splitK;
     const int Ctot = p.srcC[0] + (p.nsrc > 1 ? p.srcC[1] : 0);
     const int ntaps = p.tapD * p.tapH * p.tapW;
+    const bool dbgT = (p.debug & 8) && blockIdx.x == 0;   // per-role cycle counters of CTA 0 (rb_debug_counters)
 
     auto decode = [&](int tile, uint32_t& mt, uint32_t& tiw, uint32_t& tih, uint32_t& tid, uint32_t& tib, uint32_t& sk) {
         uint32_t sp;
@@ -122,6 +130,8 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
         // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
+        long long tW = 0;
+        const long long tA = clock64();
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
             uint32_t mt, tiw, tih, tid, tib, sk;
             decode(tile, mt, tiw, tih, tid, tib, sk);
@@ -133,21 +143,24 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                 const int iz = od0 * p.istrD + p.offD + kd;
                 for (int kh = 0; kh < p.tapH; ++kh) {
                     const int iy = oh0 * p.istrH + p.offH + kh;
-                    for (int kw = 0; kw < p.tapW; ++kw, ++t) {
+                    for (int kw = 0; kw < (p.hm ? 1 : p.tapW); ++kw, t += (p.hm ? 3 : 1)) {
                         if (t < t0 || t >= t1) continue;
                         const int ix = ow0 * p.istrW + p.offW + kw;
                         int cbase = 0;
                         for (int s = 0; s < p.nsrc; ++s) {
                             for (int c = 0; c < p.srcC[s]; c += p.KW) {
+                                const long long w0 = dbgT ? clock64() : 0;
                                 mbar_wait(empty_bar(stage), phase ^ 1u, DEVERR_WAIT_EMPTY, err_flag);
+                                if (dbgT) tW += clock64() - w0;
                                 if (elect_one()) {
                                     const uint32_t dstX = tile_base + stage * stageBytes;
                                     const uint32_t dstW = dstX + bytesX;
-                                    if (p.debug == 2) {
+                                    if (p.debug & 2) {
                                         mbar_arrive(full_bar(stage));
                                     } else {
-                                        mbar_expect_tx(full_bar(stage), stageBytes);
-                                        tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, ix, iy, iz, nb0);
+                                        mbar_expect_tx(full_bar(stage), txBytes);
+                                        if (p.hm) tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, iy, ix, iz, nb0);   // dims (c, h, w, d, n)
+                                        else tma_load_5d(dstX, &p.mapX[s], full_bar(stage), c, ix, iy, iz, nb0);
                                         tma_load_3d(dstW, &p.mapW, full_bar(stage), cbase + c, m0, t);
                                     }
                                 }
@@ -160,6 +173,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                 }
             }
         }
+        if (dbgT && lane == 0) { g_dbg[0] = (unsigned long long)tW; g_dbg[1] = (unsigned long long)(clock64() - tA); }
     } else if (warp == 1) {
         // ===================== MMA issuer: A = weights (M = 128), B = voxels (N = 256) =====================
         const uint32_t idesc = make_idesc_bf16(128, TC5T_VOX, 0, 0);
@@ -170,24 +184,36 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long tWF = 0, tWT = 0, nTiles = 0;
+        const long long tA = clock64();
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
             uint32_t mt_, tiw_, tih_, tid_, tib_, sk;
             decode(tile, mt_, tiw_, tih_, tid_, tib_, sk);
             const int t0 = (int)sk * p.tapsPer, t1 = min(ntaps, t0 + p.tapsPer);
-            const int stepsPerTile = (t1 - t0) * (Ctot / p.KW);
+            const int stepsPerTile = (p.hm ? (t1 - t0) / 3 : (t1 - t0)) * (Ctot / p.KW);
+            const long long w0 = dbgT ? clock64() : 0;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
+            if (dbgT) { tWT += clock64() - w0; ++nTiles; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC5T_VOX);
             for (int ks = 0; ks < stepsPerTile; ++ks) {
+                const long long w1 = dbgT ? clock64() : 0;
                 mbar_wait(full_bar(stage), phase, DEVERR_WAIT_FULL, err_flag);
+                if (dbgT) tWF += clock64() - w1;
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t xAddr = tile_base + stage * stageBytes;
                     const uint32_t wAddr = xAddr + bytesX;
-                    for (int k = 0; k < kPerStep && p.debug != 1; ++k) {
-                        const uint64_t da = make_smem_desc(wAddr + k * 32u, 16u, sbo, lay);
-                        const uint64_t db = make_smem_desc(xAddr + k * 32u, 16u, sbo, lay);
-                        umma_bf16(d_tmem, da, db, idesc, (ks | k) ? 1u : 0u);
+                    const int nkw = p.hm ? 3 : 1;
+                    for (int kw = 0; kw < nkw; ++kw) {
+                        // hm: tap kw = weight tile kw, B shifted by 8 rows (one w step of the [w][h] ordered box)
+                        const uint32_t wA = wAddr + (uint32_t)kw * (uint32_t)p.wRows * rowB;
+                        const uint32_t xA = xAddr + (uint32_t)kw * 8u * rowB;
+                        for (int k = 0; k < kPerStep && !(p.debug & 1); ++k) {
+                            const uint64_t da = make_smem_desc(wA + k * 32u, 16u, sbo, lay);
+                            const uint64_t db = make_smem_desc(xA + k * 32u, 16u, sbo, lay);
+                            umma_bf16(d_tmem, da, db, idesc, (ks | k | kw) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(stage));
                 }
@@ -198,21 +224,29 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (dbgT && lane == 0) {
+            g_dbg[2] = (unsigned long long)tWF; g_dbg[3] = (unsigned long long)tWT; g_dbg[4] = (unsigned long long)(clock64() - tA);
+            g_dbg[11] = (unsigned long long)nTiles;
+        }
     } else {
         // ===================== epilogue (warps 2..5): lane = output channel, column = voxel =====================
         const int quad = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
         const int spatial = tw * th * td;   // voxels of one sample inside a tile (a multiple of 32 or < 32)
+        long long tWE = 0;
+        const long long tAE = clock64();
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
             uint32_t mt, tiw, tih, tid, tib, sk;
             decode(tile, mt, tiw, tih, tid, tib, sk);
             const int co = (int)mt * 128 + quad * 32 + lane;
             const bool rowValid = co < p.Nout;
             const bool warpHasRows = (int)mt * 128 + quad * 32 < p.Nout;
+            const long long we0 = dbgT ? clock64() : 0;
             mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
+            if (dbgT) tWE += clock64() - we0;
             tc_fence_after();
-            if (warpHasRows && p.debug != 4) {
+            if (warpHasRows && !(p.debug & 4)) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC5T_VOX);
                 // destination of this lane's channel
                 const bool first = co < p.outC0;
@@ -225,7 +259,49 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                     tmem_ld_wait();
                     float s1 = 0.f, s2 = 0.f;
                     int nbStat = -1;
-                    if (p.splitK > 1) {
+                    if (p.hm) {
+                        // column n of the tile = voxel (w = n >> 3, h = n & 7); plain stride-1 convolution (checked by the host)
+                        const int ow0 = (int)tiw * 32 + (cg >> 3), oh0 = (int)tih * 8, od = (int)tid, nb = (int)tib;
+                        nbStat = nb;
+                        const size_t e0 = ((((size_t)nb * p.OD + od) * p.OH + oh0) * p.OW + ow0) * cpitch + cdst;
+                        const int rs = p.OW * cpitch;
+                        float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (oh0 + 8 <= p.OH && ow0 + 4 <= p.OW) {
+                            if (p.outF32) {
+                                float* dst = reinterpret_cast<float*>(base) + e0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (rowValid) dst[(j & 7) * rs + (j >> 3) * cpitch] = __uint_as_float(v[j]);
+                            } else {
+                                bf16* dst = reinterpret_cast<bf16*>(base) + e0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (rowValid) dst[(j & 7) * rs + (j >> 3) * cpitch] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float x = __uint_as_float(v[j]);
+                                a1[j & 3] += x;
+                                a2[j & 3] = fmaf(x, x, a2[j & 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (oh0 + (j & 7) < p.OH && ow0 + (j >> 3) < p.OW) {
+                                    const float x = __uint_as_float(v[j]);
+                                    a1[j & 3] += x;
+                                    a2[j & 3] = fmaf(x, x, a2[j & 3]);
+                                    if (rowValid) {
+                                        const size_t e = e0 + (size_t)((j & 7) * rs + (j >> 3) * cpitch);
+                                        if (p.outF32) reinterpret_cast<float*>(base)[e] = x;
+                                        else reinterpret_cast<bf16*>(base)[e] = __float2bfloat16_rn(x);
+                                    }
+                                }
+                            }
+                        }
+                        s1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+                        s2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
+                    } else if (p.splitK > 1) {
                         // partial tile of one tap slice: fp32 adds into ws[m][Nout], m = linear output-grid voxel
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -257,29 +333,45 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                             const int fd = od * p.ostrD + p.ooffD, fh = oh * p.ostrH + p.ooffH, fw0 = ow0 * p.ostrW + p.ooffW;
                             const size_t vox0 = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw0;
                             const size_t e0 = vox0 * cpitch + cdst;
-                            const size_t estep = (size_t)p.ostrW * cpitch;
+                            const int estep = p.ostrW * cpitch;       // elements between consecutive columns (fits 32 bits)
                             const int nvalid = min(32, p.OW - ow0);   // columns beyond the row end are padding
-                            if (p.outF32) {
-                                float* dst = reinterpret_cast<float*>(base) + e0;
+                            // straight-line stores and four independent statistics chains: per-column branches and a
+                            // single dependent FADD/FFMA chain made this loop ~85 cycles per column (cycle counters)
+                            float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (nvalid == 32) {
+                                if (p.outF32) {
+                                    float* dst = reinterpret_cast<float*>(base) + e0;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (rowValid) dst[j * estep] = __uint_as_float(v[j]);
+                                } else {
+                                    bf16* dst = reinterpret_cast<bf16*>(base) + e0;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (rowValid) dst[j * estep] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                                }
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid) {
-                                        const float x = __uint_as_float(v[j]);
-                                        s1 += x; s2 += x * x;
-                                        if (rowValid) dst[j * estep] = x;
-                                    }
+                                    const float x = __uint_as_float(v[j]);
+                                    a1[j & 3] += x;
+                                    a2[j & 3] = fmaf(x, x, a2[j & 3]);
                                 }
                             } else {
-                                bf16* dst = reinterpret_cast<bf16*>(base) + e0;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
                                     if (j < nvalid) {
                                         const float x = __uint_as_float(v[j]);
-                                        s1 += x; s2 += x * x;
-                                        if (rowValid) dst[j * estep] = __float2bfloat16_rn(x);
+                                        a1[j & 3] += x;
+                                        a2[j & 3] = fmaf(x, x, a2[j & 3]);
+                                        if (rowValid) {
+                                            if (p.outF32) reinterpret_cast<float*>(base)[e0 + (size_t)j * estep] = x;
+                                            else reinterpret_cast<bf16*>(base)[e0 + (size_t)j * estep] = __float2bfloat16_rn(x);
+                                        }
                                     }
                                 }
                             }
+                            s1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+                            s2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
                         }
                     } else {
 #pragma unroll
@@ -329,6 +421,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (dbgT && quad == 0 && lane == 0) { g_dbg[8] = (unsigned long long)tWE; g_dbg[10] = (unsigned long long)(clock64() - tAE); }
     }
 
     tc_fence_before();
