@@ -660,6 +660,7 @@ struct Tw52Plan {
     int kbox = 64, cw = 0, ch = 0, cd = 0, cn = 0, chunksW = 0, chunksH = 0, chunksD = 0, chunksN = 0;
     int splits = 1, chunksPerSplit = 0, stages = 0;
     size_t smem = 0;
+    bool merged = false;
 };
 
 Tw52Plan plan_tw52(const RbWgradDesc& d) {
@@ -681,6 +682,15 @@ Tw52Plan plan_tw52(const RbWgradDesc& d) {
     pl.nAtomsTotal = d.tapD * d.tapH * (d.PC / pl.pw);
     pl.mGroups = (pl.mAtomsTotal + pl.mPerGroup - 1) / pl.mPerGroup;
     pl.nGroups = (pl.nAtomsTotal + pl.nPerGroup - 1) / pl.nPerGroup;
+    // 32-channel P: all nine (kd,kh) atoms (288 columns) fit one TMEM accumulator, so one item issues both the 256- and
+    // the 32-column MMA on the same Q boxes instead of two items that each load them (the kernel is TMA-row-rate bound:
+    // 960 box rows per 64 voxels against 768 merged)
+    static const bool no_merge = getenv("RESENC_NO_WGRAD2_MERGE") != nullptr;
+    if (!no_merge && pl.nGroups > 1 && pl.nAtomsTotal * pl.pw <= 512 && pl.nAtomsTotal <= 16) {
+        pl.merged = true;
+        pl.nPerGroup = pl.nAtomsTotal;
+        pl.nGroups = 1;
+    }
     long long best = -1;
     for (int cw = 1; cw <= pl.kbox; cw <<= 1)
         for (int ch = 1; cw * ch <= pl.kbox; ch <<= 1)
@@ -704,7 +714,7 @@ Tw52Plan plan_tw52(const RbWgradDesc& d) {
     if (splits < 1) splits = 1;
     pl.chunksPerSplit = (int)((best + splits - 1) / splits);
     pl.splits = (int)((best + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
-    const size_t stageBytes = (size_t)pl.kbox * 2 * (128 + 256);
+    const size_t stageBytes = (size_t)pl.kbox * 2 * (128 + (pl.merged ? pl.nAtomsTotal * pl.pw : 256));
     int st = (int)((200 * 1024) / stageBytes);
     if (st > 8) st = 8;
     if (st < 2) return pl;
@@ -805,6 +815,7 @@ int launch_tw52(const RbWgradDesc& d, const Tw52Plan& pl, const void* P, const v
     p.PC = d.PC; p.QC[0] = d.QC0; p.QC[1] = d.nq == 2 ? d.QC1 : 0; p.nq = d.nq;
     p.pw = pl.pw; p.qw = pl.qw; p.mAtomsTotal = pl.mAtomsTotal; p.nAtomsTotal = pl.nAtomsTotal;
     p.mPerGroup = pl.mPerGroup; p.nPerGroup = pl.nPerGroup; p.mGroups = pl.mGroups; p.nGroups = pl.nGroups;
+    p.merged = pl.merged ? 1 : 0;
     p.tapD = d.tapD; p.tapH = d.tapH; p.tapW = d.tapW; p.offD = d.offD; p.offH = d.offH; p.offW = d.offW;
     p.kbox = pl.kbox; p.cw = pl.cw; p.ch = pl.ch; p.cd = pl.cd; p.cn = pl.cn;
     p.chunksW = pl.chunksW; p.chunksH = pl.chunksH; p.chunksD = pl.chunksD; p.chunksN = pl.chunksN;

@@ -29,6 +29,8 @@ struct Tc5Wgrad2Params {
     int mPerGroup;         // 128 / qw
     int nPerGroup;         // 256 / pw
     int mGroups, nGroups;
+    int merged;            // all N atoms (<= 512 columns) in one item: the Q boxes are loaded once per voxel chunk and two
+                           // MMAs (256 + rest columns) share them; single TMEM accumulator of nAtomsTotal*pw columns
     int tapD, tapH, tapW, offD, offH, offW;
     int kbox;              // voxels per stage (64 or 128)
     int cw, ch, cd, cn;    // voxel chunk box, product kbox
@@ -116,16 +118,16 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             const int c0 = sp * p.chunksPerSplit;
             const int c1 = min(nChunks, c0 + p.chunksPerSplit);
             // per-item atom tables (divisions once per item)
-            int aX[8], aC[8], aSrc[8], bY[8], bZ[8], bC[8];
+            int aX[8], aC[8], aSrc[8], bY[16], bZ[16], bC[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ja = (int)mg * p.mPerGroup + j;
+            for (int j = 0; j < 16; ++j) {
+                const int ja = (int)mg * p.mPerGroup + (j & 7);
                 const int kw = ja / qAtomsPerTap;
                 const int cb = (ja - kw * qAtomsPerTap) * p.qw;
                 const bool second = p.nq > 1 && cb >= p.QC[0];
-                aX[j] = p.offW + kw;
-                aC[j] = second ? cb - p.QC[0] : cb;
-                aSrc[j] = second ? 1 : 0;
+                aX[j & 7] = p.offW + kw;
+                aC[j & 7] = second ? cb - p.QC[0] : cb;
+                aSrc[j & 7] = second ? 1 : 0;
                 const int jb = (int)ng * p.nPerGroup + j;
                 const int s = jb / pAtomsPerTap;
                 const int kd = s / p.tapH, kh = s - kd * p.tapH;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
                         if (j < nA)
                             tma_load_5d(dstA + j * atomA, &p.mapQ[aSrc[j]], full_bar(stage), aC[j], uw + aX[j], uh, ud, n0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < 16; ++j)
                         if (j < nB)
                             tma_load_5d(dstB + j * atomB, &p.mapP, full_bar(stage), bC[j], uw, uh + bY[j], ud + bZ[j], n0);
                 }
@@ -174,7 +176,10 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             const int c0 = sp * p.chunksPerSplit;
             const int c1 = min(nChunks, c0 + p.chunksPerSplit);
             if (c0 >= c1) continue;
-            const uint32_t idesc = make_idesc_bf16(128, nB * p.pw, 1, 1);   // both operands MN-major
+            const int ncol = nB * p.pw;
+            const int n1 = ncol > 256 ? 256 : ncol, n2 = ncol - n1;
+            const uint32_t idesc = make_idesc_bf16(128, n1, 1, 1);   // both operands MN-major
+            const uint32_t idesc2 = make_idesc_bf16(128, n2 > 0 ? n2 : 8, 1, 1);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u, DEVERR_WAIT_TMEM_EMPTY, err_flag);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
@@ -188,6 +193,10 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
                         const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
                         const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);
                         umma_bf16(d_tmem, da, db, idesc, (c > c0 || k > 0) ? 1u : 0u);
+                        if (n2 > 0) {
+                            const uint64_t db2 = make_smem_desc(bAddr + (uint32_t)(256 / p.pw) * atomB + k * 2u * sboB, atomB, sboB, layB);
+                            umma_bf16(d_tmem + 256u, da, db2, idesc2, (c > c0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(stage));
                 }
@@ -196,7 +205,8 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             }
             if (elect_one()) umma_commit(tfull_bar(acc));
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (p.merged) acc_phase ^= 1u;                       // one accumulator: same barrier pair every item
+            else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ===================== epilogue: row = (kw, b), column = ((kd,kh), a) =====================
@@ -240,7 +250,8 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (p.merged) acc_phase ^= 1u;
+            else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
