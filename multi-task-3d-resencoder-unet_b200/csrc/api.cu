@@ -826,12 +826,15 @@ int launch_tw52(const RbWgradDesc& d, const Tw52Plan& pl, const void* P, const v
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(rb::tc5_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(rb::tc5_wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(rb::tc5_wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(tw52): %s", cudaGetErrorString(attr_err));
     const long long items = (long long)pl.mGroups * pl.nGroups * pl.splits;
     const long long grid = items < num_sms() ? items : num_sms();
-    rb::tc5_wgrad2_kernel<<<(int)grid, rb::TW52_THREADS, pl.smem, st>>>(p);
+    if (pl.merged) rb::tc5_wgrad2_kernel<true><<<(int)grid, rb::TW52_THREADS, pl.smem, st>>>(p);
+    else rb::tc5_wgrad2_kernel<false><<<(int)grid, rb::TW52_THREADS, pl.smem, st>>>(p);
     return check_launch("tc5_wgrad2_kernel");
 }
 

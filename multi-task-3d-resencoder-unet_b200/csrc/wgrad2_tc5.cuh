@@ -43,7 +43,10 @@ struct Tc5Wgrad2Params {
 
 static constexpr int TW52_THREADS = 192;
 
+// MERGED: separate instantiation, so that the two-group path keeps its 8-entry atom tables and single MMA per K step
+template <bool MERGED>
 __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __grid_constant__ Tc5Wgrad2Params p) {
+    constexpr int NBMAX = MERGED ? 16 : 8;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al);
@@ -118,9 +121,9 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             const int c0 = sp * p.chunksPerSplit;
             const int c1 = min(nChunks, c0 + p.chunksPerSplit);
             // per-item atom tables (divisions once per item)
-            int aX[8], aC[8], aSrc[8], bY[16], bZ[16], bC[16];
+            int aX[8], aC[8], aSrc[8], bY[NBMAX], bZ[NBMAX], bC[NBMAX];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < NBMAX; ++j) {
                 const int ja = (int)mg * p.mPerGroup + (j & 7);
                 const int kw = ja / qAtomsPerTap;
                 const int cb = (ja - kw * qAtomsPerTap) * p.qw;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
                         if (j < nA)
                             tma_load_5d(dstA + j * atomA, &p.mapQ[aSrc[j]], full_bar(stage), aC[j], uw + aX[j], uh, ud, n0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
+                    for (int j = 0; j < NBMAX; ++j)
                         if (j < nB)
                             tma_load_5d(dstB + j * atomB, &p.mapP, full_bar(stage), bC[j], uw, uh + bY[j], ud + bZ[j], n0);
                 }
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
                         const uint64_t da = make_smem_desc(aAddr + k * 2u * sboA, atomA, sboA, layA);
                         const uint64_t db = make_smem_desc(bAddr + k * 2u * sboB, atomB, sboB, layB);
                         umma_bf16(d_tmem, da, db, idesc, (c > c0 || k > 0) ? 1u : 0u);
-                        if (n2 > 0) {
+                        if (MERGED && n2 > 0) {
                             const uint64_t db2 = make_smem_desc(bAddr + (uint32_t)(256 / p.pw) * atomB + k * 2u * sboB, atomB, sboB, layB);
                             umma_bf16(d_tmem + 256u, da, db2, idesc2, (c > c0 || k > 0) ? 1u : 0u);
                         }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             }
             if (elect_one()) umma_commit(tfull_bar(acc));
             __syncwarp();
-            if (p.merged) acc_phase ^= 1u;                       // one accumulator: same barrier pair every item
+            if (MERGED) acc_phase ^= 1u;                       // one accumulator: same barrier pair every item
             else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(TW52_THREADS, 1) tc5_wgrad2_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (p.merged) acc_phase ^= 1u;
+            if (MERGED) acc_phase ^= 1u;
             else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
