@@ -167,6 +167,24 @@ int rb_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, f
  * col [NB,D,H,W,Kp] bf16, column = tap*Cin + ci, zero padded to Kp (multiple of 16). */
 int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Split-precision ("bf16x3") inference tier: the north star's "1e-4 with fp32 accumulation" bound.  A value is
+ * carried as hi = bf16(v), lo = bf16(v - hi); a voxel's activation row is the 3C channels [hi | lo | hi] and a
+ * weight row [hi_w | hi_w | lo_w], so v*w ~= hi*hi_w + lo*hi_w + hi*lo_w is ONE rb_conv_gather call with
+ * Cin' = 3*Cin and fp32 output.  These three entry points produce that layout; they replace the same reference
+ * arithmetic as their bf16 twins (builders/simple_conv_blocks.py:58-64, builders/resblocks.py:92-95,106-114,
+ * builders/encoder.py:81-86) with the normalise / gate / residual / LeakyReLU step evaluated in fp32.
+ *   rb_split_apply        z[hi|lo|hi] = act(y * scale[n,c] + shift[n,c] + (res_hi + res_lo)); y [NB,S,C] fp32,
+ *                         res / z [NB,S,3C] bf16, scale / shift [NB][C] fp32 or both NULL (identity)
+ *   rb_avgpool_split      window mean of (hi + lo) in fp32, re-split; C = logical channels, rows are 3C wide
+ *   rb_stem_im2col_split  col [NB,D,H,W,3*Kp] = [hi | lo | hi] of the rb_stem_im2col columns
+ * ------------------------------------------------------------------------------------------ */
+int rb_split_apply(const float* y, const void* res, void* z, const float* scale, const float* shift, int NB, long long S,
+                   int C, int act, float slope, void* stream);
+int rb_avgpool_split(const void* in, void* out, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream);
+int rb_stem_im2col_split(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp,
+                         void* stream);
+
 /* Weight (un)packing between the canonical parameter layout w[Cout][Cin][taps] fp32 (the reference's nn.Conv3d
  * weight, builders/simple_conv_blocks.py:43-51) and the kernels' operand layouts, tiled through shared memory:
  *   out_f[t][Cout][Cin] bf16 (fprop operand), out_d[taps-1-t][Cin][Cout] bf16 (stride-1 data-gradient operand);

@@ -61,6 +61,9 @@ SIGNATURES = {
     "rb_head_fwd": (_I, [_P, _P, _P, _P, _I, _LL, _I, _I, _I, _P]),
     "rb_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P]),
     "rb_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rb_split_apply": (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _I, _F, _P]),
+    "rb_avgpool_split": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rb_stem_im2col_split": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_pack_conv_weights": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "rb_unpack_wgrad": (_I, [_P, _P, _I, _I, _I, _P]),
     "rb_ncdhw_to_cl": (_I, [_P, _P, _I, _I, _LL, _P]),

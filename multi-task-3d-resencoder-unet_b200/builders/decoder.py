@@ -74,11 +74,7 @@ class Decoder(nn.Module):
 
     def _upsample(self, s, x):
         t = self.transpconvs[s]
-        up = ops.conv_transpose3d(x, t.weight, t.stride)
-        if t.bias is not None:
-            # rare configuration (conv_bias=True): per-channel add on the channels-last buffer, glue
-            up = (up.permute(0, 2, 3, 4, 1) + t.bias.to(up.dtype)).permute(0, 4, 1, 2, 3)
-        return up
+        return ops.conv_transpose3d(x, t.weight, t.stride, bias=t.bias)
 
     def forward(self, skips, activation=None):
         """`skips` in encoder order (bottleneck last).  `activation` ("sigmoid" | "softmax" | None) is

@@ -12,6 +12,7 @@ Block forward on the B200 path (one kernel sequence, no elementwise pass of its 
 from __future__ import annotations
 
 import numpy as np
+import torch
 from torch import nn
 
 from .. import ops
@@ -58,15 +59,33 @@ class SqueezeExcite(nn.Module):
 
 
 class DropPath(nn.Module):
+    """Stochastic depth (DNA `DropPath`, reference call sites resblocks.py:79-81,109-110): in training every sample
+    of the batch keeps its residual branch with probability 1 - drop_prob (scaled by 1 / keep).  The per-sample
+    factor is O(N); it is folded into the per-(n, c) scale / shift of the block-tail kernel, so the module is
+    never called on a full tensor."""
+
     def __init__(self, drop_prob=0., scale_by_keep=True):
         super().__init__()
-        if drop_prob != 0.:
-            _unsupported("stochastic depth (drop_prob > 0)")
-        self.drop_prob = drop_prob
+        if not 0.0 <= float(drop_prob) <= 1.0:
+            raise ValueError(f"drop_prob must lie in [0, 1], got {drop_prob}")
+        self.drop_prob = float(drop_prob)
         self.scale_by_keep = scale_by_keep
+        self.forced_factor = None      # parity tests replay the draws of a reference run through this
+
+    def factor(self, n, device):
+        """[n] fp32 tensor of 0 / (1/keep) drawn from torch's generator of `device`, or None (eval, p = 0)."""
+        if self.drop_prob == 0. or not self.training:
+            return None
+        if self.forced_factor is not None:
+            return self.forced_factor.to(device=device, dtype=torch.float32)
+        keep = 1.0 - self.drop_prob
+        f = torch.empty(n, dtype=torch.float32, device=device).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            f.div_(keep)
+        return f
 
     def forward(self, x):
-        return x
+        raise RuntimeError("DropPath is fused into the residual block tail; it is not called on its own")
 
 
 class _ResidualBlock(nn.Module):
@@ -114,7 +133,8 @@ class _ResidualBlock(nn.Module):
         if self.apply_se:
             m = self.squeeze_excitation
             se, dims = (m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias), m.dims()
-        return last(x, res=r, act=True, slope=self._slope, se=se, se_reduce_dims=dims)
+        drop = self.drop_path.factor(x.shape[0], x.device) if self.apply_stochastic_depth else None
+        return last(x, res=r, act=True, slope=self._slope, se=se, se_reduce_dims=dims, drop=drop)
 
 
 class BasicBlockD(_ResidualBlock):

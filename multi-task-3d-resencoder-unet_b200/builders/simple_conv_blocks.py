@@ -67,7 +67,7 @@ class ConvDropoutNormReLU(nn.Module):
 
     _raw_input = False      # StemConv: consumes the raw NCDHW fp32 network input
 
-    def forward(self, x, x_cat=None, res=None, act=None, slope=None, se=None, se_reduce_dims="all"):
+    def forward(self, x, x_cat=None, res=None, act=None, slope=None, se=None, se_reduce_dims="all", drop=None):
         """act( [SE]( IN( conv(cat(x, x_cat)) ) ) + res ) as ONE fused unit (ops.conv_norm_act).  Called with
         only `x` this is the reference's conv -> dropout(p=0) -> norm -> nonlin; residual blocks pass their
         tail (`res`, `act`, `se`) so the block needs no elementwise pass of its own.  A conv bias feeding
@@ -75,7 +75,7 @@ class ConvDropoutNormReLU(nn.Module):
         act = self._act if act is None else act
         slope = (self._slope or ops.LRELU_SLOPE_DEFAULT) if slope is None else slope
         z = ops.conv_norm_act(x, self.conv.weight, self.stride, x_cat, res, self.norm.weight, self.norm.bias,
-                              self.norm.eps, act, slope, se, se_reduce_dims, stem=self._raw_input)
+                              self.norm.eps, act, slope, se, se_reduce_dims, stem=self._raw_input, drop=drop)
         return ops.attach_cancelled_bias(z, self.conv.bias)
 
     def compute_conv_feature_map_size(self, input_size):

@@ -18,6 +18,7 @@
 #include "wgrad_tc5.cuh"
 #include "wgrad2_tc5.cuh"
 #include "elementwise.cuh"
+#include "split.cuh"
 #include "blend.cuh"
 
 namespace {
@@ -1190,6 +1191,39 @@ int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int
     const long long total = (long long)NB * D * H * W * (Kp / 8);
     rb::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("stem_im2col_kernel");
+}
+
+// ---- split-precision (bf16x3) inference tier: layout producers (split.cuh) ----
+int rb_split_apply(const float* y, const void* res, void* z, const float* scale, const float* shift, int NB, long long S,
+                   int C, int act, float slope, void* stream) {
+    if (!y || !z) return fail(RB_ERR_INVALID, "split_apply: null pointer");
+    if ((scale == nullptr) != (shift == nullptr)) return fail(RB_ERR_INVALID, "split_apply: scale and shift go together");
+    int rc = check_apply_shape("split_apply", NB, S, C, 0, 0);
+    if (rc) return rc;
+    if (!aligned16(y) || !aligned16(res) || !aligned16(z)) return fail(RB_ERR_INVALID, "split_apply: pointers must be 16-byte aligned");
+    rb::SplitApplyParams p{y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, act, slope};
+    const long long per = S * (C / 8);
+    rb::split_apply_kernel<<<dim3(grid_for(per, 256, 8), NB), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("split_apply_kernel");
+}
+
+int rb_avgpool_split(const void* in, void* out, int NB, int D, int H, int W, int C, int sd, int sh, int sw, void* stream) {
+    if (!in || !out) return fail(RB_ERR_INVALID, "avgpool_split: null pointer");
+    int rc = check_pool(NB, D, H, W, C, sd, sh, sw);
+    if (rc) return rc;
+    rb::PoolParams p{(const rb::bf16*)in, (rb::bf16*)out, NB, D, H, W, C, sd, sh, sw};
+    const long long total = (long long)NB * (D / sd) * (H / sh) * (W / sw) * (C / 8);
+    rb::avgpool_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("avgpool_split_kernel");
+}
+
+int rb_stem_im2col_split(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream) {
+    if (!x || !col) return fail(RB_ERR_INVALID, "stem_im2col_split: null pointer");
+    if (Kp % 8 != 0 || Kp < kd * kh * kw * Cin) return fail(RB_ERR_INVALID, "stem_im2col_split: Kp must be a multiple of 8 covering taps*Cin");
+    rb::Im2colParams p{x, (rb::bf16*)col, NB, Cin, D, H, W, kd, kh, kw, Kp};
+    const long long total = (long long)NB * D * H * W * (Kp / 8);
+    rb::stem_im2col_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("stem_im2col_split_kernel");
 }
 
 int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int Cin, int T, void* stream) {

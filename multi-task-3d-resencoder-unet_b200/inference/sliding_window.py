@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
+from .. import ops as _ops
 
 _ACT = {None: 0, "none": 0, "sigmoid": 1, "softmax": 2}
 
@@ -248,8 +249,9 @@ class SlidingWindowInferer:
 
     def __init__(self, model, targets: Dict[str, dict], patch_size, overlap: float = 0.5, batch_size: int = 1,
                  weight: str = "uniform", standardize: bool = True, in_channels: int = 1, rank: int = 0,
-                 world_size: int = 1, device=None, use_cuda_graph: bool = True):
+                 world_size: int = 1, device=None, use_cuda_graph: bool = True, precise: bool = False):
         self.model = model
+        self.precise = bool(precise)      # split-precision (bf16x3) forward: fp32-accurate logits, ~3x the conv FLOPs
         self.targets = targets
         self.patch = tuple(int(p) for p in patch_size)
         self.overlap = float(overlap)
@@ -284,14 +286,20 @@ class SlidingWindowInferer:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(2):                     # warm-up outside capture (weight packs, kernel attributes)
-                self.model(batch)
+                self._forward(batch)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            out = self.model(batch)
+            out = self._forward(batch)
         self._graph = (g, out)
         return self._graph
+
+    def _forward(self, batch):
+        if self.precise:
+            with _ops.precise_inference():
+                return self.model(batch)
+        return self.model(batch)
 
     @torch.no_grad()
     def sweep(self, volume):
@@ -329,7 +337,7 @@ class SlidingWindowInferer:
                     graph[0].replay()
                     preds = graph[1]
                 else:
-                    preds = self.model(batch)
+                    preds = self._forward(batch)
                 for j, pos in enumerate(chunk):
                     blender.add(preds, j, pos, apply_activation=True)
         finally:

@@ -69,6 +69,34 @@ KERNEL_TIMER = _KernelTimer()
 
 
 # ------------------------------------------------------------------------------------------
+# precision tier switch: bf16 operands / fp32 accumulation (default, training and inference) or the
+# split-precision "bf16x3" inference tier of precise.py (fp32-accurate results on the same kernels)
+# ------------------------------------------------------------------------------------------
+class _PreciseState:
+    on = False
+    impl = None
+
+
+@contextlib.contextmanager
+def precise_inference(impl=None):
+    """Inside this context the network's operators (conv_norm_act, conv_transpose3d, avg_pool3d, head_conv1x1) run
+    the split-precision tier: outputs within ~1e-5 relative L2 of an fp32 evaluation instead of ~1e-2.  Inference
+    only: autograd is disabled, stochastic depth must be off (eval mode).  `impl` ("mma" | "auto") selects the
+    gather-conv kernel family for the 3C-wide contractions (default: precise.IMPL)."""
+    prev = (_PreciseState.on, _PreciseState.impl)
+    _PreciseState.on, _PreciseState.impl = True, impl
+    try:
+        with torch.no_grad():
+            yield
+    finally:
+        _PreciseState.on, _PreciseState.impl = prev
+
+
+def precise_active() -> bool:
+    return _PreciseState.on
+
+
+# ------------------------------------------------------------------------------------------
 # layout helpers
 # ------------------------------------------------------------------------------------------
 def new_cl(n, c, d, h, w, device):
@@ -538,18 +566,19 @@ def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres, sign=None):
 
 class _NormState:
     """What the backward of a norm (+gate) + act needs besides y, z."""
-    __slots__ = ("small", "gamma", "has_beta", "act", "slope", "eps", "has_res", "gate", "per_w")
+    __slots__ = ("small", "gamma", "has_beta", "act", "slope", "eps", "has_res", "gate", "per_w", "n_gate")
 
 
-def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, reduce_dims="all"):
-    """z = act( [gate *] (IN(y) [* gamma + beta]) + res ).  `stats` = fp32 (sum, sumsq) from the conv epilogue.
-    gate = (fc1_w, fc1_b, fc2_w, fc2_b) or None."""
+def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, reduce_dims="all", drop=None):
+    """z = act( [gate *] [drop *] (IN(y) [* gamma + beta]) + res ).  `stats` = fp32 (sum, sumsq) from the conv epilogue.
+    gate = (fc1_w, fc1_b, fc2_w, fc2_b) or None; drop = per-sample stochastic-depth factor [N] (0 or 1/keep) or None."""
     n, c, d, h, w = y.shape
     S = d * h * w
     lib = L.load()
     st = _NormState()
     st.gamma, st.has_beta, st.act, st.slope, st.eps, st.has_res = gamma, beta is not None, act, slope, eps, res is not None
-    if gate is None:
+    st.n_gate = 0 if gate is None else 4
+    if gate is None and drop is None:
         st.gate, st.per_w = None, False
         sums = None if stats is not None else _plane_reduce(0, y, None, None, False, slope)
         small = torch.empty((4, n, c), dtype=torch.float32, device=y.device)     # mean, rstd, scale, shift
@@ -560,9 +589,11 @@ def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, r
         st.small = small
         z = _apply_fwd(y, res, small[2], small[3], False, act, slope)
         return z, st
-    # gated (squeeze-excitation) path: the O(N*W*C) part is a small differentiable torch graph
-    per_w = _se_per_w(reduce_dims)
+    # gated (squeeze-excitation and / or stochastic-depth) path: the O(N*W*C) part is a small differentiable torch graph
+    per_w = _se_per_w(reduce_dims) if gate is not None else False
     st.per_w = per_w
+    if gate is None:
+        gate = (None, None, None, None)
     if stats is not None:
         s1, s2 = stats[0].double(), stats[1].double()
     else:
@@ -575,7 +606,7 @@ def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, r
                   pw.detach().requires_grad_(True) if per_w else None]
         pl = [p.detach().requires_grad_(True) if p is not None else None for p in params]
         A, B = _gate_small_graph(leaves[0], leaves[1], leaves[2], float(S), float(d * h), pl[0], pl[1], eps,
-                                 pl[2], pl[3], pl[4], pl[5], per_w)
+                                 pl[2], pl[3], pl[4], pl[5], per_w, drop)
     st.gate = (leaves, pl, A, B)
     st.small = None
     z = _apply_fwd(y, res, A, B, per_w, act, slope)
@@ -620,7 +651,7 @@ def _norm_backward(st, y, z, dz, want_dres):
         k3 = k3 + gl[2]
     k3 = k3.float().contiguous()
     dy, dres = _apply_bwd(dz, z, y, A, k2, k3, per_w, st.act, st.slope, want_dres)
-    return dy, dres, gp[0], gp[1], tuple(gp[2:6])
+    return dy, dres, gp[0], gp[1], (tuple(gp[2:6]) if st.n_gate else None)
 
 
 def _se_per_w(reduce_dims):
@@ -631,12 +662,17 @@ def _se_per_w(reduce_dims):
     raise NotImplementedError(f"SE squeeze over dims {reduce_dims} is not implemented (use 'all' or (2, 3))")
 
 
-def _gate_small_graph(S1, S2, Pw, count, plane, gamma, beta, eps, w1, b1, w2, b2, per_w):
+def _gate_small_graph(S1, S2, Pw, count, plane, gamma, beta, eps, w1, b1, w2, b2, per_w, drop=None):
     mean = S1 / count
     var = (S2 / count - mean * mean).clamp_min(0.0)
     rstd = torch.rsqrt(var + eps)
     a0 = rstd if gamma is None else rstd * gamma.double()
     b0 = -mean * a0 if beta is None else beta.double() - mean * a0
+    if drop is not None:                          # DropPath sits between the norm and the SE gate (resblocks.py:109-112)
+        f = drop.double().reshape(-1, 1)
+        a0, b0 = a0 * f, b0 * f
+    if w1 is None:                                # stochastic depth without squeeze-excitation
+        return a0.unsqueeze(1).float().contiguous(), b0.unsqueeze(1).float().contiguous()
     if per_w:                                     # squeeze over (D, H): one value per (n, w, c)
         sq = a0.unsqueeze(1) * (Pw / plane) + b0.unsqueeze(1)
     else:                                         # global average pool of the normalised tensor
@@ -678,13 +714,13 @@ def conv3d(x, weight, stride=1, x_cat=None, impl=None):
 
 class _NormActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, res, gamma, beta, eps, act, slope, gate_dims, *gate):
+    def forward(ctx, y, res, gamma, beta, eps, act, slope, gate_dims, drop, *gate):
         y = as_prenorm(y)
         L.require_cuda(y, "instance_norm")
         res = as_cl(res) if res is not None else None
         if res is not None and res.shape != y.shape:
             raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
-        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, None, gate if gate else None, gate_dims)
+        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, None, gate if gate else None, gate_dims, drop)
         ctx.save_for_backward(y, z if act else None)
         ctx.st = st
         return z
@@ -697,19 +733,19 @@ class _NormActFn(torch.autograd.Function):
         if y.dtype == torch.float32:
             dy = dy.float()      # autograd wants the gradient in the input's dtype (stand-alone use only)
         ggate = ggate if ggate is not None else ()
-        return (dy, dres, dgamma, dbeta, None, None, None, None, *ggate)
+        return (dy, dres, dgamma, dbeta, None, None, None, None, None, *ggate)
 
 
-def instance_norm_act(y, res=None, gamma=None, beta=None, eps=1e-5, act=True, slope=LRELU_SLOPE_DEFAULT):
-    """z = [LeakyReLU]( InstanceNorm(y) [* gamma + beta] [+ res] )."""
-    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), "all")
+def instance_norm_act(y, res=None, gamma=None, beta=None, eps=1e-5, act=True, slope=LRELU_SLOPE_DEFAULT, drop=None):
+    """z = [LeakyReLU]( [drop *] (InstanceNorm(y) [* gamma + beta]) [+ res] ); drop = per-sample factor [N] or None."""
+    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), "all", drop)
 
 
 def instance_norm_se_act(y, res, gamma, beta, fc1_w, fc1_b, fc2_w, fc2_b, eps=1e-5, act=True,
-                         slope=LRELU_SLOPE_DEFAULT, reduce_dims="all"):
-    """z = [LeakyReLU]( SE(InstanceNorm(y)) + res ), SE(o) = o * sigmoid(fc2(relu(fc1(mean_dims(o)))))."""
+                         slope=LRELU_SLOPE_DEFAULT, reduce_dims="all", drop=None):
+    """z = [LeakyReLU]( SE([drop *] InstanceNorm(y)) + res ), SE(o) = o * sigmoid(fc2(relu(fc1(mean_dims(o)))))."""
     _se_per_w(reduce_dims)
-    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), reduce_dims,
+    return _NormActFn.apply(y, res, gamma, beta, float(eps), bool(act), float(slope), reduce_dims, drop,
                             fc1_w, fc1_b, fc2_w, fc2_b)
 
 
@@ -721,7 +757,7 @@ def instance_norm_se_act(y, res, gamma, beta, fc1_w, fc1_b, fc2_w, fc2_b, eps=1e
 # ------------------------------------------------------------------------------------------
 class _ConvNormActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weight, cfg, x0, x1, res, gamma, beta, *gate):
+    def forward(ctx, weight, cfg, x0, x1, res, gamma, beta, drop, *gate):
         stride, impl, eps, act, slope, gate_dims, stem = cfg
         if stem:
             src0, src1 = _stem_im2col(x0, tuple(weight.shape[2:])), None
@@ -734,7 +770,7 @@ class _ConvNormActFn(torch.autograd.Function):
         res = as_cl(res) if res is not None else None
         if res is not None and res.shape != y.shape:
             raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
-        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, stats, gate if gate else None, gate_dims)
+        z, st = _norm_forward(y, res, gamma, beta, eps, act, slope, stats, gate if gate else None, gate_dims, drop)
         ctx.save_for_backward(weight, src0, src1, y, z if act else None)
         ctx.st, ctx.cfg = st, cfg
         return z
@@ -752,18 +788,23 @@ class _ConvNormActFn(torch.autograd.Function):
         else:
             gw, gx0, gx1 = _conv_backward(weight, stride, impl, src0, src1, dy, need[0], need[2], need[3])
         ggate = ggate if ggate is not None else ()
-        return (gw, None, gx0, gx1, dres, dgamma, dbeta, *ggate)
+        return (gw, None, gx0, gx1, dres, dgamma, dbeta, None, *ggate)
 
 
 def conv_norm_act(x, weight, stride=1, x_cat=None, res=None, gamma=None, beta=None, eps=1e-5, act=True,
-                  slope=LRELU_SLOPE_DEFAULT, se=None, se_reduce_dims="all", stem=False, impl=None):
-    """act( [SE]( InstanceNorm( conv3d(cat(x, x_cat), weight, stride) ) [*gamma + beta] ) + res ).
+                  slope=LRELU_SLOPE_DEFAULT, se=None, se_reduce_dims="all", stem=False, impl=None, drop=None):
+    """act( [SE]( [drop *] InstanceNorm( conv3d(cat(x, x_cat), weight, stride) ) [*gamma + beta] ) + res ).
     se = (fc1_w, fc1_b, fc2_w, fc2_b) enables the squeeze-excitation gate; stem=True reads the raw NCDHW
-    fp32 network input (any channel count)."""
+    fp32 network input (any channel count); drop = per-sample stochastic-depth factor [N] fp32 (0 or 1/keep,
+    the DropPath of resblocks.py:109-110) folded into the per-(n, c) scale / shift of the apply pass."""
+    if _PreciseState.on:
+        from . import precise
+        return precise.conv_norm_act(x, weight, stride, x_cat, res, gamma, beta, eps, act, slope, se, se_reduce_dims,
+                                     stem, impl or _PreciseState.impl, drop)
     if se is not None:
         _se_per_w(se_reduce_dims)
     cfg = (_triple(stride), impl, float(eps), bool(act), float(slope), se_reduce_dims, bool(stem))
-    return _ConvNormActFn.apply(weight, cfg, x, x_cat, res, gamma, beta, *(se or ()))
+    return _ConvNormActFn.apply(weight, cfg, x, x_cat, res, gamma, beta, drop, *(se or ()))
 
 
 class _ZeroGradParamFn(torch.autograd.Function):
@@ -832,8 +873,16 @@ class _ConvT3dFn(torch.autograd.Function):
         return gw, None, None, gx
 
 
-def conv_transpose3d(x, weight, stride, impl=None):
-    return _ConvT3dFn.apply(weight, _triple(stride), impl, x)
+def conv_transpose3d(x, weight, stride, impl=None, bias=None):
+    """ConvTranspose3d with kernel_size == stride (builders/decoder.py:110-113,147), optional bias."""
+    if _PreciseState.on:
+        from . import precise
+        return precise.conv_transpose3d(x, weight, stride, impl or _PreciseState.impl, bias)
+    up = _ConvT3dFn.apply(weight, _triple(stride), impl, x)
+    if bias is not None:
+        # rare configuration (conv_bias=True): per-channel add on the channels-last buffer, glue
+        up = (up.permute(0, 2, 3, 4, 1) + bias.to(up.dtype)).permute(0, 4, 1, 2, 3)
+    return up
 
 
 # ------------------------------------------------------------------------------------------
@@ -864,6 +913,9 @@ class _AvgPoolFn(torch.autograd.Function):
 
 
 def avg_pool3d(x, stride):
+    if _PreciseState.on:
+        from . import precise
+        return precise.avg_pool3d(x, stride)
     return _AvgPoolFn.apply(x, _triple(stride))
 
 
@@ -907,6 +959,9 @@ class _HeadFn(torch.autograd.Function):
 
 
 def head_conv1x1(x, weight, bias, activation=None):
+    if _PreciseState.on:
+        from . import precise
+        return precise.head_conv1x1(x, weight, bias, activation)
     if weight.shape[0] > 8:
         raise NotImplementedError("task heads with more than 8 output channels are not implemented")
     act = _ACT[activation if activation is None else str(activation).lower()]

@@ -36,7 +36,12 @@ NET_CASES = {
     "aniso_8x32x32": ([8, 32, 32], 1, {"sheet": {"channels": 2, "activation": "softmax"}}, {}, "all", 1),
     "affine_16": ([16, 16, 16], 2, {"sheet": {"channels": 1, "activation": "none"}},
                   {"norm_op_kwargs": {"affine": True, "eps": 1e-5}}, "all", 1),
+    # stochastic depth (DropPath, resblocks.py:79-81,109-110) with SE behind it; the per-block draws of the
+    # reference run are stored in the fixture as `drop::<block>` so that every implementation replays them
+    "droppath_se_16": ([16, 16, 16], 1, {"sheet": {"channels": 1, "activation": "sigmoid"}},
+                       {"squeeze_excitation": True, "stochastic_depth_p": 0.3}, "all", 4),
 }
+DROP_SEED = 4321
 
 
 def seeded_state(named_shapes, seed):
@@ -97,6 +102,22 @@ def make_net_case(case):
     x, tgt = seeded_inputs(case)
     xt = torch.from_numpy(x)
     model.train()
+    # record the stochastic-depth draws (factor per sample = 0 or 1 / keep) of every residual block
+    drops = {}
+
+    def _rec(name):
+        def hook(mod, inp, outp):
+            if not mod.training or name in drops:
+                return
+            a, b = inp[0].detach().flatten(1).abs().sum(1), outp.detach().flatten(1).abs().sum(1)
+            f = torch.where(b > 0, torch.full_like(b, 1.0 / (1.0 - mod.drop_prob)), torch.zeros_like(b))
+            assert torch.allclose(a * f, b, rtol=1e-4)
+            drops.setdefault(name, f.numpy().astype(np.float32))
+        return hook
+    for n_, m_ in model.named_modules():
+        if type(m_).__name__ == "DropPath":
+            m_.register_forward_hook(_rec(n_[:-len(".drop_path")]))
+    torch.manual_seed(DROP_SEED)
     out = model(xt)
     # reference losses through the reference's own loss classes (training/losses/losses.py)
     losses_mod = rl.reference_module("training/losses/losses.py", "ref_losses")
@@ -118,6 +139,7 @@ def make_net_case(case):
     model.train()
     for p_ in model.parameters():
         p_.grad = None
+    torch.manual_seed(DROP_SEED)      # same stochastic-depth draws as the fp32 pass
     with torch.autocast("cpu", dtype=torch.bfloat16):
         ac = model(xt)
     ac_total = 0.0
@@ -145,6 +167,8 @@ def make_net_case(case):
     devs = [abs(float(ac_grads[n].double().norm()) - g) / g for (n, _), g in zip(names, gnorm)
             if ac_grads[n] is not None and g >= 1e-4 * gmax]
     rec["autocast_bf16_gradnorm_dev"] = np.float64(max(devs))
+    for k_, v_ in drops.items():
+        rec["drop::" + k_] = v_
     for t in tasks:
         rec["target::" + t] = tgt[t]
         rec["train::" + t] = out[t].detach().numpy()
@@ -205,6 +229,8 @@ def make_host_goldens():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    make_host_goldens()
-    for c in NET_CASES:
+    only = sys.argv[1:]                  # `python oracle/make_golden.py <case> ...` regenerates just those cases
+    if not only:
+        make_host_goldens()
+    for c in (only or NET_CASES):
         make_net_case(c)

@@ -134,29 +134,39 @@ def _skip(x, sd, p, stride, cin, cout):
     return x
 
 
-def _basic_block(x, sd, p, stride, cin, cout, se, reduce_dims):
+def _drop_path(o, drop, p):
+    """DNA DropPath (not in the reference repo; call sites resblocks.py:79-81,109-110,234-235): per-sample factor
+    0 or 1/keep.  `drop` maps block prefixes to the [N] factor the caller drew (so both sides share the draw)."""
+    if drop is None or p not in drop:
+        return o
+    return o * drop[p].to(o.dtype).view(-1, *([1] * (o.dim() - 1)))
+
+
+def _basic_block(x, sd, p, stride, cin, cout, se, reduce_dims, drop=None):
     """BasicBlockD.forward (resblocks.py:106-114)."""
     r = _skip(x, sd, p, stride, cin, cout)
     o = _cdnr(x, sd, p + ".conv1", stride)
     o = _cdnr(o, sd, p + ".conv2", 1, act=False)
+    o = _drop_path(o, drop, p)
     if se:
         o = _se(o, sd, p + ".squeeze_excitation", reduce_dims)
     return F.leaky_relu(o + r, 0.01)
 
 
-def _bottleneck_block(x, sd, p, stride, cin, cout, se, reduce_dims):
+def _bottleneck_block(x, sd, p, stride, cin, cout, se, reduce_dims, drop=None):
     """BottleneckD.forward (resblocks.py:231-239)."""
     r = _skip(x, sd, p, stride, cin, cout)
     o = _cdnr(x, sd, p + ".conv1", 1)
     o = _cdnr(o, sd, p + ".conv2", stride)
     o = _cdnr(o, sd, p + ".conv3", 1, act=False)
+    o = _drop_path(o, drop, p)
     if se:
         o = _se(o, sd, p + ".squeeze_excitation", reduce_dims)
     return F.leaky_relu(o + r, 0.01)
 
 
 def net_forward(sd, topo, x, tasks, training=True, se=False, reduce_dims="all",
-                block="basic", residual_encoder=True, residual_decoder=False):
+                block="basic", residual_encoder=True, residual_decoder=False, drop=None):
     """NetworkFromConfig.forward (build_network_from_config.py:312-326) = Encoder.forward
     (encoder.py:148-158) + one Decoder.forward per task (decoder.py:137-162).
 
@@ -173,7 +183,7 @@ def net_forward(sd, topo, x, tasks, training=True, se=False, reduce_dims="all",
             if residual_encoder:
                 p = f"{e}.stages.{s}.blocks.{b}"
                 fn = _basic_block if block == "basic" else _bottleneck_block
-                x = fn(x, sd, p, st, cin, cout, se, reduce_dims)
+                x = fn(x, sd, p, st, cin, cout, se, reduce_dims, drop if training else None)
             else:
                 x = _cdnr(x, sd, f"{e}.stages.{s}.0.convs.{b}", st)
             cin = cout

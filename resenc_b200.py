@@ -18,6 +18,7 @@ inference = _pkg.inference
 ops = _pkg.ops
 losses = importlib.import_module(_pkg.__name__ + ".losses")
 parallel = importlib.import_module(_pkg.__name__ + ".parallel")
+precise = importlib.import_module(_pkg.__name__ + ".precise")
 _lib = _pkg._lib
 
 

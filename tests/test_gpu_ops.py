@@ -186,6 +186,55 @@ def test_instance_norm_se_act(rb, reduce_dims, affine):
         assert rel_l2(a.grad.float(), b.grad) < 1e-2, nm
 
 
+@pytest.mark.parametrize("with_se", [False, True])
+@pytest.mark.parametrize("affine", [False, True])
+def test_instance_norm_drop_path(rb, with_se, affine):
+    """Stochastic depth (DropPath, reference resblocks.py:109-112) folded into the block tail: per-sample factor
+    0 or 1/keep between the norm and the SE gate; dropped samples pass the residual only and get zero gradient."""
+    torch.manual_seed(5)
+    n, c, rd = 4, 32, 8
+    shape = (n, c, 6, 8, 8)
+    y = q(torch.randn(shape, device="cuda") * 1.5 + 0.3)
+    res = q(torch.randn(shape, device="cuda"))
+    drop = torch.tensor([1.25, 0.0, 1.25, 0.0], device="cuda")
+    params = [torch.randn(rd, c, 1, 1, 1, device="cuda") * 0.3, torch.randn(rd, device="cuda") * 0.1,
+              torch.randn(c, rd, 1, 1, 1, device="cuda") * 0.3, torch.randn(c, device="cuda") * 0.1] if with_se else []
+    gamma = (1 + 0.2 * torch.randn(c, device="cuda")) if affine else None
+    beta = (0.3 * torch.randn(c, device="cuda")) if affine else None
+
+    def reference(yy, rr, ga, be, *se):
+        o = F.instance_norm(yy, None, None, ga, be, True, 0.0, 1e-5) * drop.view(-1, 1, 1, 1, 1)
+        if se:
+            s = o.mean((2, 3, 4), keepdim=True)
+            o = o * torch.sigmoid(F.conv3d(F.relu(F.conv3d(s, se[0], se[1])), se[2], se[3]))
+        return F.leaky_relu(o + rr, 0.01)
+
+    leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)
+    ref_in = [leaf(t) for t in [y, res, gamma, beta] + params]
+    ref = reference(*ref_in)
+    prod_in = [leaf(t) for t in [y, res, gamma, beta] + params]
+    if with_se:
+        z = rb.ops.instance_norm_se_act(*prod_in, eps=1e-5, act=True, slope=0.01, reduce_dims="all", drop=drop)
+    else:
+        z = rb.ops.instance_norm_act(*prod_in, eps=1e-5, act=True, slope=0.01, drop=drop)
+    assert rel_l2(z.float(), ref) < TOL_BF16
+    # dropped samples: lrelu(res) exactly
+    assert torch.equal(z[1].float(), F.leaky_relu(res[1].float(), 0.01).to(torch.bfloat16).float())
+    g = q(torch.randn_like(ref))
+    ref.backward(g)
+    z.backward(g.to(torch.bfloat16))
+    assert float(prod_in[0].grad[1].float().abs().max()) == 0.0 and float(prod_in[0].grad[3].float().abs().max()) == 0.0
+    names = ["y", "res", "gamma", "beta", "fc1.w", "fc1.b", "fc2.w", "fc2.b"]
+    for nm, a, b in zip(names, prod_in, ref_in):
+        if a is None:
+            continue
+        assert a.grad is not None, nm
+        if float(b.grad.norm()) < 1e-6 * max(1.0, float(b.norm())):
+            assert float(a.grad.float().norm()) < 1e-5, nm
+            continue
+        assert rel_l2(a.grad.float(), b.grad) < 1e-2, nm
+
+
 @pytest.mark.parametrize("stride", [(2, 2, 2), (1, 2, 2)])
 def test_avg_pool(rb, stride):
     torch.manual_seed(5)
@@ -366,3 +415,52 @@ def test_norm_backward_sign_from_prenorm(rb):
             ops.SIGN_FROM_PRENORM = True
     assert rel_l2(outs[1][0], outs[0][0]) < 1e-3
     assert rel_l2(outs[1][1], outs[0][1]) < 5e-3 and rel_l2(outs[1][2], outs[0][2]) < 5e-3
+
+
+def test_split_precision_layout_kernels(rb):
+    """rb_split_apply / rb_avgpool_split / rb_stem_im2col_split (include/resenc_b200.h): the [hi | lo | hi] rows
+    reproduce their fp32 source to 2^-16 relative and the fused fp32 arithmetic matches torch."""
+    P = rb.precise
+    torch.manual_seed(11)
+    n, c, d, h, w = 2, 16, 4, 6, 8
+    y = torch.randn(n, c, d, h, w, device="cuda") * 3 + 0.5
+    ycl = y.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    resv = torch.randn(n, c, d, h, w, device="cuda")
+    res = P._split_apply(resv.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3), None, None, None, False, 0.0)
+    assert tuple(res.shape) == (n, 3 * c, d, h, w) and rb.ops.is_cl(res)
+    assert torch.equal(res[:, :c], res[:, 2 * c:])
+    assert torch.equal(res[:, :c].float(), resv.to(torch.bfloat16).float())
+    assert rel_l2(P.join(res), resv) < 2 ** -16
+    scale = torch.rand(n, c, device="cuda") + 0.5
+    shift = torch.randn(n, c, device="cuda")
+    z = P._split_apply(ycl, res, scale, shift, True, 0.01)
+    ref = F.leaky_relu(y * scale.view(n, c, 1, 1, 1) + shift.view(n, c, 1, 1, 1) + P.join(res), 0.01)
+    assert rel_l2(P.join(z), ref) < 1e-5
+    pooled = P.avg_pool3d(z, (2, 2, 2))
+    assert rel_l2(P.join(pooled), F.avg_pool3d(P.join(z), 2, 2)) < 1e-5
+    pooled = P.avg_pool3d(z, (1, 2, 2))
+    assert rel_l2(P.join(pooled), F.avg_pool3d(P.join(z), (1, 2, 2), (1, 2, 2))) < 1e-5
+    # whole unit against torch fp32: conv + InstanceNorm + residual + LeakyReLU, strided and concatenated variants
+    wgt = torch.randn(24, c, 3, 3, 3, device="cuda") * 0.1
+    for stride in (1, 2):
+        out = P.conv_norm_act(z, wgt, stride=stride)
+        ref = F.leaky_relu(F.instance_norm(F.conv3d(P.join(z), wgt, None, stride, 1)), 0.01)
+        r = rel_l2(P.join(out), ref)
+        print(f"split conv_norm_act stride {stride}: rel-L2 {r:.3e}")
+        assert r < 3e-5
+    w2 = torch.randn(16, 2 * c, 3, 3, 3, device="cuda") * 0.1
+    out = P.conv_norm_act(z, w2, x_cat=res, res=res, act=True)
+    ref = F.leaky_relu(F.instance_norm(F.conv3d(torch.cat((P.join(z), P.join(res)), 1), w2, None, 1, 1)) + P.join(res), 0.01)
+    assert rel_l2(P.join(out), ref) < 3e-5
+    wt = torch.randn(c, 8, 2, 2, 2, device="cuda") * 0.2
+    bt = torch.randn(8, device="cuda")
+    up = P.conv_transpose3d(z, wt, (2, 2, 2), bias=bt)
+    assert rel_l2(P.join(up), F.conv_transpose3d(P.join(z), wt, bt, 2)) < 3e-5
+    hw, hb = torch.randn(3, 8, 1, 1, 1, device="cuda"), torch.randn(3, device="cuda")
+    assert rel_l2(P.head_conv1x1(up, hw, hb, "softmax"), torch.softmax(F.conv3d(P.join(up), hw, hb), 1)) < 3e-5
+    # stem on the raw fp32 input (2 channels)
+    xin = torch.rand(1, 2, 6, 8, 8, device="cuda")
+    ws = torch.randn(8, 2, 3, 3, 3, device="cuda") * 0.3
+    out = P.conv_norm_act(xin, ws, stem=True)
+    ref = F.leaky_relu(F.instance_norm(F.conv3d(xin, ws, None, 1, 1)), 0.01)
+    assert rel_l2(P.join(out), ref) < 3e-5

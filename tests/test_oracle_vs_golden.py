@@ -54,8 +54,10 @@ def test_oracle_network_forward_and_loss(case):
     topo = O.autoconfig(patch)
     x = torch.from_numpy(gold["x"])
     se = bool(mc.get("squeeze_excitation", False))
+    drop = {k[6:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("drop::")} or None
+    assert (drop is not None) == bool(mc.get("stochastic_depth_p", 0.0))
     with torch.no_grad():
-        out_t = O.net_forward(sd, topo, x, tasks, training=True, se=se, reduce_dims=rd)
+        out_t = O.net_forward(sd, topo, x, tasks, training=True, se=se, reduce_dims=rd, drop=drop)
         out_e = O.net_forward(sd, topo, x, tasks, training=False, se=se, reduce_dims=rd)
     total = 0.0
     for t in tasks:
