@@ -221,11 +221,22 @@ Tc5tPlan plan_tc5t(const RbConvDesc& d) {
     const int ctot = d.srcC0 + (d.nsrc == 2 ? d.srcC1 : 0);
     pl.tapsPer = ntaps;
     pl.splitK = 1;
+    static const int split_max_tiles = getenv("RESENC_SPLIT_MAX_TILES") ? atoi(getenv("RESENC_SPLIT_MAX_TILES")) : 74;
     if (pl.tiles < 48 && ntaps >= 8 && ctot >= 256 && d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1) {
         long long want = (2LL * num_sms() + pl.tiles - 1) / pl.tiles;
         if (want > ntaps) want = ntaps;
         pl.tapsPer = (int)((ntaps + want - 1) / want);
         pl.splitK = (ntaps + pl.tapsPer - 1) / pl.tapsPer;
+    } else if (pl.tiles <= split_max_tiles && ntaps >= 8 && ctot >= 256 && d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1) {
+        // up to half a wave of tiles (the 256-channel layers at 16^3: 64 tiles on 148 SMs): pick the tap split whose
+        // longest per-SM queue (items per persistent CTA x taps per item) is shortest
+        long long bestCost = (long long)ntaps + 2;     // unsplit: one item of ntaps taps per CTA (+ epilogue ~ 2 taps)
+        for (int per = 2; per < ntaps; ++per) {
+            const int sk = (ntaps + per - 1) / per;
+            const long long items = pl.tiles * sk;
+            const long long cost = ((items + num_sms() - 1) / num_sms()) * (per + 2) + 1;   // +1: finish pass
+            if (cost < bestCost) { bestCost = cost; pl.tapsPer = per; pl.splitK = sk; }
+        }
     }
     // h-major tile for plain 3-tap-wide stride-1 convolutions on rows that are whole multiples of 32 voxels: the per-tap
     // gather is TMA-row-rate bound at 64/128-byte channel rows (cycle counters: 18.6 k cycles of loads against 13.5 k of

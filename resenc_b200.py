@@ -19,6 +19,7 @@ ops = _pkg.ops
 losses = importlib.import_module(_pkg.__name__ + ".losses")
 parallel = importlib.import_module(_pkg.__name__ + ".parallel")
 precise = importlib.import_module(_pkg.__name__ + ".precise")
+training = importlib.import_module(_pkg.__name__ + ".training")
 _lib = _pkg._lib
 
 

@@ -131,3 +131,115 @@ def test_slab_exchange_matches_single_rank(tmp_path, built_lib):
     gotw = torch.cat([p["wsum"] for p in parts], 0).numpy()
     assert np.array_equal(gotw, w)
     assert np.allclose(got1, s1, atol=1e-5) and np.allclose(got3, s3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# DataParallelTrainer on CPU: replicas stay identical and equal the single-process
+# step on the mean gradient; rank 0 alone writes the reference-format checkpoint
+# ------------------------------------------------------------------------------------------
+class _TinyNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.body = torch.nn.Conv3d(1, 4, 3, padding=1)
+        self.sheet = torch.nn.Conv3d(4, 1, 1)
+        self.normals = torch.nn.Conv3d(4, 3, 1)
+
+    def forward(self, x):
+        h = torch.nn.functional.leaky_relu(self.body(x), 0.01)
+        return {"sheet": self.sheet(h), "normals": self.normals(h)}
+
+
+_TASKS = {"sheet": {"channels": 1, "activation": "sigmoid", "weight": 2.0}, "normals": {"channels": 3, "activation": "none"}}
+
+
+def _tiny_batch(step, rank):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    x = torch.rand(2, 1, 6, 6, 6, generator=g)
+    sheet = (torch.rand(2, 1, 6, 6, 6, generator=g) > 0.7).float()
+    normals = torch.nn.functional.normalize(torch.randn(2, 3, 6, 6, 6, generator=g), dim=1)
+    return x, {"sheet": sheet, "normals": normals}
+
+
+def _trainer_worker(rank, world, port, out):
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, ROOT)
+    rb = importlib.import_module("resenc_b200")
+    T = rb.training
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    assert T.init_distributed("gloo") == (rank, rank, world)
+    torch.manual_seed(0)
+    model = _TinyNet()
+    mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5)
+    tr = T.DataParallelTrainer(model, mgr, fused_losses=False)
+    assert tr.world == world and tr.rank == rank
+    losses = []
+    for step in range(3):
+        x, tgt = _tiny_batch(step, rank)
+        total, per = tr.train_step(x, tgt)
+        losses.append(float(total))
+    tr.end_epoch()
+    wrote = tr.save_checkpoint(out + ".ckpt")
+    assert wrote == (rank == 0)
+    torch.save({"params": [p.detach().clone() for p in model.parameters()], "losses": losses}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_data_parallel_trainer_matches_mean_gradient_step(tmp_path):
+    from types import SimpleNamespace
+    out = str(tmp_path / "t")
+    mp.spawn(_trainer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    parts = [torch.load(out + f".{r}") for r in range(2)]
+    for a, b in zip(parts[0]["params"], parts[1]["params"]):
+        assert torch.equal(a, b)                       # replicas stay bit-identical
+    rb = importlib.import_module("resenc_b200")
+    L = rb.losses
+    torch.manual_seed(0)
+    model = _TinyNet()
+    crit = L.task_losses(_TASKS, fused=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-4)
+    for step in range(3):
+        grads = None
+        for rank in range(2):
+            x, tgt = _tiny_batch(step, rank)
+            o = model(x)
+            loss = 2.0 * crit["sheet"](o["sheet"], tgt["sheet"]) + crit["normals"](o["normals"], tgt["normals"])
+            assert abs(float(loss) - parts[rank]["losses"][step]) < 1e-5
+            g = torch.autograd.grad(loss, list(model.parameters()))
+            grads = g if grads is None else [a + b for a, b in zip(grads, g)]
+        for p, g in zip(model.parameters(), grads):
+            p.grad = g / 2
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 3.0)
+        opt.step()
+    for a, b in zip(parts[0]["params"], model.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
+    ck = torch.load(out + ".ckpt", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "scheduler", "epoch"} and ck["epoch"] == 1     # train.py:249-254
+    assert set(ck["model"]) == set(model.state_dict())
+    # a torch.compile'd reference checkpoint (keys prefixed with _orig_mod.) loads
+    ck["model"] = {"_orig_mod." + k: v for k, v in ck["model"].items()}
+    torch.save(ck, out + ".ckpt2")
+    mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5)
+    tr = rb.training.DataParallelTrainer(_TinyNet(), mgr, fused_losses=False)
+    tr.load_checkpoint(out + ".ckpt2")
+    assert tr.epoch == 1
+    for a, b in zip(tr.model.parameters(), parts[0]["params"]):
+        assert torch.equal(a, b)
+
+
+def test_shard_indices_cover_and_balance():
+    rb = importlib.import_module("resenc_b200")
+    T = rb.training
+    idx = list(range(23))
+    for world in (1, 2, 4, 8):
+        shards = [T.shard_indices(idx, r, world) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1                     # equal step counts (no all-reduce dead-lock)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == idx[:len(idx) - len(idx) % world]
+        shards = [T.shard_indices(idx, r, world, drop_last=False) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1 and set(i for s in shards for i in s) == set(idx)
+    a = list(T.iterate_sharded(10, 3, 0, 2)) + list(T.iterate_sharded(10, 3, 1, 2))
+    assert sorted(a) == list(range(10))
+    with pytest.raises(ValueError):
+        T.shard_indices(idx, 2, 2)

@@ -338,3 +338,31 @@ def test_precise_tier_64_vs_oracle(rb):
     agree = float(((out["sheet"].cpu() > 0.5) == (ref["sheet"] > 0.5)).float().mean())
     print(f"precise 64^3 sheet threshold agreement {agree:.6f}")
     assert agree >= 0.999
+
+
+def test_trainer_step_eager_and_graph(rb):
+    """training.DataParallelTrainer on one GPU: the CUDA-graph step equals the eager step, and
+    capturing it costs no optimiser update (the first returned loss is the loss at the initial weights)."""
+    from types import SimpleNamespace
+    case = "sheet_normals_16"
+    gold = load_net_golden(case)
+    x = torch.from_numpy(gold["x"]).cuda()
+    tgt = {t: torch.from_numpy(gold["target::" + t]).cuda() for t in ("sheet", "normals")}
+    curves = {}
+    for mode in ("eager", "graph"):
+        model, mgr = _build(rb, case)
+        tm = SimpleNamespace(tasks=mgr.tasks, optimizer="AdamW", initial_lr=1e-3, weight_decay=1e-4, max_epoch=10)
+        tr = rb.training.DataParallelTrainer(model, tm, use_cuda_graph=(mode == "graph"))
+        curve = []
+        for step in range(5):
+            total, per = tr.train_step(x, tgt)
+            curve.append(float(total))
+            assert set(per) == {"sheet", "normals"}
+        curves[mode] = curve
+        rb._lib.device_error_check()
+    print("trainer curves:", curves)
+    assert abs(curves["eager"][0] - float(gold["loss_total"])) < 1e-2
+    assert abs(curves["graph"][0] - curves["eager"][0]) < 2e-3          # no hidden updates during capture
+    assert min(curves["eager"][1:]) < curves["eager"][0]                # it learns
+    for a, b in zip(curves["eager"], curves["graph"]):
+        assert abs(a - b) < 3e-2 * max(1.0, abs(a))

@@ -45,6 +45,8 @@ CASES = [
     (1, 32, 32, (40, 36, 44), (3, 3, 3), (1, 1, 1)),
     (1, 64, 32, (24, 40, 72), (1, 1, 1), (1, 1, 1)),
     (1, 32, 64, (16, 64, 64), (1, 3, 3), (1, 2, 2)),
+    # 64 tiles (under half a wave of SMs) with 27 taps of 256 channels: tap split over two CTAs per tile
+    (2, 256, 256, (16, 16, 16), (3, 3, 3), (1, 1, 1)),
 ]
 
 
@@ -75,7 +77,8 @@ def test_tc5_conv_fwd_bwd(rb, case):
     assert rel_l2(outs["tc5"][0], outs["mma"][0]) < 3e-3
 
 
-@pytest.mark.parametrize("dims,c,co", [((8, 8, 8), 64, 64), ((32, 32, 32), 32, 32), ((16, 48, 40), 64, 64)])
+@pytest.mark.parametrize("dims,c,co", [((8, 8, 8), 64, 64), ((32, 32, 32), 32, 32), ((16, 48, 40), 64, 64),
+                                       ((16, 16, 16), 256, 256)])
 def test_tc5_two_sources(rb, dims, c, co):
     torch.manual_seed(1)
     a = q(torch.randn(2, c, *dims, device="cuda"))
