@@ -351,6 +351,25 @@ class SlidingWindowInferer:
         return self.sweep(volume).finalize(keep_float=keep_float)
 
 
+    def run_to_zarr(self, volume, root: str, compressor="zlib", threads: int = 8):
+        """Single-rank sweep whose finalised planes stream into `<target>_final` zarr v2 arrays (the layout of
+        inference.py:213-263; see zarr_writer.py): one chunk row of planes is finalised on the GPU and copied to the
+        host while the pool compresses and writes the previous ones.  Returns the FinalVolumeWriter (closed)."""
+        from .zarr_writer import FinalVolumeWriter
+        if self.world != 1:
+            raise RuntimeError("run_to_zarr() is single-rank; under torch.distributed every rank calls sweep() + "
+                               "merge_slabs() and submits its own z-range to a FinalVolumeWriter(create=rank == 0)")
+        vol_shape = tuple(int(s) for s in volume.shape[-3:])
+        blender = self.sweep(volume)
+        writer = FinalVolumeWriter(root, self.targets, vol_shape, self.patch, compressor=compressor, threads=threads)
+        try:
+            for z in range(0, vol_shape[0], self.patch[0]):
+                writer.submit(z, blender.finalize(z, min(z + self.patch[0], vol_shape[0])))
+        finally:
+            writer.close()
+        return writer
+
+
 def plan_slab_exchange(z_starts: Sequence[int], patch_z: int, vol_z: int, world_size: int):
     """Pure host logic of the end-of-sweep exchange.  Returns (pairs, own) where own[r] = [lo, hi) is the
     z-range rank r finalises and pairs = [(src, dst, lo, hi)]: planes [lo, hi) of src's slab that must be
