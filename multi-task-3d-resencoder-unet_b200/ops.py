@@ -21,6 +21,7 @@ import itertools
 import os
 
 import torch
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook
 
 from . import _lib as L
 
@@ -257,11 +258,29 @@ MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
 SIGN_FROM_PRENORM = os.environ.get("RESENC_NO_SIGN_FROM_PRENORM") is None
 
 
+# Fused optimisers (torch.optim.AdamW(fused=True), `torch._fused_adamw_`) update parameters in place WITHOUT bumping
+# `Tensor._version`, so the version alone cannot key the pack cache: every optimiser step anywhere in the process
+# advances this epoch (global post-step hook) and invalidates all cached packs.
+_PACK_EPOCH = [0]
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    _PACK_EPOCH[0] += 1
+
+
+_register_step_hook(_on_optimizer_step)
+
+
+def invalidate_weight_packs():
+    """Call after modifying parameters through an API that neither bumps `Tensor._version` nor is an optimiser step."""
+    _PACK_EPOCH[0] += 1
+
+
 def _cached_pack(weight, kind, fn):
     if not PACK_CACHE:
         with torch.no_grad():
             return fn()
-    key = (weight._version, weight.data_ptr(), str(weight.device))
+    key = (weight._version, _PACK_EPOCH[0], weight.data_ptr(), str(weight.device))
     cache = getattr(weight, "_rb_pack", None)
     if cache is None or cache.get("key") != key:
         cache = {"key": key}

@@ -24,7 +24,7 @@ from . import ops
 BF16 = torch.bfloat16
 # which gather-conv implementation runs the 3C-wide contractions ("auto" = the tcgen05 kernels where the widened
 # shapes qualify, "mma" = the shape-generic mma.sync kernel)
-IMPL = os.environ.get("RESENC_PRECISE_IMPL", "mma")
+IMPL = os.environ.get("RESENC_PRECISE_IMPL", "auto")
 
 
 def _split(w: torch.Tensor):

@@ -262,3 +262,22 @@ def test_zarr_v2_final_writer_roundtrip(rb, tmp_path):
             assert np.array_equal(raw[:5, :4, :2], sheet[32:, 16:, 24:]) and not raw[5:].any()
     with pytest.raises(NotImplementedError):
         inf.FinalVolumeWriter(str(tmp_path / "x.zarr"), targets, vol, patch, compressor="blosc")
+
+
+def test_weight_pack_cache_sees_fused_optimizer_updates(rb):
+    """torch's fused optimisers update parameters without bumping Tensor._version; the pack cache must not serve the
+    pre-update bf16 operand (found by the trainer test: eager fused-AdamW training otherwise learns on stale packs)."""
+    ops = rb.ops
+    w = torch.nn.Parameter(torch.randn(8, 8, 3, 3, 3))
+    a = ops.pack_conv_fprop(w)
+    assert ops.pack_conv_fprop(w) is a                                    # cached while nothing changes
+    w.grad = torch.ones_like(w)
+    opt = torch.optim.AdamW([w], lr=0.5, fused=True)
+    v = w._version
+    opt.step()
+    b = ops.pack_conv_fprop(w)
+    exp = w.detach().permute(2, 3, 4, 0, 1).reshape(27, 8, 8).to(torch.bfloat16)
+    assert torch.equal(b, exp) and not torch.equal(a, b), f"stale pack (version {v} -> {w._version})"
+    with torch.no_grad():
+        w.add_(1.0)                                                       # ordinary in-place update: version bump
+    assert torch.equal(ops.pack_conv_fprop(w), w.detach().permute(2, 3, 4, 0, 1).reshape(27, 8, 8).to(torch.bfloat16))

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--weight", default="gaussian", choices=["uniform", "gaussian"])
     ap.add_argument("--warmup-patches", type=int, default=4)
+    ap.add_argument("--precise", action="store_true", help="split-precision (bf16x3) forward: fp32-accurate logits")
+    ap.add_argument("--precise-impl", default=None, choices=[None, "mma", "auto"])
     args = ap.parse_args()
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -58,13 +60,15 @@ def main():
     # inference config adds none on top (avoids the reference's double-sigmoid quirk)
     targets = {"sheet": {"channels": 1, "activation": "none"}, "normals": {"channels": 3, "activation": "none"}}
     sw = inf.SlidingWindowInferer(model, targets, (P,) * 3, overlap=args.overlap, batch_size=args.batch, weight=args.weight,
-                                  rank=rank, world_size=world, device=dev)
+                                  rank=rank, world_size=world, device=dev, precise=args.precise)
+    if args.precise_impl:
+        rb.precise.IMPL = args.precise_impl
     positions, z_lo, z_hi, (zs, ys, xs) = sw.plan(volume.shape)
     # warm-up: a few patches through the network (weight packing, kernel attribute setup)
     with torch.no_grad():
         x = torch.rand(args.batch, 1, P, P, P, device=dev)
         for _ in range(max(1, args.warmup_patches // args.batch)):
-            model(x)
+            sw._forward(x)
     torch.cuda.synchronize()
     if world > 1:
         # establish the point-to-point connections the slab exchange uses (one-time NCCL setup, not part of a sweep)
@@ -108,7 +112,7 @@ def main():
                                    f"batch {args.batch}, z-slab sharded over {world} GPU(s), sheet(1) + normals(3)"},
             "e2e": {"value": V ** 3 / (ms_wall * 1e-3), "unit": "voxels/s", "ms": ms_wall,
                     "h2d_bytes": getattr(sw, "h2d_bytes", 0), "d2h_bytes_rank0": d2h},
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16x3 (split precision, fp32-accurate)" if args.precise else "bf16", "data": "synthetic",
         }
         print(json.dumps(line))
     if world > 1:
