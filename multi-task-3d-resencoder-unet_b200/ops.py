@@ -256,6 +256,8 @@ MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
 # lrelu'(z) from the fp32 pre-norm tensor and the forward's folded scale / shift (2 of 8-10 bytes per element less in
 # both backward passes; 32.5 -> 32.1 ms per step).  RESENC_NO_SIGN_FROM_PRENORM=1 restores the read of z.
 SIGN_FROM_PRENORM = os.environ.get("RESENC_NO_SIGN_FROM_PRENORM") is None
+# weight gradient of the deep (small-grid) layers on a side stream, concurrent with the data gradient
+CONCURRENT_WGRAD = os.environ.get("RESENC_NO_CONCURRENT_WGRAD") is None
 
 
 # Fused optimisers (torch.optim.AdamW(fused=True), `torch._fused_adamw_`) update parameters in place WITHOUT bumping
@@ -459,10 +461,48 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
     in_dims = tuple(x0.shape[2:])
     od = tuple(dy.shape[2:])
     gw = gx0 = gx1 = None
+    need1 = need1 and x1 is not None
     if need_w:
+        # deep layers (<= 32 k output voxels: the 16^3 / 8^3 / 4^3 stages) fill less than half of the SMs with either
+        # gradient kernel, and the two only share their input dy: the weight gradient runs on a side stream next to
+        # the data gradient (fork / join around this function, also inside CUDA graph capture)
+        fork = (CONCURRENT_WGRAD and (need0 or need1) and dy.is_cuda and n * od[0] * od[1] * od[2] <= 32768)
+        if fork:
+            cur = torch.cuda.current_stream(dy.device)
+            side = _side_stream(dy.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride, impl=impl)
+                gw = unpack_wgrad(dw, co, ci, k)
+            try:
+                return (gw, *_conv_backward_data(weight, stride, impl, x0, x1, dy, need0, need1))
+            finally:
+                cur.wait_stream(side)     # joined before anything that was allocated here can be freed or reused
         dw = _launch_wgrad(dy, x0, x1, grid=od, qdims=in_dims, taps=k, off=tuple(-p for p in pad), istr=stride, impl=impl)
         gw = unpack_wgrad(dw, co, ci, k)
-    need1 = need1 and x1 is not None
+    return (gw, *_conv_backward_data(weight, stride, impl, x0, x1, dy, need0, need1))
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
+def _conv_backward_data(weight, stride, impl, x0, x1, dy, need0, need1):
+    """Data gradient(s) of `_conv_forward` w.r.t. its one or two sources; returns (gx0, gx1)."""
+    co, ci, kd, kh, kw = weight.shape
+    k = (kd, kh, kw)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    n = x0.shape[0]
+    in_dims = tuple(x0.shape[2:])
+    od = tuple(dy.shape[2:])
+    gx0 = gx1 = None
     if need0 or need1:
         c0 = x0.shape[1]
         merged = _merged_dgrad_plan(k, stride, pad, in_dims, od) if MERGED_STRIDED_DGRAD else None
@@ -473,7 +513,7 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
             _launch_gather(dy, None, pack_conv_dgrad_merged(weight, merged, stride), gx0, gx1, in_dims=od,
                            taps=tuple(a[0] for a in merged), off=tuple(a[1] for a in merged), istr=(1, 1, 1), out_grid=od,
                            nout=npar * ci, mode=1, ostr=stride, full=in_dims, ps=stride, psC=ci, impl=impl)
-            return gw, (gx0 if need0 else None), (gx1 if need1 else None)
+            return (gx0 if need0 else None), (gx1 if need1 else None)
         classes = [_axis_classes(k[a], stride[a], pad[a], in_dims[a]) for a in range(3)]
         empty = any(len(cls[2]) == 0 for axis in classes for cls in axis)
         mk = zeros_cl if empty else new_cl
@@ -492,7 +532,7 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
             gx0 = None
         if not need1:
             gx1 = None
-    return gw, gx0, gx1
+    return gx0, gx1
 
 
 # stem: im2col of the raw NCDHW fp32 input, then a 1-tap GEMM over K = taps * Cin (padded to 16)
