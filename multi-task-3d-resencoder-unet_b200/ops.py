@@ -258,6 +258,7 @@ MERGED_STRIDED_DGRAD = os.environ.get("RESENC_NO_MERGED_DGRAD") is None
 SIGN_FROM_PRENORM = os.environ.get("RESENC_NO_SIGN_FROM_PRENORM") is None
 # weight gradient of the deep (small-grid) layers on a side stream, concurrent with the data gradient
 CONCURRENT_WGRAD = os.environ.get("RESENC_NO_CONCURRENT_WGRAD") is None
+CONCURRENT_WGRAD_MAX_VOXELS = int(os.environ.get("RESENC_CONCURRENT_WGRAD_MAX_VOXELS", 1 << 40))
 
 
 # Fused optimisers (torch.optim.AdamW(fused=True), `torch._fused_adamw_`) update parameters in place WITHOUT bumping
@@ -463,10 +464,11 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
     gw = gx0 = gx1 = None
     need1 = need1 and x1 is not None
     if need_w:
-        # deep layers (<= 32 k output voxels: the 16^3 / 8^3 / 4^3 stages) fill less than half of the SMs with either
-        # gradient kernel, and the two only share their input dy: the weight gradient runs on a side stream next to
-        # the data gradient (fork / join around this function, also inside CUDA graph capture)
-        fork = (CONCURRENT_WGRAD and (need0 or need1) and dy.is_cuda and n * od[0] * od[1] * od[2] <= 32768)
+        # the two gradient kernels only share their input dy: the weight gradient runs on a side stream next to the
+        # data gradient (fork / join around this function, also inside CUDA graph capture).  The deep layers (16^3 /
+        # 8^3 / 4^3) fill less than half of the SMs with either kernel (30.4 -> 29.7 ms per step); on the large layers
+        # the tail of one persistent kernel overlaps the head of the other (-> 29.2 ms)
+        fork = (CONCURRENT_WGRAD and (need0 or need1) and dy.is_cuda and n * od[0] * od[1] * od[2] <= CONCURRENT_WGRAD_MAX_VOXELS)
         if fork:
             cur = torch.cuda.current_stream(dy.device)
             side = _side_stream(dy.device)
@@ -487,10 +489,13 @@ _SIDE_STREAMS = {}
 
 
 def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """The side stream paired with the CURRENT stream of `device` (decoders running on their own streams fork to
+    their own side streams, so the forks add no dependencies between them)."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return st
 
 
@@ -921,14 +926,21 @@ class _ConvT3dFn(torch.autograd.Function):
         full = tuple(dy.shape[2:])
         npar = sd * sh * sw
         gw = gx = None
+        fork = None
         if ctx.needs_input_grad[0]:
-            dw = _launch_wgrad(x, dy, None, grid=in_dims, qdims=full, taps=stride, off=(0, 0, 0), istr=stride, impl=impl)
-            gw = unpack_wgrad(dw, ci, co, (sd, sh, sw))
+            if CONCURRENT_WGRAD and ctx.needs_input_grad[3] and dy.is_cuda:
+                fork = (torch.cuda.current_stream(dy.device), _side_stream(dy.device))    # see _conv_backward
+                fork[1].wait_stream(fork[0])
+            with (torch.cuda.stream(fork[1]) if fork else contextlib.nullcontext()):
+                dw = _launch_wgrad(x, dy, None, grid=in_dims, qdims=full, taps=stride, off=(0, 0, 0), istr=stride, impl=impl)
+                gw = unpack_wgrad(dw, ci, co, (sd, sh, sw))
         if ctx.needs_input_grad[3]:
             gx = new_cl(n, ci, *in_dims, x.device)
             wpk = weight.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(BF16).contiguous()
             _launch_gather(dy, None, wpk, gx, None, in_dims=full, taps=stride, off=(0, 0, 0), istr=stride,
                            out_grid=in_dims, nout=ci, impl=impl)
+        if fork:
+            fork[0].wait_stream(fork[1])
         return gw, None, None, gx
 
 
