@@ -380,10 +380,16 @@ def main():
                          "launches_per_step": conv["launches"] / max(args.steps, 1),
                          "kernel_ms_per_step": conv["ms"] / max(args.steps, 1),
                          "share_of_step": conv["ms"] / ms_dev if ms_dev else None,
-                         "measured_in": "eager pass of the same K steps, CUDA-event span around every launch",
+                         "measured_in": "eager pass of the same K steps, CUDA-event span around every launch, the wgrad side-stream "
+                                        "fork switched off so that each span times one kernel running alone",
                          "whole_step_tflops": step_flops * args.steps / (ms_dev * 1e-3) / 1e12},
             "kernel_ms_per_step": {k: v["ms"] / max(args.steps, 1) for k, v in kstat.items()},
         }
+        try:    # counters of the round's ncu --set full capture (never measured in this run: a pointer to the evidence)
+            with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+                line["roofline"]["ncu"] = json.load(f)
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             p = args.cpu_sample_patch
             rate, sec = cpu_step_rate(p, 1, 3, 1, topology_patch=P)

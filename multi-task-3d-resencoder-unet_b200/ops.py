@@ -470,7 +470,9 @@ def _conv_backward(weight, stride, impl, x0, x1, dy, need_w, need0, need1):
         # data gradient (fork / join around this function, also inside CUDA graph capture).  The deep layers (16^3 /
         # 8^3 / 4^3) fill less than half of the SMs with either kernel (30.4 -> 29.7 ms per step); on the large layers
         # the tail of one persistent kernel overlaps the head of the other (-> 29.2 ms)
-        fork = (CONCURRENT_WGRAD and (need0 or need1) and dy.is_cuda and n * od[0] * od[1] * od[2] <= CONCURRENT_WGRAD_MAX_VOXELS)
+        # (not while bench.py brackets every launch with CUDA events: a span must time one kernel running alone)
+        fork = (CONCURRENT_WGRAD and not KERNEL_TIMER.on and (need0 or need1) and dy.is_cuda
+                and n * od[0] * od[1] * od[2] <= CONCURRENT_WGRAD_MAX_VOXELS)
         if fork:
             cur = torch.cuda.current_stream(dy.device)
             side = _side_stream(dy.device)
@@ -930,7 +932,7 @@ class _ConvT3dFn(torch.autograd.Function):
         gw = gx = None
         fork = None
         if ctx.needs_input_grad[0]:
-            if CONCURRENT_CONVT_WGRAD and ctx.needs_input_grad[3] and dy.is_cuda:
+            if CONCURRENT_CONVT_WGRAD and not KERNEL_TIMER.on and ctx.needs_input_grad[3] and dy.is_cuda:
                 fork = (torch.cuda.current_stream(dy.device), _side_stream(dy.device))    # see _conv_backward
                 fork[1].wait_stream(fork[0])
             with (torch.cuda.stream(fork[1]) if fork else contextlib.nullcontext()):
