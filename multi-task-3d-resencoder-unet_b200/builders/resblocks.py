@@ -243,7 +243,9 @@ class StackedResidualBlocks(nn.Module):
         if x_cat is not None:
             # decoder stages built from residual blocks see the concatenation (decoder.py:147);
             # materialise it once, the block then reads it twice (conv1 and the projection skip)
-            import torch
+            if ops.precise_active():
+                # a channel concatenation of two [hi | lo | hi] rows is not a split row of the concatenation
+                _unsupported("residual decoder stages in the split-precision inference tier")
             x = torch.cat((ops.as_cl(x), ops.as_cl(x_cat)), 1)
         for blk in self.blocks:
             x = blk(x)

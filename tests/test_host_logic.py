@@ -281,3 +281,31 @@ def test_weight_pack_cache_sees_fused_optimizer_updates(rb):
     with torch.no_grad():
         w.add_(1.0)                                                       # ordinary in-place update: version bump
     assert torch.equal(ops.pack_conv_fprop(w), w.detach().permute(2, 3, 4, 0, 1).reshape(27, 8, 8).to(torch.bfloat16))
+
+
+def test_split_precision_weight_rows(rb):
+    """precise._pack3: [hi | hi | lo] rows reproduce the fp32 weight to 2^-16 relative when paired with activation
+    rows [hi | lo | hi] (the dropped lo*lo term is second order), and the context manager restores the bf16 tier."""
+    P = rb.precise
+    torch.manual_seed(3)
+    w = torch.randn(5, 7, 16) * 0.1
+    pk = P._pack3(w)
+    assert pk.dtype == torch.bfloat16 and tuple(pk.shape) == (5, 7, 48)
+    hi, hi2, lo = pk[..., :16].float(), pk[..., 16:32].float(), pk[..., 32:].float()
+    assert torch.equal(hi, hi2) and torch.equal(hi, w.to(torch.bfloat16).float())
+    assert float(((hi + lo) - w).abs().max() / w.abs().max()) < 2.0 ** -16
+    x = torch.randn(16)
+    xh = x.to(torch.bfloat16).float()
+    xl = (x - xh).to(torch.bfloat16).float()
+    row = torch.cat((xh, xl, xh))
+    got = (pk.float() * row).sum(-1)                       # hi*hi_w + lo*hi_w + hi*lo_w
+    ref = (w.double() * x.double()).sum(-1)
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    plain = (w.to(torch.bfloat16).float() * xh).sum(-1)    # the bf16 tier's operands
+    assert float((plain.double() - ref).abs().max()) > 10 * float((got.double() - ref).abs().max())
+    assert not rb.ops.precise_active()
+    with rb.ops.precise_inference(impl="mma"):
+        assert rb.ops.precise_active() and not torch.is_grad_enabled()
+        with pytest.raises(rb._lib.ResencLibraryError):
+            P.avg_pool3d(torch.zeros(1, 24, 2, 2, 2), 2)     # CPU tensor: the tier has no CPU fallback either
+    assert not rb.ops.precise_active() and torch.is_grad_enabled()
