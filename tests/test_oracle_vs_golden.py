@@ -92,3 +92,33 @@ def test_oracle_blend_roundtrip():
     exp = ((np.array([0.0, 0.6, 0.8], np.float32) + 1) / 2 * 65535)
     got = out["normals"][:, 3, 3, 3].astype(np.float64)
     assert np.all(np.abs(got - exp) <= 1.0)
+
+
+def test_whole_net_sanity_value_of_the_survey():
+    """SURVEY 8(c) "whole-net sanity": torch.manual_seed(0); build the 64^3 two-task network; x = torch.rand(1,1,64^3);
+    sheet target (rand > 0.8), normals target normalize(randn); BCEDice + MaskedCosine = 1.66644 on the reference
+    (torch 2.11 CPU).  Reproducing it needs (a) the drop-in's constructors to consume the RNG exactly like the
+    reference's (same module creation order, PyTorch default init) and (b) the oracle's forward and losses."""
+    import contextlib
+    import io
+    from types import SimpleNamespace
+
+    import resenc_b200 as rb
+    tasks = {"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}}
+    mgr = SimpleNamespace(tasks=tasks, train_patch_size=[64] * 3, train_batch_size=1, in_channels=1, vram_max=16.0,
+                          autoconfigure=True, model_config={})
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = rb.NetworkFromConfig(mgr)
+    x = torch.rand(1, 1, 64, 64, 64)
+    ts = (torch.rand(1, 1, 64, 64, 64) > 0.8).float()
+    tn = torch.nn.functional.normalize(torch.randn(1, 3, 64, 64, 64), dim=1)
+    assert abs(sum(p.numel() for p in model.parameters()) / 1e6 - 118.09) < 0.01          # SURVEY topology row
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    topo = O.autoconfig([64] * 3)
+    with torch.no_grad():
+        out = O.net_forward(sd, topo, x, tasks, training=True)
+    loss = O.bce_dice_loss(out["sheet"], ts) + O.masked_cosine_loss(out["normals"], tn)
+    assert abs(float(loss) - 1.66644) < 1e-4
+    assert abs(float(out["sheet"].mean()) - 0.22254) < 1e-4 and abs(float(out["sheet"].std()) - 0.31666) < 1e-4
+    assert abs(float(out["normals"].mean()) + 0.28349) < 1e-4 and abs(float(out["normals"].std()) - 0.38100) < 1e-4
