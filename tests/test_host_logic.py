@@ -309,3 +309,35 @@ def test_split_precision_weight_rows(rb):
         with pytest.raises(rb._lib.ResencLibraryError):
             P.avg_pool3d(torch.zeros(1, 24, 2, 2, 2), 2)     # CPU tensor: the tier has no CPU fallback either
     assert not rb.ops.precise_active() and torch.is_grad_enabled()
+
+
+def test_topology_census_matches_survey(rb):
+    """SURVEY 0.6 / 0.8 / 8(c) censuses measured on the reference, reproduced by the drop-in on the meta device:
+    parameter counts, unique parameters vs state_dict keys (aliases), module counts, stage counts."""
+    import contextlib
+    import io
+    from collections import Counter
+    from types import SimpleNamespace
+    two = {"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}}
+    ink = {"ink": {"channels": 1, "activation": "sigmoid"}}
+
+    def census(patch, tasks, cin=1, mc=None):
+        mgr = SimpleNamespace(tasks=tasks, train_patch_size=list(patch), train_batch_size=2, in_channels=cin, vram_max=16.0,
+                              autoconfigure=True, model_config=mc or {})
+        with torch.device("meta"), contextlib.redirect_stdout(io.StringIO()):
+            m = rb.NetworkFromConfig(mgr)
+        c = Counter(type(x).__name__ for x in m.modules())
+        return (round(sum(p.numel() for p in m.parameters()) / 1e6, 2), len(list(m.parameters())), len(m.state_dict()),
+                c["Conv3d"], c["ConvTranspose3d"], c["InstanceNorm3d"], c["AvgPool3d"], m.num_stages)
+
+    # 128^3 and 192^3: the same 6 stages, 235.53 M parameters; 69 convs used per forward + 8 unused deep-supervision heads
+    assert census([128] * 3, two) == (235.53, 97, 392, 77, 10, 67, 5, 6)
+    assert census([192] * 3, two) == census([128] * 3, two)
+    # BASELINE config 4: 96^3, 4 input channels, one task, SE on
+    assert census([96] * 3, ink, 4, {"squeeze_excitation": True})[0] == 112.26
+    # 64^3, two tasks, SE on: 157 unique parameters behind 550 state_dict keys (SURVEY 0.8)
+    assert census([64] * 3, two, 1, {"squeeze_excitation": True})[1:3] == (157, 550)
+    assert census([64] * 3, two)[0] == 118.09
+    # ink.yaml's literal patch: 7 stages with anisotropic strides, 312 M parameters (SURVEY 0.5)
+    c = census([14, 256, 256], ink, 1, {"squeeze_excitation": True, "conv_bias": True})
+    assert c[-1] == 7 and abs(c[0] - 312.27) < 0.01
