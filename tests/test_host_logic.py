@@ -341,3 +341,31 @@ def test_topology_census_matches_survey(rb):
     # ink.yaml's literal patch: 7 stages with anisotropic strides, 312 M parameters
     c = census([14, 256, 256], ink, 1, {"squeeze_excitation": True, "conv_bias": True})
     assert c[-1] == 7 and abs(c[0] - 312.27) < 0.01
+
+
+def test_manual_config_reachability_matrix_matches_survey(rb):
+    """SURVEY Appendix A reachability matrix (manual config, 6 stages to 320 features, SE on, two tasks), measured on
+    the reference: which block classes a (encoder, bottleneck, decoder) triple builds and the parameter counts."""
+    import contextlib
+    import io
+    from types import SimpleNamespace
+    two = {"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}}
+    base = dict(features_per_stage=[32, 64, 128, 256, 320, 320], num_stages=6, n_blocks_per_stage=[1, 3, 4, 6, 6, 6],
+                kernel_sizes=[[3, 3, 3]] * 6, n_conv_per_stage_decoder=[1] * 5, strides=[[1, 1, 1]] + [[2, 2, 2]] * 5,
+                squeeze_excitation=True)
+    expect = [("BasicBlockD", "BasicBlockD", "ConvBlock", 114.6, "BasicBlockD", 26),
+              ("BottleneckBlockD", "BottleneckBlockD", "ConvBlock", 28.2, "BottleneckD", 26),
+              ("BasicBlockD", "BottleneckBlockD", "ConvBlock", 114.6, "BasicBlockD", 26),      # encoder.py:74-77
+              ("BasicBlockD", "BasicBlockD", "ResidualBlock", 125.6, "BasicBlockD", 36),       # + 5 per decoder, no SE
+              ("ConvBlock", "BasicBlockD", "ConvBlock", 68.3, "BasicBlockD", 0)]               # plain conv encoder
+    for enc, bott, dec, mparams, cls, nblocks in expect:
+        mc = dict(base, basic_encoder_block=enc, bottleneck_block=bott, basic_decoder_block=dec)
+        mgr = SimpleNamespace(tasks=two, train_patch_size=[128] * 3, train_batch_size=2, in_channels=1, vram_max=16.0,
+                              autoconfigure=False, model_config=mc)
+        with torch.device("meta"), contextlib.redirect_stdout(io.StringIO()):
+            m = rb.NetworkFromConfig(mgr)
+        assert round(sum(p.numel() for p in m.parameters()) / 1e6, 1) == mparams, (enc, bott, dec)
+        # block modules, counted once (each decoder holds the shared encoder as a child: modules() de-duplicates)
+        assert sum(type(x).__name__ == cls for x in m.modules()) == nblocks, (enc, bott, dec)
+        n_se = sum(type(x).__name__ == "SqueezeExcite" for x in m.modules())
+        assert n_se == (26 if enc != "ConvBlock" else 0)
