@@ -14,6 +14,7 @@ the only exchange is one mean all-reduce of the gradients per step:
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List
 
 import torch
@@ -54,6 +55,7 @@ class GradientBuckets:
             b["pending"] = len(b["params"])
             b["touched"] = 0
             b["work"] = None
+        self._sync = True
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.bytes_per_step = sum(b["flat"].numel() * 4 for b in self.buckets)
 
@@ -85,7 +87,19 @@ class GradientBuckets:
                 b["flat"].div_(self.world)
             b["work"] = dist.all_reduce(b["flat"], group=self.group, async_op=True)
 
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context only add into the flat buckets; the
+        all-reduce happens in the first backward outside it (like DistributedDataParallel.no_sync)."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
+
     def _on_grad(self, p):
+        if not self._sync:
+            return
         b = self.buckets[self._index[id(p)]]
         b["pending"] -= 1
         b["touched"] += 1

@@ -22,6 +22,7 @@ part of the hot path and stay with the caller.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
@@ -129,7 +130,10 @@ class DataParallelTrainer:
             self._zero_grad()
         outputs = self.model(inputs)
         total, per = self._loss(outputs, targets)
-        (total / self.accumulate).backward()
+        # micro-batches before the update only accumulate into the flat buckets; the all-reduce rides the last backward
+        hold = self.buckets.no_sync() if (self.buckets is not None and not do_update) else contextlib.nullcontext()
+        with hold:
+            (total / self.accumulate).backward()
         self._micro += 1
         if do_update:
             if self.buckets is not None:
@@ -142,13 +146,11 @@ class DataParallelTrainer:
     def train_step(self, inputs: torch.Tensor, targets: Dict[str, torch.Tensor], last_in_epoch: bool = False):
         """Forward, weighted multi-task loss, backward; every `gradient_accumulation`-th call (or when
         `last_in_epoch`) the gradients are all-reduced, clipped and applied.  Returns (total_loss, {task: loss})
-        as device tensors (no host synchronisation).  Gradient accumulation is single-process only."""
+        as device tensors (no host synchronisation).  Under data parallelism the accumulated gradient is reduced
+        once, during the backward pass of the updating micro-batch."""
         self.model.train()
         if self.use_graph:
             return self._graphed_step(inputs, targets)
-        if self.buckets is not None and self.accumulate > 1:
-            raise NotImplementedError("gradient accumulation > 1 with bucketed all-reduce (buckets fire on the first "
-                                      "micro-batch); use accumulation 1 or a larger per-GPU batch")
         do_update = (self._micro + 1) % self.accumulate == 0 or last_in_epoch
         return self._micro_step(inputs, targets, do_update)
 

@@ -160,7 +160,7 @@ def _tiny_batch(step, rank):
     return x, {"sheet": sheet, "normals": normals}
 
 
-def _trainer_worker(rank, world, port, out):
+def _trainer_worker(rank, world, port, out, accumulate=1):
     import sys
     from types import SimpleNamespace
     sys.path.insert(0, ROOT)
@@ -171,11 +171,12 @@ def _trainer_worker(rank, world, port, out):
     assert T.init_distributed("gloo") == (rank, rank, world)
     torch.manual_seed(0)
     model = _TinyNet()
-    mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5)
+    mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5,
+                          gradient_accumulation=accumulate)
     tr = T.DataParallelTrainer(model, mgr, fused_losses=False)
     assert tr.world == world and tr.rank == rank
     losses = []
-    for step in range(3):
+    for step in range(3 * accumulate):
         x, tgt = _tiny_batch(step, rank)
         total, per = tr.train_step(x, tgt)
         losses.append(float(total))
@@ -243,3 +244,35 @@ def test_shard_indices_cover_and_balance():
     assert sorted(a) == list(range(10))
     with pytest.raises(ValueError):
         T.shard_indices(idx, 2, 2)
+
+
+def test_data_parallel_trainer_gradient_accumulation(tmp_path):
+    """gradient_accumulation = 2 under data parallelism (train.py:222-230): micro-batches accumulate locally
+    (GradientBuckets.no_sync), the all-reduce rides the updating backward; equals the single-process step on the
+    mean gradient over ranks x micro-batches."""
+    out = str(tmp_path / "a")
+    mp.spawn(_trainer_worker, args=(2, _free_port(), out, 2), nprocs=2, join=True)
+    parts = [torch.load(out + f".{r}") for r in range(2)]
+    for a, b in zip(parts[0]["params"], parts[1]["params"]):
+        assert torch.equal(a, b)
+    rb = importlib.import_module("resenc_b200")
+    crit = rb.losses.task_losses(_TASKS, fused=False)
+    torch.manual_seed(0)
+    model = _TinyNet()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-4)
+    for upd in range(3):
+        grads = None
+        for micro in range(2):
+            for rank in range(2):
+                x, tgt = _tiny_batch(2 * upd + micro, rank)
+                o = model(x)
+                loss = 2.0 * crit["sheet"](o["sheet"], tgt["sheet"]) + crit["normals"](o["normals"], tgt["normals"])
+                assert abs(float(loss) - parts[rank]["losses"][2 * upd + micro]) < 1e-5
+                g = torch.autograd.grad(loss, list(model.parameters()))
+                grads = g if grads is None else [a + b for a, b in zip(grads, g)]
+        for p, g in zip(model.parameters(), grads):
+            p.grad = g / 4
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 3.0)
+        opt.step()
+    for a, b in zip(parts[0]["params"], model.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
