@@ -202,17 +202,22 @@ class DataParallelTrainer:
         self.epoch += 1
 
     def state_dict(self):
+        """The reference's checkpoint dictionary; 'epoch' is the 0-based index of the last finished epoch
+        (train.py:249-254 saves the loop variable, :164 resumes at checkpoint['epoch'] + 1)."""
         return {"model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
-                "scheduler": self.scheduler.state_dict(), "epoch": self.epoch}
+                "scheduler": self.scheduler.state_dict(), "epoch": self.epoch - 1}
 
-    def save_checkpoint(self, path: str) -> bool:
-        """Rank 0 writes the reference's checkpoint dictionary (train.py:249-254); other ranks only synchronise."""
+    def save_checkpoint(self, path: str, keep_newest: Optional[int] = None) -> bool:
+        """Rank 0 writes the reference's checkpoint dictionary (train.py:249-254) atomically; other ranks only
+        synchronise.  `keep_newest` = N prunes older `<model_name>_*.pth` siblings like train.py:256-265 (N = 10 there)."""
         wrote = False
         if self.rank == 0:
             tmp = f"{path}.tmp"
             torch.save(self.state_dict(), tmp)
             os.replace(tmp, path)
             wrote = True
+            if keep_newest:
+                prune_checkpoints(path, keep_newest)
         if self.world > 1:
             dist.barrier()
         return wrote
@@ -225,9 +230,26 @@ class DataParallelTrainer:
                 self.optimizer.load_state_dict(ck["optimizer"])
             if "scheduler" in ck:
                 self.scheduler.load_state_dict(ck["scheduler"])
-            self.epoch = int(ck.get("epoch", 0))
+            self.epoch = int(ck.get("epoch", -1)) + 1          # the epoch to run next (train.py:164)
         self._graph = None
         return ck
+
+
+def prune_checkpoints(latest_path: str, keep: int = 10):
+    """Keep the `keep` newest `<stem>_*.pth` files next to `latest_path` (train.py:256-265: sorted by mtime)."""
+    import glob
+    import re
+    d, base = os.path.split(os.path.abspath(latest_path))
+    m = re.match(r"(.*)_\d+\.pth$", base)
+    if not m:
+        return []
+    files = sorted(glob.glob(os.path.join(d, glob.escape(m.group(1)) + "_*.pth")), key=os.path.getmtime)
+    removed = []
+    while len(files) > keep:
+        oldest = files.pop(0)
+        os.unlink(oldest)
+        removed.append(oldest)
+    return removed
 
 
 def iterate_sharded(dataset_len: int, epoch: int, rank: int, world_size: int, seed: int = 0) -> Iterable[int]:

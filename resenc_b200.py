@@ -20,6 +20,7 @@ losses = importlib.import_module(_pkg.__name__ + ".losses")
 parallel = importlib.import_module(_pkg.__name__ + ".parallel")
 precise = importlib.import_module(_pkg.__name__ + ".precise")
 training = importlib.import_module(_pkg.__name__ + ".training")
+tracing = importlib.import_module(_pkg.__name__ + ".tracing")
 _lib = _pkg._lib
 
 

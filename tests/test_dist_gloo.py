@@ -216,7 +216,7 @@ def test_data_parallel_trainer_matches_mean_gradient_step(tmp_path):
     for a, b in zip(parts[0]["params"], model.parameters()):
         assert torch.allclose(a, b, atol=1e-6)
     ck = torch.load(out + ".ckpt", weights_only=False)
-    assert set(ck) == {"model", "optimizer", "scheduler", "epoch"} and ck["epoch"] == 1     # train.py:249-254
+    assert set(ck) == {"model", "optimizer", "scheduler", "epoch"} and ck["epoch"] == 0     # train.py:249-254: 0-based
     assert set(ck["model"]) == set(model.state_dict())
     # a torch.compile'd reference checkpoint (keys prefixed with _orig_mod.) loads
     ck["model"] = {"_orig_mod." + k: v for k, v in ck["model"].items()}
@@ -224,7 +224,15 @@ def test_data_parallel_trainer_matches_mean_gradient_step(tmp_path):
     mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5)
     tr = rb.training.DataParallelTrainer(_TinyNet(), mgr, fused_losses=False)
     tr.load_checkpoint(out + ".ckpt2")
-    assert tr.epoch == 1
+    assert tr.epoch == 1                                 # resumes at checkpoint['epoch'] + 1 (train.py:164)
+    # rolling window of checkpoints (train.py:256-265)
+    import time
+    for e in range(1, 6):
+        tr.epoch = e
+        tr.save_checkpoint(str(tmp_path / f"Model_{e}.pth"), keep_newest=3)
+        time.sleep(0.02)
+    assert sorted(os.listdir(tmp_path)).count("Model_1.pth") == 0
+    assert [f for f in sorted(os.listdir(tmp_path)) if f.startswith("Model_")] == ["Model_3.pth", "Model_4.pth", "Model_5.pth"]
     for a, b in zip(tr.model.parameters(), parts[0]["params"]):
         assert torch.equal(a, b)
 

@@ -369,3 +369,20 @@ def test_manual_config_reachability_matrix_matches_survey(rb):
         assert sum(type(x).__name__ == cls for x in m.modules()) == nblocks, (enc, bott, dec)
         n_se = sum(type(x).__name__ == "SqueezeExcite" for x in m.modules())
         assert n_se == (26 if enc != "ConvBlock" else 0)
+
+
+def test_nvtx_hooks_attach_and_detach(rb):
+    """tracing.enable_nvtx: one push / pop pair per block-level module (the shared encoder once, although every
+    decoder lists it as a child), removable without a trace."""
+    mgr, _ = case_mgr("sheet_normals_16")
+    model = quiet_build(rb.NetworkFromConfig, mgr)
+    n_hooks = lambda: sum(len(m._forward_hooks) + len(m._forward_pre_hooks) + len(m._backward_hooks) + len(m._backward_pre_hooks)
+                          for m in model.modules())
+    assert n_hooks() == 0
+    h = rb.tracing.enable_nvtx(model)
+    assert "shared_encoder" in h.names and "task_decoders.sheet" in h.names
+    assert "shared_encoder.stages.1.blocks.0" in h.names and "shared_encoder.stem.convs.0" in h.names
+    assert not any(n.startswith("task_decoders.sheet.encoder") for n in h.names)       # aliases instrumented once
+    assert len(h.names) == len(set(h.names)) and n_hooks() == 4 * len(h.names)
+    h.remove()
+    assert n_hooks() == 0
