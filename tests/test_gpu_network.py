@@ -99,7 +99,9 @@ def test_network_matches_reference_golden(rb, case):
         # cent in rel-L2 whatever the kernel (PyTorch's bf16 autocast of the reference is stored as calibration)
         ac_dev = float(gold["autocast_bf16_gradnorm_dev"])
         print(f"{case}: worst grad-norm deviation {worst:.3e} ({worst_name}); torch bf16 autocast: {ac_dev:.3e}")
-        assert worst < max(8e-2, 2.0 * ac_dev), worst_name
+        # floor 0.15: the figure moves by +-0.05 between runs (atomics order), most on the half-dropped batch of the
+        # stochastic-depth fixture
+        assert worst < max(0.15, 2.0 * ac_dev), worst_name
         print(f"{case}: worst SE-gate grad-norm deviation {worst_se:.3e}")
         assert worst_se < max(0.35, 2.0 * ac_dev)
         for k in gold.files:
