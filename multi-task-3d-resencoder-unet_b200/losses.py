@@ -48,6 +48,26 @@ class BCEWithLogitsLossLabelSmoothing(nn.Module):
         return F.binary_cross_entropy_with_logits(logits, smoothed, reduction=self.reduction)
 
 
+class BCEWithLogitsLossZSmooth(nn.Module):
+    """Label smoothing that grows linearly with the distance from the centre z slice: alpha(z) = center +
+    (edge - center) * |z - (D-1)/2| / (D // 2), target -> y * (1 - 2 alpha) + alpha, then BCE-with-logits
+    (losses.py:240-304)."""
+
+    def __init__(self, center_smoothing: float = 0.1, edge_smoothing: float = 0.4, reduction: str = "mean"):
+        super().__init__()
+        self.center_smoothing, self.edge_smoothing, self.reduction = center_smoothing, edge_smoothing, reduction
+
+    def forward(self, logits, targets):
+        if logits.shape != targets.shape or logits.dim() != 5:
+            raise ValueError("BCEWithLogitsLossZSmooth expects matching [B, C, D, H, W] tensors")
+        D = logits.shape[2]
+        z = torch.arange(D, device=logits.device, dtype=logits.dtype)
+        ratio = torch.abs(z - (D - 1) / 2.0) / (D // 2)
+        alpha = (self.center_smoothing + (self.edge_smoothing - self.center_smoothing) * ratio).view(1, 1, D, 1, 1)
+        smoothed = targets * (1.0 - 2.0 * alpha) + alpha
+        return F.binary_cross_entropy_with_logits(logits, smoothed, reduction=self.reduction)
+
+
 class BCEDiceLoss(nn.Module):
     def __init__(self, alpha: float, beta: float):
         super().__init__()
@@ -156,3 +176,31 @@ def task_losses(tasks, fused: bool = True):
     cos = FusedMaskedCosineLoss if fused else MaskedCosineLoss
     bd = FusedBCEDiceLoss if fused else BCEDiceLoss
     return {t: (cos() if t == "normals" and info.get("channels") == 3 else bd(0.5, 0.5)) for t, info in tasks.items()}
+
+
+# name -> class, the table BaseTrainer._build_loss resolves `tasks[t]["loss_fn"]` against (train.py:47-56)
+LOSS_FN_MAP = {
+    "BCEDiceLoss": BCEDiceLoss,
+    "BCEWithLogitsLossLabelSmoothing": BCEWithLogitsLossLabelSmoothing,
+    "BCEWithLogitsLossZSmooth": BCEWithLogitsLossZSmooth,
+    "BCEWithLogitsLoss": nn.BCEWithLogitsLoss,
+    "BCELoss": nn.BCELoss,
+    "CrossEntropyLoss": nn.CrossEntropyLoss,
+    "MSELoss": nn.MSELoss,
+    "MaskedCosineLoss": MaskedCosineLoss,
+}
+_FUSED = {"BCEDiceLoss": FusedBCEDiceLoss, "MaskedCosineLoss": FusedMaskedCosineLoss}
+
+
+def build_task_losses(tasks, fused: bool = True):
+    """BaseTrainer._build_loss (train.py:45-66): per task `loss_fn` (default "BCEDiceLoss") constructed with
+    `loss_kwargs`; unknown names raise ValueError like the reference.  `fused` swaps in the CUDA versions of the two
+    losses that have one (same values)."""
+    out = {}
+    for t, info in tasks.items():
+        name = info.get("loss_fn", "BCEDiceLoss")
+        if name not in LOSS_FN_MAP:
+            raise ValueError(f"Loss function {name} not found in LOSS_FN_MAP. Add it to the mapping and try again.")
+        cls = _FUSED.get(name, LOSS_FN_MAP[name]) if fused else LOSS_FN_MAP[name]
+        out[t] = cls(**info.get("loss_kwargs", {}))
+    return out

@@ -30,7 +30,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .losses import task_losses
+from .losses import build_task_losses, task_losses
 from .parallel import GradientBuckets
 
 CLIP_NORM = 3.0          # train.py:227
@@ -90,7 +90,12 @@ class DataParallelTrainer:
         self.use_graph = bool(use_cuda_graph)
         if self.use_graph and self.accumulate != 1:
             raise NotImplementedError("whole-step CUDA graph capture with gradient accumulation > 1")
-        self.criteria = task_losses(self.tasks, fused=fused_losses)
+        # tasks that name a `loss_fn` follow the reference's table (train.py:45-66); without one the BASELINE pairing
+        # applies (MaskedCosineLoss for a 3-channel "normals" task, BCEDiceLoss(0.5, 0.5) otherwise)
+        if any("loss_fn" in info for info in self.tasks.values()):
+            self.criteria = build_task_losses(self.tasks, fused=fused_losses)
+        else:
+            self.criteria = task_losses(self.tasks, fused=fused_losses)
         self.weights = {t: float(info.get("weight", 1.0)) for t, info in self.tasks.items()}
         lr = float(getattr(mgr, "initial_lr", 1e-3))
         wd = float(getattr(mgr, "weight_decay", 1e-4))

@@ -227,10 +227,45 @@ def make_host_goldens():
     print("host goldens:", len(pos), "position cases,", len(gau), "gaussian,", len(topo), "topology")
 
 
+def make_loss_goldens():
+    """Values and gradient norms of the reference trainer's loss table (train.py:47-56 over
+    training/losses/losses.py) on seeded inputs -> tests/golden/loss_goldens.json."""
+    L = rl.reference_module("training/losses/losses.py", "ref_losses")
+    rng = np.random.default_rng(77)
+    logits = torch.from_numpy(rng.standard_normal((2, 2, 5, 6, 7)).astype(np.float32) * 2)
+    target = torch.from_numpy((rng.random((2, 2, 5, 6, 7)) > 0.7).astype(np.float32))
+    vec_p = torch.from_numpy(rng.standard_normal((2, 3, 5, 6, 7)).astype(np.float32))
+    vec_t = rng.standard_normal((2, 3, 5, 6, 7)).astype(np.float32)
+    vec_t /= np.linalg.norm(vec_t, axis=1, keepdims=True)
+    vec_t[:, :, :2] = 0                                # masked-out voxels
+    vec_t = torch.from_numpy(vec_t)
+    cases = [("BCEDiceLoss", {"alpha": 0.5, "beta": 0.5}, "bin"), ("BCEDiceLoss", {"alpha": 0.3, "beta": 1.0}, "bin"),
+             ("BCEWithLogitsLossLabelSmoothing", {}, "bin"), ("BCEWithLogitsLossLabelSmoothing", {"smoothing": 0.25}, "bin"),
+             ("BCEWithLogitsLossZSmooth", {}, "bin"), ("BCEWithLogitsLossZSmooth", {"center_smoothing": 0.05, "edge_smoothing": 0.3}, "bin"),
+             ("MaskedCosineLoss", {}, "vec")]
+    out = []
+    for name, kw, kind in cases:
+        fn = getattr(L, name)(**kw)
+        x = (logits if kind == "bin" else vec_p).clone().requires_grad_(True)
+        t = target if kind == "bin" else vec_t
+        v = fn(x, t)
+        v.backward()
+        out.append({"loss_fn": name, "loss_kwargs": kw, "kind": kind, "value": float(v),
+                    "grad_norm": float(x.grad.double().norm()), "grad_sum": float(x.grad.double().sum())})
+    with open(os.path.join(GOLD, "loss_goldens.json"), "w") as f:
+        json.dump({"seed": 77, "cases": out}, f, indent=1)
+    print("loss goldens:", [(c["loss_fn"], round(c["value"], 5)) for c in out])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     only = sys.argv[1:]                  # `python oracle/make_golden.py <case> ...` regenerates just those cases
     if not only:
         make_host_goldens()
+        make_loss_goldens()
+    if only == ["losses"]:
+        make_loss_goldens()
+        only = ["__none__"]
     for c in (only or NET_CASES):
-        make_net_case(c)
+        if c in NET_CASES:
+            make_net_case(c)

@@ -386,3 +386,32 @@ def test_nvtx_hooks_attach_and_detach(rb):
     assert len(h.names) == len(set(h.names)) and n_hooks() == 4 * len(h.names)
     h.remove()
     assert n_hooks() == 0
+
+
+def test_loss_table_matches_reference_goldens(rb):
+    """losses.LOSS_FN_MAP / build_task_losses against values and gradients of the reference trainer's loss classes
+    (tests/golden/loss_goldens.json, written by oracle/make_golden.py from training/losses/losses.py)."""
+    gold = json.load(open(os.path.join(GOLDEN, "loss_goldens.json")))
+    rng = np.random.default_rng(gold["seed"])
+    logits = torch.from_numpy(rng.standard_normal((2, 2, 5, 6, 7)).astype(np.float32) * 2)
+    target = torch.from_numpy((rng.random((2, 2, 5, 6, 7)) > 0.7).astype(np.float32))
+    vec_p = torch.from_numpy(rng.standard_normal((2, 3, 5, 6, 7)).astype(np.float32))
+    vec_t = rng.standard_normal((2, 3, 5, 6, 7)).astype(np.float32)
+    vec_t /= np.linalg.norm(vec_t, axis=1, keepdims=True)
+    vec_t[:, :, :2] = 0
+    vec_t = torch.from_numpy(vec_t)
+    for fused in (False, True):          # on CPU tensors the fused classes take their composition path
+        for c in gold["cases"]:
+            fn = rb.losses.build_task_losses({"t": {"loss_fn": c["loss_fn"], "loss_kwargs": c["loss_kwargs"]}}, fused)["t"]
+            x = (logits if c["kind"] == "bin" else vec_p).clone().requires_grad_(True)
+            v = fn(x, target if c["kind"] == "bin" else vec_t)
+            v.backward()
+            assert abs(float(v) - c["value"]) < 1e-6, c
+            assert abs(float(x.grad.double().norm()) - c["grad_norm"]) < 1e-7 + 1e-5 * c["grad_norm"], c
+            assert abs(float(x.grad.double().sum()) - c["grad_sum"]) < 1e-6, c
+    assert set(rb.losses.LOSS_FN_MAP) == {"BCEDiceLoss", "BCEWithLogitsLossLabelSmoothing", "BCEWithLogitsLossZSmooth",
+                                          "BCEWithLogitsLoss", "BCELoss", "CrossEntropyLoss", "MSELoss", "MaskedCosineLoss"}
+    with pytest.raises(ValueError):
+        rb.losses.build_task_losses({"t": {"loss_fn": "FocalLoss"}})
+    with pytest.raises(TypeError):       # the reference's default (BCEDiceLoss without kwargs) fails the same way
+        rb.losses.build_task_losses({"t": {}})
