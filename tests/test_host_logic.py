@@ -415,3 +415,51 @@ def test_loss_table_matches_reference_goldens(rb):
         rb.losses.build_task_losses({"t": {"loss_fn": "FocalLoss"}})
     with pytest.raises(TypeError):       # the reference's default (BCEDiceLoss without kwargs) fails the same way
         rb.losses.build_task_losses({"t": {}})
+
+
+def test_slab_exchange_plan_property(rb):
+    """For random volumes / patches / overlaps / world sizes: after applying the planned plane transfers, every rank's
+    own z-range holds exactly what a single-rank sweep accumulates there, the own ranges tile [0, Z) without overlap,
+    and planes only ever travel forward (src < dst)."""
+    from hypothesis import given, settings, strategies as st
+    inf = rb.inference
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(8, 200), st.integers(4, 64), st.sampled_from([0.0, 0.1, 0.25, 0.5, 0.6, 0.75]), st.integers(1, 9))
+    def check(vol_z, patch_z, overlap, world):
+        if patch_z > vol_z:
+            return
+        step = max(1, int(round(patch_z * (1 - overlap))))
+        zs = inf.generate_positions(0, vol_z, patch_z, step)
+        full = np.zeros(vol_z, np.int64)
+        for z in zs:
+            full[z:z + patch_z] += 1
+        runs = inf.shard_z_starts(zs, world)
+        assert sum(runs, []) == list(zs)
+        slabs = {}
+        for r, run in enumerate(runs):
+            if not run:
+                continue
+            lo, hi = run[0], run[-1] + patch_z
+            a = np.zeros(hi - lo, np.int64)
+            for z in run:
+                a[z - lo:z - lo + patch_z] += 1
+            slabs[r] = (lo, a)
+        pairs, own = inf.plan_slab_exchange(zs, patch_z, vol_z, world)
+        for src, dst, lo, hi in pairs:       # in order and in place, exactly as merge_slabs sends / receives / adds
+            assert src < dst and lo < hi
+            slo, sa = slabs[src]
+            dlo, da = slabs[dst]
+            assert own[dst][0] <= lo and hi <= own[dst][1]            # only planes the receiver owns travel
+            da[lo - dlo:hi - dlo] += sa[lo - slo:hi - slo]
+        covered = np.zeros(vol_z, np.int64)
+        for r, (lo, hi) in enumerate(own):
+            if hi <= lo:
+                assert not runs[r]
+                continue
+            covered[lo:hi] += 1
+            slo, sa = slabs[r]
+            assert np.array_equal(sa[lo - slo:hi - slo], full[lo:hi]), (vol_z, patch_z, overlap, world, r)
+        assert (covered == 1).all()
+
+    check()
