@@ -463,3 +463,32 @@ def test_slab_exchange_plan_property(rb):
         assert (covered == 1).all()
 
     check()
+
+
+def test_enumeration_and_gaussian_match_oracle_on_random_shapes(rb):
+    """Product enumeration / importance map against the oracle (itself pinned to the reference's goldens) on random
+    geometries: bit-exact tables, bit-exact fp32 maps."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import resenc_oracle as O
+    inf = rb.inference
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 400), st.integers(1, 96), st.floats(0.0, 0.9))
+    def positions(vol, patch, overlap):
+        step = max(1, int(round(patch * (1 - overlap))))
+        if patch > vol:
+            with pytest.raises(ValueError):
+                inf.generate_positions(0, vol, patch, step)
+            return
+        assert list(inf.generate_positions(0, vol, patch, step)) == list(O.positions_1d(0, vol, patch, step))
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.tuples(st.integers(2, 40), st.integers(2, 40), st.integers(2, 40)))
+    def gaussian(tile):
+        a = inf.compute_gaussian_3d(tile)
+        a = a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+        b = O.gaussian_map(tile)
+        assert a.dtype == np.float32 and a.tobytes() == np.asarray(b, np.float32).tobytes(), tile
+
+    positions()
+    gaussian()
