@@ -199,3 +199,80 @@ class FinalVolumeWriter:
         if self.pool is not None:
             self.pool.shutdown(wait=True)
             self.pool = None
+
+
+class ZarrArrayReader:
+    """Read-only view of a zarr v2 array directory with zarr's slicing interface (`.shape`, `.dtype`, `a[z0:z1]`,
+    `a[..., z0:z1, y0:y1, x0:x1]`), enough for `DeviceVolume` / `SlidingWindowInferer` to consume a volume without the
+    `zarr` package.  Codecs: none and zlib (what `ZarrArrayWriter` writes); a Blosc-compressed array raises
+    `NotImplementedError` (no Blosc decoder in this image - open it with zarr itself)."""
+
+    def __init__(self, path: str):
+        with open(os.path.join(path, ".zarray")) as f:
+            meta = json.load(f)
+        if meta.get("zarr_format") != 2 or meta.get("order", "C") != "C" or meta.get("filters"):
+            raise NotImplementedError("only unfiltered C-order zarr v2 arrays are supported")
+        comp = meta.get("compressor")
+        if comp is not None and comp.get("id") != "zlib":
+            raise NotImplementedError(f"compressor {comp.get('id')!r}: only zlib / none can be decoded here")
+        self.path = path
+        self.shape = tuple(meta["shape"])
+        self.chunks = tuple(meta["chunks"])
+        self.dtype = np.dtype(meta["dtype"])
+        self.fill_value = meta.get("fill_value") or 0
+        self.sep = meta.get("dimension_separator", ".")
+        self._zlib = comp is not None
+        self.ndim = len(self.shape)
+
+    def _chunk(self, idx):
+        fn = os.path.join(self.path, self.sep.join(str(i) for i in idx))
+        if not os.path.exists(fn):
+            return np.full(self.chunks, self.fill_value, self.dtype)
+        with open(fn, "rb") as f:
+            raw = f.read()
+        if self._zlib:
+            raw = zlib.decompress(raw)
+        return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks)
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        if any(k is Ellipsis for k in key):
+            i = [k is Ellipsis for k in key].index(True)
+            key = key[:i] + (slice(None),) * (self.ndim - len(key) + 1) + key[i + 1:]
+        key = key + (slice(None),) * (self.ndim - len(key))
+        if len(key) != self.ndim:
+            raise IndexError(f"too many indices for a {self.ndim}-D array")
+        ranges, squeeze = [], []
+        for ax, k in enumerate(key):
+            if isinstance(k, (int, np.integer)):
+                k = int(k) + (self.shape[ax] if k < 0 else 0)
+                if not 0 <= k < self.shape[ax]:
+                    raise IndexError(f"index {k} out of range for axis {ax}")
+                ranges.append((k, k + 1))
+                squeeze.append(ax)
+            elif isinstance(k, slice):
+                lo, hi, stp = k.indices(self.shape[ax])
+                if stp != 1:
+                    raise NotImplementedError("strided slices are not supported")
+                ranges.append((lo, max(lo, hi)))
+            else:
+                raise NotImplementedError(f"index type {type(k).__name__}")
+        out = np.empty([hi - lo for lo, hi in ranges], self.dtype)
+        grid = [range(lo // c, -(-hi // c)) if hi > lo else range(0) for (lo, hi), c in zip(ranges, self.chunks)]
+        for idx in np.ndindex(*[len(g) for g in grid]):
+            cidx = tuple(g[i] for g, i in zip(grid, idx))
+            blk = self._chunk(cidx)
+            src, dst = [], []
+            for ax, ci in enumerate(cidx):
+                c0 = ci * self.chunks[ax]
+                lo, hi = max(ranges[ax][0], c0), min(ranges[ax][1], c0 + self.chunks[ax])
+                src.append(slice(lo - c0, hi - c0))
+                dst.append(slice(lo - ranges[ax][0], hi - ranges[ax][0]))
+            out[tuple(dst)] = blk[tuple(src)]
+        return out.squeeze(axis=tuple(squeeze)) if squeeze else out
+
+
+def open_zarr_array(root: str, name: Optional[str] = None) -> ZarrArrayReader:
+    """`open_zarr_array("out.zarr", "sheet_final")` or `open_zarr_array("vol.zarr/0")`."""
+    return ZarrArrayReader(os.path.join(root, name) if name else root)

@@ -257,6 +257,13 @@ def test_zarr_v2_final_writer_roundtrip(rb, tmp_path):
         assert os.path.exists(os.path.join(root, "normals_final", "0.1.1.1"))
         assert np.array_equal(w.arrays["sheet"].read(), sheet)
         assert np.array_equal(w.arrays["normals"].read(), normals)
+        # read back through the zarr-style reader (what DeviceVolume slices): whole array, z-ranges, sub-boxes, ints
+        rs, rn = inf.open_zarr_array(root, "sheet_final"), inf.open_zarr_array(root, "normals_final")
+        assert rs.shape == vol and rs.dtype == np.uint8 and rn.shape == (3, *vol) and rn.dtype == np.uint16
+        assert np.array_equal(rs[:], sheet) and np.array_equal(rn[...], normals)
+        assert np.array_equal(rs[5:33], sheet[5:33]) and np.array_equal(rs[17], sheet[17])
+        assert np.array_equal(rn[..., 3:20, 7:19, 11:26], normals[..., 3:20, 7:19, 11:26])
+        assert np.array_equal(rn[1, 30:, :, -3:], normals[1, 30:, :, -3:]) and rs[4:4].shape == (0, 20, 26)
         if comp is None:                                  # raw chunk = C-order bytes of the padded chunk
             raw = np.fromfile(os.path.join(root, "sheet_final", "2.2.2"), dtype=np.uint8).reshape(patch)
             assert np.array_equal(raw[:5, :4, :2], sheet[32:, 16:, 24:]) and not raw[5:].any()
