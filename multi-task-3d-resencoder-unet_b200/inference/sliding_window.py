@@ -280,8 +280,13 @@ class SlidingWindowInferer:
     def _graphed_forward(self, batch: torch.Tensor):
         """Capture model(batch) once for full batches (static shapes, ~350 launches per forward): replaying the
         graph removes the host launch latency of the deep, tiny layers.  `batch` is the static input buffer."""
-        if self._graph is not None:
+        # the captured kernels read the packed weights that were cached at capture time: if the parameters have changed
+        # since (training between two sweeps, load_state_dict) those packs are stale or already freed - capture again
+        sig = (_ops._PACK_EPOCH[0], tuple(p._version for p in self.model.parameters()))
+        if self._graph is not None and getattr(self, "_graph_sig", None) == sig:
             return self._graph
+        self._graph = None
+        self._graph_sig = sig
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -314,7 +319,10 @@ class SlidingWindowInferer:
         was_training = self.model.training
         self.model.eval()
         B = self.batch_size
-        static = torch.empty((B, 1, *self.patch), dtype=torch.float32, device=self.device)
+        if getattr(self, "_static", None) is None:
+            # one input buffer per inferer: a captured graph reads this tensor, so it must outlive the sweep
+            self._static = torch.empty((B, 1, *self.patch), dtype=torch.float32, device=self.device)
+        static = self._static
         try:
             graph = None
             if self.use_cuda_graph and len(positions) >= 2 * B:

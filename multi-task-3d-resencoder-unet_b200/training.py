@@ -167,6 +167,9 @@ class DataParallelTrainer:
         for k, v in targets.items():
             self._static_tg[k].copy_(v, non_blocking=True)
         self._graph[0].replay()
+        # a replay updates the parameters without running any Python (no Tensor._version bump, no optimiser hook):
+        # packs cached by an earlier eager / eval forward must not survive it
+        ops.invalidate_weight_packs()
         return self._graph[1]
 
     def _capture(self, inputs, targets):

@@ -198,3 +198,4 @@ def test_sweep_to_zarr_and_precise_sweep(rb, tmp_path):
         # (numerics of the tier are pinned in test_gpu_network.py; here: the sweep plumbing.  Re-normalised normals of a
         # random-init network amplify the bf16 tier's error wherever the blended vector is short, hence the loose bound)
         assert (d > (3 if t == "sheet" else 1500)).mean() < (0.01 if t == "sheet" else 0.05), t
+
