@@ -1,3 +1,7 @@
+#!/bin/bash
+# End-of-round evidence capture (round 1: 640 s of box time, of which ~8 min are the two ncu passes - ncu first re-runs
+# the command once without profiling, then replays every kernel; budget for it).
+#   gpurun --timeout 1500 -- 'bash tools/evidence.sh 2>&1 | tail -15'
 set -x
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1x.json 2> gpurun_out/bench_r1x.err
 python tools/conv_bench.py --iters 5 --out gpurun_out/convbench_r1x.json > gpurun_out/convbench_r1x.txt 2>&1
