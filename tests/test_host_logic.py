@@ -499,3 +499,57 @@ def test_enumeration_and_gaussian_match_oracle_on_random_shapes(rb):
 
     positions()
     gaussian()
+
+
+def test_per_class_strided_dgrad_decomposition_property(rb):
+    """Host side of the per-parity-class data gradient (ops._axis_classes / pack_conv_dgrad_class, the path for grids
+    that do not tile exactly): every input coordinate i = s*j + r receives from outputs j + off + t through the class's
+    tap list.  Emulated in torch on random kernel / stride / (odd) sizes and compared with autograd."""
+    import itertools
+
+    import torch.nn.functional as F
+    from hypothesis import given, settings, strategies as st
+    ops = rb.ops
+    ax = st.tuples(st.sampled_from([1, 3]), st.sampled_from([1, 2]), st.integers(1, 9))
+
+    @settings(max_examples=60, deadline=None)
+    @given(ax, ax, ax)
+    def check(a0, a1, a2):
+        k, stride, dims = zip(a0, a1, a2)
+        torch.manual_seed(1)
+        co, ci = 8, 16
+        w = torch.randn(co, ci, *k)
+        x = torch.randn(1, ci, *dims, requires_grad=True)
+        pad = tuple((kk - 1) // 2 for kk in k)
+        y = F.conv3d(x, w.to(torch.bfloat16).float(), None, stride, pad)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        od = tuple(y.shape[2:])
+        classes = [ops._axis_classes(k[a], stride[a], pad[a], dims[a]) for a in range(3)]
+        dx = torch.zeros(1, ci, *dims)
+        for cd, ch, cw in itertools.product(*classes):
+            if not (cd[2] and ch[2] and cw[2]):
+                continue                                   # class without a kernel index: gradient stays zero
+            wpk = ops.pack_conv_dgrad_class(w, cd[2], ch[2], cw[2]).float()      # [taps][ci][co]
+            grid = (cd[1], ch[1], cw[1])
+            acc = torch.zeros(1, ci, *grid)
+            t = 0
+            for td in range(len(cd[2])):
+                for th in range(len(ch[2])):
+                    for tw in range(len(cw[2])):
+                        # gather dy at j + off + t with zero fill outside [0, od)
+                        src = torch.zeros(1, co, *grid)
+                        rng = []
+                        for g, o, n in zip(grid, (cd[3] + td, ch[3] + th, cw[3] + tw), od):
+                            lo, hi = max(0, -o), min(g, n - o)
+                            rng.append((lo, hi, o))
+                        if all(hi > lo for lo, hi, _ in rng):
+                            (l0, h0, o0), (l1, h1, o1), (l2, h2, o2) = rng
+                            src[:, :, l0:h0, l1:h1, l2:h2] = dy[:, :, l0 + o0:h0 + o0, l1 + o1:h1 + o1, l2 + o2:h2 + o2]
+                        acc += torch.einsum("bcdhw,nc->bndhw", src, wpk[t])
+                        t += 1
+            dx[:, :, cd[0]::stride[0], ch[0]::stride[1], cw[0]::stride[2]] = acc
+        den = float(x.grad.norm())
+        assert float((dx - x.grad).norm()) <= 1e-5 * max(den, 1e-6) + 1e-6, (k, stride, dims)
+
+    check()
