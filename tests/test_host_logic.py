@@ -553,3 +553,44 @@ def test_per_class_strided_dgrad_decomposition_property(rb):
         assert float((dx - x.grad).norm()) <= 1e-5 * max(den, 1e-6) + 1e-6, (k, stride, dims)
 
     check()
+
+
+def test_transposed_conv_formulations_property(rb):
+    """Host formulation of ConvTranspose3d(kernel == stride) (ops._ConvT3dFn): forward = one 1-tap GEMM with N columns
+    [(parity, co)] stored pixel-shuffled; data gradient = a stride-s, s^3-tap gather over dy.  Emulated in torch with
+    the same packs and compared with F.conv_transpose3d / autograd on random strides and sizes."""
+    import torch.nn.functional as F
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.tuples(st.sampled_from([1, 2]), st.sampled_from([1, 2]), st.sampled_from([1, 2])),
+           st.tuples(st.integers(1, 5), st.integers(1, 5), st.integers(1, 5)))
+    def check(stride, dims):
+        torch.manual_seed(2)
+        ci, co = 16, 8
+        sd, sh, sw = stride
+        w = torch.randn(ci, co, *stride)
+        x = torch.randn(2, ci, *dims, requires_grad=True)
+        wq = w.to(torch.bfloat16).float()
+        ref = F.conv_transpose3d(x, wq, None, stride)
+        g = torch.randn_like(ref)
+        ref.backward(g)
+        npar = sd * sh * sw
+        # forward pack exactly as ops._ConvT3dFn builds it: rows = (parity, co), cols = ci
+        wpk = w.detach().permute(2, 3, 4, 1, 0).reshape(1, npar * co, ci).to(torch.bfloat16).float()
+        cols = torch.einsum("bcdhw,nc->bndhw", x.detach(), wpk[0])                     # [B, npar*co, d, h, w]
+        c6 = cols.view(2, sd, sh, sw, co, *dims)
+        y = c6.permute(0, 4, 5, 1, 6, 2, 7, 3).reshape(2, co, *[d * s for d, s in zip(dims, stride)])
+        assert float((y - ref.detach()).norm()) <= 1e-5 * float(ref.detach().norm()) + 1e-6
+        # data gradient pack: taps = parities, [tap][ci][co]; gather dy at s*i + p
+        wd = w.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(torch.bfloat16).float()
+        dx = torch.zeros(2, ci, *dims)
+        t = 0
+        for pd in range(sd):
+            for ph in range(sh):
+                for pw in range(sw):
+                    dx += torch.einsum("bcdhw,nc->bndhw", g[:, :, pd::sd, ph::sh, pw::sw], wd[t])
+                    t += 1
+        assert float((dx - x.grad).norm()) <= 1e-5 * float(x.grad.norm()) + 1e-6
+
+    check()
