@@ -209,12 +209,31 @@ int rb_blend_accumulate(const float* pred, const float* weight, float* sum, floa
                         int z0, int y0, int x0, int activation, void* stream);
 int rb_blend_finalize_cast(const float* sum, const float* wsum, void* out, float* favg,
                            long long V, int C, int kind, void* stream);
+/* All targets of one patch in one launch (the loop over `infer_output_targets`, inference.py:139-157): per element the
+ * same arithmetic as rb_blend_accumulate, 16-byte vector path when PX, VX, x0 are multiples of 4.  `targets` is a HOST
+ * array; `wsum` is the one shared count / weight-sum volume (the reference's per-target counts are identical). */
+typedef struct RbBlendTarget {
+    const float* pred;   /* device [C][PZ][PY][PX] fp32, one patch */
+    float* sum;          /* device [C][VZ][VY][VX] fp32 */
+    int C;               /* 1..8 */
+    int activation;      /* 0 none, 1 sigmoid, 2 softmax over C (inference.py:124-133) */
+} RbBlendTarget;
+int rb_blend_accumulate_multi(const RbBlendTarget* targets, int ntargets, const float* weight, float* wsum,
+                              int PZ, int PY, int PX, int VZ, int VY, int VX, int z0, int y0, int x0, void* stream);
+/* rb_blend_finalize_cast with the sum channels `sum_cstride` elements apart (finalise a z-range of a slab in place). */
+int rb_blend_finalize_cast2(const float* sum, long long sum_cstride, const float* wsum, void* out, float* favg,
+                            long long V, int C, int kind, void* stream);
 int rb_blend_add(float* dst, const float* src, long long n, void* stream);
 
 /* Patch extraction + per-patch standardisation, dataloading/inference_dataset.py:62-75.
  * vol: device uint8/uint16 [VZ][VY][VX]; stats: device double[2] scratch; out: fp32 [PZ][PY][PX]. */
 int rb_extract_patch(const void* vol, int is_u16, int VZ, int VY, int VX, int z0, int y0, int x0,
                      int PZ, int PY, int PX, int standardize, double* stats, float* out, void* stream);
+
+/* Batched form: `nb` (<= 16) patches per call, origins = HOST int[nb][3] (z0, y0, x0), stats device double[nb][2],
+ * out fp32 [nb][PZ][PY][PX] (the batch the network reads, inference_dataset.py:62-75 + the DataLoader collate). */
+int rb_extract_patches(const void* vol, int is_u16, int VZ, int VY, int VX, const int* origins, int nb,
+                       int PZ, int PY, int PX, int standardize, double* stats, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused task losses on the fp32 NCDHW logits (training/losses/losses.py): BCEDiceLoss :307-318 (label-smoothed

@@ -37,6 +37,10 @@ class WgradDesc(C.Structure):
         "offD", "offH", "offW", "istrD", "istrH", "istrW", "splits", "impl")]
 
 
+class BlendTarget(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("sum", C.c_void_p), ("C", C.c_int), ("activation", C.c_int)]
+
+
 _P, _I, _LL, _F, _D, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/resenc_b200.h declares
@@ -71,6 +75,9 @@ SIGNATURES = {
     "rb_blend_accumulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_blend_finalize_cast": (_I, [_P, _P, _P, _P, _LL, _I, _I, _P]),
     "rb_blend_add": (_I, [_P, _P, _LL, _P]),
+    "rb_blend_accumulate_multi": (_I, [C.POINTER(BlendTarget), _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rb_blend_finalize_cast2": (_I, [_P, _LL, _P, _P, _P, _LL, _I, _I, _P]),
+    "rb_extract_patches": (_I, [_P, _I, _I, _I, _I, C.POINTER(C.c_int), _I, _I, _I, _I, _I, _P, _P, _P]),
     "rb_extract_patch": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rb_loss_bce_dice_reduce": (_I, [_P, _P, _P, _I, _I, _LL, _F, _P]),
     "rb_loss_bce_dice_grad": (_I, [_P, _P, _P, _P, _P, _I, _I, _LL, _F, _F, _F, _F, _P]),

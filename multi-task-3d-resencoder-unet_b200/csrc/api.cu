@@ -1292,6 +1292,71 @@ int rb_blend_finalize_cast(const float* sum, const float* wsum, void* out, float
     return check_launch("blend_finalize_cast_kernel");
 }
 
+int rb_blend_accumulate_multi(const RbBlendTarget* targets, int ntargets, const float* weight, float* wsum, int PZ, int PY, int PX,
+                              int VZ, int VY, int VX, int z0, int y0, int x0, void* stream) {
+    if (!targets || ntargets < 1 || ntargets > rb::BLEND_MAX_TARGETS)
+        return fail(RB_ERR_INVALID, "blend_accumulate_multi: need 1..%d targets", rb::BLEND_MAX_TARGETS);
+    if (PZ < 1 || PY < 1 || PX < 1 || VZ < 1 || VY < 1 || VX < 1) return fail(RB_ERR_INVALID, "blend_accumulate_multi: bad shape");
+    if ((long long)PZ * PY * PX >= (1LL << 31)) return fail(RB_ERR_INVALID, "blend_accumulate_multi: patch exceeds 2^31 voxels");
+    rb::BlendMultiParams p;
+    memset(&p, 0, sizeof(p));
+    bool vec = PX % 4 == 0 && VX % 4 == 0 && x0 % 4 == 0 && x0 >= 0 && x0 + PX <= VX && aligned16(weight) && aligned16(wsum);
+    for (int i = 0; i < ntargets; ++i) {
+        const RbBlendTarget& t = targets[i];
+        if (!t.pred || !t.sum) return fail(RB_ERR_INVALID, "blend_accumulate_multi: null pointer in target %d", i);
+        if (t.C < 1 || t.C > rb::BLEND_MAX_C) return fail(RB_ERR_INVALID, "blend_accumulate_multi: target %d needs 1..%d channels", i, rb::BLEND_MAX_C);
+        if (t.activation < 0 || t.activation > 2) return fail(RB_ERR_INVALID, "blend_accumulate_multi: bad activation in target %d", i);
+        p.t[i].pred = t.pred; p.t[i].sum = t.sum; p.t[i].C = t.C; p.t[i].activation = t.activation;
+        vec = vec && aligned16(t.pred) && aligned16(t.sum) && ((long long)PZ * PY * PX) % 4 == 0 && ((long long)VZ * VY * VX) % 4 == 0;
+    }
+    p.nt = ntargets; p.weight = weight; p.wsum = wsum;
+    p.PZ = PZ; p.PY = PY; p.PX = PX; p.VZ = VZ; p.VY = VY; p.VX = VX; p.z0 = z0; p.y0 = y0; p.x0 = x0;
+    const long long PS = (long long)PZ * PY * PX;
+    if (vec) rb::blend_accumulate_multi_kernel<4><<<grid_for(PS / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+    else rb::blend_accumulate_multi_kernel<1><<<grid_for(PS, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("blend_accumulate_multi_kernel");
+}
+
+int rb_blend_finalize_cast2(const float* sum, long long sum_cstride, const float* wsum, void* out, float* favg, long long V, int C,
+                            int kind, void* stream) {
+    if (!sum || !wsum || !out) return fail(RB_ERR_INVALID, "blend_finalize_cast2: null pointer");
+    if (kind != 0 && kind != 1) return fail(RB_ERR_INVALID, "blend_finalize_cast2: kind must be 0 or 1");
+    if (C < 1 || C > rb::BLEND_MAX_C || V < 1 || sum_cstride < V) return fail(RB_ERR_INVALID, "blend_finalize_cast2: bad shape");
+    rb::FinalizeCast2Params p{sum, wsum, out, favg, V, sum_cstride, C, kind};
+    const bool vec = V % 4 == 0 && sum_cstride % 4 == 0 && aligned16(sum) && aligned16(wsum) && aligned16(favg) &&
+                     (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    if (vec) rb::blend_finalize_cast2_kernel<4><<<grid_for(V / 4, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+    else rb::blend_finalize_cast2_kernel<1><<<grid_for(V, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("blend_finalize_cast2_kernel");
+}
+
+int rb_extract_patches(const void* vol, int is_u16, int VZ, int VY, int VX, const int* origins, int nb, int PZ, int PY, int PX,
+                       int standardize, double* stats, float* out, void* stream) {
+    if (!vol || !out || !origins || (standardize && !stats)) return fail(RB_ERR_INVALID, "extract_patches: null pointer");
+    if (nb < 1 || nb > rb::EXTRACT_MAX_BATCH) return fail(RB_ERR_INVALID, "extract_patches: need 1..%d patches per call", rb::EXTRACT_MAX_BATCH);
+    if ((long long)PZ * PY * PX >= (1LL << 31)) return fail(RB_ERR_INVALID, "extract_patches: patch exceeds 2^31 voxels");
+    cudaStream_t st = (cudaStream_t)stream;
+    rb::ExtractBatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.vol = vol; p.is_u16 = is_u16; p.VZ = VZ; p.VY = VY; p.VX = VX; p.PZ = PZ; p.PY = PY; p.PX = PX; p.nb = nb;
+    p.stats = stats; p.out = out; p.standardize = standardize;
+    for (int b = 0; b < nb; ++b) {
+        const int z0 = origins[3 * b], y0 = origins[3 * b + 1], x0 = origins[3 * b + 2];
+        if (z0 < 0 || y0 < 0 || x0 < 0 || z0 + PZ > VZ || y0 + PY > VY || x0 + PX > VX)
+            return fail(RB_ERR_INVALID, "extract_patches: patch %d outside the volume", b);
+        p.z0[b] = z0; p.y0[b] = y0; p.x0[b] = x0;
+    }
+    const long long PS = (long long)PZ * PY * PX;
+    if (standardize) {
+        RB_CUDA(cudaMemsetAsync(stats, 0, (size_t)nb * 2 * sizeof(double), st));
+        rb::patch_stats_batch_kernel<<<dim3(grid_for(PS, 256, 2), nb), 256, 0, st>>>(p);
+        int rc = check_launch("patch_stats_batch_kernel");
+        if (rc) return rc;
+    }
+    rb::patch_write_batch_kernel<<<dim3(grid_for(PS, 256, 8), nb), 256, 0, st>>>(p);
+    return check_launch("patch_write_batch_kernel");
+}
+
 int rb_blend_add(float* dst, const float* src, long long n, void* stream) {
     if (!dst || !src || n < 0) return fail(RB_ERR_INVALID, "blend_add: bad arguments");
     if (n == 0) return RB_OK;

@@ -147,14 +147,17 @@ class SlabBlender:
         self.wsum = torch.zeros((depth, Y, X), dtype=torch.float32, device=self.device)
         self._lib = L.load()
 
-    def add(self, preds: Dict[str, torch.Tensor], index: int, position, apply_activation: bool = True):
+    def add(self, preds: Dict[str, torch.Tensor], index: int, position, apply_activation: bool = True,
+            per_target_launches: bool = False):
         """Accumulate sample `index` of a batch of predictions {target: [B, c, pz, py, px] fp32}
-        at volume position (z0, y0, x0)."""
+        at volume position (z0, y0, x0): one launch for all targets (rb_blend_accumulate_multi).
+        `per_target_launches=True` runs the round-1 kernel, one launch per target (cross-check in the tests)."""
         z0, y0, x0 = (int(v) for v in position)
         st = L.stream_ptr(self.device)
         _, Y, X = self.vol_shape
         depth = self.z_hi - self.z_lo
-        first = True
+        items = []
+        keep = []
         for t, info in self.targets.items():
             p = preds[t]
             if p.dtype != torch.float32 or not p.is_contiguous():
@@ -163,13 +166,26 @@ class SlabBlender:
             c = info["channels"]
             if p.shape[1] != c:
                 raise ValueError(f"target {t}: prediction has {p.shape[1]} channels, config says {c}")
-            pz, py, px = p.shape[2:]
             act = _ACT[str(info.get("activation", "none")).lower()] if apply_activation else 0
             one = p[index]
-            L.check(self._lib.rb_blend_accumulate(
-                one.data_ptr(), L.ptr(self.weight), self.sums[t].data_ptr(), self.wsum.data_ptr() if first else None,
-                c, pz, py, px, depth, Y, X, z0 - self.z_lo, y0, x0, act, st), "rb_blend_accumulate")
-            first = False
+            keep.append(one)
+            items.append((t, one, c, act))
+        pz, py, px = items[0][1].shape[1:]
+        if any(tuple(o.shape[1:]) != (pz, py, px) for _, o, _, _ in items):
+            raise ValueError("all targets of a patch must share its spatial shape")
+        if per_target_launches:
+            first = True
+            for t, one, c, act in items:
+                L.check(self._lib.rb_blend_accumulate(
+                    one.data_ptr(), L.ptr(self.weight), self.sums[t].data_ptr(), self.wsum.data_ptr() if first else None,
+                    c, pz, py, px, depth, Y, X, z0 - self.z_lo, y0, x0, act, st), "rb_blend_accumulate")
+                first = False
+            return
+        arr = (L.BlendTarget * len(items))()
+        for k, (t, one, c, act) in enumerate(items):
+            arr[k].pred, arr[k].sum, arr[k].C, arr[k].activation = one.data_ptr(), self.sums[t].data_ptr(), c, act
+        L.check(self._lib.rb_blend_accumulate_multi(arr, len(items), L.ptr(self.weight), self.wsum.data_ptr(), pz, py, px,
+                                                    depth, Y, X, z0 - self.z_lo, y0, x0, st), "rb_blend_accumulate_multi")
 
     def finalize(self, z_from: Optional[int] = None, z_to: Optional[int] = None, keep_float: bool = False):
         """Finalise + cast the planes [z_from, z_to) (volume coordinates, default: whole slab).
@@ -183,18 +199,21 @@ class SlabBlender:
         out, flt = {}, {}
         st = L.stream_ptr(self.device)
         a = z_from - self.z_lo
-        wsum = self.wsum[a:a + nz].contiguous()
+        depth = self.z_hi - self.z_lo
+        wsum = self.wsum[a:a + nz]                      # contiguous z-range of the slab
         for t, info in self.targets.items():
             c = info["channels"]
             normals = t.lower() == "normals"
-            s = self.sums[t][:, a:a + nz].contiguous()
+            s = self.sums[t][:, a:a + nz]               # channels `depth * Y * X` apart: finalised in place, no copy
             res = torch.empty((c, nz, Y, X), dtype=torch.uint16 if normals else torch.uint8, device=self.device)
             f = torch.empty((c, nz, Y, X), dtype=torch.float32, device=self.device) if keep_float else None
-            L.check(self._lib.rb_blend_finalize_cast(s.data_ptr(), wsum.data_ptr(), res.data_ptr(), L.ptr(f), V, c,
-                                                     1 if normals else 0, st), "rb_blend_finalize_cast")
+            L.check(self._lib.rb_blend_finalize_cast2(s.data_ptr(), depth * Y * X, wsum.data_ptr(), res.data_ptr(), L.ptr(f),
+                                                      V, c, 1 if normals else 0, st), "rb_blend_finalize_cast2")
             out[t] = res[0] if c == 1 else res
             if keep_float:
                 flt[t] = f[0] if c == 1 else f
+        # a device-side pipeline time-out in any kernel that fed these sums must not end up in a written volume
+        L.device_error_check()
         return (out, flt) if keep_float else out
 
 
@@ -234,6 +253,27 @@ class DeviceVolume:
                                            self.shape[2], z0 - self.z_lo, y0, x0, pz, py, px, 1 if standardize else 0,
                                            self._stats.data_ptr(), out.data_ptr(), L.stream_ptr(self.device)),
                 "rb_extract_patch")
+
+    MAX_BATCH = 16
+
+    def extract_batch(self, positions, patch_size, out: torch.Tensor, standardize: bool = True):
+        """All patches of a forward batch in two launches: out fp32 [len(positions), 1, pz, py, px] (contiguous)."""
+        import ctypes as C
+        nb = len(positions)
+        pz, py, px = (int(p) for p in patch_size)
+        if not out.is_contiguous() or out.dtype != torch.float32 or out.numel() != nb * pz * py * px:
+            raise ValueError("extract_batch: `out` must be a contiguous fp32 [nb, 1, pz, py, px] buffer")
+        if getattr(self, "_bstats", None) is None:
+            self._bstats = torch.zeros(2 * self.MAX_BATCH, dtype=torch.float64, device=self.device)
+        for i in range(0, nb, self.MAX_BATCH):
+            chunk = positions[i:i + self.MAX_BATCH]
+            org = (C.c_int * (3 * len(chunk)))()
+            for j, (z0, y0, x0) in enumerate(chunk):
+                org[3 * j], org[3 * j + 1], org[3 * j + 2] = int(z0) - self.z_lo, int(y0), int(x0)
+            L.check(self._lib.rb_extract_patches(self.data.data_ptr(), self.is_u16, self.z_hi - self.z_lo, self.shape[1],
+                                                 self.shape[2], org, len(chunk), pz, py, px, 1 if standardize else 0,
+                                                 self._bstats.data_ptr(), out[i:i + len(chunk)].data_ptr(),
+                                                 L.stream_ptr(self.device)), "rb_extract_patches")
 
 
 # ------------------------------------------------------------------------------------------
@@ -339,8 +379,7 @@ class SlidingWindowInferer:
                 full = len(chunk) == B
                 batch = static if full else torch.empty((len(chunk), 1, *self.patch), dtype=torch.float32,
                                                         device=self.device)
-                for j, pos in enumerate(chunk):
-                    dvol.extract(pos, self.patch, batch[j, 0], self.standardize)
+                dvol.extract_batch(chunk, self.patch, batch, self.standardize)
                 if graph is not None and full:
                     graph[0].replay()
                     preds = graph[1]
@@ -350,6 +389,7 @@ class SlidingWindowInferer:
                     blender.add(preds, j, pos, apply_activation=True)
         finally:
             self.model.train(was_training)
+        L.device_error_check()       # a timed-out pipeline must surface here, not as a silently wrong volume
         return blender
 
     def run(self, volume, keep_float: bool = False):

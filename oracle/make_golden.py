@@ -40,8 +40,50 @@ NET_CASES = {
     # reference run are stored in the fixture as `drop::<block>` so that every implementation replays them
     "droppath_se_16": ([16, 16, 16], 1, {"sheet": {"channels": 1, "activation": "sigmoid"}},
                        {"squeeze_excitation": True, "stochastic_depth_p": 0.3}, "all", 4),
+    # --- round 2: block families / decoder variants that only a manual config reaches ---
+    # BottleneckD (resblocks.py:135-239): 1x1 -> k^3 (stride) -> 1x1, bottleneck_channels = features // 4
+    "bottleneck_16": ([16, 16, 16], 1,
+                      {"sheet": {"channels": 1, "activation": "sigmoid"},
+                       "normals": {"channels": 3, "activation": "none"}},
+                      dict(features_per_stage=[32, 64, 128], num_stages=3, n_blocks_per_stage=[1, 2, 2],
+                           kernel_sizes=[[3, 3, 3]] * 3, n_conv_per_stage_decoder=[1, 1],
+                           strides=[[1, 1, 1], [2, 2, 2], [2, 2, 2]], basic_encoder_block="BottleneckBlockD",
+                           bottleneck_block="BottleneckBlockD", basic_decoder_block="ConvBlock"), "all", 2),
+    # residual decoder stages (decoder.py:68-95): StackedResidualBlocks on cat(up, skip), two blocks in the first stage
+    "resdec_16": ([16, 16, 16], 1,
+                  {"sheet": {"channels": 1, "activation": "sigmoid"},
+                   "normals": {"channels": 3, "activation": "none"}},
+                  dict(features_per_stage=[32, 64, 128], num_stages=3, n_blocks_per_stage=[1, 2, 2],
+                       kernel_sizes=[[3, 3, 3]] * 3, n_conv_per_stage_decoder=[2, 1],
+                       strides=[[1, 1, 1], [2, 2, 2], [2, 2, 2]], basic_encoder_block="BasicBlockD",
+                       bottleneck_block="BasicBlockD", basic_decoder_block="ResidualBlock"), "all", 2),
+    # default autoconfigured network at a geometry that selects the fast kernels (slab fprop / dgrad at W = 64,
+    # weights-on-M h-major tiles, two-sided tap-stacked wgrad) with gradients; eval outputs are not stored (the
+    # network has no train / eval difference besides the head activation) to keep the fixture small
+    "default_32x64x64": ([32, 64, 64], 1,
+                         {"sheet": {"channels": 1, "activation": "sigmoid"},
+                          "normals": {"channels": 3, "activation": "none"}}, {}, "all", 1),
+}
+# per-case switches that do not fit the 6-tuple: autoconfigure flag, which oracle block family, what is stored
+NET_EXTRA = {
+    "bottleneck_16": {"autoconfigure": False, "block": "bottleneck"},
+    "resdec_16": {"autoconfigure": False, "residual_decoder": True},
+    "default_32x64x64": {"store_eval": False},
 }
 DROP_SEED = 4321
+
+
+def oracle_kwargs(case):
+    """Arguments of resenc_oracle.net_forward that select the block family / decoder variant of `case`."""
+    ex = NET_EXTRA.get(case, {})
+    return {"block": ex.get("block", "basic"), "residual_decoder": bool(ex.get("residual_decoder", False))}
+
+
+def oracle_topology(case):
+    patch, _, _, mc, _, _ = NET_CASES[case]
+    if NET_EXTRA.get(case, {}).get("autoconfigure", True):
+        return O.autoconfig(patch)
+    return O.manual_topology(mc)
 
 
 def seeded_state(named_shapes, seed):
@@ -92,8 +134,9 @@ def unique_named_params(model):
 
 def make_net_case(case):
     patch, cin, tasks, mc, rd, batch = NET_CASES[case]
-    model = rl.build_reference(rl.make_mgr(patch, tasks, in_channels=cin, batch=batch, model_config=mc),
-                               se_reduce_dims=rd)
+    extra = NET_EXTRA.get(case, {})
+    model = rl.build_reference(rl.make_mgr(patch, tasks, in_channels=cin, batch=batch, model_config=mc,
+                                           autoconfigure=extra.get("autoconfigure", True)), se_reduce_dims=rd)
     names = unique_named_params(model)
     st = seeded_state(names, seed=7)
     with torch.no_grad():
@@ -172,7 +215,8 @@ def make_net_case(case):
     for t in tasks:
         rec["target::" + t] = tgt[t]
         rec["train::" + t] = out[t].detach().numpy()
-        rec["eval::" + t] = ev[t].numpy()
+        if extra.get("store_eval", True):
+            rec["eval::" + t] = ev[t].numpy()
         rec["loss::" + t] = np.float64(per[t])
         a, b = ac[t].float(), out[t].detach()
         rec["autocast_bf16_rel::" + t] = np.float64(float((a - b).norm() / b.norm()))

@@ -80,6 +80,19 @@ def autoconfig(patch_size):
     )
 
 
+def manual_topology(model_config):
+    """build_network_from_config.py:81-148: the manual (autoconfigure=False) branch reads these keys verbatim."""
+    mc = model_config
+    return SimpleNamespace(
+        n_stages=int(mc["num_stages"]),
+        features=list(mc["features_per_stage"]),
+        n_blocks=list(mc["n_blocks_per_stage"]),
+        strides=tuple(tuple(s) for s in mc["strides"]),
+        kernels=tuple(tuple(k) for k in mc["kernel_sizes"]),
+        n_conv_dec=list(mc["n_conv_per_stage_decoder"]),
+    )
+
+
 def se_rd_channels(c, ratio=1.0 / 16, divisor=8):
     """timm/DNA make_divisible(c*ratio, 8, round_limit=0.) — parity unpinned."""
     v = c * ratio

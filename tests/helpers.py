@@ -14,7 +14,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from oracle.make_golden import NET_CASES, seeded_inputs, seeded_state  # noqa: E402  (test infrastructure)
+from oracle.make_golden import (NET_CASES, NET_EXTRA, oracle_kwargs, oracle_topology, seeded_inputs,  # noqa: E402,F401
+                                seeded_state)                                                       # (test infrastructure)
 
 
 def rel_l2(a, b):
@@ -31,7 +32,18 @@ def make_mgr(patch, tasks, in_channels=1, batch=1, model_config=None, autoconfig
 
 def case_mgr(case):
     patch, cin, tasks, mc, rd, batch = NET_CASES[case]
-    return make_mgr(patch, tasks, in_channels=cin, batch=batch, model_config=mc), rd
+    auto = NET_EXTRA.get(case, {}).get("autoconfigure", True)
+    return make_mgr(patch, tasks, in_channels=cin, batch=batch, model_config=mc, autoconfigure=auto), rd
+
+
+def golden_eval(gold, task, activation):
+    """Reference eval-mode output of `task`: stored, or (fixtures without `eval::`, i.e. no stochastic depth) the head
+    activation of build_network_from_config.py:322-323 applied to the stored training-mode logits."""
+    if "eval::" + task in gold.files:
+        return torch.from_numpy(gold["eval::" + task])
+    logits = torch.from_numpy(gold["train::" + task])
+    act = str(activation).lower()
+    return torch.sigmoid(logits) if act == "sigmoid" else torch.softmax(logits, 1) if act == "softmax" else logits
 
 
 def load_keys(case):

@@ -199,3 +199,112 @@ def test_sweep_to_zarr_and_precise_sweep(rb, tmp_path):
         # random-init network amplify the bf16 tier's error wherever the blended vector is short, hence the loose bound)
         assert (d > (3 if t == "sheet" else 1500)).mean() < (0.01 if t == "sheet" else 0.05), t
 
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: the one-launch multi-target kernel, the fused second activation (inference.py:124-133),
+# batched extraction, in-place z-range finalise
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vol,patch,overlap", [((32, 32, 32), (16, 16, 16), 0.5), ((19, 23, 21), (8, 8, 8), 0.1),
+                                               ((24, 20, 30), (16, 16, 12), 0.5)])
+@pytest.mark.parametrize("weight", ["uniform", "gaussian"])
+def test_multi_target_launch_equals_per_target_launches(rb, vol, patch, overlap, weight):
+    """rb_blend_accumulate_multi (vector and scalar paths) against the round-1 one-launch-per-target kernel: same bits."""
+    inf = rb.inference
+    pos = inf.all_positions(vol, patch, overlap)
+    preds = {t: torch.from_numpy(v).cuda() for t, v in _random_preds(len(pos), patch, 3).items()}
+    a = inf.SlabBlender(TARGETS, vol, patch, 0, vol[0], "cuda", weight)
+    b = inf.SlabBlender(TARGETS, vol, patch, 0, vol[0], "cuda", weight)
+    for j, p in enumerate(pos):
+        a.add(preds, j, p)
+        b.add(preds, j, p, per_target_launches=True)
+    for t in TARGETS:
+        assert torch.equal(a.sums[t], b.sums[t]), t
+    assert torch.equal(a.wsum, b.wsum)
+
+
+@pytest.mark.parametrize("weight", ["uniform", "gaussian"])
+def test_blend_with_fused_activation(rb, weight):
+    """The reference applies sigmoid / softmax to the model output before accumulating (inference.py:124-133); the
+    blend kernel fuses it.  Checker: torch.sigmoid / torch.softmax (CUDA, fp32) -> oracle accumulate -> oracle finalise.
+    Tolerance: the in-kernel expf forms may differ from torch's by a few ulp per activated value, so the accumulated
+    sums agree to 1e-6 x (number of contributions) absolute (activated values are in [0, 1], running sums below 8,
+    whose fp32 ulp is 4.8e-7) and the uint8 outputs agree exactly
+    on >= 99.9 % of the voxels and never differ by more than one level."""
+    inf = rb.inference
+    vol, patch = (32, 24, 40), (16, 16, 16)
+    targets = {"sheet": {"channels": 1, "activation": "sigmoid"}, "cls": {"channels": 3, "activation": "softmax"},
+               "raw": {"channels": 2, "activation": "none"}}
+    pos = inf.all_positions(vol, patch, 0.5)
+    rng = np.random.default_rng(21)
+    logits = {"sheet": (rng.standard_normal((len(pos), 1, *patch)) * 3).astype(np.float32),
+              "cls": (rng.standard_normal((len(pos), 3, *patch)) * 4).astype(np.float32),
+              "raw": rng.random((len(pos), 2, *patch), dtype=np.float32)}
+    dev = {t: torch.from_numpy(v).cuda() for t, v in logits.items()}
+    activated = {"sheet": torch.sigmoid(dev["sheet"]).cpu().numpy(), "cls": torch.softmax(dev["cls"], 1).cpu().numpy(),
+                 "raw": logits["raw"]}
+    if weight == "uniform":
+        sums, cnt = O.blend_reference(activated, pos, vol, targets)
+    else:
+        sums, cnt = O.blend_weighted_reference(activated, pos, vol, targets, O.gaussian_map(patch))
+    exp = O.finalize_reference(sums, cnt, targets)
+    bl = inf.SlabBlender(targets, vol, patch, 0, vol[0], "cuda", weight)
+    legacy = inf.SlabBlender(targets, vol, patch, 0, vol[0], "cuda", weight)
+    for j, p in enumerate(pos):
+        bl.add(dev, j, p, apply_activation=True)
+        legacy.add(dev, j, p, apply_activation=True, per_target_launches=True)
+    ncontrib = 8.0          # overlap 0.5 in 3-D: at most 8 patches touch a voxel
+    for t in targets:
+        got = bl.sums[t].cpu().numpy()
+        ref = sums[t] if sums[t].ndim == 4 else sums[t][None]
+        err = np.abs(got - ref).max()
+        print(f"fused activation [{weight}] {t}: max |sum - oracle| {err:.3e}")
+        assert err <= 1e-6 * ncontrib, (t, err)
+        assert torch.equal(bl.sums[t], legacy.sums[t]), t     # both kernels evaluate the same expression
+    assert np.array_equal(bl.wsum.cpu().numpy(), cnt["sheet"])
+    assert np.array_equal(bl.sums["raw"].cpu().numpy(), sums["raw"])      # identity activation stays bit-exact
+    out = bl.finalize()
+    for t in targets:
+        a, b = out[t].cpu().numpy().astype(np.int64), exp[t].astype(np.int64)
+        assert (a == b).mean() >= 0.999 and np.abs(a - b).max() <= 1, t
+
+
+def test_extract_batch_equals_single_extracts(rb):
+    inf = rb.inference
+    rng = np.random.default_rng(6)
+    vol = rng.integers(0, 65536, size=(40, 48, 56)).astype(np.uint16)
+    dv = inf.DeviceVolume(vol, 8, 40, "cuda")
+    patch = (16, 24, 20)
+    positions = [(8, 0, 0), (24, 24, 36), (13, 7, 9), (20, 11, 30), (9, 24, 1)]
+    for std in (True, False):
+        batch = torch.empty((len(positions), 1, *patch), dtype=torch.float32, device="cuda")
+        dv.extract_batch(positions, patch, batch, standardize=std)
+        one = torch.empty(patch, dtype=torch.float32, device="cuda")
+        for j, p in enumerate(positions):
+            dv.extract(p, patch, one, standardize=std)
+            if std:   # the two statistics reductions add their partial sums in different orders
+                assert torch.allclose(batch[j, 0], one, rtol=1e-5, atol=1e-6)
+                z, y, x = p
+                ref = O.standardize_patch(vol[z:z + 16, y:y + 24, x:x + 20].astype(np.float32) / np.float32(65535))
+                assert np.allclose(batch[j, 0].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+            else:
+                assert torch.equal(batch[j, 0], one)
+    with pytest.raises(rb._lib.ResencLibraryError):
+        dv.extract_batch([(30, 0, 0)], patch, torch.empty((1, 1, *patch), dtype=torch.float32, device="cuda"))
+
+
+def test_finalize_z_range_in_place_equals_whole_volume(rb):
+    """finalize(z_from, z_to) reads a z-range of the slab in place (channel stride = slab size): equal to the slices of
+    the whole-slab result, for vector-friendly and odd plane sizes."""
+    inf = rb.inference
+    for vol, patch in (((24, 16, 16), (8, 8, 8)), ((21, 9, 7), (7, 3, 7))):
+        pos = inf.all_positions(vol, patch, 0.5)
+        preds = {t: torch.from_numpy(v).cuda() for t, v in _random_preds(len(pos), patch, 8).items()}
+        bl = inf.SlabBlender(TARGETS, vol, patch, 0, vol[0], "cuda", "uniform")
+        for j, p in enumerate(pos):
+            bl.add(preds, j, p)
+        whole, wf = bl.finalize(keep_float=True)
+        part, pf = bl.finalize(5, 13, keep_float=True)
+        for t in TARGETS:
+            assert torch.equal(part[t], whole[t][..., 5:13, :, :]), t
+            assert torch.equal(pf[t], wf[t][..., 5:13, :, :]), t

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, NET_CASES, golden_state, load_keys, load_net_golden, rel_l2
+from helpers import (GOLDEN, NET_CASES, golden_eval, golden_state, load_keys, load_net_golden, oracle_kwargs, oracle_topology,
+                     rel_l2)
 from oracle import resenc_oracle as O
 
 
@@ -51,18 +52,19 @@ def test_oracle_network_forward_and_loss(case):
     sd_unique = golden_state(case)
     # the oracle walks reference key names; build the aliased dict the reference's state_dict has
     sd = dict(sd_unique)
-    topo = O.autoconfig(patch)
+    topo = oracle_topology(case)
+    kw = oracle_kwargs(case)
     x = torch.from_numpy(gold["x"])
     se = bool(mc.get("squeeze_excitation", False))
     drop = {k[6:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("drop::")} or None
     assert (drop is not None) == bool(mc.get("stochastic_depth_p", 0.0))
     with torch.no_grad():
-        out_t = O.net_forward(sd, topo, x, tasks, training=True, se=se, reduce_dims=rd, drop=drop)
-        out_e = O.net_forward(sd, topo, x, tasks, training=False, se=se, reduce_dims=rd)
+        out_t = O.net_forward(sd, topo, x, tasks, training=True, se=se, reduce_dims=rd, drop=drop, **kw)
+        out_e = O.net_forward(sd, topo, x, tasks, training=False, se=se, reduce_dims=rd, **kw)
     total = 0.0
     for t in tasks:
         assert rel_l2(out_t[t], gold["train::" + t]) < 2e-5, (case, t)
-        assert rel_l2(out_e[t], gold["eval::" + t]) < 2e-5, (case, t)
+        assert rel_l2(out_e[t], golden_eval(gold, t, tasks[t]["activation"])) < 2e-5, (case, t)
         tgt = torch.from_numpy(gold["target::" + t])
         l = O.masked_cosine_loss(out_t[t], tgt) if t == "normals" else O.bce_dice_loss(out_t[t], tgt)
         assert abs(float(l) - float(gold["loss::" + t])) < 2e-5
