@@ -4,11 +4,13 @@ batch 2 per GPU, bf16 kernels, synthetic data, 1..8 B200 data-parallel.
 
     python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
     torchrun ... bench.py --gpus N --steps K --warmup W            # one rank per GPU (NCCL)
-    python bench.py --impl reference --steps K --warmup W          # CPU baseline arm (oracle port)
+    python bench.py --impl reference --steps K --warmup W          # CPU arm: the UNMODIFIED reference (oracle/_ref)
 
 A "step" = forward + multi-task loss + backward + grad-clip + AdamW update on one batch that is
 already resident in HBM (`value`), and the same step with the batch copied from pinned host memory
-and the loss read back every step (`e2e`).  Prints ONE JSON line on rank 0.
+and the loss read back every step (`e2e`).  Prints ONE JSON line on rank 0.  The line also carries an
+`inference` object: BASELINE config 3 (sliding window over a synthetic 1024^3 uint8 volume, 128^3 patches, 50 %
+overlap, Gaussian blend, z-slab sharded at N > 1) with its own value / e2e / tensor + HBM rooflines / cpu_baseline.
 """
 import argparse
 import contextlib
@@ -40,9 +42,15 @@ def parse():
     ap.add_argument("--patch", type=int, default=128)
     ap.add_argument("--batch", type=int, default=2, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-patch", type=int, default=64)
     ap.add_argument("--profile-kernels", action="store_true", default=True)
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--mode", default="both", choices=["both", "train", "infer"],
+                    help="both: train step line with the `inference` object attached (default); train / infer: one of them")
+    ap.add_argument("--infer-volume", type=int, default=1024, help="edge of the synthetic uint8 volume (config 3: 1024)")
+    ap.add_argument("--infer-batch", type=int, default=2, help="patches per forward in the sweep")
+    ap.add_argument("--infer-overlap", type=float, default=0.5)
+    ap.add_argument("--infer-weight", default="gaussian", choices=["gaussian", "uniform"])
+    ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="--impl reference: time budget of the K + W sample steps")
     return ap.parse_args()
 
 
@@ -70,57 +78,154 @@ def gpu_losses(out, tgt, crit):
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arms (the oracle port of the reference's PyTorch path, timed on the host cores)
+# CPU arms: the reference's own PyTorch path on the host cores.  `oracle/_ref` (byte-for-byte copy of the reference's
+# builders/ + losses made by oracle/build_ref.py, git-ignored, travels with the snapshot) when present -> kind
+# "reference"; otherwise the oracle port of the same arithmetic -> kind "port".
 # ------------------------------------------------------------------------------------------
-def cpu_step_rate(patch, batch, steps, warmup, topology_patch=None):
-    """voxels/s of fwd + loss + bwd + AdamW with the oracle's functional network on the CPU.  `topology_patch`
-    selects the network (the 128^3 autoconfiguration: 6 stages, 235.5 M parameters) independently of the size of
-    the sample that is pushed through it."""
-    topology_patch = topology_patch or patch
-    from oracle import resenc_oracle as O
-    import resenc_b200 as rb
-    torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        shell = rb.NetworkFromConfig(make_mgr(topology_patch, batch))        # parameter container only (CPU)
-    params = {n: p.detach().clone().requires_grad_(True) for n, p in shell.named_parameters()}
-    topo = O.autoconfig([topology_patch] * 3)
-    opt = torch.optim.AdamW(list(params.values()), lr=1e-3, weight_decay=1e-4)
-    x, tgt = synthetic_batch(batch, patch, "cpu", 0)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        out = O.net_forward(params, topo, x, TASKS, training=True)
-        loss = losses(out, tgt, O)
-        opt.zero_grad(set_to_none=True)
+class CpuArm:
+    def __init__(self, topology_patch, batch):
+        torch.set_num_threads(os.cpu_count())
+        torch.manual_seed(0)
+        self.kind = "port"
+        self.patch = topology_patch
+        try:
+            from oracle import reference_loader as rl
+            if rl.use_ref_copy():
+                self.model = rl.build_reference(rl.make_mgr([topology_patch] * 3, TASKS, batch=batch))
+                L = rl.reference_module("training/losses/losses.py", "ref_losses")
+                self.crit = {"sheet": L.BCEDiceLoss(0.5, 0.5), "normals": L.MaskedCosineLoss()}
+                self.params = list(self.model.parameters())
+                self.kind = "reference"
+        except Exception as e:   # pragma: no cover - the copy is optional, the port always exists
+            print(f"[bench] oracle/_ref not usable ({e!r}); timing the oracle port", file=sys.stderr)
+        if self.kind == "port":
+            from oracle import resenc_oracle as O
+            import resenc_b200 as rb
+            with contextlib.redirect_stdout(io.StringIO()):
+                shell = rb.NetworkFromConfig(make_mgr(topology_patch, batch))        # parameter container only (CPU)
+            self.pdict = {n: p.detach().clone().requires_grad_(True) for n, p in shell.named_parameters()}
+            self.params = list(self.pdict.values())
+            self.topo = O.autoconfig([topology_patch] * 3)
+            self.O = O
+        self.opt = torch.optim.AdamW(self.params, lr=1e-3, weight_decay=1e-4)
+        self.n_params = sum(p.numel() for p in self.params)
+
+    def describe(self):
+        return ("the UNMODIFIED reference (oracle/_ref: builders/ + training/losses/losses.py, DNA shim), fp32 eager"
+                if self.kind == "reference" else "oracle port of the reference (oracle/resenc_oracle.py), fp32 eager")
+
+    def forward(self, x, training=True):
+        if self.kind == "reference":
+            self.model.train(training)
+            return self.model(x)
+        return self.O.net_forward(self.pdict, self.topo, x, TASKS, training=training)
+
+    def train_step(self, x, tgt):
+        out = self.forward(x, True)
+        if self.kind == "reference":
+            loss = sum(self.crit[t](out[t], tgt[t]) for t in TASKS)
+        else:
+            loss = losses(out, tgt, self.O)
+        self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_([p for p in params.values() if p.grad is not None], 3.0)
-        opt.step()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return batch * patch ** 3 / sec, sec
+        torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], 3.0)   # train.py:227
+        self.opt.step()
+        return float(loss.detach())
+
+    def time_steps(self, patch, batch, steps, warmup):
+        x, tgt = synthetic_batch(batch, patch, "cpu", 0)
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            self.train_step(x, tgt)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        sec = sum(times) / max(len(times), 1)
+        return batch * patch ** 3 / sec, sec
 
 
 def run_reference_arm(args):
+    """`--impl reference`: K timed + W warm-up steps of the reference's training step (fwd + losses + bwd + clip +
+    AdamW) on the host cores.  The full config (128^3 x batch 2) costs tens of seconds per step on a host CPU, so each
+    step is a bounded sample of the workload - the largest of {P^3 x B, P^3 x 1, 96^3 x 1, 64^3 x 1} through the SAME
+    P^3-autoconfigured network for which (K + W) steps fit `--cpu-budget-s` (estimated from one probe step) - and ONE
+    full-config step is timed next to it (`cpu_baseline.full_config`) so that the same-config rate is on record."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    p = args.cpu_sample_patch
-    rate, sec = cpu_step_rate(p, 1, args.steps, args.warmup, topology_patch=args.patch)
+    P, B = args.patch, args.batch
+    arm = CpuArm(P, B)
+    probe_patch = min(64, P)
+    _, probe = arm.time_steps(probe_patch, 1, 1, 1)                      # seconds for probe_patch^3 x 1
+    per_voxel = probe / probe_patch ** 3
+    cands = [(P, B), (P, 1), (96, 1), (64, 1), (32, 1)]
+    cands = [(p, b) for p, b in cands if p <= P and p % 32 == 0]
+    n = args.steps + args.warmup
+    choice = cands[-1]
+    for p, b in cands:
+        if per_voxel * p ** 3 * b * n <= args.cpu_budget_s:
+            choice = (p, b)
+            break
+    rate, sec = arm.time_steps(choice[0], choice[1], args.steps, args.warmup)
+    full = None
+    if choice != (P, B):
+        frate, fsec = arm.time_steps(P, B, 1, 0)
+        full = {"value": frate, "unit": "voxels/s", "s_per_step": fsec, "steps": 1,
+                "sample": f"{P}^3 x{B}: the whole config-2 batch, one step, no warm-up"}
     cores = os.cpu_count()
-    sample = (f"{p}^3 x1 crop per timed step through the same {args.patch}^3-autoconfigured network "
-              f"(6 stages, 235.5 M parameters), fwd+loss+bwd+clip+AdamW, fp32 eager, all host threads")
+    sample = (f"{choice[0]}^3 x{choice[1]} per timed step through the {P}^3-autoconfigured network ({arm.n_params / 1e6:.1f} M "
+              f"parameters), fwd+loss+bwd+clip+AdamW, {arm.describe()}, {torch.get_num_threads()} threads, {sec:.2f} s/step")
+    cb = {"value": rate, "unit": "voxels/s", "cores": cores, "kind": arm.kind, "sample": sample}
+    if full:
+        cb["full_config"] = full
     line = {
         "impl": "reference", "metric": "train voxels/s", "value": rate, "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ResEncM-autoconfig {args.patch}^3 batch {args.batch}/GPU multi-task train step "
-                               f"(sheet 1ch BCEDice + normals 3ch MaskedCosine, AdamW)"},
-        "cpu_baseline": {"value": rate, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"ResEncM-autoconfig {P}^3 batch {B}/GPU multi-task train step (sheet 1ch BCEDice + "
+                               f"normals 3ch MaskedCosine, grad-clip 3, AdamW)",
+                   "sample_per_step": f"{choice[0]}^3 x{choice[1]} of that workload (host CPU, bounded; see cpu_baseline)"},
+        "cpu_baseline": cb,
         "e2e": {"value": rate, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_train(P, B):
+    """The in-line cpu_baseline of the GPU arm (N = 1): ONE full-config step of the reference on the host cores after a
+    64^3 warm-up step (about 10-40 s of CPU work)."""
+    arm = CpuArm(P, B)
+    arm.time_steps(min(64, P), 1, 1, 0)
+    rate, sec = arm.time_steps(P, B, 1, 0)
+    return {"value": rate, "unit": "voxels/s", "cores": os.cpu_count(), "kind": arm.kind,
+            "sample": f"{P}^3 x{B} (the whole config-2 batch), one timed step after a 64^3 warm-up step, fwd+loss+bwd+clip+"
+                      f"AdamW, {arm.describe()}, {torch.get_num_threads()} threads, {sec:.2f} s/step"}, arm
+
+
+def cpu_baseline_infer(arm, P, n_patches_total, vol_voxels, patches=2):
+    """Sliding-window CPU baseline: `patches` 128^3 forwards of the reference network + the numpy blend loop
+    of inference.py:135-157, extrapolated linearly to the whole patch grid (stated as extrapolated)."""
+    import numpy as np
+    from oracle import resenc_oracle as O
+    targets = {"sheet": {"channels": 1}, "normals": {"channels": 3}}
+    rng = np.random.default_rng(0)
+    t0 = time.perf_counter()
+    preds = {"sheet": [], "normals": []}
+    with torch.no_grad():
+        for i in range(patches):
+            x = torch.from_numpy(O.standardize_patch(rng.integers(0, 256, size=(P, P, P)).astype(np.float32) / np.float32(255)))
+            out = arm.forward(x[None, None], training=False)
+            for t in preds:
+                preds[t].append(out[t].numpy())
+    preds = {t: np.concatenate(v) for t, v in preds.items()}
+    pos = [(0, 0, i * (P // 2)) for i in range(patches)]
+    vol = (P, P, P + (patches - 1) * (P // 2))
+    sums, cnt = O.blend_reference(preds, pos, vol, targets)
+    O.finalize_reference(sums, cnt, targets)
+    sec = (time.perf_counter() - t0) / patches
+    return {"value": vol_voxels / (sec * n_patches_total), "unit": "voxels/s", "cores": os.cpu_count(), "kind": arm.kind,
+            "sample": f"{patches} patches of {P}^3 (standardise + reference forward + numpy accumulate / finalise / cast), "
+                      f"{sec:.2f} s/patch, EXTRAPOLATED linearly to the {n_patches_total} patches of the sweep"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -175,6 +280,173 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # main arm
 # ------------------------------------------------------------------------------------------
+# SURVEY 8(d) algorithmic bytes of the HBM-bound sliding-window kernels (c_tot = 4: sheet 1 + normals 3; fp32 logits)
+BLEND_BYTES_PER_PATCH_VOXEL = 4 * 4 + 8 * 4 + 8 + 4      # read pred 4*c_tot, RMW sum 8*c_tot, RMW weight-sum 8, weight map 4
+FINALIZE_BYTES_PER_ELEMENT = {1: 4 + 4 + 1, 3: 4 + 4 / 3 + 2}   # per (voxel, channel): sum + shared wsum read, uint8 | uint16 write
+EXTRACT_BYTES_PER_VOXEL = 1 * 2 + 4                      # uint8 read twice (statistics, write) + fp32 write
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
+    """BASELINE config 3: sliding-window inference over a synthetic uint8 volume (default 1024^3), 128^3 patches, 50 %
+    overlap, Gaussian blend; the z-start list is sharded over the ranks (no traffic during the sweep, one neighbour
+    exchange of the shared planes at the end).  Device-timed with CUDA events, max over ranks."""
+    import numpy as np
+    inf = rb.inference
+    P, V, B = args.patch, args.infer_volume, args.infer_batch
+    targets = {"sheet": {"channels": 1, "activation": "none"}, "normals": {"channels": 3, "activation": "none"}}
+    # (the model applies the training-config activation in eval mode, build_network_from_config.py:322-323; the
+    # inference config adds none on top)
+    model.eval()
+    rb.ops.invalidate_weight_packs()
+    sw = inf.SlidingWindowInferer(model, targets, (P,) * 3, overlap=args.infer_overlap, batch_size=B, weight=args.infer_weight,
+                                  rank=rank, world_size=world, device=dev)
+    rng = np.random.default_rng(1234)
+    volume = rng.integers(0, 256, size=(V, V, V), dtype=np.uint8)
+    positions, z_lo, z_hi, (zs, ys, xs) = sw.plan(volume.shape)
+    n_total = len(zs) * len(ys) * len(xs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + per-kernel spans: a short sweep with CUDA events around every blend / extract launch ----
+    dvol = sw.load_volume(volume)
+    torch.cuda.synchronize()
+    sw.sweep(volume, dvol=dvol, max_patches=4 * B)                       # graph capture, weight packs
+    rb.ops.KERNEL_TIMER.enable(True)
+    l0 = rb._lib.launch_count()
+    bl = sw.sweep(volume, dvol=dvol, max_patches=8 * B)
+    nz = min(P, z_hi - z_lo)
+    bl.finalize(z_lo, z_lo + nz)
+    kstat = rb.ops.KERNEL_TIMER.summary()
+    rb.ops.KERNEL_TIMER.enable(False)
+    launches_probe = rb._lib.launch_count() - l0
+    del bl
+    if world > 1:
+        pairs, _ = inf.plan_slab_exchange(zs, P, V, world)                # one-time NCCL point-to-point set-up
+        one = torch.zeros(1, device=dev)
+        for src, dst, _, _ in pairs:
+            if rank == src:
+                dist.send(one, dst)
+            elif rank == dst:
+                dist.recv(one, src)
+    # forward alone: graph replays of one batch
+    fwd_ms = None
+    if sw._graph is not None:
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        f0.record()
+        for _ in range(10):
+            sw._graph[0].replay()
+        f1.record()
+        torch.cuda.synchronize()
+        fwd_ms = f0.elapsed_time(f1) / 10
+    del dvol
+    torch.cuda.empty_cache()
+
+    # ---- the timed sweep: H2D of the slab | sweep | slab merge + finalise + cast | D2H of the finalised slab ----
+    out_host = None
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    l1 = rb._lib.launch_count()
+    barrier()
+    ev[0].record()
+    dvol = sw.load_volume(volume)
+    ev[1].record()
+    blender = sw.sweep(volume, dvol=dvol)
+    ev[2].record()
+    own = inf.merge_slabs(blender, zs, rank, world) if world > 1 else (0, V)
+    out = blender.finalize(*own) if own[1] > own[0] else {}
+    ev[3].record()
+    out_host = {t: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for t, v in out.items()}
+    for t, v in out.items():
+        out_host[t].copy_(v, non_blocking=True)
+    ev[4].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = rb._lib.launch_count() - l1
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]               # h2d, sweep, merge+finalise, d2h
+    tt = torch.tensor([ms[1] + ms[2], sum(ms), ms[0], ms[1], ms[2], ms[3]], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(len(positions)), float(sw.h2d_bytes), float(sum(v.numel() * v.element_size() for v in out.values()))],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    rb._lib.device_error_check()
+    checksum = {t: int(v.to(torch.int64).sum()) for t, v in out_host.items()} if rank == 0 else None
+    del blender, out, dvol
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    n_patches, h2d, d2h = int(cnt[0]), int(cnt[1]), int(cnt[2])
+    peaks = load_peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_bw = peaks.get("hbm_gbs", 6500.0)
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    n_stages = model.num_stages
+    fwd_flops = FWD_FLOP_PER_VOXEL.get(n_stages, 937.9e3) * P ** 3 * B
+    res = {
+        "metric": "infer output voxels/s", "value": V ** 3 / (ms_dev * 1e-3), "unit": "voxels/s", "n_gpus": world,
+        "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+        "patch_voxels_per_s": n_patches * P ** 3 / (ms_dev * 1e-3), "patches": n_patches, "ms_total": ms_dev,
+        "ms_per_patch": float(tt[3]) / max(1.0, n_patches / world),
+        "ms": {"h2d_volume": float(tt[2]), "sweep": float(tt[3]), "merge_finalize_cast": float(tt[4]), "d2h_result": float(tt[5])},
+        "config": {"workload": f"sliding-window inference, synthetic {V}^3 uint8 volume, {P}^3 patches, overlap "
+                               f"{args.infer_overlap} ({len(zs)}x{len(ys)}x{len(xs)} = {n_total} patches), {args.infer_weight} blend, "
+                               f"{B} patches per forward, sheet(1) + normals(3), per-patch standardisation on device",
+                   "parallelism": f"z-slab x{world}" if world > 1 else "1 GPU, whole volume resident",
+                   "launch": "CUDA-graph replay of the forward; extract / blend launches per batch / patch",
+                   "l2": "accumulators (21.5 GB at 1024^3) and the per-forward activations exceed the 126 MB L2"},
+        "e2e": {"value": V ** 3 / (ms_e2e * 1e-3), "unit": "voxels/s", "ms": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "note": "one step = one whole sweep: pinned-pageable H2D of the uint8 slab(s) + "
+                "sweep + merge + finalise + D2H of the uint8/uint16 result into pinned host memory"},
+        "gpu_launches": int(launches), "clocks": clocks, "result_checksum": checksum,
+    }
+    rl = {}
+    if fwd_ms:
+        ach = fwd_flops / (fwd_ms * 1e-3) / 1e12
+        rl["forward"] = {"bound": "tensor", "kernel": f"network forward, {B} patches (CUDA-graph replay, all kernels)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "ms": fwd_ms,
+                         "algorithmic": f"{FWD_FLOP_PER_VOXEL.get(n_stages, 937.9e3) / 1e3:.1f} kFLOP per patch voxel (SURVEY 8d)",
+                         "peak_source": src + " bf16_tflops_sustained"}
+    for kind, per_unit, what in (("blend_accumulate", BLEND_BYTES_PER_PATCH_VOXEL, "B per patch voxel"),
+                                 ("extract_patches", EXTRACT_BYTES_PER_VOXEL, "B per patch voxel"),
+                                 ("blend_finalize_cast", None, "B per (voxel, channel)")):
+        k = kstat.get(kind)
+        if not k or k["ms"] <= 0:
+            continue
+        if kind == "blend_finalize_cast":
+            # spans carry voxels x channels; sheet (c = 1) 9 B, normals (c = 3) 22/3 B per element => 27 B per output voxel
+            nbytes = k["flops"] / 4 * 27.0
+        else:
+            nbytes = k["flops"] * per_unit
+        ach = nbytes / (k["ms"] * 1e-3) / 1e9
+        rl[kind] = {"bound": "hbm", "achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw,
+                    "launches": k["launches"], "us_per_launch": k["ms"] * 1e3 / k["launches"],
+                    "algorithmic": (f"{per_unit} {what}" if per_unit else "27 B per output voxel at c_tot = 4") + " (SURVEY 8d)",
+                    "traffic": None, "peak_source": src + " hbm_gbs"}
+    res["roofline"] = rl
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            arm = cpu_arm or CpuArm(P, B)
+            res["cpu_baseline"] = cpu_baseline_infer(arm, P, n_total, V ** 3)
+        except Exception as e:   # pragma: no cover
+            res["cpu_baseline"] = {"error": repr(e)}
+    return res
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -215,6 +487,47 @@ def main():
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = rb.NetworkFromConfig(make_mgr(P, B)).to(dev)
+    line, graph, cpu_arm = None, None, None
+    if args.mode in ("both", "train"):
+        line, graph, cpu_arm = run_train(args, rb, par, loss_mod, model, dev, rank, world, local, dist)
+    if args.mode in ("both", "infer"):
+        if graph is not None:
+            graph.reset()
+            graph = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        try:
+            inf_res = run_infer(args, rb, model, dev, rank, world, dist, cpu_arm)
+        except Exception as e:   # the training line must survive a failure of the second half
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            inf_res = {"error": repr(e)}
+        if rank == 0:
+            if line is None:
+                line = dict(inf_res)
+                line.setdefault("steps", 1)
+                line.setdefault("warmup", 1)
+                line.setdefault("vs_baseline", None)
+            else:
+                line["inference"] = inf_res
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        # a communicator whose collectives were captured into a CUDA graph can block in destroy_process_group():
+        # drop the graph first, and never let tear-down outlive the measurement (the line above is already printed)
+        sys.stdout.flush()
+        if graph is not None:
+            graph.reset()
+        torch.cuda.synchronize()
+        dist.barrier()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        dist.destroy_process_group()
+
+
+def run_train(args, rb, par, loss_mod, model, dev, rank, world, local, dist):
+    P, B = args.patch, args.batch
     n_stages = model.num_stages
     crit = loss_mod.task_losses(make_mgr(P, B).tasks)
     model.train()
@@ -346,17 +659,14 @@ def main():
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     rb._lib.device_error_check()
 
+    line, cpu_arm = None, None
     if rank == 0:
         vox = B * P ** 3 * args.steps * world
         value = vox / (ms_dev * 1e-3)
         e2e = vox / (ms_e2e * 1e-3)
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
+        peaks = load_peaks()
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_bw = peaks.get("hbm_gbs", 6500.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         conv = kstat.get("conv", {"flops": 0.0, "ms": 0.0, "launches": 0})
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else None
@@ -390,26 +700,29 @@ def main():
                 line["roofline"]["ncu"] = json.load(f)
         except Exception:
             pass
+        # HBM-bound kernels of the step (InstanceNorm statistics / apply passes, forward and backward): algorithmic bytes
+        # (4 B per element forward, 10 B backward, +2 per residual gradient; bf16 in / out) over their
+        # CUDA-event time
+        nk = [kstat[k] for k in ("norm_reduce", "norm_apply") if k in kstat]
+        if nk and sum(k["ms"] for k in nk) > 0:
+            nbytes, nms = sum(k.get("bytes", 0.0) for k in nk), sum(k["ms"] for k in nk)
+            act = sum(k.get("bytes_moved", 0.0) for k in nk)
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "norm_act_fwd / plane_reduce / norm_act_bwd (InstanceNorm + LeakyReLU + "
+                                    "residual + SE gate passes)", "achieved": nbytes / (nms * 1e-3) / 1e9, "peak": peak_bw,
+                                    "unit": "GB/s", "frac": nbytes / (nms * 1e-3) / 1e9 / peak_bw,
+                                    "algorithmic_gb_per_step": nbytes / 1e9 / max(args.steps, 1),
+                                    "moved_gb_per_step": act / 1e9 / max(args.steps, 1),
+                                    "moved_gbs": act / (nms * 1e-3) / 1e9,
+                                    "kernel_ms_per_step": nms / max(args.steps, 1), "traffic": None,
+                                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s"),
+                                    "note": "achieved = SURVEY 8(d) algorithmic bytes / time; moved = bytes this design reads and "
+                                            "writes (the pre-norm tensor is kept in fp32: 4 B instead of 2 per element and pass)"}
         if world == 1 and not args.no_cpu_baseline:
-            p = args.cpu_sample_patch
-            rate, sec = cpu_step_rate(p, 1, 3, 1, topology_patch=P)
-            line["cpu_baseline"] = {"value": rate, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{p}^3 x1 crop through the same {P}^3-autoconfigured network (fwd+loss+bwd+"
-                                              f"clip+AdamW), oracle port of the reference, fp32 eager, 1 warm-up + 3 "
-                                              f"timed, {sec:.2f} s/step"}
-        print(json.dumps(line))
-    if world > 1:
-        # a communicator whose collectives were captured into a CUDA graph can block in destroy_process_group():
-        # drop the graph first, and never let tear-down outlive the measurement (the line above is already printed)
-        sys.stdout.flush()
-        if graph is not None:
-            graph.reset()
-        torch.cuda.synchronize()
-        dist.barrier()
-        killer = threading.Timer(20.0, lambda: os._exit(0))
-        killer.daemon = True
-        killer.start()
-        dist.destroy_process_group()
+            try:
+                line["cpu_baseline"], cpu_arm = cpu_baseline_train(P, B)
+            except Exception as e:   # pragma: no cover
+                line["cpu_baseline"] = {"error": repr(e)}
+    return (line if rank == 0 else None), graph, cpu_arm
 
 
 if __name__ == "__main__":

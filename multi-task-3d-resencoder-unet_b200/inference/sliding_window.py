@@ -184,8 +184,10 @@ class SlabBlender:
         arr = (L.BlendTarget * len(items))()
         for k, (t, one, c, act) in enumerate(items):
             arr[k].pred, arr[k].sum, arr[k].C, arr[k].activation = one.data_ptr(), self.sums[t].data_ptr(), c, act
-        L.check(self._lib.rb_blend_accumulate_multi(arr, len(items), L.ptr(self.weight), self.wsum.data_ptr(), pz, py, px,
-                                                    depth, Y, X, z0 - self.z_lo, y0, x0, st), "rb_blend_accumulate_multi")
+        with _ops.KERNEL_TIMER.span("blend_accumulate", float(pz * py * px)):
+            rc = self._lib.rb_blend_accumulate_multi(arr, len(items), L.ptr(self.weight), self.wsum.data_ptr(), pz, py, px,
+                                                     depth, Y, X, z0 - self.z_lo, y0, x0, st)
+        L.check(rc, "rb_blend_accumulate_multi")
 
     def finalize(self, z_from: Optional[int] = None, z_to: Optional[int] = None, keep_float: bool = False):
         """Finalise + cast the planes [z_from, z_to) (volume coordinates, default: whole slab).
@@ -207,8 +209,10 @@ class SlabBlender:
             s = self.sums[t][:, a:a + nz]               # channels `depth * Y * X` apart: finalised in place, no copy
             res = torch.empty((c, nz, Y, X), dtype=torch.uint16 if normals else torch.uint8, device=self.device)
             f = torch.empty((c, nz, Y, X), dtype=torch.float32, device=self.device) if keep_float else None
-            L.check(self._lib.rb_blend_finalize_cast2(s.data_ptr(), depth * Y * X, wsum.data_ptr(), res.data_ptr(), L.ptr(f),
-                                                      V, c, 1 if normals else 0, st), "rb_blend_finalize_cast2")
+            with _ops.KERNEL_TIMER.span("blend_finalize_cast", float(V) * c):
+                rc = self._lib.rb_blend_finalize_cast2(s.data_ptr(), depth * Y * X, wsum.data_ptr(), res.data_ptr(), L.ptr(f),
+                                                       V, c, 1 if normals else 0, st)
+            L.check(rc, "rb_blend_finalize_cast2")
             out[t] = res[0] if c == 1 else res
             if keep_float:
                 flt[t] = f[0] if c == 1 else f
@@ -270,10 +274,12 @@ class DeviceVolume:
             org = (C.c_int * (3 * len(chunk)))()
             for j, (z0, y0, x0) in enumerate(chunk):
                 org[3 * j], org[3 * j + 1], org[3 * j + 2] = int(z0) - self.z_lo, int(y0), int(x0)
-            L.check(self._lib.rb_extract_patches(self.data.data_ptr(), self.is_u16, self.z_hi - self.z_lo, self.shape[1],
-                                                 self.shape[2], org, len(chunk), pz, py, px, 1 if standardize else 0,
-                                                 self._bstats.data_ptr(), out[i:i + len(chunk)].data_ptr(),
-                                                 L.stream_ptr(self.device)), "rb_extract_patches")
+            with _ops.KERNEL_TIMER.span("extract_patches", float(len(chunk) * pz * py * px)):
+                rc = self._lib.rb_extract_patches(self.data.data_ptr(), self.is_u16, self.z_hi - self.z_lo, self.shape[1],
+                                                  self.shape[2], org, len(chunk), pz, py, px, 1 if standardize else 0,
+                                                  self._bstats.data_ptr(), out[i:i + len(chunk)].data_ptr(),
+                                                  L.stream_ptr(self.device))
+            L.check(rc, "rb_extract_patches")
 
 
 # ------------------------------------------------------------------------------------------
@@ -346,16 +352,29 @@ class SlidingWindowInferer:
                 return self.model(batch)
         return self.model(batch)
 
+    def load_volume(self, volume):
+        """This rank's z-slab of the input volume, copied to HBM (the only host->device traffic of a sweep)."""
+        vol_shape = tuple(int(s) for s in volume.shape[-3:])
+        _, z_lo, z_hi, _ = self.plan(vol_shape)
+        return DeviceVolume(volume, z_lo, z_hi, self.device)
+
     @torch.no_grad()
-    def sweep(self, volume):
-        """Accumulate this rank's patches.  Returns the SlabBlender (un-finalised)."""
+    def sweep(self, volume, dvol: Optional["DeviceVolume"] = None, max_patches: Optional[int] = None):
+        """Accumulate this rank's patches.  Returns the SlabBlender (un-finalised).  `dvol` = the slab already resident
+        in HBM (`load_volume`); `max_patches` truncates the sweep (profiling runs)."""
         vol_shape = tuple(int(s) for s in volume.shape[-3:])
         positions, z_lo, z_hi, _ = self.plan(vol_shape)
+        if max_patches is not None:
+            positions = positions[:max_patches]
         blender = SlabBlender(self.targets, vol_shape, self.patch, z_lo, z_hi, self.device, self.weight)
         if not positions:
             return blender
-        dvol = DeviceVolume(volume, z_lo, z_hi, self.device)
+        if dvol is None:
+            dvol = DeviceVolume(volume, z_lo, z_hi, self.device)
+        elif (dvol.z_lo, dvol.z_hi) != (z_lo, z_hi) or dvol.shape != vol_shape:
+            raise ValueError("sweep: the resident slab does not match this rank's z-range")
         self.h2d_bytes = dvol.h2d_bytes
+        self.n_patches = len(positions)
         was_training = self.model.training
         self.model.eval()
         B = self.batch_size

@@ -43,7 +43,8 @@ class _KernelTimer:
             self.records = []
 
     @contextlib.contextmanager
-    def span(self, kind, flops=0.0):
+    def span(self, kind, flops=0.0, nbytes=0.0, moved=0.0):
+        """flops / nbytes: ALGORITHMIC work of the launch; moved: bytes this implementation touches."""
         if not self.on:
             yield
             return
@@ -51,17 +52,19 @@ class _KernelTimer:
         a.record()
         yield
         b.record()
-        self.records.append((kind, flops, a, b))
+        self.records.append((kind, flops, a, b, nbytes, moved))
 
     def summary(self):
         if not self.records:
             return {}
         torch.cuda.synchronize()
         out = {}
-        for kind, flops, a, b in self.records:
-            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        for kind, flops, a, b, nbytes, moved in self.records:
+            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0, "bytes": 0.0, "bytes_moved": 0.0})
             d["ms"] += a.elapsed_time(b)
             d["flops"] += flops
+            d["bytes"] += nbytes
+            d["bytes_moved"] += moved
             d["launches"] += 1
         return out
 
@@ -195,7 +198,8 @@ def _make_desc(src0, src1, out0, out1, *, in_dims, taps, off, istr, out_grid, no
 
 
 def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode=0,
-                   ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0, impl=None, stats=None, want_stats=False):
+                   ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0, impl=None, stats=None, want_stats=False,
+                   algo_flops=None):
     """One rb_conv_gather call.  src* are NDHWC bf16 activations, out* NDHWC bf16 or fp32 (logical NCDHW views).
     stats=(sum, sumsq) fp32 [NB, Nout] are filled by the tcgen05 epilogue; with want_stats=True they are
     allocated here when (and only when) the library will run the tcgen05 kernel, and returned (else None)."""
@@ -212,7 +216,10 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
     ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src0.device) if ws_bytes else None
     ssum, ssq = (None, None) if stats is None else stats
-    flops = 2.0 * d.NB * d.OD * d.OH * d.OW * nout * (d.srcC0 + d.srcC1) * taps[0] * taps[1] * taps[2]
+    # `algo_flops`: callers whose operand carries structural zeros (the merged strided data gradient) pass the
+    # algorithmic count instead of the padded GEMM size
+    flops = algo_flops if algo_flops is not None else \
+        2.0 * d.NB * d.OD * d.OH * d.OW * nout * (d.srcC0 + d.srcC1) * taps[0] * taps[1] * taps[2]
     with KERNEL_TIMER.span("conv", flops):
         rc = lib.rb_conv_gather(C.byref(d), src0.data_ptr(), L.ptr(src1), wpk.data_ptr(), out0.data_ptr(), L.ptr(out1),
                                 L.ptr(ssum), L.ptr(ssq), L.ptr(ws), ws_bytes, L.stream_ptr())
@@ -521,7 +528,8 @@ def _conv_backward_data(weight, stride, impl, x0, x1, dy, need0, need1):
             npar = stride[0] * stride[1] * stride[2]
             _launch_gather(dy, None, pack_conv_dgrad_merged(weight, merged, stride), gx0, gx1, in_dims=od,
                            taps=tuple(a[0] for a in merged), off=tuple(a[1] for a in merged), istr=(1, 1, 1), out_grid=od,
-                           nout=npar * ci, mode=1, ostr=stride, full=in_dims, ps=stride, psC=ci, impl=impl)
+                           nout=npar * ci, mode=1, ostr=stride, full=in_dims, ps=stride, psC=ci, impl=impl,
+                           algo_flops=2.0 * n * od[0] * od[1] * od[2] * co * ci * k[0] * k[1] * k[2])
             return (gx0 if need0 else None), (gx1 if need1 else None)
         classes = [_axis_classes(k[a], stride[a], pad[a], in_dims[a]) for a in range(3)]
         empty = any(len(cls[2]) == 0 for axis in classes for cls in axis)
@@ -600,7 +608,11 @@ def _plane_reduce(kind, y, dz, z, per_w, slope, sign=None):
     n, c, d, h, w = y.shape
     g = w if per_w else 1
     out = torch.empty((n, g, c, 2), dtype=torch.float64, device=y.device)
-    with KERNEL_TIMER.span("norm_reduce"):
+    el = float(n * c * d * h * w)
+    yb = 4 if y.dtype == torch.float32 else 2
+    # algorithmic: forward statistics ride the conv epilogue (0 B); backward reduce reads dz + y in bf16 (4 B / element)
+    with KERNEL_TIMER.span("norm_reduce", nbytes=el * (4 if kind == 1 else 2),
+                           moved=el * (yb + (2 if kind == 1 else 0) + (2 if z is not None else 0))):
         rc = L.load().rb_plane_reduce(kind, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(dz), L.ptr(z),
                                       L.ptr(sign[0]) if sign else None, L.ptr(sign[1]) if sign else None,
                                       out.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, float(slope), L.stream_ptr())
@@ -611,7 +623,10 @@ def _plane_reduce(kind, y, dz, z, per_w, slope, sign=None):
 def _apply_fwd(y, res, A, B, per_w, act, slope):
     n, c, d, h, w = y.shape
     z = new_cl(n, c, d, h, w, y.device)
-    with KERNEL_TIMER.span("norm_apply"):
+    el = float(n * c * d * h * w)
+    yb = 4 if y.dtype == torch.float32 else 2
+    with KERNEL_TIMER.span("norm_apply", nbytes=el * (4 + (2 if res is not None else 0)),
+                           moved=el * (yb + 2 + (2 if res is not None else 0))):
         rc = L.load().rb_norm_act_fwd(y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(res), z.data_ptr(),
                                       A.data_ptr(), B.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, 1 if act else 0,
                                       float(slope), L.stream_ptr())
@@ -623,7 +638,11 @@ def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres, sign=None):
     n, c, d, h, w = y.shape
     dy = new_cl(n, c, d, h, w, y.device)
     dres = new_cl(n, c, d, h, w, y.device) if want_dres else None
-    with KERNEL_TIMER.span("norm_apply"):
+    el = float(n * c * d * h * w)
+    yb = 4 if y.dtype == torch.float32 else 2
+    # algorithmic: read dz + y (bf16), write dy (+ dres): 6 (+2) B / element; the activation sign comes with y
+    with KERNEL_TIMER.span("norm_apply", nbytes=el * (6 + (2 if want_dres else 0)),
+                           moved=el * (2 + yb + 2 + (2 if z is not None else 0) + (2 if want_dres else 0))):
         rc = L.load().rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), L.ptr(sign[0]) if sign else None,
                                       L.ptr(sign[1]) if sign else None, y.data_ptr(), 1 if y.dtype == torch.float32 else 0,
                                       dy.data_ptr(), L.ptr(dres), k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), n,

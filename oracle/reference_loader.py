@@ -14,6 +14,18 @@ REFERENCE_ROOT = os.environ.get("RESENC_REFERENCE_ROOT", "/root/reference")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dna_shim")
 
 
+_REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+
+
+def use_ref_copy():
+    """Point the loader at `oracle/_ref/reference` (the byte-for-byte copy made by oracle/build_ref.py, which travels
+    to the GPU box) when /root/reference itself is absent.  Returns True when a reference tree is importable."""
+    global REFERENCE_ROOT
+    if not available() and os.path.isdir(os.path.join(_REF_COPY, "builders")):
+        REFERENCE_ROOT = _REF_COPY
+    return available()
+
+
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "builders"))
 
