@@ -31,7 +31,8 @@ import torch.distributed as dist
 
 from . import ops
 from .losses import build_task_losses, task_losses
-from .parallel import GradientBuckets
+from . import _lib as L
+from .parallel import GradientBuckets, broadcast_parameters
 
 CLIP_NORM = 3.0          # train.py:227
 
@@ -80,8 +81,9 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model: torch.nn.Module, mgr, use_cuda_graph: bool = False, fused_losses: bool = True,
-                 process_group=None):
+                 process_group=None, grad_comm_dtype: Optional[torch.dtype] = None):
         self.model = model
+        self.group = process_group
         self.mgr = mgr
         self.tasks = mgr.tasks
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -99,18 +101,26 @@ class DataParallelTrainer:
         self.weights = {t: float(info.get("weight", 1.0)) for t, info in self.tasks.items()}
         lr = float(getattr(mgr, "initial_lr", 1e-3))
         wd = float(getattr(mgr, "weight_decay", 1e-4))
-        if getattr(mgr, "optimizer", "AdamW") == "SGD":
+        # replicas must start identical whatever each rank's seed was: rank 0's parameters and buffers win
+        if self.world > 1:
+            broadcast_parameters(model, 0, process_group)
+        dev = next(model.parameters()).device
+        on_gpu = dev.type == "cuda"
+        self._is_sgd = getattr(mgr, "optimizer", "AdamW") == "SGD"
+        if self._is_sgd:
+            # SGD bakes a Python-float lr into the captured kernels: the graph is re-captured whenever the schedule moves
+            # the lr (end_epoch), see _lr_signature
             self.optimizer = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, nesterov=True, weight_decay=wd)
         else:
-            dev = next(model.parameters()).device
-            on_gpu = dev.type == "cuda"
             if self.use_graph and on_gpu:
                 lr = torch.tensor(lr, dtype=torch.float32, device=dev)   # a tensor lr stays adjustable after capture
             self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd, fused=on_gpu,
                                                capturable=self.use_graph and on_gpu)
+        self._lr_tensors = [g["lr"] for g in self.optimizer.param_groups if torch.is_tensor(g["lr"])]
         self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=int(getattr(mgr, "max_epoch", 1000)),
                                                                     eta_min=0)
-        self.buckets = GradientBuckets(model, process_group=process_group) if self.world > 1 else None
+        self.buckets = (GradientBuckets(model, process_group=process_group, comm_dtype=grad_comm_dtype)
+                        if self.world > 1 else None)
         self.params = list(model.parameters())
         self._micro = 0
         self._graph = None
@@ -160,9 +170,17 @@ class DataParallelTrainer:
         return self._micro_step(inputs, targets, do_update)
 
     # -- whole-step CUDA graph ------------------------------------------------------------------------
+    def _lr_signature(self):
+        """Learning rates that are Python floats are constants of a captured graph; device-tensor rates are read by
+        every replay.  The signature of the former decides whether a captured step is still valid."""
+        return tuple(float(g["lr"]) for g in self.optimizer.param_groups if not torch.is_tensor(g["lr"]))
+
     def _graphed_step(self, inputs, targets):
+        if self._graph is not None and self._graph_lr != self._lr_signature():
+            self._graph = None                     # the schedule moved a baked-in lr (SGD): capture again
         if self._graph is None:
             self._capture(inputs, targets)
+            self._graph_lr = self._lr_signature()
         self._static_in.copy_(inputs, non_blocking=True)
         for k, v in targets.items():
             self._static_tg[k].copy_(v, non_blocking=True)
@@ -205,8 +223,26 @@ class DataParallelTrainer:
                         v.copy_(old[k]) if k in old else v.zero_()     # zero == freshly initialised AdamW / SGD state
 
     # -- epoch bookkeeping ------------------------------------------------------------------------
+    def _restore_device_lr(self):
+        """`optimizer.load_state_dict` (and a scheduler stepping a float) can replace the device-tensor lr of a
+        capturable optimiser by a float or a CPU tensor, which a re-captured graph would bake in as a constant: put the
+        loaded value back into the original device tensors."""
+        if not self._lr_tensors:
+            return
+        for g, t in zip(self.optimizer.param_groups, self._lr_tensors):
+            if g["lr"] is not t:
+                t.fill_(float(g["lr"]))
+                g["lr"] = t
+
+    def check_device(self):
+        """Raise if any kernel recorded a pipeline time-out since the last check (synchronises the current stream)."""
+        if next(self.model.parameters()).is_cuda:
+            L.device_error_check()
+
     def end_epoch(self):
+        self.check_device()
         self.scheduler.step()
+        self._restore_device_lr()
         self.epoch += 1
 
     def state_dict(self):
@@ -219,6 +255,7 @@ class DataParallelTrainer:
         """Rank 0 writes the reference's checkpoint dictionary (train.py:249-254) atomically; other ranks only
         synchronise.  `keep_newest` = N prunes older `<model_name>_*.pth` siblings like train.py:256-265 (N = 10 there)."""
         wrote = False
+        self.check_device()           # never write weights that a timed-out kernel may have corrupted
         if self.rank == 0:
             tmp = f"{path}.tmp"
             torch.save(self.state_dict(), tmp)
@@ -239,6 +276,10 @@ class DataParallelTrainer:
             if "scheduler" in ck:
                 self.scheduler.load_state_dict(ck["scheduler"])
             self.epoch = int(ck.get("epoch", -1)) + 1          # the epoch to run next (train.py:164)
+            self._restore_device_lr()
+        if self.world > 1:
+            broadcast_parameters(self.model, 0, self.group)    # every rank read the file; rank 0's copy is authoritative
+        ops.invalidate_weight_packs()
         self._graph = None
         return ck
 

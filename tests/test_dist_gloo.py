@@ -39,7 +39,7 @@ class _Tiny(torch.nn.Module):
         return self.b(torch.relu(self.a(x)))
 
 
-def _grad_worker(rank, world, port, out):
+def _grad_worker(rank, world, port, out, wire=None):
     import sys
     sys.path.insert(0, ROOT)
     rb = importlib.import_module("resenc_b200")
@@ -47,26 +47,38 @@ def _grad_worker(rank, world, port, out):
     _init(rank, world, port)
     torch.manual_seed(0)
     model = _Tiny()
-    buckets = par.GradientBuckets(model, bucket_bytes=256)     # tiny buckets: several per step
+    buckets = par.GradientBuckets(model, bucket_bytes=256, comm_dtype=wire)     # tiny buckets: several per step
     assert len(buckets.params) == 6 and len(buckets.buckets) >= 3
-    res = []
-    for step in range(2):
+    res, stats = [], []
+    for step in range(3):
         torch.manual_seed(100 * step + rank)
         x = torch.randn(5, 8)
         buckets.zero_grad()
         model(x).square().sum().backward()
         buckets.finish()
-        res.append(torch.cat([p.grad.flatten() for p in model.parameters()]).clone())
+        res.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten()
+                              for p in model.parameters()]).clone())
+        stats.append({"in_backward": buckets.launched_in_backward, "in_finish": buckets.launched_in_finish,
+                      "buckets": len(buckets.buckets), "skipped": len(buckets.skipped), "rebuilds": buckets.rebuilds,
+                      "unused_grad_is_none": all(p.grad is None for p in model.unused.parameters())})
     if rank == 0:
-        torch.save(res, out)
+        torch.save({"grads": res, "stats": stats}, out)
     dist.destroy_process_group()
 
 
 def test_gradient_buckets_allreduce_mean(tmp_path):
     out = str(tmp_path / "g.pt")
     mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    got = torch.load(out)
-    for step in range(2):
+    saved = torch.load(out)
+    got, stats = saved["grads"], saved["stats"]
+    # step 0 runs on the registration-order cut: the never-used head sits inside a bucket, which therefore only launches
+    # in finish().  Its arrival order re-cuts the buckets at step 1: from then on the unused parameters sit in no bucket
+    # (.grad is None, as on the single-GPU path) and EVERY bucket launches while backward is still running.
+    assert stats[0]["in_finish"] >= 1 and not stats[0]["unused_grad_is_none"]
+    for st in stats[1:]:
+        assert st["rebuilds"] == 1 and st["skipped"] == 2 and st["unused_grad_is_none"]
+        assert st["in_finish"] == 0 and st["in_backward"] == st["buckets"] >= 2, st
+    for step in range(3):
         ref = []
         for rank in range(2):
             torch.manual_seed(0)
@@ -76,6 +88,26 @@ def test_gradient_buckets_allreduce_mean(tmp_path):
             m(x).square().sum().backward()
             ref.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for p in m.parameters()]))
         assert torch.allclose(got[step], (ref[0] + ref[1]) / 2, atol=1e-6)
+
+
+def test_gradient_buckets_bf16_wire(tmp_path):
+    """comm_dtype=bfloat16: the mean gradient travels as bf16 (half the bytes) and comes back widened; equal to the
+    fp32 mean within bf16 rounding."""
+    out = str(tmp_path / "g16.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out, torch.bfloat16), nprocs=2, join=True)
+    got = torch.load(out)["grads"]
+    for step in range(3):
+        ref = []
+        for rank in range(2):
+            torch.manual_seed(0)
+            m = _Tiny()
+            torch.manual_seed(100 * step + rank)
+            x = torch.randn(5, 8)
+            m(x).square().sum().backward()
+            ref.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for p in m.parameters()]))
+        mean = (ref[0] + ref[1]) / 2
+        assert torch.allclose(got[step], mean, rtol=2e-2, atol=1e-3 * float(mean.abs().max()))
+        assert not torch.equal(got[step], mean)          # it really went through bf16
 
 
 def _slab_worker(rank, world, port, out):
@@ -169,7 +201,7 @@ def _trainer_worker(rank, world, port, out, accumulate=1):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     assert T.init_distributed("gloo") == (rank, rank, world)
-    torch.manual_seed(0)
+    torch.manual_seed(7 * rank)      # every rank seeds differently: the trainer must broadcast rank 0's replica
     model = _TinyNet()
     mgr = SimpleNamespace(tasks=_TASKS, optimizer="AdamW", initial_lr=1e-2, weight_decay=1e-4, max_epoch=5,
                           gradient_accumulation=accumulate)
