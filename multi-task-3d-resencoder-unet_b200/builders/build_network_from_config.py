@@ -8,6 +8,8 @@ in train mode, activated in eval mode (:312-326).  All arithmetic runs on the sm
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -34,6 +36,9 @@ def _report(title, obj, names):
     for n in names:
         print(f"{n}: {getattr(obj, n)}")
     print("-" * 61)
+
+
+_COMPILE_DISABLE = os.environ.get("RESENC_COMPILE_DISABLE") is not None
 
 
 class NetworkFromConfig(nn.Module):
@@ -164,9 +169,20 @@ class NetworkFromConfig(nn.Module):
                  "squeeze_excitation", "squeeze_excitation_reduction_ratio", "patch_size", "batch_size", "in_channels",
                  "vram_target", "autoconfigure", "tasks"))
 
-    @torch.compiler.disable
     def forward(self, x):
-        """The kernels are launched through ctypes; under torch.compile this method runs eagerly."""
+        """Eager: the fused units are autograd.Functions launching the C ABI through ctypes.  Under `torch.compile`
+        (train.py:133, inference.py:37) Dynamo traces this method and the fused units appear as `resenc_b200::*` custom
+        operators (custom_ops.py: fake + autograd + autocast rules) - opaque graph nodes, no graph break.
+        RESENC_COMPILE_DISABLE=1 restores the round-1 behaviour (the whole forward runs eagerly under a compiled caller)."""
+        if _COMPILE_DISABLE:
+            return self._forward_not_traced(x)
+        return self._forward_impl(x)
+
+    @torch.compiler.disable
+    def _forward_not_traced(self, x):
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         if not self.return_skips:
             raise NotImplementedError("return_skips=False leaves the decoders without skips (as in the reference)")
         with torch.autocast("cuda", enabled=False):

@@ -27,6 +27,11 @@ from . import _lib as L
 
 BF16 = torch.bfloat16
 LRELU_SLOPE_DEFAULT = 0.01
+# The fused units are registered twice: as torch.autograd.Functions (eager: no dispatcher overhead on ~700 launches per
+# step) and as `torch.library` custom ops (custom_ops.py: fake + autograd + autocast rules) which Dynamo sees as opaque
+# graph nodes under torch.compile (reference train.py:133, inference.py:37).  RESENC_FORCE_CUSTOM_OPS=1 sends eager
+# calls through the custom ops as well (tests).
+FORCE_CUSTOM_OPS = os.environ.get("RESENC_FORCE_CUSTOM_OPS") is not None
 
 
 class _KernelTimer:
@@ -120,6 +125,9 @@ def as_cl(x: torch.Tensor) -> torch.Tensor:
     """Return `x` as a dense NDHWC bf16 activation (no copy when it already is one)."""
     if is_cl(x):
         return x
+    if torch.compiler.is_compiling():
+        # traced by Dynamo (module-level glue such as the residual decoder's concatenation): torch ops only
+        return x.to(BF16).contiguous(memory_format=torch.channels_last_3d)
     L.require_cuda(x, "as_cl")
     if x.dim() != 5:
         raise ValueError(f"expected a 5-D [N, C, D, H, W] tensor, got shape {tuple(x.shape)}")
@@ -653,7 +661,7 @@ def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres, sign=None):
 
 class _NormState:
     """What the backward of a norm (+gate) + act needs besides y, z."""
-    __slots__ = ("small", "gamma", "has_beta", "act", "slope", "eps", "has_res", "gate", "per_w", "n_gate")
+    __slots__ = ("small", "gamma", "has_beta", "act", "slope", "eps", "has_res", "gate", "per_w", "n_gate", "sums")
 
 
 def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, reduce_dims="all", drop=None):
@@ -665,6 +673,7 @@ def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, r
     st = _NormState()
     st.gamma, st.has_beta, st.act, st.slope, st.eps, st.has_res = gamma, beta is not None, act, slope, eps, res is not None
     st.n_gate = 0 if gate is None else 4
+    st.sums = None
     if gate is None and drop is None:
         st.gate, st.per_w = None, False
         sums = None if stats is not None else _plane_reduce(0, y, None, None, False, slope)
@@ -696,8 +705,23 @@ def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, r
                                  pl[2], pl[3], pl[4], pl[5], per_w, drop)
     st.gate = (leaves, pl, A, B)
     st.small = None
+    st.sums = (s1.detach(), s2.detach(), pw.detach() if per_w else None)     # enough to rebuild the small graph
     z = _apply_fwd(y, res, A, B, per_w, act, slope)
     return z, st
+
+
+def _rebuild_gate_state(st, s1, s2, pw, S, plane, gamma, beta, gate, drop):
+    """The gated path's O(N*W*C) torch graph from its leaves (custom-op backward: the forward op cannot hand a
+    Python graph to the backward op, only tensors)."""
+    params = [gamma, beta, *(gate if gate is not None else (None, None, None, None))]
+    with torch.enable_grad():
+        leaves = [s1.detach().clone().requires_grad_(True), s2.detach().clone().requires_grad_(True),
+                  pw.detach().clone().requires_grad_(True) if pw is not None else None]
+        pl = [p.detach().requires_grad_(True) if p is not None else None for p in params]
+        A, B = _gate_small_graph(leaves[0], leaves[1], leaves[2], float(S), float(plane), pl[0], pl[1], st.eps,
+                                 pl[2], pl[3], pl[4], pl[5], st.per_w, drop)
+    st.gate = (leaves, pl, A, B)
+    return st
 
 
 def _norm_backward(st, y, z, dz, want_dres):
@@ -890,6 +914,9 @@ def conv_norm_act(x, weight, stride=1, x_cat=None, res=None, gamma=None, beta=No
                                      stem, impl or _PreciseState.impl, drop)
     if se is not None:
         _se_per_w(se_reduce_dims)
+    if torch.compiler.is_compiling() or FORCE_CUSTOM_OPS:
+        return custom_ops.conv_norm_act(x, weight, _triple(stride), x_cat, res, gamma, beta, float(eps), bool(act),
+                                        float(slope), se, se_reduce_dims, bool(stem), impl, drop)
     cfg = (_triple(stride), impl, float(eps), bool(act), float(slope), se_reduce_dims, bool(stem))
     return _ConvNormActFn.apply(weight, cfg, x, x_cat, res, gamma, beta, drop, *(se or ()))
 
@@ -972,7 +999,10 @@ def conv_transpose3d(x, weight, stride, impl=None, bias=None):
     if _PreciseState.on:
         from . import precise
         return precise.conv_transpose3d(x, weight, stride, impl or _PreciseState.impl, bias)
-    up = _ConvT3dFn.apply(weight, _triple(stride), impl, x)
+    if torch.compiler.is_compiling() or FORCE_CUSTOM_OPS:
+        up = custom_ops.conv_transpose3d(x, weight, _triple(stride), impl)
+    else:
+        up = _ConvT3dFn.apply(weight, _triple(stride), impl, x)
     if bias is not None:
         # rare configuration (conv_bias=True): per-channel add on the channels-last buffer, glue
         up = (up.permute(0, 2, 3, 4, 1) + bias.to(up.dtype)).permute(0, 4, 1, 2, 3)
@@ -1010,6 +1040,8 @@ def avg_pool3d(x, stride):
     if _PreciseState.on:
         from . import precise
         return precise.avg_pool3d(x, stride)
+    if torch.compiler.is_compiling() or FORCE_CUSTOM_OPS:
+        return custom_ops.avg_pool3d(x, _triple(stride))
     return _AvgPoolFn.apply(x, _triple(stride))
 
 
@@ -1059,6 +1091,8 @@ def head_conv1x1(x, weight, bias, activation=None):
     if weight.shape[0] > 8:
         raise NotImplementedError("task heads with more than 8 output channels are not implemented")
     act = _ACT[activation if activation is None else str(activation).lower()]
+    if torch.compiler.is_compiling() or FORCE_CUSTOM_OPS:
+        return custom_ops.head_conv1x1(x, weight, bias, act)
     return _HeadFn.apply(x, weight, bias, act)
 
 
@@ -1086,3 +1120,7 @@ def stem_conv3d(x, weight, impl=None):
     if x.shape[1] != weight.shape[1]:
         raise ValueError(f"stem conv: weight expects {weight.shape[1]} input channels, got {x.shape[1]}")
     return _StemConvFn.apply(x, weight, impl)
+
+
+# the torch.library registration of the same units (imported last: it builds on the primitives above)
+from . import custom_ops  # noqa: E402
