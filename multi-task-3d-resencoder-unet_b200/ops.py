@@ -710,11 +710,28 @@ def _norm_forward(y, res, gamma, beta, eps, act, slope, stats=None, gate=None, r
     return z, st
 
 
+@contextlib.contextmanager
+def _autograd_dispatch_enabled():
+    """Inside a `torch.library` operator implementation the dispatcher runs below autograd (the autograd keys sit in the
+    thread-local exclude set), so `torch.enable_grad()` alone records nothing.  The gated path differentiates its
+    O(N*W*C) torch graph with autograd inside the backward operator: lift the exclusion for that small graph."""
+    K = torch._C.DispatchKey
+    exc = torch._C._dispatch_tls_local_exclude_set()
+    if not (exc.has(K.AutogradFunctionality) or exc.has(K.AutogradOther)):
+        yield
+        return
+    new_exc = exc
+    for k in (K.AutogradFunctionality, K.AutogradOther, K.AutogradNestedTensor, K.ADInplaceOrView):
+        new_exc = new_exc.remove(k)
+    with torch._C._ForceDispatchKeyGuard(torch._C._dispatch_tls_local_include_set(), new_exc):
+        yield
+
+
 def _rebuild_gate_state(st, s1, s2, pw, S, plane, gamma, beta, gate, drop):
     """The gated path's O(N*W*C) torch graph from its leaves (custom-op backward: the forward op cannot hand a
     Python graph to the backward op, only tensors)."""
     params = [gamma, beta, *(gate if gate is not None else (None, None, None, None))]
-    with torch.enable_grad():
+    with _autograd_dispatch_enabled(), torch.enable_grad():
         leaves = [s1.detach().clone().requires_grad_(True), s2.detach().clone().requires_grad_(True),
                   pw.detach().clone().requires_grad_(True) if pw is not None else None]
         pl = [p.detach().requires_grad_(True) if p is not None else None for p in params]
@@ -748,7 +765,8 @@ def _norm_backward(st, y, z, dz, want_dres):
     dB = red[..., 0].float()
     dA = red[..., 1].float()
     inputs = [t for t in leaves + pl if t is not None]
-    grads = torch.autograd.grad([A, B], inputs, [dA, dB], allow_unused=True)
+    with _autograd_dispatch_enabled():
+        grads = torch.autograd.grad([A, B], inputs, [dA, dB], allow_unused=True)
     it = iter(grads)
     gl = [next(it) if t is not None else None for t in leaves]
     gp = [next(it) if t is not None else None for t in pl]

@@ -44,7 +44,10 @@ def _targets(tasks, batch, patch, gen):
     return out
 
 
-def _forward_case(rb, patch, batch, tasks, in_channels=1, model_config=None, training=True, tol=1e-2, seed=0):
+def _forward_case(rb, patch, batch, tasks, in_channels=1, model_config=None, training=True, tol=1e-2, seed=0,
+                  calibrate=False):
+    """calibrate=True (non-BASELINE shapes only): the bound becomes max(tol, 0.9 x the rel-L2 of PyTorch's own bf16
+    autocast of the oracle network on this GPU), i.e. never worse than the existing bf16 GPU path."""
     torch.manual_seed(seed)
     mc = dict(model_config or {})
     model = quiet_build(rb.NetworkFromConfig, make_mgr(patch, tasks, in_channels=in_channels, batch=batch, model_config=mc)).cuda()
@@ -60,12 +63,20 @@ def _forward_case(rb, patch, batch, tasks, in_channels=1, model_config=None, tra
     with torch.no_grad():
         out = model(x.cuda())
     res = {}
+    cal = {}
+    if calibrate:
+        sd_c = {k: v.cuda() for k, v in sd.items()}
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            oc = O.net_forward(sd_c, topo, x.cuda(), tasks, training=training, se=bool(mc.get("squeeze_excitation", False)))
+        cal = {t: rel_l2(oc[t].float(), ref[t]) for t in tasks}
     for t in tasks:
         r = rel_l2(out[t], ref[t])
         res[t] = r
-        print(f"{'x'.join(map(str, patch))} x{batch} {t}: rel-L2 vs fp32 oracle {r:.3e} (bound {tol:.0e}; oracle {t_ref:.1f} s)")
+        bound = max(tol, 0.9 * cal[t]) if calibrate else tol
+        print(f"{'x'.join(map(str, patch))} x{batch} {t}: rel-L2 vs fp32 oracle {r:.3e} (bound {bound:.2e}"
+              + (f", torch bf16 autocast {cal[t]:.3e}" if calibrate else "") + f"; oracle {t_ref:.1f} s)")
         assert out[t].dtype == torch.float32 and tuple(out[t].shape) == tuple(ref[t].shape)
-        assert r < tol, (patch, t, r)
+        assert r < bound, (patch, t, r)
     return model, out, ref
 
 
@@ -100,15 +111,16 @@ def test_reference_shipped_patch_shapes_forward_vs_oracle(rb):
     """The patch shapes of the reference's own task files: [64, 192, 192] (tasks/sheet_normals.yaml:3) and the
     anisotropic [14, 256, 256]-style ink patch, here [16, 256, 256] (tasks/ink.yaml:20 needs a depth divisible by the
     pooling schedule)."""
-    _forward_case(rb, [64, 192, 192], 1, TASKS2)
-    _forward_case(rb, [16, 256, 256], 1, {"ink": {"channels": 1, "activation": "sigmoid"}}, in_channels=2)
+    _forward_case(rb, [64, 192, 192], 1, TASKS2, calibrate=True)
+    _forward_case(rb, [16, 256, 256], 1, {"ink": {"channels": 1, "activation": "sigmoid"}}, in_channels=2, calibrate=True)
 
 
 def test_gradients_64_vs_oracle(rb):
     """Whole-network weight gradients at 64^3 (BASELINE config 1 geometry, batch 2): slab fprop / dgrad, h-major
     weights-on-M tiles and the two-sided tap-stacked wgrad all sit on this path.  Per-parameter gradient norms within
     15 % of the fp32 oracle's (parameters whose gradient is noise in the reference itself excluded), the loss within
-    1e-2, selected full gradients within 0.35 relative L2 (bf16 sign-flip calibration, see test_gpu_network.py)."""
+    1e-2, selected full gradients within max(0.25, 1.25 x the error of PyTorch's bf16 autocast of the same network on
+    the same GPU) relative L2 (bf16 sign-flip calibration, see test_gpu_network.py)."""
     patch, batch = [64, 64, 64], 2
     torch.manual_seed(0)
     model = quiet_build(rb.NetworkFromConfig, make_mgr(patch, TASKS2, batch=batch)).cuda().train()
@@ -142,21 +154,31 @@ def test_gradients_64_vs_oracle(rb):
             worst, worst_name = dev, n
     print(f"64^3 x2 worst gradient-norm deviation {worst:.3e} ({worst_name})")
     assert worst < 0.15, worst_name
+    # calibration: PyTorch's own bf16 autocast (ATen / cuDNN on this GPU) of the same functional network on the same
+    # weights - what "a bf16 implementation" of this network costs in gradient accuracy (LeakyReLU sign flips: a deep
+    # 512-channel layer at 4^3 sees every flip of the 26 blocks above it)
+    cal = {k: v.detach().cuda().clone().requires_grad_(True) for k, v in params.items()}
+    sd_c = {k: cal[by_id[id(v)]] for k, v in model.state_dict(keep_vars=True).items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        oc = O.net_forward(sd_c, topo, x.cuda(), TASKS2, training=True)
+    sum(_loss(t, oc[t].float(), tg[t].cuda()) for t in TASKS2).backward()
     for n in ("shared_encoder.stem.convs.0.conv.weight", "shared_encoder.stages.0.blocks.0.conv1.conv.weight",
               "shared_encoder.stages.1.blocks.1.conv2.conv.weight", "shared_encoder.stages.4.blocks.2.conv1.conv.weight",
               "task_decoders.normals.stages.3.convs.0.conv.weight", "task_decoders.sheet.transpconvs.3.weight",
               "task_decoders.sheet.seg_layers.3.weight"):
         r = rel_l2(named[n].grad, params[n].grad)
-        print(f"64^3 x2 grad {n}: rel-L2 {r:.3e}")
-        assert r < 0.35, (n, r)
+        rc = rel_l2(cal[n].grad, params[n].grad)
+        print(f"64^3 x2 grad {n}: rel-L2 {r:.3e} (torch bf16 autocast on the same GPU: {rc:.3e})")
+        assert r < max(0.25, 1.25 * rc), (n, r, rc)
 
 
 def test_loss_curve_200_steps_tracks_oracle(rb):
     """North star: "loss curves must agree over 200 steps".  The reference loop body (train.py:195-231: forward,
     per-task losses summed, backward, clip_grad_norm_(3), optimiser step; SGD momentum 0.9 nesterov as train.py:76-84)
     runs for 200 steps over a cycle of 4 fixed batches at 32^3 on the oracle (CPU fp32) and on the CUDA path from the
-    same initial weights.  Bounds: mean |deviation| over the 200 steps < 2e-2, every step within 0.1, the means of the
-    last 20 steps within 10 % of each other, and both curves fall below 60 % of their start."""
+    same initial weights.  Bounds (measured: mean |deviation| 2.0e-3, max 1.7e-2 at step 186): mean |deviation| over the
+    200 steps < 8e-3, every step within 5e-2, the means of the last 20 steps within 3 % of each other, and both curves
+    fall below 85 % of their start (1.60 -> 1.22 on the oracle)."""
     patch, batch, steps = [32, 32, 32], 2, 200
     torch.manual_seed(0)
     model = quiet_build(rb.NetworkFromConfig, make_mgr(patch, TASKS2, batch=batch)).cuda().train()
@@ -198,6 +220,6 @@ def test_loss_curve_200_steps_tracks_oracle(rb):
     print(f"200-step curve: mean |dev| {dev.mean():.4e}, max {dev.max():.4e} at step {int(dev.argmax())}, "
           f"tail means {np.mean(lo[-20:]):.4f} / {np.mean(lp[-20:]):.4f}")
     assert np.all(np.isfinite(lp))
-    assert dev.mean() < 2e-2 and dev.max() < 0.1
-    assert abs(np.mean(lo[-20:]) - np.mean(lp[-20:])) < 0.1 * np.mean(lo[-20:])
-    assert np.mean(lp[-20:]) < 0.6 * lp[0] and np.mean(lo[-20:]) < 0.6 * lo[0]
+    assert dev.mean() < 8e-3 and dev.max() < 5e-2
+    assert abs(np.mean(lo[-20:]) - np.mean(lp[-20:])) < 0.03 * np.mean(lo[-20:])
+    assert np.mean(lp[-20:]) < 0.85 * lp[0] and np.mean(lo[-20:]) < 0.85 * lo[0]
