@@ -274,7 +274,12 @@ bool auto_prefers_tc5t(const RbConvDesc& d, const Tc5tPlan& pl) {
     const int ntaps = d.tapD * d.tapH * d.tapW;
     static const bool force = getenv("RESENC_FORCE_TC5T") != nullptr;   // experiments
     if (force) return true;
-    return ntaps * ctot >= 864 && ctot >= 64;
+    if (ntaps * ctot >= 864 && ctot >= 64) return true;
+    // 32-channel full-resolution layers that the slab kernel does not take (W not in {32, 64, 96, 128}: 192^3 patches, the
+    // reference's [64, 192, 192]): the h-major tile loads 9 boxes of 272 rows instead of 27 boxes of 256 per 256 voxels,
+    // and the per-tap kernels are TMA-row-rate bound at 64-byte rows (1.26 ms against 0.275 for 32->32 @128^3)
+    static const bool no_hm32 = getenv("RESENC_NO_TC5T_HM32") != nullptr;
+    return !no_hm32 && pl.hm && ntaps == 27 && ctot >= 32 && d.Nout >= 32;
 }
 
 int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const void* src1, const void* w, void* out0,
@@ -367,10 +372,13 @@ SlabPlan plan_slab(const RbConvDesc& d) {
     if (d.srcC0 != 32 || (d.nsrc == 2 && d.srcC1 != 32)) return pl;
     if (!((d.Nout == 32 && d.outC0 == 32 && d.outC1 == 0) || (d.Nout == 64 && d.outC0 == 32 && d.outC1 == 32))) return pl;
     if (d.nsrc == 2 && !d.outF32) return pl;   // the second source accumulates into an fp32 destination
-    if (d.IW != 32 && d.IW != 64 && d.IW != 128) return pl;
+    // a tile = R full rows of W voxels on the N side of the MMA: N = R * W must be a multiple of 64 (two warp groups x
+    // 64-column hand-offs) and <= 256, rows must start at multiples of 32 columns; W = 192 (R = 1) needs four 36 KB
+    // planes + 72 KB of weights + staging > 227 KB of shared memory and stays on the h-major gather kernel
+    if (d.IW != 32 && d.IW != 64 && d.IW != 96 && d.IW != 128) return pl;
     pl.R = 256 / d.IW;
     if (d.IH % pl.R != 0) return pl;
-    pl.lw = d.IW == 32 ? 5 : d.IW == 64 ? 6 : 7;
+    pl.lw = d.IW == 32 ? 5 : d.IW == 64 ? 6 : 7;   // (informational; the kernel indexes with R and W)
     pl.hTiles = d.IH / pl.R;
     // output planes per work item: whole waves of CTAs first, then fewer halo re-loads
     double bestScore = -1.0;
@@ -1245,6 +1253,13 @@ int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(rb::pack_conv_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
     dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+    static const bool no_vec = getenv("RESENC_NO_VEC_PACK") != nullptr;
+    if (!no_vec && Cin % 32 == 0 && aligned16(w) && (reinterpret_cast<uintptr_t>(out_f) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out_d) & 3u) == 0) {
+        static std::once_flag once2;
+        std::call_once(once2, [] { cudaFuncSetAttribute(rb::pack_conv_weights_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+        rb::pack_conv_weights_vec_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+        return check_launch("pack_conv_weights_vec_kernel");
+    }
     rb::pack_conv_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("pack_conv_weights_kernel");
 }

@@ -329,6 +329,20 @@ def _pack_kernel(weight, want_f, want_d):
     return f, d
 
 
+# PACK_CACHE off (a CUDA graph of a training step is being captured or replayed eagerly): packs are not kept across
+# optimiser steps, but within one step the fprop and the stride-1 data-gradient operand of a weight still come from ONE
+# launch (one read of the fp32 parameter instead of two): forward packs both when the weight will need a gradient, the
+# backward pass picks the second one up.  Entries die with the optimiser epoch.
+_STEP_PACKS = {"epoch": -1, "packs": {}}
+
+
+def _step_packs():
+    if _STEP_PACKS["epoch"] != _PACK_EPOCH[0]:
+        _STEP_PACKS["epoch"] = _PACK_EPOCH[0]
+        _STEP_PACKS["packs"] = {}
+    return _STEP_PACKS["packs"]
+
+
 def pack_conv_fprop(weight):
     """[Cout, Cin, kd, kh, kw] -> [taps][Cout][Cin] bf16."""
     if not weight.is_cuda or weight.dtype != torch.float32:
@@ -336,7 +350,12 @@ def pack_conv_fprop(weight):
         return _cached_pack(weight, "f", lambda: weight.detach().permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci)
                             .to(BF16).contiguous())
     if not PACK_CACHE:
-        return _pack_kernel(weight, True, False)[0]
+        want_d = weight.requires_grad and torch.is_grad_enabled()
+        if not want_d:
+            return _pack_kernel(weight, True, False)[0]
+        f, d = _pack_kernel(weight, True, True)
+        _step_packs()[id(weight)] = (weight, d)
+        return f
     both = _cached_pack(weight, "fd", lambda: _pack_kernel(weight, True, True))
     return both[0]
 
@@ -344,6 +363,9 @@ def pack_conv_fprop(weight):
 def pack_conv_dgrad_full(weight):
     """Stride-1 data-gradient operand: all taps, flipped, [taps][Cin][Cout] bf16."""
     if not PACK_CACHE:
+        hit = _step_packs().pop(id(weight), None)
+        if hit is not None and hit[0] is weight:
+            return hit[1]
         return _pack_kernel(weight, False, True)[1]
     return _cached_pack(weight, "fd", lambda: _pack_kernel(weight, True, True))[1]
 

@@ -346,7 +346,7 @@ def test_fused_conv_norm_act_unit(rb, case):
 
 
 @pytest.mark.parametrize("co,ci,k", [(32, 32, (3, 3, 3)), (64, 128, (3, 3, 3)), (40, 24, (1, 3, 3)), (512, 1024, (3, 3, 3)),
-                                     (64, 32, (1, 1, 1))])
+                                     (64, 32, (1, 1, 1)), (72, 64, (3, 3, 3)), (33, 32, (2, 2, 2)), (256, 512, (2, 2, 2))])
 def test_weight_pack_unpack_kernels(rb, co, ci, k):
     """Tiled pack / unpack kernels == the torch permutes they replace (bit-exact)."""
     ops = rb.ops

@@ -139,7 +139,8 @@ def test_tc5_fused_statistics(rb):
         assert rel_l2(st[1], (y32.double() ** 2).sum((2, 3, 4))) < 2e-5
 
 
-SLAB_CASES = [(1, (64, 64, 64)), (1, (24, 32, 128)), (2, (40, 32, 32)), (2, (10, 64, 64))]
+SLAB_CASES = [(1, (64, 64, 64)), (1, (24, 32, 128)), (2, (40, 32, 32)), (2, (10, 64, 64)),
+              (1, (40, 48, 96)), (2, (18, 96, 96))]      # W = 96: tiles of two rows, N = 192 accumulator columns
 
 
 @pytest.mark.parametrize("n,dims", SLAB_CASES, ids=lambda v: str(v).replace(" ", ""))

@@ -67,7 +67,15 @@ def main():
     ap.add_argument("--prenorm", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--stats", type=int, default=1)
     ap.add_argument("--skip-bwd", action="store_true")
+    ap.add_argument("--layer", action="append", default=[],
+                    help="extra layer 'name,kind,cin,cout,dim,stride' (kind conv3|conv1|cat3|convT); replaces the built-in table")
     args = ap.parse_args()
+    global LAYERS
+    if args.layer:
+        LAYERS = []
+        for spec in args.layer:
+            name, kind, cin, cout, dim, s_ = spec.split(",")
+            LAYERS.append((name, kind, int(cin), int(cout), int(dim), int(s_), 1))
     torch.manual_seed(0)
     dev = "cuda"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
