@@ -126,6 +126,7 @@ def test_custom_ops_opcheck_and_match_eager_functions(rb):
         (out["sheet"].mean() + out["normals"].square().mean()).backward()
         return {k: v.detach().clone() for k, v in out.items()}, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
     o1, g1 = run()
+    o1b, g1b = run()                       # run-to-run spread of one route (fp32 atomics order in statistics / split-K)
     rb.ops.FORCE_CUSTOM_OPS = True
     try:
         o2, g2 = run()
@@ -134,9 +135,11 @@ def test_custom_ops_opcheck_and_match_eager_functions(rb):
     for t in o1:
         assert rel_l2(o2[t], o1[t]) < 5e-3, t
     assert set(g1) == set(g2)
-    worst = max(rel_l2(g2[n], g1[n]) for n in g1 if float(g1[n].norm()) > 1e-6)
-    print(f"custom-op route vs autograd.Function route: worst gradient rel-L2 {worst:.3e}")
-    assert worst < 0.1
+    names = [n for n in g1 if float(g1[n].norm()) > 1e-6]
+    noise = max(rel_l2(g1b[n], g1[n]) for n in names)
+    worst = max(rel_l2(g2[n], g1[n]) for n in names)
+    print(f"custom-op route vs autograd.Function route: worst gradient rel-L2 {worst:.3e} (two runs of one route: {noise:.3e})")
+    assert worst < max(0.05, 3.0 * noise)
     rb._lib.device_error_check()
 
 
