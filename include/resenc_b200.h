@@ -37,7 +37,8 @@ enum RbConvImpl {
     RB_IMPL_MMA_SYNC = 1, /* shape-generic warp-level tensor path (cross-check + odd shapes) */
     RB_IMPL_TCGEN05 = 2,  /* TMA + tcgen05.mma + TMEM; RB_ERR_UNSUPPORTED if the shape does not qualify */
     RB_IMPL_TCGEN05_SPLITK = 3, /* only returned by rb_conv_gather_plan: tcgen05 with taps split over the chip
-                                   (needs the workspace, produces no fused statistics) */
+                                   (needs the workspace: one fp32 slice per tap split; the finish pass sums the slices
+                                   and takes the fused statistics) */
     RB_IMPL_TCGEN05_SLAB = 4    /* only returned by rb_conv_gather_plan: the z-marching tcgen05 kernel for 3x3x3
                                    stride-1 convolutions between 32-channel tensors (fused statistics available) */
 };
@@ -99,7 +100,8 @@ int rb_conv_gather(const RbConvDesc* d, const void* src0, const void* src1, cons
                    void* workspace, size_t workspace_bytes, void* stream);
 /* Which implementation rb_conv_gather will run for this descriptor: RB_IMPL_MMA_SYNC, RB_IMPL_TCGEN05 or
  * RB_IMPL_TCGEN05_SPLITK / RB_IMPL_TCGEN05_SLAB (negative status if a forced implementation cannot run it).
- * Fused statistics are produced only for RB_IMPL_TCGEN05 and RB_IMPL_TCGEN05_SLAB. */
+ * Fused statistics are produced by every tcgen05 variant (RB_IMPL_TCGEN05, _SLAB, _SPLITK: the finish pass of the
+ * tap-split kernel takes them), not by RB_IMPL_MMA_SYNC. */
 int rb_conv_gather_plan(const RbConvDesc* d);
 /* 1 if the tcgen05 kernel can run this descriptor. */
 int rb_conv_gather_tc5_supported(const RbConvDesc* d);

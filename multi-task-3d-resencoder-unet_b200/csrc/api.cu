@@ -222,19 +222,18 @@ Tc5tPlan plan_tc5t(const RbConvDesc& d) {
     pl.tapsPer = ntaps;
     pl.splitK = 1;
     static const int split_max_tiles = getenv("RESENC_SPLIT_MAX_TILES") ? atoi(getenv("RESENC_SPLIT_MAX_TILES")) : 74;
-    if (pl.tiles < 48 && ntaps >= 8 && ctot >= 256 && d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1) {
-        long long want = (2LL * num_sms() + pl.tiles - 1) / pl.tiles;
-        if (want > ntaps) want = ntaps;
-        pl.tapsPer = (int)((ntaps + want - 1) / want);
-        pl.splitK = (ntaps + pl.tapsPer - 1) / pl.tapsPer;
-    } else if (pl.tiles <= split_max_tiles && ntaps >= 8 && ctot >= 256 && d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1) {
-        // up to half a wave of tiles (the 256-channel layers at 16^3: 64 tiles on 148 SMs): pick the tap split whose
-        // longest per-SM queue (items per persistent CTA x taps per item) is shortest
-        long long bestCost = (long long)ntaps + 2;     // unsplit: one item of ntaps taps per CTA (+ epilogue ~ 2 taps)
-        for (int per = 2; per < ntaps; ++per) {
+    // Up to half a wave of tiles (4^3 / 8^3: 4-16 tiles, the 256-channel layers at 16^3: 64 tiles on 148 SMs): split the
+    // taps over the chip.  Every (tile, tap slice) item stores its partial tile into its own workspace slice and
+    // split_finish_kernel sums them (no atomics), so the cost model is simply the longest per-SM queue: items per
+    // persistent CTA x (taps per item + ~2 taps worth of pipeline fill and epilogue), + 1 for the finish pass.
+    const bool plain = d.ostrD == 1 && d.ostrH == 1 && d.ostrW == 1 && d.ooffD == 0 && d.ooffH == 0 && d.ooffW == 0 &&
+                       d.FD == d.OD && d.FH == d.OH && d.FW == d.OW && d.Nout % 32 == 0 && (d.outC1 == 0 || d.outC0 % 32 == 0);
+    if (pl.tiles <= split_max_tiles && ntaps >= 8 && ctot >= 256 && plain) {
+        long long bestCost = (long long)ntaps + 2;     // unsplit: one item of ntaps taps per CTA
+        for (int per = 1; per < ntaps; ++per) {
             const int sk = (ntaps + per - 1) / per;
             const long long items = pl.tiles * sk;
-            const long long cost = ((items + num_sms() - 1) / num_sms()) * (per + 2) + 1;   // +1: finish pass
+            const long long cost = ((items + num_sms() - 1) / num_sms()) * (per + 2) + 1;
             if (cost < bestCost) { bestCost = cost; pl.tapsPer = per; pl.splitK = sk; }
         }
     }
@@ -337,6 +336,7 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
     p.splitK = pl.splitK; p.tapsPer = pl.tapsPer; p.fdSplitK = rb::make_fastdiv(pl.splitK); p.ws = ws;
+    p.wsSlice = (long long)d.NB * d.OD * d.OH * d.OW * d.Nout;
     {
         static const int dbg = getenv("RESENC_TC5T_DEBUG") ? atoi(getenv("RESENC_TC5T_DEBUG")) : 0;
         p.debug = dbg & 15;
@@ -907,7 +907,8 @@ ConvDecision decide_conv(const RbConvDesc& d, bool stats_requested) {
     r.pl = plan_tc5(d);
     r.plt = plan_tc5t(d);
     static const bool no_t = getenv("RESENC_NO_TC5T") != nullptr;
-    const bool split_ok = r.plt.ok && r.plt.splitK > 1 && !no_t && !stats_requested;
+    const bool split_ok = r.plt.ok && r.plt.splitK > 1 && !no_t;   // split_finish_kernel takes the statistics
+    (void)stats_requested;
     if (split_ok) { r.choice = CH_TC5T_SPLIT; return r; }
     const bool tc5 = d.impl == RB_IMPL_TCGEN05 ? r.pl.ok : auto_prefers_tc5(d, r.pl);
     if (tc5) {
@@ -934,7 +935,7 @@ size_t rb_conv_gather_workspace(const RbConvDesc* d) {
     if (!d) return 0;
     const ConvDecision r = decide_conv(*d, false);
     const size_t full = (size_t)d->NB * d->OD * d->OH * d->OW * d->Nout * sizeof(float);
-    if (r.choice == CH_TC5T_SPLIT) return full;
+    if (r.choice == CH_TC5T_SPLIT) return full * (size_t)r.plt.splitK;     // one slice per tap split
     if (r.choice == CH_MMA && generic_splitk(*d) > 1) return full;
     return 0;
 }
@@ -972,7 +973,11 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     const size_t need = (size_t)M * d.Nout * sizeof(float);
 
     ConvDecision dec = decide_conv(d, stat_sum != nullptr);
-    if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need)) dec = decide_conv(d, true);  // no room: unsplit
+    if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need * (size_t)dec.plt.splitK)) {
+        // no room for the per-slice workspace: run the same kernel unsplit
+        dec.plt.splitK = 1; dec.plt.tapsPer = d.tapD * d.tapH * d.tapW;
+        dec.choice = CH_TC5T;
+    }
     if (dec.choice == CH_UNSUPPORTED) return fail(RB_ERR_UNSUPPORTED, "conv: shape does not qualify for the tcgen05 kernel");
     if (dec.choice == CH_SLAB) return launch_slab(d, dec.pls, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
     if (dec.choice == CH_TC5) return launch_tc5(d, dec.pl, src0, src1, w, out0, out1, stat_sum, stat_sq, st);
@@ -982,15 +987,19 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
         return launch_tc5t(d, plt, src0, src1, w, out0, out1, stat_sum, stat_sq, nullptr, st);
     }
     if (dec.choice == CH_TC5T_SPLIT) {
-        RB_CUDA(cudaMemsetAsync(workspace, 0, need, st));
         rc = launch_tc5t(d, dec.plt, src0, src1, w, out0, out1, nullptr, nullptr, (float*)workspace, st);
         if (rc) return rc;
-        rb::GConvParams p;
-        fill_generic_params(d, src0, src1, w, out0, out1, p);
-        p.splitK = dec.plt.splitK;
-        p.ws = (float*)workspace;
-        rb::gather_finish_kernel<<<grid_for(M * (d.Nout / 2), 256), 256, 0, st>>>(p);
-        return check_launch("gather_finish_kernel");
+        rb::SplitFinishParams f;
+        memset(&f, 0, sizeof(f));
+        f.ws = (const float*)workspace; f.sliceStride = (long long)M * d.Nout; f.slices = dec.plt.splitK;
+        f.S = d.OD * d.OH * d.OW; f.NB = d.NB; f.Nout = d.Nout;
+        f.out0 = out0; f.out1 = out1; f.outC0 = d.outC0; f.outC1 = d.outC1; f.outF32 = d.outF32;
+        f.stat_sum = stat_sum; f.stat_sq = stat_sq;
+        f.vpw = f.S <= 1024 ? 16 : 64;
+        f.runsPerSample = (f.S + 8 * f.vpw - 1) / (8 * f.vpw);
+        const long long blocks = (long long)d.NB * f.runsPerSample * (d.Nout / 32);
+        rb::split_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);
+        return check_launch("split_finish_kernel");
     }
     if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");
 
@@ -1270,7 +1279,9 @@ int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int T, void* st
     rb::WUnpackParams p{dwp, grad, A, B, T};
     const size_t smem = (size_t)8 * (32 * T + 1) * sizeof(float);
     dim3 grid((B + 31) / 32, (A + 7) / 8);
-    rb::unpack_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    if (T == 27) rb::unpack_wgrad_kernel<27><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else if (T == 8) rb::unpack_wgrad_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else rb::unpack_wgrad_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("unpack_wgrad_kernel");
 }
 

@@ -233,6 +233,75 @@ __global__ void __launch_bounds__(256) gather_finish_kernel(const GConvParams p)
     }
 }
 
+// Finish pass of the tap-split tcgen05 convolution (conv_tc5t.cuh, deep 4^3 / 8^3 / 16^3 layers):
+//   out[m][c] = sum_slices ws[slice][m][c]   (bf16 or fp32 destination, plain stride-1 convolution: voxel m of the output
+//   grid is voxel m of the destination), plus the InstanceNorm statistics sum / sum of squares per (sample, channel)
+//   of the stored values - the statistics the unsplit kernels take in their epilogue.
+// A warp owns 32 consecutive channels (lane = channel: 128-byte rows of the workspace) and VPW consecutive voxels of one
+// sample; the 8 warps of a block cover 8 consecutive voxel runs of the same (sample, channel group), so the statistics
+// are combined in shared memory and cost 64 atomics per block.
+struct SplitFinishParams {
+    const float* ws;      // [slices][M][Nout]
+    long long sliceStride;
+    int slices;
+    int S;                // voxels per sample
+    int NB, Nout;
+    void* out0;
+    void* out1;
+    int outC0, outC1, outF32;
+    float* stat_sum;      // [NB][Nout] or null
+    float* stat_sq;
+    int vpw;              // voxels per warp
+    int runsPerSample;    // ceil(S / (8 * vpw))
+};
+
+__global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishParams p) {
+    __shared__ float red[2][8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cgroups = p.Nout >> 5;
+    int b = blockIdx.x;
+    const int cgI = b % cgroups; b /= cgroups;
+    const int run = b % p.runsPerSample;
+    const int nb = b / p.runsPerSample;
+    const int c = cgI * 32 + lane;
+    const int v0 = (run * 8 + warp) * p.vpw;
+    const int v1 = min(p.S, v0 + p.vpw);
+    const bool first = c < p.outC0;
+    const int cdst = first ? c : c - p.outC0;
+    const int cpitch = first ? p.outC0 : p.outC1;
+    void* const base = first ? p.out0 : p.out1;
+    float s1 = 0.f, s2 = 0.f;
+    for (int v = v0; v < v1; ++v) {
+        const size_t m = (size_t)nb * p.S + v;
+        const float* src = p.ws + m * p.Nout + c;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int sl = 0;
+        for (; sl + 4 <= p.slices; sl += 4) {
+            a0 += __ldcs(src + (size_t)sl * p.sliceStride);
+            a1 += __ldcs(src + (size_t)(sl + 1) * p.sliceStride);
+            a2 += __ldcs(src + (size_t)(sl + 2) * p.sliceStride);
+            a3 += __ldcs(src + (size_t)(sl + 3) * p.sliceStride);
+        }
+        for (; sl < p.slices; ++sl) a0 += __ldcs(src + (size_t)sl * p.sliceStride);
+        const float x = (a0 + a1) + (a2 + a3);
+        if (p.outF32) reinterpret_cast<float*>(base)[m * cpitch + cdst] = x;
+        else reinterpret_cast<bf16*>(base)[m * cpitch + cdst] = __float2bfloat16_rn(x);
+        s1 += x;
+        s2 = fmaf(x, x, s2);
+    }
+    if (p.stat_sum != nullptr) {
+        red[0][warp][lane] = s1;
+        red[1][warp][lane] = s2;
+        __syncthreads();
+        if (warp < 2) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += red[warp][w][lane];
+            atomicAdd((warp == 0 ? p.stat_sum : p.stat_sq) + (size_t)nb * p.Nout + c, a);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Weight gradient:  dW[tap][a][b] += sum_m P[m][a] * Q[gather(m, tap)][b]
 //   conv wgrad : P = dy (a = Cout) on the output grid, Q = x (b = Cin, two sources allowed)

@@ -45,10 +45,12 @@ struct Tc5tConvParams {
     int statSmem;
     FastDiv fdTilesM, fdTilesW, fdTilesH, fdTilesD;
     // split-K over taps for the deep layers (few voxels, huge K): each work item takes `tapsPer` consecutive taps and
-    // adds its fp32 partial tile into ws[voxel][Nout] with red.global; gather_finish_kernel stores the result
+    // stores its fp32 partial tile into ws[slice][voxel][Nout]; split_finish_kernel sums the slices, stores the result
+    // and accumulates the InstanceNorm statistics
     int splitK, tapsPer;
     FastDiv fdSplitK;
     float* ws;
+    long long wsSlice;    // elements per workspace slice (= output voxels x Nout)
     int debug;   // profiling experiments only (RESENC_TC5T_DEBUG bit mask): 1 skip MMAs, 2 skip TMA loads, 4 skip the epilogue body
 };
 
@@ -302,7 +304,11 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                         s1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
                         s2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
                     } else if (p.splitK > 1) {
-                        // partial tile of one tap slice: fp32 adds into ws[m][Nout], m = linear output-grid voxel
+                        // partial tile of one tap slice -> its own workspace slice ws[sk][m][Nout] (m = linear output-grid
+                        // voxel) with plain coalesced stores (lane = channel).  Round 1 added all slices into one buffer
+                        // with red.global: ~145 cycles per instruction under 14-27-fold address contention, 60-70 % of the
+                        // kernel (profiles/r2_deep_probe.txt); split_finish_kernel sums the slices instead.
+                        float* const wsl = p.ws + (size_t)sk * p.wsSlice;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int r = cg + j;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                                       nb = (int)tib * tn + in;
                             if (rowValid && ow < p.OW && oh < p.OH && od < p.OD && nb < p.NB) {
                                 const size_t m = (((size_t)nb * p.OD + od) * p.OH + oh) * p.OW + ow;
-                                atomicAdd(p.ws + m * p.Nout + co, __uint_as_float(v[j]));
+                                wsl[m * p.Nout + co] = __uint_as_float(v[j]);
                             }
                         }
                     } else if (p.lw >= 5) {

@@ -218,7 +218,7 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
         plan = lib.rb_conv_gather_plan(C.byref(d))
         if plan < 0:
             L.check(plan, "rb_conv_gather_plan")
-        if plan in (L.IMPL_TCGEN05, L.IMPL_TCGEN05_SLAB):
+        if plan in (L.IMPL_TCGEN05, L.IMPL_TCGEN05_SLAB, L.IMPL_TCGEN05_SPLITK):
             st = torch.zeros((2, d.NB, nout), dtype=torch.float32, device=src0.device)
             stats = (st[0], st[1])
     ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))
@@ -350,7 +350,7 @@ def pack_conv_fprop(weight):
         return _cached_pack(weight, "f", lambda: weight.detach().permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci)
                             .to(BF16).contiguous())
     if not PACK_CACHE:
-        want_d = weight.requires_grad and torch.is_grad_enabled()
+        want_d = weight.requires_grad      # (grad mode is off inside autograd.Function.forward: not a usable signal)
         if not want_d:
             return _pack_kernel(weight, True, False)[0]
         f, d = _pack_kernel(weight, True, True)
