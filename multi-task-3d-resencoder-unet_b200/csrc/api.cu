@@ -336,7 +336,7 @@ int launch_tc5t(const RbConvDesc& d, const Tc5tPlan& pl, const void* src0, const
     p.fdTilesM = rb::make_fastdiv(pl.tilesM); p.fdTilesW = rb::make_fastdiv(pl.tilesW);
     p.fdTilesH = rb::make_fastdiv(pl.tilesH); p.fdTilesD = rb::make_fastdiv(pl.tilesD);
     p.splitK = pl.splitK; p.tapsPer = pl.tapsPer; p.fdSplitK = rb::make_fastdiv(pl.splitK); p.ws = ws;
-    p.wsSlice = (long long)d.NB * d.OD * d.OH * d.OW * d.Nout;
+    p.wsSlice = (pl.tiles / pl.tilesM) * 256LL * d.Nout;
     {
         static const int dbg = getenv("RESENC_TC5T_DEBUG") ? atoi(getenv("RESENC_TC5T_DEBUG")) : 0;
         p.debug = dbg & 15;
@@ -935,7 +935,8 @@ size_t rb_conv_gather_workspace(const RbConvDesc* d) {
     if (!d) return 0;
     const ConvDecision r = decide_conv(*d, false);
     const size_t full = (size_t)d->NB * d->OD * d->OH * d->OW * d->Nout * sizeof(float);
-    if (r.choice == CH_TC5T_SPLIT) return full * (size_t)r.plt.splitK;     // one slice per tap split
+    if (r.choice == CH_TC5T_SPLIT)      // one slice per tap split, in tile-local order (tiles padded to 256 voxels)
+        return (size_t)(r.plt.tiles / r.plt.tilesM) * 256 * d->Nout * sizeof(float) * (size_t)r.plt.splitK;
     if (r.choice == CH_MMA && generic_splitk(*d) > 1) return full;
     return 0;
 }
@@ -973,7 +974,9 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
     const size_t need = (size_t)M * d.Nout * sizeof(float);
 
     ConvDecision dec = decide_conv(d, stat_sum != nullptr);
-    if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need * (size_t)dec.plt.splitK)) {
+    const size_t need_split = dec.choice == CH_TC5T_SPLIT
+        ? (size_t)(dec.plt.tiles / dec.plt.tilesM) * 256 * d.Nout * sizeof(float) * (size_t)dec.plt.splitK : 0;
+    if (dec.choice == CH_TC5T_SPLIT && (workspace == nullptr || workspace_bytes < need_split)) {
         // no room for the per-slice workspace: run the same kernel unsplit
         dec.plt.splitK = 1; dec.plt.tapsPer = d.tapD * d.tapH * d.tapW;
         dec.choice = CH_TC5T;
@@ -991,11 +994,13 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
         if (rc) return rc;
         rb::SplitFinishParams f;
         memset(&f, 0, sizeof(f));
-        f.ws = (const float*)workspace; f.sliceStride = (long long)M * d.Nout; f.slices = dec.plt.splitK;
+        f.ws = (const float*)workspace; f.sliceStride = (dec.plt.tiles / dec.plt.tilesM) * 256LL * d.Nout; f.slices = dec.plt.splitK;
         f.S = d.OD * d.OH * d.OW; f.NB = d.NB; f.Nout = d.Nout;
+        f.OW = d.OW; f.OH = d.OH; f.OD = d.OD; f.lw = dec.plt.lw; f.lh = dec.plt.lh; f.ld = dec.plt.ld;
+        f.tilesW = dec.plt.tilesW; f.tilesH = dec.plt.tilesH; f.tilesD = dec.plt.tilesD;
         f.out0 = out0; f.out1 = out1; f.outC0 = d.outC0; f.outC1 = d.outC1; f.outF32 = d.outF32;
         f.stat_sum = stat_sum; f.stat_sq = stat_sq;
-        f.vpw = f.S <= 1024 ? 16 : 64;
+        f.vpw = f.S <= 256 ? 1 : f.S <= 1024 ? 2 : 16;   // >= 256 blocks even for the 4^3 layers (the pass is latency bound)
         f.runsPerSample = (f.S + 8 * f.vpw - 1) / (8 * f.vpw);
         const long long blocks = (long long)d.NB * f.runsPerSample * (d.Nout / 32);
         rb::split_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);

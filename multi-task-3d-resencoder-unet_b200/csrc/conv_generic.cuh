@@ -234,18 +234,21 @@ __global__ void __launch_bounds__(256) gather_finish_kernel(const GConvParams p)
 }
 
 // Finish pass of the tap-split tcgen05 convolution (conv_tc5t.cuh, deep 4^3 / 8^3 / 16^3 layers):
-//   out[m][c] = sum_slices ws[slice][m][c]   (bf16 or fp32 destination, plain stride-1 convolution: voxel m of the output
-//   grid is voxel m of the destination), plus the InstanceNorm statistics sum / sum of squares per (sample, channel)
-//   of the stored values - the statistics the unsplit kernels take in their epilogue.
-// A warp owns 32 consecutive channels (lane = channel: 128-byte rows of the workspace) and VPW consecutive voxels of one
-// sample; the 8 warps of a block cover 8 consecutive voxel runs of the same (sample, channel group), so the statistics
-// are combined in shared memory and cost 64 atomics per block.
+//   out[m][c] = sum_slices ws[slice][tile(m)][column(m)][c]   (bf16 or fp32 destination, plain stride-1 convolution: voxel m
+//   of the output grid is voxel m of the destination), plus the InstanceNorm statistics sum / sum of squares per
+//   (sample, channel) of the stored values - the statistics the unsplit kernels take in their epilogue.
+// A warp owns 32 consecutive channels (lane = channel: 128-byte rows of the workspace) and `vpw` consecutive voxels of
+// one sample, all slice loads of a voxel in flight at once; the 8 warps of a block cover 8 consecutive voxel runs of the
+// same (sample, channel group), so the statistics are combined in shared memory and cost 64 atomics per block.
 struct SplitFinishParams {
-    const float* ws;      // [slices][M][Nout]
+    const float* ws;      // [slices][voxel tiles][256][Nout]
     long long sliceStride;
     int slices;
     int S;                // voxels per sample
     int NB, Nout;
+    int OW, OH, OD;
+    int lw, lh, ld;       // log2 tile box extents; tn = 256 >> (lw + lh + ld) samples per tile
+    int tilesW, tilesH, tilesD;
     void* out0;
     void* out1;
     int outC0, outC1, outF32;
@@ -270,20 +273,37 @@ __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishPara
     const int cdst = first ? c : c - p.outC0;
     const int cpitch = first ? p.outC0 : p.outC1;
     void* const base = first ? p.out0 : p.out1;
+    const int ls = p.lw + p.lh + p.ld;
+    const int tib = nb >> (8 - ls), in = nb & ((256 >> ls) - 1);
     float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
     for (int v = v0; v < v1; ++v) {
-        const size_t m = (size_t)nb * p.S + v;
-        const float* src = p.ws + m * p.Nout + c;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int ow = v % p.OW, t = v / p.OW;
+        const int oh = t % p.OH, od = t / p.OH;
+        const int tiw = ow >> p.lw, tih = oh >> p.lh, tid = od >> p.ld;
+        const int r = (ow & ((1 << p.lw) - 1)) | ((oh & ((1 << p.lh) - 1)) << p.lw) | ((od & ((1 << p.ld) - 1)) << (p.lw + p.lh)) | (in << ls);
+        const size_t tileLin = (((size_t)tib * p.tilesD + tid) * p.tilesH + tih) * p.tilesW + tiw;
+        const float* src = p.ws + (tileLin * 256 + r) * p.Nout + c;
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = 0.f;
         int sl = 0;
-        for (; sl + 4 <= p.slices; sl += 4) {
-            a0 += __ldcs(src + (size_t)sl * p.sliceStride);
-            a1 += __ldcs(src + (size_t)(sl + 1) * p.sliceStride);
-            a2 += __ldcs(src + (size_t)(sl + 2) * p.sliceStride);
-            a3 += __ldcs(src + (size_t)(sl + 3) * p.sliceStride);
+        for (; sl + 8 <= p.slices; sl += 8) {
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __ldcs(src + (size_t)(sl + k) * p.sliceStride);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += x[k];
         }
-        for (; sl < p.slices; ++sl) a0 += __ldcs(src + (size_t)sl * p.sliceStride);
-        const float x = (a0 + a1) + (a2 + a3);
+        {
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = (sl + k < p.slices) ? __ldcs(src + (size_t)(sl + k) * p.sliceStride) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += x[k];
+        }
+        const float x = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        const size_t m = (size_t)nb * p.S + v;
         if (p.outF32) reinterpret_cast<float*>(base)[m * cpitch + cdst] = x;
         else reinterpret_cast<bf16*>(base)[m * cpitch + cdst] = __float2bfloat16_rn(x);
         s1 += x;

@@ -50,7 +50,7 @@ struct Tc5tConvParams {
     int splitK, tapsPer;
     FastDiv fdSplitK;
     float* ws;
-    long long wsSlice;    // elements per workspace slice (= output voxels x Nout)
+    long long wsSlice;    // elements per workspace slice (= voxel tiles x 256 x Nout)
     int debug;   // profiling experiments only (RESENC_TC5T_DEBUG bit mask): 1 skip MMAs, 2 skip TMA loads, 4 skip the epilogue body
 };
 
@@ -304,24 +304,18 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                         s1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
                         s2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
                     } else if (p.splitK > 1) {
-                        // partial tile of one tap slice -> its own workspace slice ws[sk][m][Nout] (m = linear output-grid
-                        // voxel) with plain coalesced stores (lane = channel).  Round 1 added all slices into one buffer
-                        // with red.global: ~145 cycles per instruction under 14-27-fold address contention, 60-70 % of the
-                        // kernel (profiles/r2_deep_probe.txt); split_finish_kernel sums the slices instead.
-                        float* const wsl = p.ws + (size_t)sk * p.wsSlice;
+                        // partial tile of one tap slice -> its own workspace slice, in TILE-LOCAL order
+                        // ws[sk][voxel tile][column][Nout]: one address per column group and a constant stride, straight-line
+                        // coalesced stores (lane = channel).  Round 1 decomposed every column into (n, d, h, w), bounds-checked
+                        // it and added it into ONE buffer with red.global: a dependent 64-bit integer chain + a branch per
+                        // column with a single warp per scheduler (~200 cycles per column, 60-70 % of the kernel,
+                        // profiles/r2_deep_probe.txt).  split_finish_kernel maps voxels back to (tile, column), sums the
+                        // slices and takes the statistics.
+                        const size_t tileLin = (((size_t)tib * p.tilesD + tid) * p.tilesH + tih) * p.tilesW + tiw;
+                        float* dst = p.ws + (size_t)sk * p.wsSlice + (tileLin * TC5T_VOX + cg) * p.Nout + co;
+                        if (rowValid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int r = cg + j;
-                            const int iw = r & (tw - 1);
-                            const int ih = (r >> p.lw) & (th - 1);
-                            const int id = (r >> (p.lw + p.lh)) & (td - 1);
-                            const int in = r >> (p.lw + p.lh + p.ld);
-                            const int ow = (int)tiw * tw + iw, oh = (int)tih * th + ih, od = (int)tid * td + id,
-                                      nb = (int)tib * tn + in;
-                            if (rowValid && ow < p.OW && oh < p.OH && od < p.OD && nb < p.NB) {
-                                const size_t m = (((size_t)nb * p.OD + od) * p.OH + oh) * p.OW + ow;
-                                wsl[m * p.Nout + co] = __uint_as_float(v[j]);
-                            }
+                            for (int j = 0; j < 32; ++j) dst[j * p.Nout] = __uint_as_float(v[j]);
                         }
                     } else if (p.lw >= 5) {
                         // the 32 columns of this group are 32 consecutive voxels of one W row: one address
