@@ -1000,7 +1000,7 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
         f.tilesW = dec.plt.tilesW; f.tilesH = dec.plt.tilesH; f.tilesD = dec.plt.tilesD;
         f.out0 = out0; f.out1 = out1; f.outC0 = d.outC0; f.outC1 = d.outC1; f.outF32 = d.outF32;
         f.stat_sum = stat_sum; f.stat_sq = stat_sq;
-        f.vpw = f.S <= 256 ? 1 : f.S <= 1024 ? 2 : 16;   // >= 256 blocks even for the 4^3 layers (the pass is latency bound)
+        f.vpw = f.S <= 1024 ? 4 : 16;   // a warp moves 4 voxels x 32 channels per instruction; the pass is latency bound
         f.runsPerSample = (f.S + 8 * f.vpw - 1) / (8 * f.vpw);
         const long long blocks = (long long)d.NB * f.runsPerSample * (d.Nout / 32);
         rb::split_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);

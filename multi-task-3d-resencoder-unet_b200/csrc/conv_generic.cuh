@@ -259,6 +259,7 @@ struct SplitFinishParams {
 };
 
 __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishParams p) {
+    // lane = (voxel sub-index lane >> 3, channel quad lane & 7): one warp instruction moves 4 voxels x 32 channels (512 B)
     __shared__ float red[2][8][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cgroups = p.Nout >> 5;
@@ -266,58 +267,66 @@ __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishPara
     const int cgI = b % cgroups; b /= cgroups;
     const int run = b % p.runsPerSample;
     const int nb = b / p.runsPerSample;
-    const int c = cgI * 32 + lane;
-    const int v0 = (run * 8 + warp) * p.vpw;
-    const int v1 = min(p.S, v0 + p.vpw);
+    const int c = cgI * 32 + (lane & 7) * 4;          // first of this lane's 4 channels
+    const int vbeg = (run * 8 + warp) * p.vpw;
+    const int vend = min(p.S, vbeg + p.vpw);
     const bool first = c < p.outC0;
     const int cdst = first ? c : c - p.outC0;
     const int cpitch = first ? p.outC0 : p.outC1;
     void* const base = first ? p.out0 : p.out1;
     const int ls = p.lw + p.lh + p.ld;
     const int tib = nb >> (8 - ls), in = nb & ((256 >> ls) - 1);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 2
-    for (int v = v0; v < v1; ++v) {
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v = vbeg + (lane >> 3); v < vend; v += 4) {
         const int ow = v % p.OW, t = v / p.OW;
         const int oh = t % p.OH, od = t / p.OH;
         const int tiw = ow >> p.lw, tih = oh >> p.lh, tid = od >> p.ld;
         const int r = (ow & ((1 << p.lw) - 1)) | ((oh & ((1 << p.lh) - 1)) << p.lw) | ((od & ((1 << p.ld) - 1)) << (p.lw + p.lh)) | (in << ls);
         const size_t tileLin = (((size_t)tib * p.tilesD + tid) * p.tilesH + tih) * p.tilesW + tiw;
-        const float* src = p.ws + (tileLin * 256 + r) * p.Nout + c;
-        float a[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] = 0.f;
+        const float4* src = reinterpret_cast<const float4*>(p.ws + (tileLin * 256 + r) * p.Nout + c);
+        const size_t ss = (size_t)p.sliceStride >> 2;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
         int sl = 0;
-        for (; sl + 8 <= p.slices; sl += 8) {
-            float x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = __ldcs(src + (size_t)(sl + k) * p.sliceStride);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += x[k];
+        for (; sl + 4 <= p.slices; sl += 4) {
+            const float4 x0 = __ldcs(src + (size_t)sl * ss), x1 = __ldcs(src + (size_t)(sl + 1) * ss);
+            const float4 x2 = __ldcs(src + (size_t)(sl + 2) * ss), x3 = __ldcs(src + (size_t)(sl + 3) * ss);
+            a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+            a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
+            a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
+            a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
         }
-        {
-            float x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = (sl + k < p.slices) ? __ldcs(src + (size_t)(sl + k) * p.sliceStride) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += x[k];
+        for (; sl < p.slices; ++sl) {
+            const float4 x0 = __ldcs(src + (size_t)sl * ss);
+            a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
         }
-        const float x = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        float x[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                      (a0.w + a1.w) + (a2.w + a3.w)};
         const size_t m = (size_t)nb * p.S + v;
-        if (p.outF32) reinterpret_cast<float*>(base)[m * cpitch + cdst] = x;
-        else reinterpret_cast<bf16*>(base)[m * cpitch + cdst] = __float2bfloat16_rn(x);
-        s1 += x;
-        s2 = fmaf(x, x, s2);
+        if (p.outF32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + m * cpitch + cdst) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(base) + m * cpitch + cdst) =
+                make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1[k] += x[k]; s2[k] = fmaf(x[k], x[k], s2[k]); }
     }
     if (p.stat_sum != nullptr) {
-        red[0][warp][lane] = s1;
-        red[1][warp][lane] = s2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);  s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 8);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16); s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { red[0][warp][lane * 4 + k] = s1[k]; red[1][warp][lane * 4 + k] = s2[k]; }
+        }
         __syncthreads();
         if (warp < 2) {
             float a = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) a += red[warp][w][lane];
-            atomicAdd((warp == 0 ? p.stat_sum : p.stat_sq) + (size_t)nb * p.Nout + c, a);
+            atomicAdd((warp == 0 ? p.stat_sum : p.stat_sq) + (size_t)nb * p.Nout + cgI * 32 + lane, a);
         }
     }
 }
