@@ -366,6 +366,7 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
     if rank == 0:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev_merge = torch.cuda.Event(enable_timing=True)
     l1 = rb._lib.launch_count()
     barrier()
     ev[0].record()
@@ -374,6 +375,7 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
     blender = sw.sweep(volume, dvol=dvol)
     ev[2].record()
     own = inf.merge_slabs(blender, zs, rank, world) if world > 1 else (0, V)
+    ev_merge.record()
     out = blender.finalize(*own) if own[1] > own[0] else {}
     ev[3].record()
     for t, v in out.items():
@@ -383,7 +385,7 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
     clocks = sampler.stop() if rank == 0 else None
     launches = rb._lib.launch_count() - l1
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]               # h2d, sweep, merge+finalise, d2h
-    tt = torch.tensor([ms[1] + ms[2], sum(ms), ms[0], ms[1], ms[2], ms[3]], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms[1] + ms[2], sum(ms), ms[0], ms[1], ms[2], ms[3], ev[2].elapsed_time(ev_merge)], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(len(positions)), float(sw.h2d_bytes), float(sum(v.numel() * v.element_size() for v in out.values()))],
                        dtype=torch.float64, device=dev)
     if world > 1:
@@ -408,7 +410,8 @@ def run_infer(args, rb, model, dev, rank, world, dist, cpu_arm=None):
         "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic",
         "patch_voxels_per_s": n_patches * P ** 3 / (ms_dev * 1e-3), "patches": n_patches, "ms_total": ms_dev,
         "ms_per_patch": float(tt[3]) / max(1.0, n_patches / world),
-        "ms": {"h2d_volume": float(tt[2]), "sweep": float(tt[3]), "merge_finalize_cast": float(tt[4]), "d2h_result": float(tt[5])},
+        "ms": {"h2d_volume": float(tt[2]), "sweep": float(tt[3]), "merge_finalize_cast": float(tt[4]), "d2h_result": float(tt[5]),
+               "slab_merge_only": float(tt[6])},
         "config": {"workload": f"sliding-window inference, synthetic {V}^3 uint8 volume, {P}^3 patches, overlap "
                                f"{args.infer_overlap} ({len(zs)}x{len(ys)}x{len(xs)} = {n_total} patches), {args.infer_weight} blend, "
                                f"{B} patches per forward, sheet(1) + normals(3), per-patch standardisation on device",
