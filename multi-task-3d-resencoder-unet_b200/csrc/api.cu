@@ -437,17 +437,20 @@ int launch_slab_one(const RbConvDesc& d, const SlabPlan& pl, const void* src, in
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(rb::slab_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const void* fns[6] = {(const void*)rb::slab_conv_kernel<0, 256>, (const void*)rb::slab_conv_kernel<1, 256>,
+                              (const void*)rb::slab_conv_kernel<2, 256>, (const void*)rb::slab_conv_kernel<0, 192>,
+                              (const void*)rb::slab_conv_kernel<1, 192>, (const void*)rb::slab_conv_kernel<2, 192>};
+        for (int i = 0; i < 6 && attr_err == cudaSuccess; ++i)
+            attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(slab): %s", cudaGetErrorString(attr_err));
     const long long grid = pl.items < num_sms() ? pl.items : num_sms();
-    if (!d.outF32) rb::slab_conv_kernel<0><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
-    else if (!accumulate) rb::slab_conv_kernel<1><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
-    else rb::slab_conv_kernel<2><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p);
+    const int mode = !d.outF32 ? 0 : !accumulate ? 1 : 2;
+    const bool n192 = pl.R * d.IW == 192;
+#define RB_SLAB_LAUNCH(M, N) rb::slab_conv_kernel<M, N><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p)
+    if (!n192) { if (mode == 0) RB_SLAB_LAUNCH(0, 256); else if (mode == 1) RB_SLAB_LAUNCH(1, 256); else RB_SLAB_LAUNCH(2, 256); }
+    else { if (mode == 0) RB_SLAB_LAUNCH(0, 192); else if (mode == 1) RB_SLAB_LAUNCH(1, 192); else RB_SLAB_LAUNCH(2, 192); }
+#undef RB_SLAB_LAUNCH
     return check_launch("slab_conv_kernel");
 }
 
@@ -1001,9 +1004,10 @@ int rb_conv_gather(const RbConvDesc* dp, const void* src0, const void* src1, con
         f.out0 = out0; f.out1 = out1; f.outC0 = d.outC0; f.outC1 = d.outC1; f.outF32 = d.outF32;
         f.stat_sum = stat_sum; f.stat_sq = stat_sq;
         f.vpw = f.S <= 1024 ? 4 : 16;   // a warp moves 4 voxels x 32 channels per instruction; the pass is latency bound
-        f.runsPerSample = (f.S + 8 * f.vpw - 1) / (8 * f.vpw);
+        const int nw = f.S <= 256 ? 2 : 8;       // warps per block
+        f.runsPerSample = (f.S + nw * f.vpw - 1) / (nw * f.vpw);
         const long long blocks = (long long)d.NB * f.runsPerSample * (d.Nout / 32);
-        rb::split_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);
+        rb::split_finish_kernel<<<(unsigned)blocks, 32 * nw, 0, st>>>(f);
         return check_launch("split_finish_kernel");
     }
     if (stat_sum) return fail(RB_ERR_UNSUPPORTED, "conv: fused statistics need the tcgen05 path");

@@ -255,20 +255,21 @@ struct SplitFinishParams {
     float* stat_sum;      // [NB][Nout] or null
     float* stat_sq;
     int vpw;              // voxels per warp
-    int runsPerSample;    // ceil(S / (8 * vpw))
+    int runsPerSample;    // ceil(S / (warps per block * vpw))
 };
 
 __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishParams p) {
     // lane = (voxel sub-index lane >> 3, channel quad lane & 7): one warp instruction moves 4 voxels x 32 channels (512 B)
     __shared__ float red[2][8][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = blockDim.x >> 5;                   // 8 warps, or 2 for the tiny 4^3 planes (more blocks: latency bound)
     const int cgroups = p.Nout >> 5;
     int b = blockIdx.x;
     const int cgI = b % cgroups; b /= cgroups;
     const int run = b % p.runsPerSample;
     const int nb = b / p.runsPerSample;
     const int c = cgI * 32 + (lane & 7) * 4;          // first of this lane's 4 channels
-    const int vbeg = (run * 8 + warp) * p.vpw;
+    const int vbeg = (run * nw + warp) * p.vpw;
     const int vend = min(p.S, vbeg + p.vpw);
     const bool first = c < p.outC0;
     const int cdst = first ? c : c - p.outC0;
@@ -324,8 +325,7 @@ __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishPara
         __syncthreads();
         if (warp < 2) {
             float a = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) a += red[warp][w][lane];
+            for (int w = 0; w < nw; ++w) a += red[warp][w][lane];
             atomicAdd((warp == 0 ? p.stat_sum : p.stat_sq) + (size_t)nb * p.Nout + cgI * 32 + lane, a);
         }
     }

@@ -60,8 +60,8 @@ static constexpr int SLAB_OBYTES = 2 * SLAB_SGROUP * 4;   // 2 column groups x 2
 // voxel a + i receives column a + i + Q - 1 of this warp's partial sums (zero where that column is W padding), written
 // as [channel = lane][voxel] rows with 16-byte stores into side buffer Q/2 of staging set (cnt & 1).  Even chunks
 // (set 0) are consumed by the centre warp of lane quarter 1, odd chunks (set 1) by the one of quarter 3.
-template <int Q>
-__device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, int lane, int W, int ncols, uint32_t sfull0,
+template <int Q, int NCOLS>
+__device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, int lane, int Wm, uint32_t sfull0,
                                             uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait, const float* yrow) {
     uint32_t v0[32], v1[32], ex[1];
     ex[0] = 0u;
@@ -76,7 +76,7 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
     tmem_ld_32x32b_x32(t_addr + a, v0);
     tmem_ld_32x32b_x32(t_addr + a + 32, v1);
     if (Q == 0 && a > 0) tmem_ld_32x32b_x1(t_addr + a - 1, ex);
-    if (Q == 2 && a + 64 < ncols) tmem_ld_32x32b_x1(t_addr + a + 64, ex);
+    if (Q == 2 && a + 64 < NCOLS) tmem_ld_32x32b_x1(t_addr + a + 64, ex);
     tmem_ld_wait();
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -95,10 +95,15 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
                     const int c = i + Q - 1;   // column relative to a
                     const uint32_t x = c < 0 ? ex[0] : c < 32 ? v0[c & 31] : c < 64 ? v1[c & 31] : ex[0];
                     f[k] = __uint_as_float(x);
-                    // only the first / last voxel of a W row can be padding, and rows start at multiples of 32 (W % 32 == 0):
-                    // the modulo (W need not be a power of two) is evaluated for two candidate columns per call only
-                    if (Q == 0 && (i & 31) == 0 && ((a + i) % W) == 0) f[k] = 0.f;
-                    if (Q == 2 && (i & 31) == 31 && ((a + i) % W) == W - 1) f[k] = 0.f;
+                    // only the first / last voxel of a W row can be padding, and rows start at multiples of 32 (W % 32 == 0).
+                    // NCOLS == 256: W is a power of two (mask Wm = W - 1); NCOLS == 192: W = 96, two rows per tile
+                    if (NCOLS == 256) {
+                        if (Q == 0 && (i & 31) == 0 && ((a + i) & Wm) == 0) f[k] = 0.f;
+                        if (Q == 2 && (i & 31) == 31 && ((a + i) & Wm) == Wm) f[k] = 0.f;
+                    } else {
+                        if (Q == 0 && (i & 31) == 0 && ((a + i) % 96) == 0) f[k] = 0.f;
+                        if (Q == 2 && (i & 31) == 31 && ((a + i) % 96) == 95) f[k] = 0.f;
+                    }
                     if (yrow != nullptr && (i >> 5) == (Q == 0 ? 0 : 1)) f[k] += y[i & 31];
                 }
                 *reinterpret_cast<float4*>(dst + vec * 4) = make_float4(f[0], f[1], f[2], f[3]);
@@ -111,7 +116,8 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
 }
 
 // MODE: 0 = bf16 destination, 1 = fp32 destination, 2 = fp32 destination, out += result
-template <int MODE>
+// NCOLS: accumulator columns of a tile = R * W (256 for W in {32, 64, 128}, 192 for W = 96)
+template <int MODE, int NCOLS = 256>
 __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
         if (dbgT && lane == 0) { g_dbg[0] = (unsigned long long)tW; g_dbg[1] = (unsigned long long)(clock64() - tA); }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)(p.R * p.W), 0, 0);   // N = 256, or 192 for W = 96
+        const uint32_t idesc = make_idesc_bf16(128, NCOLS, 0, 0);
         const uint32_t lay = swizzle_layout_code(64);
         const uint32_t rowBytes = (uint32_t)p.W * 64u;
         mbar_wait(w_bar, 0u, DEVERR_WAIT_FULL, err_flag);
@@ -275,7 +281,8 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
         // channel), accumulates the statistics and stores.  Two centre quarters = two warp schedulers for the store work.
         const int q = warp & 3;
         const int g = warp >= 6 ? 1 : 0;   // warps 2..5 / 6..9
-        const int ncols = p.R * p.W;           // valid accumulator columns of a tile
+        const int Wm = p.W - 1;
+        constexpr int ncols = NCOLS;           // valid accumulator columns of a tile
         float* const stg = O + g * SLAB_SGROUP;
         const uint32_t sfull0 = bar_base + 104u + 32u * g, sempty0 = sfull0 + 16u;
         uint32_t cnt = 0;
@@ -296,18 +303,18 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                 const size_t voxT = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;   // voxel of tile column 0
                 if (p.debug & 4) {
                 } else if (q == 0) {
-                    for (int a = g * 128; a < min(g * 128 + 128, ncols); a += 64)
-                        slab_side64<0>(t_addr, a, stg, lane, p.W, ncols, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                    for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64)
+                        slab_side64<0, NCOLS>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
                                        MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
                 } else if (q == 2) {
-                    for (int a = g * 128; a < min(g * 128 + 128, ncols); a += 64)
-                        slab_side64<2>(t_addr, a, stg, lane, p.W, ncols, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                    for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64)
+                        slab_side64<2, NCOLS>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
                                        MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
                 } else {
                     // centre warp of lane quarter 1 (even chunks, staging set 0) or 3 (odd chunks, set 1): both quarters hold
                     // the kw = 1 partial sums because the centre weights sit in M rows 32..63 and again in rows 96..127
                     const uint32_t b = q == 1 ? 0u : 1u;
-                    for (int a = g * 128; a < min(g * 128 + 128, ncols); a += 64) {
+                    for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64) {
                         uint32_t va[16], vb[16];
                         const long long l0 = dbgT ? clock64() : 0;
                         tmem_ld_32x32b_x16(t_addr + a + (int)b * SLAB_CHUNK, va);
