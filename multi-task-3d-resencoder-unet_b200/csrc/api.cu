@@ -659,6 +659,10 @@ Tw5Plan plan_tw5(const RbWgradDesc& d) {
     const int taps = pl.swap ? pl.tapGroups : taps_all;
     const long long base_items = (long long)pl.aTiles * pl.bTiles * taps;
     long long splits = d.splits > 0 ? d.splits : (3LL * num_sms() + base_items - 1) / base_items;
+    // a wave or more of (tile, tap) items already (the 512-channel layers: 216 / 432 items): no voxel split, so that every
+    // element has one writer - plain stores, no zero-fill, no red.global (enc_s4 wgrad: 60 us at 18 % of peak with 3 splits)
+    static const bool no_single = getenv("RESENC_WGRAD_ALWAYS_SPLIT") != nullptr;
+    if (d.splits <= 0 && !no_single && !pl.swap && base_items >= num_sms()) splits = 1;
     long long maxs = (best + 3) / 4;      // at least 4 chunks (256 voxels) per item
     if (maxs < 1) maxs = 1;
     if (splits > maxs) splits = maxs;
