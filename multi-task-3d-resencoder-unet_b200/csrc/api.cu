@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/resenc_b200.h"
 #include "common.cuh"
@@ -76,6 +77,61 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// ---- CUtensorMap cache ("the library allocates nothing persistent except cached CUtensorMaps keyed by
+// (pointer, shape)").  A training step encodes ~2000 descriptors; the caching allocator hands the same buffers to the
+// same layers step after step, so after the first step every descriptor is a table hit (~0.1 us) instead of a driver
+// call (~1 us).  Only matters for eager launches - a CUDA-graph replay carries its descriptors as kernel parameters.
+struct TmapKey {
+    uint64_t ptr, dims[5], strides[4];
+    uint32_t box[5], estr[5], rank, dtype, swizzle, l2;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+
+EncodeTiledFn g_real_encode = nullptr;
+std::mutex g_tmap_mutex;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>* g_tmap_cache = nullptr;
+std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+
+CUresult encode_cached(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                       const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                       CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+    static const bool off = getenv("RESENC_NO_TMAP_CACHE") != nullptr;
+    if (off || rank > 5 || il != CU_TENSOR_MAP_INTERLEAVE_NONE || oob != CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        return g_real_encode(out, dt, rank, ptr, dims, strides, box, estr, il, sw, l2, oob);
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.ptr = (uint64_t)(uintptr_t)ptr; k.rank = rank; k.dtype = (uint32_t)dt; k.swizzle = (uint32_t)sw; k.l2 = (uint32_t)l2;
+    for (cuuint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.estr[i] = estr[i]; }
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+    {
+        std::lock_guard<std::mutex> lock(g_tmap_mutex);
+        if (!g_tmap_cache) g_tmap_cache = new std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>();
+        auto it = g_tmap_cache->find(k);
+        if (it != g_tmap_cache->end()) {
+            memcpy(out, &it->second, sizeof(CUtensorMap));
+            g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+            return CUDA_SUCCESS;
+        }
+    }
+    CUresult r = g_real_encode(out, dt, rank, ptr, dims, strides, box, estr, il, sw, l2, oob);
+    if (r == CUDA_SUCCESS) {
+        std::lock_guard<std::mutex> lock(g_tmap_mutex);
+        if (g_tmap_cache->size() > 32768) g_tmap_cache->clear();      // bounded: 8 MB
+        g_tmap_cache->emplace(k, *out);
+        g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+    }
+    return r;
+}
+
 EncodeTiledFn encode_tiled_fn() {
     // cuTensorMapEncodeTiled is a driver call: the calling thread (e.g. an autograd worker that has not touched the
     // runtime yet) must have the primary context bound, which any runtime call does
@@ -92,8 +148,9 @@ EncodeTiledFn encode_tiled_fn() {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(p);
+        g_real_encode = fn;
     });
-    return fn;
+    return fn ? encode_cached : nullptr;
 }
 
 CUtensorMapSwizzle swizzle_for(int kw) {

@@ -205,6 +205,9 @@ def _make_desc(src0, src1, out0, out1, *, in_dims, taps, off, istr, out_grid, no
     return d
 
 
+_DESC_CACHE = {}
+
+
 def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode=0,
                    ostr=(1, 1, 1), ooff=(0, 0, 0), full=None, ps=None, psC=0, impl=None, stats=None, want_stats=False,
                    algo_flops=None):
@@ -212,16 +215,28 @@ def _launch_gather(src0, src1, wpk, out0, out1, *, in_dims, taps, off, istr, out
     stats=(sum, sumsq) fp32 [NB, Nout] are filled by the tcgen05 epilogue; with want_stats=True they are
     allocated here when (and only when) the library will run the tcgen05 kernel, and returned (else None)."""
     lib = L.load()
-    d = _make_desc(src0, src1, out0, out1, in_dims=in_dims, taps=taps, off=off, istr=istr, out_grid=out_grid, nout=nout,
-                   mode=mode, ostr=ostr, ooff=ooff, full=full, ps=ps, psC=psC, impl=impl)
-    if want_stats and stats is None:
+    # descriptor, kernel choice and workspace size depend on shapes only: built once per distinct launch geometry (the
+    # ~40 ctypes field writes + two library queries cost ~20 us per launch in the eager path otherwise)
+    key = (tuple(src0.shape), None if src1 is None else tuple(src1.shape), tuple(out0.shape), out0.dtype,
+           None if out1 is None else tuple(out1.shape), tuple(in_dims), tuple(taps), tuple(off), tuple(istr), tuple(out_grid), nout,
+           mode, tuple(ostr), tuple(ooff), None if full is None else tuple(full), None if ps is None else tuple(ps), psC, impl,
+           L.default_impl())
+    hit = _DESC_CACHE.get(key)
+    if hit is None:
+        d = _make_desc(src0, src1, out0, out1, in_dims=in_dims, taps=taps, off=off, istr=istr, out_grid=out_grid, nout=nout,
+                       mode=mode, ostr=ostr, ooff=ooff, full=full, ps=ps, psC=psC, impl=impl)
         plan = lib.rb_conv_gather_plan(C.byref(d))
+        ws_bytes = lib.rb_conv_gather_workspace(C.byref(d)) if plan >= 0 else 0
+        if len(_DESC_CACHE) > 4096:
+            _DESC_CACHE.clear()
+        hit = _DESC_CACHE[key] = (d, plan, ws_bytes)
+    d, plan, ws_bytes = hit
+    if want_stats and stats is None:
         if plan < 0:
             L.check(plan, "rb_conv_gather_plan")
         if plan in (L.IMPL_TCGEN05, L.IMPL_TCGEN05_SLAB, L.IMPL_TCGEN05_SPLITK):
             st = torch.zeros((2, d.NB, nout), dtype=torch.float32, device=src0.device)
             stats = (st[0], st[1])
-    ws_bytes = lib.rb_conv_gather_workspace(C.byref(d))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=src0.device) if ws_bytes else None
     ssum, ssq = (None, None) if stats is None else stats
     # `algo_flops`: callers whose operand carries structural zeros (the merged strided data gradient) pass the
