@@ -115,8 +115,23 @@ def check(rc: int, what: str):
         raise ResencLibraryError(f"{what} failed ({rc}): {last_error()}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """cudaStream_t of torch's current stream on `device` (default: the current device).  `torch.cuda.current_stream()`
+    builds a Python Stream object per call (~4 us, ~900 calls per eager training step); the raw accessor is a plain C call."""
+    if _raw_stream is None:
+        return torch.cuda.current_stream(device).cuda_stream
+    if device is None:
+        idx = torch._C._cuda_getDevice()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        idx = torch.device(device).index
+        if idx is None:
+            idx = torch._C._cuda_getDevice()
+    return _raw_stream(idx)
 
 
 def ptr(t):
