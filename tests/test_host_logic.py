@@ -2,6 +2,7 @@
 surface (state_dict keys, constructor errors) and the C-ABI library's exports."""
 import ctypes
 import hashlib
+import importlib
 import json
 import os
 import re
@@ -594,3 +595,25 @@ def test_transposed_conv_formulations_property(rb):
         assert float((dx - x.grad).norm()) <= 1e-5 * float(x.grad.norm()) + 1e-6
 
     check()
+
+
+def test_gradient_buckets_skip_the_never_used_heads_of_the_real_network(rb):
+    """the deep-supervision heads `task_decoders.<t>.seg_layers[:-1]` never receive a gradient
+    (builders/decoder.py:128-131).  They are known up front, sit in no bucket and keep .grad None, so the buckets that
+    become ready first in backward (the decoders') can launch their all-reduce during backward."""
+    par = importlib.import_module(rb._pkg.__name__ + ".parallel")
+    tasks = {"sheet": {"channels": 1, "activation": "sigmoid"}, "normals": {"channels": 3, "activation": "none"}}
+    model = quiet_build(rb.NetworkFromConfig, make_mgr([128, 128, 128], tasks, batch=2))
+    unused = par.never_used_parameters(model)
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert len(unused) == 16 and all(".seg_layers." in names[id(p)] and not names[id(p)].split(".seg_layers.")[1].startswith("4.")
+                                     for p in unused)
+    buckets = par.GradientBuckets(model, bucket_bytes=64 << 20)
+    bucketed = {id(p) for b in buckets.buckets for p in b["params"]}
+    assert not (bucketed & {id(p) for p in unused})
+    assert len(bucketed) + 16 == len(list(model.parameters()))
+    assert all(p.grad is None for p in model.parameters())
+    # fp32 on the wire: 4 bytes per bucketed parameter; bf16: 2
+    n = sum(p.numel() for p in model.parameters()) - sum(p.numel() for p in unused)
+    assert buckets.bytes_per_step == 4 * n
+    assert par.GradientBuckets(model, comm_dtype=torch.bfloat16).bytes_per_step == 2 * n
