@@ -428,7 +428,7 @@ SlabPlan plan_slab(const RbConvDesc& d) {
     if (d.OD != d.ID || d.OH != d.IH || d.OW != d.IW || d.FD != d.OD || d.FH != d.OH || d.FW != d.OW) return pl;
     if (d.srcC0 != 32 || (d.nsrc == 2 && d.srcC1 != 32)) return pl;
     if (!((d.Nout == 32 && d.outC0 == 32 && d.outC1 == 0) || (d.Nout == 64 && d.outC0 == 32 && d.outC1 == 32))) return pl;
-    if (d.nsrc == 2 && !d.outF32) return pl;   // the second source accumulates into an fp32 destination
+    if (d.nsrc == 2 && !d.outF32) return pl;   // the second source accumulates into an fp32 / fp16 destination
     // a tile = R full rows of W voxels on the N side of the MMA: N = R * W must be a multiple of 64 (two warp groups x
     // 64-column hand-offs) and <= 256, rows must start at multiples of 32 columns; W = 192 (R = 1) needs four 36 KB
     // planes + 72 KB of weights + staging > 227 KB of shared memory and stays on the h-major gather kernel
@@ -494,19 +494,25 @@ int launch_slab_one(const RbConvDesc& d, const SlabPlan& pl, const void* src, in
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        const void* fns[6] = {(const void*)rb::slab_conv_kernel<0, 256>, (const void*)rb::slab_conv_kernel<1, 256>,
-                              (const void*)rb::slab_conv_kernel<2, 256>, (const void*)rb::slab_conv_kernel<0, 192>,
-                              (const void*)rb::slab_conv_kernel<1, 192>, (const void*)rb::slab_conv_kernel<2, 192>};
-        for (int i = 0; i < 6 && attr_err == cudaSuccess; ++i)
+        const void* fns[10] = {(const void*)rb::slab_conv_kernel<0, 256>, (const void*)rb::slab_conv_kernel<1, 256>,
+                               (const void*)rb::slab_conv_kernel<2, 256>, (const void*)rb::slab_conv_kernel<3, 256>,
+                               (const void*)rb::slab_conv_kernel<4, 256>, (const void*)rb::slab_conv_kernel<0, 192>,
+                               (const void*)rb::slab_conv_kernel<1, 192>, (const void*)rb::slab_conv_kernel<2, 192>,
+                               (const void*)rb::slab_conv_kernel<3, 192>, (const void*)rb::slab_conv_kernel<4, 192>};
+        for (int i = 0; i < 10 && attr_err == cudaSuccess; ++i)
             attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(slab): %s", cudaGetErrorString(attr_err));
     const long long grid = pl.items < num_sms() ? pl.items : num_sms();
-    const int mode = !d.outF32 ? 0 : !accumulate ? 1 : 2;
+    // destination element type (RbConvDesc.outF32): 0 bf16, 1 fp32, 2 fp16; the second source of a virtual concat accumulates
+    const int mode = d.outF32 == 0 ? 0 : d.outF32 == 1 ? (accumulate ? 2 : 1) : (accumulate ? 4 : 3);
     const bool n192 = pl.R * d.IW == 192;
 #define RB_SLAB_LAUNCH(M, N) rb::slab_conv_kernel<M, N><<<(int)grid, rb::SLAB_THREADS, pl.smem, st>>>(p)
-    if (!n192) { if (mode == 0) RB_SLAB_LAUNCH(0, 256); else if (mode == 1) RB_SLAB_LAUNCH(1, 256); else RB_SLAB_LAUNCH(2, 256); }
-    else { if (mode == 0) RB_SLAB_LAUNCH(0, 192); else if (mode == 1) RB_SLAB_LAUNCH(1, 192); else RB_SLAB_LAUNCH(2, 192); }
+#define RB_SLAB_MODES(N) \
+    switch (mode) { case 0: RB_SLAB_LAUNCH(0, N); break; case 1: RB_SLAB_LAUNCH(1, N); break; case 2: RB_SLAB_LAUNCH(2, N); break; \
+                    case 3: RB_SLAB_LAUNCH(3, N); break; default: RB_SLAB_LAUNCH(4, N); break; }
+    if (!n192) { RB_SLAB_MODES(256) } else { RB_SLAB_MODES(192) }
+#undef RB_SLAB_MODES
 #undef RB_SLAB_LAUNCH
     return check_launch("slab_conv_kernel");
 }
@@ -539,6 +545,7 @@ int validate_conv(const RbConvDesc& d) {
         return fail(RB_ERR_INVALID, "conv: strides must be >= 1");
     if (d.outC0 <= 0 || d.outC0 % 8 != 0 || d.outC1 < 0 || d.outC1 % 8 != 0)
         return fail(RB_ERR_INVALID, "conv: destination channels must be multiples of 8");
+    if (d.outF32 < 0 || d.outF32 > 2) return fail(RB_ERR_INVALID, "conv: outF32 must be 0 (bf16), 1 (fp32) or 2 (fp16)");
     if (d.mode == 0) {
         if (d.Nout != d.outC0 + d.outC1) return fail(RB_ERR_INVALID, "conv: Nout != outC0 + outC1");
         if ((long long)(d.OD - 1) * d.ostrD + d.ooffD >= d.FD || (long long)(d.OH - 1) * d.ostrH + d.ooffH >= d.FH ||
@@ -1157,7 +1164,7 @@ int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const vo
     cudaStream_t st = (cudaStream_t)stream;
     rb::ReduceParams p;
     p.y = y; p.dz = (const rb::bf16*)dz; p.z = (const rb::bf16*)z; p.out = out; p.sgnA = sign_scale; p.sgnB = sign_shift;
-    p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind; p.yF32 = y_f32 ? 1 : 0;
+    p.S = S; p.C = C; p.W = W; p.perW = perW; p.slope = slope; p.kind = kind; p.yF32 = y_f32;
     const int cg = C / 8;
     const int rows = 256 / cg > 0 ? 256 / cg : 1;
     int gx;
@@ -1204,7 +1211,7 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
     if (!y || !z || !scale || !shift) return fail(RB_ERR_INVALID, "norm_act_fwd: null pointer");
     int rc = check_apply_shape("norm_act_fwd", NB, S, C, W, perW);
     if (rc) return rc;
-    rb::ApplyParams p{y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0};
+    rb::ApplyParams p{y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope, y_f32};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
     rb::norm_act_fwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
@@ -1219,7 +1226,7 @@ int rb_norm_act_bwd(const void* dz, const void* z, const float* sign_scale, cons
     int rc = check_apply_shape("norm_act_bwd", NB, S, C, W, perW);
     if (rc) return rc;
     rb::ApplyBwdParams p{(const rb::bf16*)dz, (const rb::bf16*)z, y, (rb::bf16*)dy, (rb::bf16*)dres,
-                         k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32 ? 1 : 0, sign_scale, sign_shift};
+                         k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32, sign_scale, sign_shift};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
     rb::norm_act_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);

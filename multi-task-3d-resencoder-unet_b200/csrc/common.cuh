@@ -233,6 +233,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+// fp16 with saturation (the pre-norm conv outputs can be stored as fp16: 3 more mantissa bits than bf16, half the bytes of
+// fp32; cvt.satfinite clamps to +-65504 instead of producing inf).  out mode convention of the conv epilogues:
+// 0 = bf16, 1 = fp32, 2 = fp16.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool f16) { return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ unsigned short cvt16(float x, bool f16) {
+    if (f16) {
+        unsigned short h;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+        return h;
+    }
+    return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float f16lo(uint32_t v) {
+    float f;
+    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo; }" : "=f"(f) : "r"(v));
+    return f;
+}
+__device__ __forceinline__ float f16hi(uint32_t v) {
+    float f;
+    asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, hi; }" : "=f"(f) : "r"(v));
+    return f;
+}
+
 // fp32 x4 reduction into global memory (16-byte aligned), one L2 operation per lane.
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

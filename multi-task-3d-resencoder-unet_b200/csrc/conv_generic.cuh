@@ -21,7 +21,7 @@ struct GConvParams {
     void* out0;
     void* out1;
     int outC0, outC1, psC, psD, psH, psW;
-    int outF32;  // destinations are fp32
+    int outF32;  // destination element type: 0 bf16, 1 fp32, 2 fp16
     int splitK;  // > 1: blockIdx.z takes a contiguous slice of the (tap, k-chunk) loop and adds fp32
     float* ws;   //      partials into ws[m][Nout] (zeroed by the host); gather_finish_kernel stores
 };
@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(GC_THREADS) gather_conv_mma_kernel(const GConv
                 const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
                 void* base = (ch < p.outC0) ? p.out0 : p.out1;
                 const size_t eoff = (ch < p.outC0) ? vox * p.outC0 + ch : vox * p.outC1 + (ch - p.outC0);
-                if (p.outF32)
+                if (p.outF32 == 1)
                     *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + eoff) =
                         make_float2(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
                 else
                     *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(base) + eoff) =
-                        pack_bf16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+                        pack16(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1], p.outF32 == 2);
             }
         }
     }
@@ -226,10 +226,10 @@ __global__ void __launch_bounds__(256) gather_finish_kernel(const GConvParams p)
         const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
         void* base = (ch < p.outC0) ? p.out0 : p.out1;
         const size_t eoff = (ch < p.outC0) ? vox * p.outC0 + ch : vox * p.outC1 + (ch - p.outC0);
-        if (p.outF32)
+        if (p.outF32 == 1)
             *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + eoff) = v;
         else
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(base) + eoff) = pack_bf16(v.x, v.y);
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(base) + eoff) = pack16(v.x, v.y, p.outF32 == 2);
     }
 }
 
@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(256) split_finish_kernel(const SplitFinishPara
         float x[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
                       (a0.w + a1.w) + (a2.w + a3.w)};
         const size_t m = (size_t)nb * p.S + v;
-        if (p.outF32) {
+        if (p.outF32 == 1) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + m * cpitch + cdst) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
             *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(base) + m * cpitch + cdst) =
-                make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+                make_uint2(pack16(x[0], x[1], p.outF32 == 2), pack16(x[2], x[3], p.outF32 == 2));
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) { s1[k] += x[k]; s2[k] = fmaf(x[k], x[k], s2[k]); }

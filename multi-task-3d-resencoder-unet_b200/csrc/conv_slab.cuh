@@ -60,18 +60,25 @@ static constexpr int SLAB_OBYTES = 2 * SLAB_SGROUP * 4;   // 2 column groups x 2
 // voxel a + i receives column a + i + Q - 1 of this warp's partial sums (zero where that column is W padding), written
 // as [channel = lane][voxel] rows with 16-byte stores into side buffer Q/2 of staging set (cnt & 1).  Even chunks
 // (set 0) are consumed by the centre warp of lane quarter 1, odd chunks (set 1) by the one of quarter 3.
-template <int Q, int NCOLS>
+template <int Q, int NCOLS, bool YH>
 __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, int lane, int Wm, uint32_t sfull0,
-                                            uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait, const float* yrow) {
+                                            uint32_t sempty0, uint32_t& cnt, uint32_t err_flag, bool skip, long long* tWait, const void* yrow) {
     uint32_t v0[32], v1[32], ex[1];
     ex[0] = 0u;
-    // accumulate mode (second source of a virtual concat): this side warp also adds the existing fp32 output of half of
+    // accumulate mode (second source of a virtual concat): this side warp also adds the existing fp32 / fp16 (YH) output of half of
     // its 64 voxels (Q = 0: the first 32, Q = 2: the last 32) - the loads overlap the TMEM loads, and the side warps
     // have the slack the centre warps lack
     float y[32];
     if (yrow != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = __ldcs(yrow + (size_t)((Q == 0 ? 0 : 32) + i) * 32);
+        for (int i = 0; i < 32; ++i) {
+            if (YH) {
+                const unsigned short hv = __ldcs(reinterpret_cast<const unsigned short*>(yrow) + (size_t)((Q == 0 ? 0 : 32) + i) * 32);
+                y[i] = f16lo((uint32_t)hv);
+            } else {
+                y[i] = __ldcs(reinterpret_cast<const float*>(yrow) + (size_t)((Q == 0 ? 0 : 32) + i) * 32);
+            }
+        }
     }
     tmem_ld_32x32b_x32(t_addr + a, v0);
     tmem_ld_32x32b_x32(t_addr + a + 32, v1);
@@ -115,7 +122,8 @@ __device__ __forceinline__ void slab_side64(uint32_t t_addr, int a, float* stg, 
     }
 }
 
-// MODE: 0 = bf16 destination, 1 = fp32 destination, 2 = fp32 destination, out += result
+// MODE: 0 = bf16 destination, 1 = fp32 destination, 2 = fp32 destination, out += result,
+//       3 = fp16 destination (saturating), 4 = fp16 destination, out += result
 // NCOLS: accumulator columns of a tile = R * W (256 for W in {32, 64, 128}, 192 for W = 96)
 template <int MODE, int NCOLS = 256>
 __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid_constant__ SlabConvParams p) {
@@ -304,12 +312,14 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                 if (p.debug & 4) {
                 } else if (q == 0) {
                     for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64)
-                        slab_side64<0, NCOLS>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
-                                       MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
+                        slab_side64<0, NCOLS, MODE == 4>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                                       MODE == 2 ? (const void*)(reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane) :
+                                       MODE == 4 ? (const void*)(reinterpret_cast<const unsigned short*>(p.out) + (voxT + a) * 32 + lane) : nullptr);
                 } else if (q == 2) {
                     for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64)
-                        slab_side64<2, NCOLS>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
-                                       MODE == 2 ? reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane : nullptr);
+                        slab_side64<2, NCOLS, MODE == 4>(t_addr, a, stg, lane, Wm, sfull0, sempty0, cnt, err_flag, (p.debug & 8) != 0, dbgT ? &tWS : nullptr,
+                                       MODE == 2 ? (const void*)(reinterpret_cast<const float*>(p.out) + (voxT + a) * 32 + lane) :
+                                       MODE == 4 ? (const void*)(reinterpret_cast<const unsigned short*>(p.out) + (voxT + a) * 32 + lane) : nullptr);
                 } else {
                     // centre warp of lane quarter 1 (even chunks, staging set 0) or 3 (odd chunks, set 1): both quarters hold
                     // the kw = 1 partial sums because the centre weights sit in M rows 32..63 and again in rows 96..127
@@ -341,10 +351,10 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
                                     x[vec * 4 + 2] = __uint_as_float(half ? vb[vec * 4 + 2] : va[vec * 4 + 2]) + (l.z + r.z);
                                     x[vec * 4 + 3] = __uint_as_float(half ? vb[vec * 4 + 3] : va[vec * 4 + 3]) + (l.w + r.w);
                                 }
-                                if (MODE == 0) {
-                                    bf16* gp = reinterpret_cast<bf16*>(p.out) + e0;
+                                if (MODE == 0 || MODE >= 3) {
+                                    unsigned short* gp = reinterpret_cast<unsigned short*>(p.out) + e0;
 #pragma unroll
-                                    for (int ii = 0; ii < SLAB_CHUNK; ++ii) gp[ii * 32] = __float2bfloat16_rn(x[ii]);
+                                    for (int ii = 0; ii < SLAB_CHUNK; ++ii) gp[ii * 32] = cvt16(x[ii], MODE >= 3);
                                 } else {
                                     float* gp = reinterpret_cast<float*>(p.out) + e0;
 #pragma unroll

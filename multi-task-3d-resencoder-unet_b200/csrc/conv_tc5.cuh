@@ -48,7 +48,7 @@ struct Tc5ConvParams {
     int stages;
     float* stat_sum;  // optional [NB][Nout] per-(n,c) sum of outputs   (fp32, atomics)
     float* stat_sq;   // optional [NB][Nout] per-(n,c) sum of squares
-    int outF32;       // 1: destinations are fp32 (pre-norm activations keep the full accumulator)
+    int outF32;       // destination element type: 0 bf16, 1 fp32 (full accumulator), 2 fp16 (pre-norm activations)
     int statSmem;     // 1: statistics are accumulated in shared memory per CTA and flushed once at the end
     FastDiv fdTilesN, fdTilesW, fdTilesH, fdTilesD;   // tile index decode without integer division
     FastDiv fdTw, fdTwTh, fdTwThTd;                    // row -> (iw, ih, id, in) inside a tile
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                         if (ch0 < p.outC0) { base = p.out0; eoff = vox * p.outC0 + ch0; lim = p.outC0 - ch0; }
                         else { base = p.out1; eoff = vox * p.outC1 + (ch0 - p.outC0); lim = p.outC1 - (ch0 - p.outC0); }
                         if (p.mode == 1) lim = min(lim, p.psC - ch0);
-                        if (p.outF32) {
+                        if (p.outF32 == 1) {
                             float* dst = reinterpret_cast<float*>(base) + eoff;
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
@@ -347,10 +347,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) tc5_gather_conv_kernel(const _
                             for (int q = 0; q < 4; ++q) {
                                 if (q * 8 < lim) {
                                     uint4 o;
-                                    o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-                                    o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-                                    o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-                                    o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+                                    const bool h = p.outF32 == 2;
+                                    o.x = pack16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]), h);
+                                    o.y = pack16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]), h);
+                                    o.z = pack16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]), h);
+                                    o.w = pack16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]), h);
                                     *reinterpret_cast<uint4*>(dst + q * 8) = o;
                                 }
                             }

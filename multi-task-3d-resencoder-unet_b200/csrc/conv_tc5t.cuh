@@ -269,16 +269,17 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                         const int rs = p.OW * cpitch;
                         float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
                         if (oh0 + 8 <= p.OH && ow0 + 4 <= p.OW) {
-                            if (p.outF32) {
+                            if (p.outF32 == 1) {
                                 float* dst = reinterpret_cast<float*>(base) + e0;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
                                     if (rowValid) dst[(j & 7) * rs + (j >> 3) * cpitch] = __uint_as_float(v[j]);
                             } else {
-                                bf16* dst = reinterpret_cast<bf16*>(base) + e0;
+                                unsigned short* dst = reinterpret_cast<unsigned short*>(base) + e0;
+                                const bool h16 = p.outF32 == 2;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (rowValid) dst[(j & 7) * rs + (j >> 3) * cpitch] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                                    if (rowValid) dst[(j & 7) * rs + (j >> 3) * cpitch] = cvt16(__uint_as_float(v[j]), h16);
                             }
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                                     a2[j & 3] = fmaf(x, x, a2[j & 3]);
                                     if (rowValid) {
                                         const size_t e = e0 + (size_t)((j & 7) * rs + (j >> 3) * cpitch);
-                                        if (p.outF32) reinterpret_cast<float*>(base)[e] = x;
-                                        else reinterpret_cast<bf16*>(base)[e] = __float2bfloat16_rn(x);
+                                        if (p.outF32 == 1) reinterpret_cast<float*>(base)[e] = x;
+                                        else reinterpret_cast<unsigned short*>(base)[e] = cvt16(x, p.outF32 == 2);
                                     }
                                 }
                             }
@@ -339,16 +340,17 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                             // single dependent FADD/FFMA chain made this loop ~85 cycles per column (cycle counters)
                             float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
                             if (nvalid == 32) {
-                                if (p.outF32) {
+                                if (p.outF32 == 1) {
                                     float* dst = reinterpret_cast<float*>(base) + e0;
 #pragma unroll
                                     for (int j = 0; j < 32; ++j)
                                         if (rowValid) dst[j * estep] = __uint_as_float(v[j]);
                                 } else {
-                                    bf16* dst = reinterpret_cast<bf16*>(base) + e0;
+                                    unsigned short* dst = reinterpret_cast<unsigned short*>(base) + e0;
+                                const bool h16 = p.outF32 == 2;
 #pragma unroll
                                     for (int j = 0; j < 32; ++j)
-                                        if (rowValid) dst[j * estep] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                                        if (rowValid) dst[j * estep] = cvt16(__uint_as_float(v[j]), h16);
                                 }
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
@@ -364,8 +366,8 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                                         a1[j & 3] += x;
                                         a2[j & 3] = fmaf(x, x, a2[j & 3]);
                                         if (rowValid) {
-                                            if (p.outF32) reinterpret_cast<float*>(base)[e0 + (size_t)j * estep] = x;
-                                            else reinterpret_cast<bf16*>(base)[e0 + (size_t)j * estep] = __float2bfloat16_rn(x);
+                                            if (p.outF32 == 1) reinterpret_cast<float*>(base)[e0 + (size_t)j * estep] = x;
+                                            else reinterpret_cast<unsigned short*>(base)[e0 + (size_t)j * estep] = cvt16(x, p.outF32 == 2);
                                         }
                                     }
                                 }
@@ -397,8 +399,8 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) tc5t_gather_conv_kernel(const
                             if (rowValid) {
                                 const int fd = od * p.ostrD + p.ooffD, fh = oh * p.ostrH + p.ooffH, fw = ow * p.ostrW + p.ooffW;
                                 const size_t vox = (((size_t)nb * p.FD + fd) * p.FH + fh) * p.FW + fw;
-                                if (p.outF32) reinterpret_cast<float*>(base)[vox * cpitch + cdst] = x;
-                                else reinterpret_cast<bf16*>(base)[vox * cpitch + cdst] = __float2bfloat16_rn(x);
+                                if (p.outF32 == 1) reinterpret_cast<float*>(base)[vox * cpitch + cdst] = x;
+                                else reinterpret_cast<unsigned short*>(base)[vox * cpitch + cdst] = cvt16(x, p.outF32 == 2);
                             }
                         }
                     }

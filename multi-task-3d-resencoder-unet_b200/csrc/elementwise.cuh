@@ -31,14 +31,18 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     return r;
 }
 
-// 8 consecutive channels of a pre-norm tensor that is either bf16 or fp32 (elem = element offset)
+// 8 consecutive channels of a pre-norm tensor: f32 = 0 bf16, 1 fp32, 2 fp16 (elem = element offset)
 __device__ __forceinline__ void load8_prenorm(const void* base, size_t elem, int f32, float (&f)[8]) {
-    if (f32) {
+    if (f32 == 1) {
         const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
         float4 a, b;
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(q));
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(q + 1));
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else if (f32 == 2) {     // fp16 pre-norm tensor
+        const uint4 v = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(base) + elem));
+        f[0] = f16lo(v.x); f[1] = f16hi(v.x); f[2] = f16lo(v.y); f[3] = f16hi(v.y);
+        f[4] = f16lo(v.z); f[5] = f16hi(v.z); f[6] = f16lo(v.w); f[7] = f16hi(v.w);
     } else {
         unpack8(ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem)), f);
     }

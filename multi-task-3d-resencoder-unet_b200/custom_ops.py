@@ -61,7 +61,7 @@ def _conv_norm_act(x0: Tensor, weight: Tensor, x1: Optional[Tensor], res: Option
                    beta: Optional[Tensor], drop: Optional[Tensor], se_w1: Optional[Tensor], se_b1: Optional[Tensor],
                    se_w2: Optional[Tensor], se_b2: Optional[Tensor], stride: List[int], eps: float, act: bool,
                    slope: float, gate_dims: str, stem: bool, impl: str) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Returns (z, y, small, s12, pw): z = the activation; y = the fp32 pre-norm conv output; small = [4, N, C]
+    """Returns (z, y, small, s12, pw): z = the activation; y = the pre-norm conv output (ops.PRENORM_DTYPE); small = [4, N, C]
     (mean, rstd, scale, shift) on the plain path; s12 = double [2, N, C] plane sums and pw = double [N, W, C] on the
     gated path (zero-element tensors where not applicable).  All but z exist for the backward operator."""
     stride_t = tuple(int(s) for s in stride)
@@ -92,7 +92,7 @@ def _(x0, weight, x1, res, gamma, beta, drop, se_w1, se_b1, se_w2, se_b2, stride
     n = x0.shape[0]
     od = tuple(x0.shape[2:]) if stem else ops._conv_out_dims(tuple(x0.shape[2:]), k, tuple(stride))
     z = x0.new_empty((n, *od, co), dtype=torch.bfloat16).permute(0, 4, 1, 2, 3)
-    y = x0.new_empty((n, *od, co), dtype=torch.float32).permute(0, 4, 1, 2, 3)
+    y = x0.new_empty((n, *od, co), dtype=ops.PRENORM_DTYPE).permute(0, 4, 1, 2, 3)
     gated = se_w1 is not None or drop is not None
     if not gated:
         return z, y, x0.new_empty((4, n, co), dtype=torch.float32), x0.new_empty(0, dtype=torch.float64), \

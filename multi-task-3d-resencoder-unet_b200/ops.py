@@ -170,9 +170,28 @@ def is_cl_f32(x: torch.Tensor) -> bool:
     return x.dim() == 5 and x.dtype == torch.float32 and x.permute(0, 2, 3, 4, 1).is_contiguous()
 
 
+# Element type of the pre-norm conv output inside the fused conv + norm + act unit.  The InstanceNorm statistics always
+# come from the fp32 accumulators (conv epilogue / finish pass); only the tensor the normalise pass and the backward pass
+# re-read is stored.  fp16 (default): 11-bit significand - 8x finer than the bf16 rounding every stored activation gets
+# anyway, so the outputs move by ~1 % of the bf16 tier's own error - at half the bytes of fp32 on five passes per layer
+# (conv store, normalise read, two backward reads; saturating stores: |y| is clamped to 65504 instead of overflowing).
+# RESENC_PRENORM=f32 restores the round-1 layout.
+PRENORM_DTYPE = {"f32": torch.float32, "f16": torch.float16}[os.environ.get("RESENC_PRENORM", "f16")]
+_YMODE = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}
+
+
+def new_prenorm(n, c, d, h, w, device):
+    """Pre-norm conv output: logical [n, c, d, h, w], memory NDHWC in PRENORM_DTYPE."""
+    return torch.empty((n, d, h, w, c), dtype=PRENORM_DTYPE, device=device).permute(0, 4, 1, 2, 3)
+
+
+def is_prenorm(x: torch.Tensor) -> bool:
+    return x.dim() == 5 and x.dtype in (torch.float32, torch.float16) and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
 def as_prenorm(y: torch.Tensor) -> torch.Tensor:
     """Pre-norm tensors are accepted as NDHWC fp32 (kept) or anything `as_cl` can turn into NDHWC bf16."""
-    return y if is_cl_f32(y) and y.shape[1] % 8 == 0 and y.is_cuda else as_cl(y)
+    return y if is_prenorm(y) and y.shape[1] % 8 == 0 and y.is_cuda else as_cl(y)
 
 
 def _make_desc(src0, src1, out0, out1, *, in_dims, taps, off, istr, out_grid, nout, mode, ostr, ooff, full, ps, psC, impl):
@@ -201,7 +220,7 @@ def _make_desc(src0, src1, out0, out1, *, in_dims, taps, off, istr, out_grid, no
         d.psC = 0
     d.impl = L.default_impl() if impl is None else L.impl_code(impl)
     d.splitK = 0
-    d.outF32 = 1 if out0.dtype == torch.float32 else 0
+    d.outF32 = _YMODE[out0.dtype]
     return d
 
 
@@ -501,7 +520,7 @@ def _conv_forward(weight, stride, impl, x0, x1, out_f32=False, want_stats=False)
     n = x0.shape[0]
     in_dims = tuple(x0.shape[2:])
     od = _conv_out_dims(in_dims, k, stride)
-    y = (new_cl_f32 if out_f32 else new_cl)(n, co, *od, x0.device)
+    y = (new_prenorm if out_f32 else new_cl)(n, co, *od, x0.device)
     stats = _launch_gather(x0, x1, pack_conv_fprop(weight), y, None, in_dims=in_dims, taps=k,
                            off=tuple(-((kk - 1) // 2) for kk in k), istr=stride, out_grid=od, nout=co, impl=impl,
                            want_stats=want_stats)
@@ -630,7 +649,7 @@ def _stem_pack(weight, kp):
 def _stem_forward(weight, impl, col, out_f32=False, want_stats=False):
     co = weight.shape[0]
     n, kp, d, h, w = col.shape
-    y = (new_cl_f32 if out_f32 else new_cl)(n, co, d, h, w, col.device)
+    y = (new_prenorm if out_f32 else new_cl)(n, co, d, h, w, col.device)
     stats = _launch_gather(col, None, _stem_pack(weight, kp), y, None, in_dims=(d, h, w), taps=(1, 1, 1), off=(0, 0, 0),
                            istr=(1, 1, 1), out_grid=(d, h, w), nout=co, impl=impl, want_stats=want_stats)
     return y, stats
@@ -658,7 +677,7 @@ def _plane_reduce(kind, y, dz, z, per_w, slope, sign=None):
     # algorithmic: forward statistics ride the conv epilogue (0 B); backward reduce reads dz + y in bf16 (4 B / element)
     with KERNEL_TIMER.span("norm_reduce", nbytes=el * (4 if kind == 1 else 2),
                            moved=el * (yb + (2 if kind == 1 else 0) + (2 if z is not None else 0))):
-        rc = L.load().rb_plane_reduce(kind, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(dz), L.ptr(z),
+        rc = L.load().rb_plane_reduce(kind, y.data_ptr(), _YMODE[y.dtype], L.ptr(dz), L.ptr(z),
                                       L.ptr(sign[0]) if sign else None, L.ptr(sign[1]) if sign else None,
                                       out.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, float(slope), L.stream_ptr())
     L.check(rc, "rb_plane_reduce")
@@ -672,7 +691,7 @@ def _apply_fwd(y, res, A, B, per_w, act, slope):
     yb = 4 if y.dtype == torch.float32 else 2
     with KERNEL_TIMER.span("norm_apply", nbytes=el * (4 + (2 if res is not None else 0)),
                            moved=el * (yb + 2 + (2 if res is not None else 0))):
-        rc = L.load().rb_norm_act_fwd(y.data_ptr(), 1 if y.dtype == torch.float32 else 0, L.ptr(res), z.data_ptr(),
+        rc = L.load().rb_norm_act_fwd(y.data_ptr(), _YMODE[y.dtype], L.ptr(res), z.data_ptr(),
                                       A.data_ptr(), B.data_ptr(), n, d * h * w, c, w, 1 if per_w else 0, 1 if act else 0,
                                       float(slope), L.stream_ptr())
     L.check(rc, "rb_norm_act_fwd")
@@ -689,7 +708,7 @@ def _apply_bwd(dz, z, y, k1, k2, k3, per_w, act, slope, want_dres, sign=None):
     with KERNEL_TIMER.span("norm_apply", nbytes=el * (6 + (2 if want_dres else 0)),
                            moved=el * (2 + yb + 2 + (2 if z is not None else 0) + (2 if want_dres else 0))):
         rc = L.load().rb_norm_act_bwd(dz.data_ptr(), L.ptr(z), L.ptr(sign[0]) if sign else None,
-                                      L.ptr(sign[1]) if sign else None, y.data_ptr(), 1 if y.dtype == torch.float32 else 0,
+                                      L.ptr(sign[1]) if sign else None, y.data_ptr(), _YMODE[y.dtype],
                                       dy.data_ptr(), L.ptr(dres), k1.data_ptr(), k2.data_ptr(), k3.data_ptr(), n,
                                       d * h * w, c, w, 1 if per_w else 0, 1 if act else 0, float(slope), L.stream_ptr())
     L.check(rc, "rb_norm_act_bwd")
@@ -896,8 +915,8 @@ class _NormActFn(torch.autograd.Function):
         y, z = ctx.saved_tensors
         st = ctx.st
         dy, dres, dgamma, dbeta, ggate = _norm_backward(st, y, z, as_cl(dz), st.has_res and ctx.needs_input_grad[1])
-        if y.dtype == torch.float32:
-            dy = dy.float()      # autograd wants the gradient in the input's dtype (stand-alone use only)
+        if y.dtype != dy.dtype:
+            dy = dy.to(y.dtype)      # autograd wants the gradient in the input's dtype (stand-alone use only)
         ggate = ggate if ggate is not None else ()
         return (dy, dres, dgamma, dbeta, None, None, None, None, None, *ggate)
 

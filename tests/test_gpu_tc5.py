@@ -187,6 +187,15 @@ def test_slab_conv(rb, n, dims):
     assert rel_l2(st2[0], z32.double().sum((2, 3, 4))) < 2e-5
     assert rel_l2(st2[1], (z32.double() ** 2).sum((2, 3, 4))) < 2e-5
 
+    # fp16 destinations (the pre-norm layout of the fused unit): one source, then the accumulate pass of the second source
+    y16h = torch.empty((n, *dims, 32), dtype=torch.float16, device="cuda").permute(0, 4, 1, 2, 3)
+    sth = ops._launch_gather(acl, None, ops.pack_conv_fprop(w1), y16h, None, nout=32, want_stats=True, **kw)
+    assert sth is not None and rel_l2(y16h.float(), ref1) < 6e-4
+    assert rel_l2(sth[0], y32.double().sum((2, 3, 4))) < 2e-5          # statistics come from the fp32 accumulators
+    z16h = torch.empty((n, *dims, 32), dtype=torch.float16, device="cuda").permute(0, 4, 1, 2, 3)
+    sth2 = ops._launch_gather(acl, bcl, ops.pack_conv_fprop(w2), z16h, None, nout=32, want_stats=True, **kw)
+    assert sth2 is not None and rel_l2(z16h.float(), ref2) < 1e-3
+
     # data gradient of the two-source conv: one 32-channel source, two 32-channel destinations
     ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
     g = q(torch.randn_like(ref2))
@@ -297,8 +306,9 @@ def test_conv_kernels_stay_inside_their_buffers(rb, case):
     nel = n * od[0] * od[1] * od[2] * cout
     G = 4096                                      # guard elements either side (16-byte aligned for both dtypes)
     SENT = 12345.0
-    for f32 in (False, True):
-        big = torch.full((nel + 2 * G,), SENT, dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+    for dt, tol in ((torch.bfloat16, TOL), (torch.float32, TOL), (torch.float16, TOL)):
+        big = torch.full((nel + 2 * G,), SENT, dtype=dt, device="cuda")
+        sent = big[0].clone()
         y = big[G:G + nel].view(n, *od, cout).permute(0, 4, 1, 2, 3)
         sbig = torch.full((2 * n * cout + 2 * 64,), SENT, dtype=torch.float32, device="cuda")
         st = sbig[64:64 + 2 * n * cout].view(2, n, cout)
@@ -308,10 +318,11 @@ def test_conv_kernels_stay_inside_their_buffers(rb, case):
                            out_grid=od, nout=cout, stats=(st[0], st[1]))
         torch.cuda.synchronize()
         rb._lib.device_error_check()
-        assert bool((big[:G] == SENT).all()) and bool((big[G + nel:] == SENT).all()), "conv wrote outside its destination"
+        assert bool((big[:G] == sent).all()) and bool((big[G + nel:] == sent).all()), "conv wrote outside its destination"
         assert bool((sbig[:64] == SENT).all()) and bool((sbig[64 + 2 * n * cout:] == SENT).all()), "statistics overran"
         ref = F.conv3d(x.float(), q(w), None, s, pad)
-        assert rel_l2(y.float(), ref) < TOL
+        r = rel_l2(y.float(), ref)
+        assert r < (tol if dt == torch.bfloat16 else 6e-4 if dt == torch.float16 else 1e-4), (dt, r)
         assert rel_l2(st[0], ref.double().sum((2, 3, 4))) < 5e-3
     # data gradient and weight gradient through the same descriptors (allocated by the library's host side)
     xr = x.detach().clone().requires_grad_(True)
