@@ -1214,9 +1214,11 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
     rb::ApplyParams p{y, (const rb::bf16*)res, (rb::bf16*)z, scale, shift, S, NB, C, W, perW, act, slope, y_f32};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
-    static const int variant = getenv("RESENC_NORM_VARIANT") ? atoi(getenv("RESENC_NORM_VARIANT")) : 1;
+    static const int variant = getenv("RESENC_NORM_VARIANT") ? atoi(getenv("RESENC_NORM_VARIANT")) : 0;
     const int cg = C / 8;
-    if (variant >= 1 && !perW && (cg & (cg - 1)) == 0 && cg <= 64) {     // coefficients hoisted, two groups in flight
+    // variant 1 (coefficients hoisted, two groups in flight) measured SLOWER (profiles/r2_norm_bench.txt: 113 / 62 registers
+    // cost more occupancy than the saved L1 loads give back): kept behind RESENC_NORM_VARIANT=1 for the record
+    if (variant >= 1 && !perW && (cg & (cg - 1)) == 0 && cg <= 64) {
         gx = grid_for((per + 1) / 2, 256, 8);
         rb::norm_act_fwd_v1_kernel<2><<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_fwd_v1_kernel");
@@ -1236,7 +1238,7 @@ int rb_norm_act_bwd(const void* dz, const void* z, const float* sign_scale, cons
                          k1, k2, k3, S, NB, C, W, perW, act, slope, y_f32, sign_scale, sign_shift};
     const long long per = S * (C / 8);
     int gx = grid_for(per, 256, 8);
-    static const int variant = getenv("RESENC_NORM_VARIANT") ? atoi(getenv("RESENC_NORM_VARIANT")) : 1;
+    static const int variant = getenv("RESENC_NORM_VARIANT") ? atoi(getenv("RESENC_NORM_VARIANT")) : 0;
     const int cg = C / 8;
     if (variant >= 1 && !perW && (cg & (cg - 1)) == 0 && cg <= 64) {
         gx = grid_for((per + 1) / 2, 256, 8);

@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
 // grid-stride iteration because the stride is a multiple of C/8) instead of 4-10 float4 L1 loads per 8 elements, and
 // U = 2 independent 8-element groups are in flight per iteration.  The round-1 kernels above ran the 128^3 launches at
 // 4.5 TB/s (bwd) / 5.4 TB/s (fwd with a 2-byte pre-norm tensor): load-instruction bound, not DRAM bound.
+// MEASURED SLOWER than the round-1 kernels (tools/norm_bench.py, profiles/r2_norm_bench.txt: 137 vs 127 us forward,
+// 353 vs 279 us backward at 32 ch @128^3 x2 - 62 / 113 registers cost more occupancy than the saved L1 loads return),
+// so they are NOT the default (RESENC_NORM_VARIANT=1 selects them).
 // ---------------------------------------------------------------------------------------
 template <int U>
 __global__ void __launch_bounds__(256) norm_act_fwd_v1_kernel(const ApplyParams p) {
