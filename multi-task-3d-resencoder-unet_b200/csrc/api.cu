@@ -1223,6 +1223,12 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
         rb::norm_act_fwd_v1_kernel<2><<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_fwd_v1_kernel");
     }
+    static const bool no_x2 = getenv("RESENC_NO_NORM_X2") != nullptr;
+    if (!no_x2 && y_f32 != 1 && C % 16 == 0) {     // 2-byte pre-norm tensor: two vectors per thread (bytes in flight)
+        gx = grid_for(per / 2, 256, 8);
+        rb::norm_act_fwd_x2_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("norm_act_fwd_x2_kernel");
+    }
     rb::norm_act_fwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_act_fwd_kernel");
 }

@@ -234,6 +234,50 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const ApplyParams p) 
     }
 }
 
+// Two consecutive 8-channel vectors per thread (C % 16 == 0): with a 2-byte pre-norm tensor the kernel above has ONE
+// 16-byte streaming load in flight per thread (24 KB per SM: bytes-in-flight bound at ~4.2 TB/s, tools/norm_bench.py);
+// here a thread streams 32 contiguous bytes of y (and of the residual) and stores 32 contiguous bytes of z.
+__global__ void __launch_bounds__(256) norm_act_fwd_x2_kernel(const ApplyParams p) {
+    const uint32_t cg = (uint32_t)p.C >> 3;                 // even
+    const uint32_t per = (uint32_t)p.S * cg;                // vectors per sample (even)
+    const uint32_t pairs = per >> 1;
+    const int nb = blockIdx.y;
+    const uint4* rv = p.res ? reinterpret_cast<const uint4*>(p.res) + (size_t)nb * per : nullptr;
+    uint4* zv = reinterpret_cast<uint4*>(p.z) + (size_t)nb * per;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
+        const uint32_t i = q * 2;
+        const uint32_t g = i % cg;
+        const uint32_t v = i / cg;
+        const size_t cidx = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
+        float a[2][8], r[2][8];
+        load8_prenorm(p.y, ((size_t)nb * per + i) * 8, p.yF32, a[0]);
+        load8_prenorm(p.y, ((size_t)nb * per + i + 1) * 8, p.yF32, a[1]);
+        if (rv != nullptr) {
+            unpack8(ld_stream(rv + i), r[0]);
+            unpack8(ld_stream(rv + i + 1), r[1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float sc[8], sh[8];
+            *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx + u * 8));
+            *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx + u * 8 + 4));
+            *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx + u * 8));
+            *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx + u * 8 + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[u][j] = fmaf(a[u][j], sc[j], sh[j]);
+            if (rv != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[u][j] += r[u][j];
+            }
+            if (p.act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[u][j] = a[u][j] > 0.f ? a[u][j] : a[u][j] * p.slope;
+            }
+            zv[i + u] = pack8(a[u]);
+        }
+    }
+}
+
 // Backward of the fused apply + InstanceNorm:
 //   g    = dz * lrelu'(z)                 (z = saved output; act==0 => g = dz)
 //   dres = g                              (only when dres != null)
