@@ -1223,8 +1223,11 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
         rb::norm_act_fwd_v1_kernel<2><<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_fwd_v1_kernel");
     }
-    static const bool no_x2 = getenv("RESENC_NO_NORM_X2") != nullptr;
-    if (!no_x2 && y_f32 != 1 && C % 16 == 0) {     // 2-byte pre-norm tensor: two vectors per thread (bytes in flight)
+    // two vectors per thread: 121 vs 127 us on the 128^3 launches but 37 vs 35 / 21 vs 15 us on the 64^3 / 32^3 ones
+    // (tools/norm_bench.py) - the pass sits at the mixed read / write DRAM limit (~4.4 TB/s at 1:1), not at a
+    // bytes-in-flight limit; opt-in only
+    static const bool x2 = getenv("RESENC_NORM_X2") != nullptr;
+    if (x2 && y_f32 != 1 && C % 16 == 0) {
         gx = grid_for(per / 2, 256, 8);
         rb::norm_act_fwd_x2_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_fwd_x2_kernel");
