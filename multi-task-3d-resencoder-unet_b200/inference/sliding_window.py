@@ -487,16 +487,27 @@ def merge_slabs(blender: SlabBlender, z_starts: Sequence[int], rank: int, world_
     import torch.distributed as dist
     pairs, own = plan_slab_exchange(z_starts, blender.patch[0], blender.vol_shape[0], world_size)
     names = list(blender.sums.keys())
+    # every rank posts ALL its sends and receives at once (one batched point-to-point group): the exchanges of different
+    # neighbour pairs run concurrently.  Round-2 measurement at 8 GPUs: the previous blocking send / recv loop walked the
+    # pairs in order, so rank r + 1 could not send before it had received from rank r - a serial chain of 7 exchanges,
+    # 0.87 s for 1.3 GB per pair.
+    ops, received, keep = [], [], []
     for src, dst, lo, hi in pairs:
         a, b = lo - blender.z_lo, hi - blender.z_lo
         if rank == src:
-            for t in names:
-                dist.send(blender.sums[t][:, a:b].contiguous(), dst, group=group)
-            dist.send(blender.wsum[a:b].contiguous(), dst, group=group)
+            for t in names + [None]:
+                part = (blender.wsum[a:b] if t is None else blender.sums[t][:, a:b]).contiguous()
+                keep.append(part)
+                ops.append(dist.P2POp(dist.isend, part, dst, group))
         elif rank == dst:
             for t in names + [None]:
                 tgt = blender.wsum[a:b] if t is None else blender.sums[t][:, a:b]
                 buf = torch.empty(tgt.shape, dtype=tgt.dtype, device=tgt.device)
-                dist.recv(buf, src, group=group)
-                add_fn(tgt, buf)
+                ops.append(dist.P2POp(dist.irecv, buf, src, group))
+                received.append((tgt, buf))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for tgt, buf in received:
+        add_fn(tgt, buf)
     return own[rank]
