@@ -165,6 +165,16 @@ int rb_head_fwd(const void* x, const float* w, const float* b, float* out, int N
 int rb_head_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db,
                 int NB, long long S, int C, int K, void* stream);
 
+/* Inference tail of a task decoder as ONE pass (no autograd): the last conv block's InstanceNorm + LeakyReLU
+ * (builders/simple_conv_blocks.py:58-60; + residual, builders/resblocks.py:113-114) followed by the 1x1x1 head
+ * (builders/decoder.py:144-152) and the eval-mode activation (builders/build_network_from_config.py:322-323).
+ * The decoder's last activation is never stored: y (pre-norm, y_mode 0 bf16 / 1 fp32 / 2 fp16, NDHWC) is read once,
+ * out is NCDHW fp32 [NB][K][S].  scale / shift [NB][C] as produced by rb_in_finalize_fwd.  C / 8 must be a power of
+ * two <= 32 (RB_ERR_UNSUPPORTED otherwise: the caller runs rb_norm_act_fwd + rb_head_fwd). */
+int rb_norm_act_head_fwd(const void* y, int y_mode, const void* res, const float* scale, const float* shift,
+                         const float* w, const float* b, float* out, int NB, long long S, int C, int K,
+                         int act, float slope, int head_act, void* stream);
+
 /* Stem im2col (builders/encoder.py:81-86, Cin not a multiple of 8): x NCDHW fp32 ->
  * col [NB,D,H,W,Kp] bf16, column = tap*Cin + ci, zero padded to Kp (multiple of 16). */
 int rb_stem_im2col(const float* x, void* col, int NB, int Cin, int D, int H, int W, int kd, int kh, int kw, int Kp, void* stream);

@@ -84,6 +84,12 @@ class Decoder(nn.Module):
         last = len(self.stages) - 1
         for s in range(len(self.stages)):
             up = self._upsample(s, low)
+            if s == last and not self.deep_supervision and isinstance(self.stages[s], StackedConvBlocks):
+                # the full-resolution activation feeds the head and nothing else: the last conv unit applies the head
+                # itself (in inference as one pass that never stores the activation, ops.conv_norm_act_head)
+                h = self.seg_layers[-1]
+                outs.append(self.stages[s](up, skips[-(s + 2)], head=(h.weight, h.bias, activation)))
+                break
             low = self.stages[s](up, skips[-(s + 2)])
             if self.deep_supervision:
                 h = self.seg_layers[s]

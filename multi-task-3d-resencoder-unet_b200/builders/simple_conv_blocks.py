@@ -67,16 +67,22 @@ class ConvDropoutNormReLU(nn.Module):
 
     _raw_input = False      # StemConv: consumes the raw NCDHW fp32 network input
 
-    def forward(self, x, x_cat=None, res=None, act=None, slope=None, se=None, se_reduce_dims="all", drop=None):
+    def forward(self, x, x_cat=None, res=None, act=None, slope=None, se=None, se_reduce_dims="all", drop=None, head=None):
         """act( [SE]( IN( conv(cat(x, x_cat)) ) ) + res ) as ONE fused unit (ops.conv_norm_act).  Called with
         only `x` this is the reference's conv -> dropout(p=0) -> norm -> nonlin; residual blocks pass their
         tail (`res`, `act`, `se`) so the block needs no elementwise pass of its own.  A conv bias feeding
         InstanceNorm cancels exactly: it is not applied and receives the exact gradient, zero."""
         act = self._act if act is None else act
         slope = (self._slope or ops.LRELU_SLOPE_DEFAULT) if slope is None else slope
+        if ops.can_fuse_head(self.conv.weight, head, se, drop):
+            # inference: `head` = (weight, bias, activation) of the task's 1x1x1 seg layer consumes this unit's output and
+            # nothing else does - norm + act + head run as one pass and the activation is never stored
+            return ops.conv_norm_act_head(x, self.conv.weight, self.stride, x_cat, res, self.norm.weight, self.norm.bias,
+                                          self.norm.eps, act, slope, self._raw_input, head)
         z = ops.conv_norm_act(x, self.conv.weight, self.stride, x_cat, res, self.norm.weight, self.norm.bias,
                               self.norm.eps, act, slope, se, se_reduce_dims, stem=self._raw_input, drop=drop)
-        return ops.attach_cancelled_bias(z, self.conv.bias)
+        z = ops.attach_cancelled_bias(z, self.conv.bias)
+        return z if head is None else ops.head_conv1x1(z, *head)
 
     def compute_conv_feature_map_size(self, input_size):
         assert len(input_size) == len(self.stride), "give the spatial size only, e.g. (x, y, z)"
@@ -109,9 +115,12 @@ class StackedConvBlocks(nn.Module):
         self.output_channels = output_channels[-1]
         self.initial_stride = maybe_convert_scalar_to_list(conv_op, initial_stride)
 
-    def forward(self, x, x_cat=None):
+    def forward(self, x, x_cat=None, head=None):
+        """`head` (weight, bias, activation): the task head applied to the last conv unit's output (decoder tail)."""
+        last = len(self.convs) - 1
         for i, blk in enumerate(self.convs):
-            x = blk(x, x_cat) if i == 0 else blk(x)
+            hd = head if i == last else None
+            x = blk(x, x_cat, head=hd) if i == 0 else blk(x, head=hd)
         return x
 
     def compute_conv_feature_map_size(self, input_size):

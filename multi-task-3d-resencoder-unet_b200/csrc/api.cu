@@ -1287,13 +1287,46 @@ int rb_avgpool_bwd(const void* dout, void* din, int NB, int D, int H, int W, int
     return check_launch("avgpool_bwd_kernel");
 }
 
+static int launch_norm_head(const void* y, int y_mode, const void* res, const float* scale, const float* shift, const float* w,
+                            const float* b, float* out, int NB, long long S, int C, int K, int act, float slope, int head_act,
+                            void* stream) {
+    rb::NormHeadParams p{y, (const rb::bf16*)res, scale, shift, w, b, out, S, NB, C, K, act, head_act, slope, y_mode};
+    const size_t smem = (size_t)(K * C + K) * sizeof(float);
+    const int vpw = 32 / (C / 8);                                   // voxels per warp instruction
+    const long long warpIters = (S + vpw - 1) / vpw;                // per sample
+    int gx = (int)std::min<long long>((warpIters + 15) / 16, (long long)num_sms() * 8);   // 8 warps x 2 voxel sets per block pass
+    if (gx < 1) gx = 1;
+    const dim3 grid(gx, NB);
+    if (K == 1) rb::norm_act_head_fwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else if (K <= 4) rb::norm_act_head_fwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    else rb::norm_act_head_fwd_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("norm_act_head_fwd_kernel");
+}
+
 int rb_head_fwd(const void* x, const float* w, const float* b, float* out, int NB, long long S, int C, int K, int act, void* stream) {
     if (!x || !w || !out) return fail(RB_ERR_INVALID, "head_fwd: null pointer");
     if (K < 1 || K > rb::HEAD_MAXK || C <= 0 || C % 8 != 0 || C > 1024) return fail(RB_ERR_INVALID, "head_fwd: need 1 <= K <= 8, C %% 8 == 0, C <= 1024");
+    const int cg = C / 8;
+    static const bool legacy = getenv("RESENC_HEAD_LEGACY") != nullptr;
+    if (!legacy && (cg & (cg - 1)) == 0 && cg <= 32 && S < (1LL << 31))   // coalesced (voxel, channel-group) lanes
+        return launch_norm_head(x, 0, nullptr, nullptr, nullptr, w, b, out, NB, S, C, K, 0, 0.f, act, stream);
     rb::HeadParams p{(const rb::bf16*)x, w, b, out, S, NB, C, K, act};
     const size_t smem = (size_t)(K * C + K) * sizeof(float);
     rb::head_fwd_kernel<<<grid_for((long long)NB * S, 256), 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("head_fwd_kernel");
+}
+
+int rb_norm_act_head_fwd(const void* y, int y_mode, const void* res, const float* scale, const float* shift, const float* w,
+                         const float* b, float* out, int NB, long long S, int C, int K, int act, float slope, int head_act,
+                         void* stream) {
+    if (!y || !scale || !shift || !w || !out) return fail(RB_ERR_INVALID, "norm_act_head_fwd: null pointer");
+    if (K < 1 || K > rb::HEAD_MAXK) return fail(RB_ERR_INVALID, "norm_act_head_fwd: need 1 <= K <= 8");
+    const int cg = C / 8;
+    if (C <= 0 || C % 8 != 0 || (cg & (cg - 1)) != 0 || cg > 32)
+        return fail(RB_ERR_UNSUPPORTED, "norm_act_head_fwd: C / 8 must be a power of two <= 32 (C = %d)", C);
+    if (NB <= 0 || S <= 0 || S >= (1LL << 31)) return fail(RB_ERR_INVALID, "norm_act_head_fwd: bad shape");
+    if (y_mode < 0 || y_mode > 2 || head_act < 0 || head_act > 2) return fail(RB_ERR_INVALID, "norm_act_head_fwd: bad mode");
+    return launch_norm_head(y, y_mode, res, scale, shift, w, b, out, NB, S, C, K, act, slope, head_act, stream);
 }
 
 int rb_head_bwd(const void* x, const float* w, const float* dl, void* dx, float* dw, float* db, int NB, long long S, int C,

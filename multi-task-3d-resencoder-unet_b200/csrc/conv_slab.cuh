@@ -44,7 +44,7 @@ struct SlabConvParams {
     float* stat_sum;    // [NB][statPitch] at channel statC0 + co, or nullptr
     float* stat_sq;
     int statPitch, statC0;
-    int debug;   // profiling experiments (RESENC_SLAB_DEBUG bit mask): 1 skip MMAs, 2 skip plane loads, 4 skip epilogue, 8 skip staging, 16 skip output
+    int debug;   // profiling experiments (RESENC_SLAB_DEBUG bit mask): 1 skip MMAs, 2 skip plane loads, 4 skip epilogue, 8 skip staging, 16 skip output, 64 no prefetch of the existing output (accumulate modes)
 };
 
 static constexpr int SLAB_THREADS = 320;   // warps: 0 TMA, 1 MMA, 2..5 and 6..9 epilogue (TMEM lane quarter = warp & 3)
@@ -303,12 +303,27 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) slab_conv_kernel(const __grid
             decode(item, n, d0, nOut, h0);
             float s1 = 0.f, s2 = 0.f;
             for (int j = 0; j < nOut; ++j) {
+                const size_t voxT = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;   // voxel of tile column 0
+                if ((MODE == 2 || MODE == 4) && (q == 0 || q == 2) && !(p.debug & 64)) {
+                    // accumulate modes: a side warp adds the existing output of 32 voxels per 64-column call (slab_side64).
+                    // Those loads used to be issued inside the call, their DRAM latency (two calls per tile) exposed on the
+                    // epilogue's critical path: 0.82 ms against 0.49 ms for the plain store mode.  The addresses depend on
+                    // the tile only, so both calls' lines are requested here, BEFORE the wait for the tile's MMAs.
+                    constexpr int ESZ = MODE == 2 ? 4 : 2;
+                    constexpr int LINES = 32 * 32 * ESZ / 128;           // 128-byte lines per call: 16 (fp16) / 32 (fp32)
+                    const char* yb = reinterpret_cast<const char*>(p.out) + (voxT + (size_t)(g * 128 + (q == 0 ? 0 : 32))) * (32 * ESZ);
+#pragma unroll
+                    for (int c = 0; c < 2 * LINES; c += 32) {
+                        const int idx = c + lane, call = idx / LINES, line = idx % LINES;
+                        if (g * 128 + call * 64 < ncols)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(yb + (size_t)call * (64 * 32 * ESZ) + (size_t)line * 128));
+                    }
+                }
                 const long long w0 = dbgT ? clock64() : 0;
                 mbar_wait(tfull_bar(acc), acc_phase, DEVERR_WAIT_TMEM_FULL, err_flag);
                 if (dbgT) { tWT += clock64() - w0; ++nT; }
                 tc_fence_after();
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-                const size_t voxT = (((size_t)n * p.D + (d0 + j)) * p.H + h0) * (size_t)p.W;   // voxel of tile column 0
                 if (p.debug & 4) {
                 } else if (q == 0) {
                     for (int a = g * 128; a < (g * 128 + 128 < ncols ? g * 128 + 128 : ncols); a += 64)

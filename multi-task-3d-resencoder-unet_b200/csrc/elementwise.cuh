@@ -587,6 +587,117 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused tail of a task decoder in inference (no autograd):
+//     logits = head( act( y * scale[n,c] + shift[n,c] + res ) )          decoder.py:144-152 (last stage -> seg_layers[-1])
+// The last activation z of a decoder is consumed only by its 1x1x1 head, so writing it (2 B / element) and reading it
+// back (2 B) is pure HBM traffic: this kernel reads the pre-norm tensor once and writes K fp32 logit planes.  z is
+// rounded to bf16 in registers, so the logits match the two-kernel path up to the summation order of the dot product.
+// scale == nullptr: plain head on a stored bf16 activation (rb_head_fwd's coalesced path).
+// Thread = (voxel, 8-channel group): a warp instruction reads 512 contiguous bytes; the C/8 lanes of a voxel combine
+// their partial dot products with a butterfly (C/8 a power of two <= 32, host-checked).
+// ---------------------------------------------------------------------------------------
+struct NormHeadParams {
+    const void* y;        // [NB, S, C] pre-norm (yF32: 0 bf16, 1 fp32, 2 fp16), or the stored activation when scale == null
+    const bf16* res;      // may be null
+    const float* scale;   // [NB][C] or null
+    const float* shift;
+    const float* w;       // [K][C]
+    const float* b;       // [K] or null
+    float* out;           // [NB][K][S]
+    long long S;
+    int NB, C, K, act, head_act;
+    float slope;
+    int yF32;
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(256, 4) norm_act_head_fwd_kernel(const NormHeadParams p) {
+    extern __shared__ float hw[];  // [K][C] + [K]
+    for (int i = threadIdx.x; i < p.K * p.C; i += blockDim.x) hw[i] = p.w[i];
+    for (int i = threadIdx.x; i < p.K; i += blockDim.x) hw[p.K * p.C + i] = p.b ? p.b[i] : 0.f;
+    __syncthreads();
+    const uint32_t cg = (uint32_t)p.C >> 3;          // lanes per voxel
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t g = lane & (cg - 1u);
+    const uint32_t vpw = 32u / cg;                   // voxels per warp instruction
+    const int nb = blockIdx.y;
+    const uint32_t S = (uint32_t)p.S;
+    const size_t base = (size_t)nb * p.S;
+    const uint32_t stride = gridDim.x * 8u * vpw;
+    // the loop variable is warp-uniform (first voxel of the warp's group): the shuffles below run with all lanes
+    for (uint32_t v0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * vpw; v0 < S; v0 += 2u * stride) {
+        float a[2][8], r[2][8];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t v = v0 + u * stride + lane / cg;
+            ok[u] = v < S;
+            const size_t off = (base + (ok[u] ? v : 0u)) * p.C + g * 8;
+            load8_prenorm(p.y, off, p.scale != nullptr ? p.yF32 : 0, a[u]);
+            if (p.res != nullptr) unpack8(ld_stream(reinterpret_cast<const uint4*>(p.res + off)), r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (v0 + u * stride >= S) break;   // warp-uniform
+            if (p.scale != nullptr) {
+                // coefficients re-read per vector (L1 hits) rather than held in 16 registers (occupancy: 4 blocks per SM)
+                const size_t cs = (size_t)nb * p.C + g * 8;
+                float sc[8], sh[8];
+                *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cs));
+                *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cs + 4));
+                *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + cs));
+                *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + cs + 4));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = fmaf(a[u][j], sc[j], sh[j]);
+                    if (p.res != nullptr) t += r[u][j];
+                    if (p.act) t = t > 0.f ? t : t * p.slope;
+                    a[u][j] = t;
+                }
+                // what the stored activation would hold: round to bf16 (packed converts - the scalar F2F.BF16 form is a
+                // quarter-rate instruction and held the first version of this kernel at 1.9 TB/s)
+                unpack8(pack8(a[u]), a[u]);
+            }
+            float acc[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                acc[k] = 0.f;
+                if (k < p.K) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(hw + k * p.C + g * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(hw + k * p.C + g * 8 + 4);
+                    acc[k] = fmaf(a[u][0], w0.x, fmaf(a[u][1], w0.y, fmaf(a[u][2], w0.z, a[u][3] * w0.w))) +
+                             fmaf(a[u][4], w1.x, fmaf(a[u][5], w1.y, fmaf(a[u][6], w1.z, a[u][7] * w1.w)));
+                }
+            }
+            for (uint32_t m = 1; m < cg; m <<= 1) {
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], m);
+            }
+            if (g == 0 && ok[u]) {
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) acc[k] += k < p.K ? hw[p.K * p.C + k] : 0.f;
+                if (p.head_act == 1) {
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) acc[k] = 1.f / (1.f + expf(-acc[k]));
+                } else if (p.head_act == 2) {
+                    float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) if (k < p.K) mx = fmaxf(mx, acc[k]);
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) if (k < p.K) { acc[k] = expf(acc[k] - mx); sum += acc[k]; }
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) acc[k] /= sum;
+                }
+                const uint32_t v = v0 + u * stride + lane / cg;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k)
+                    if (k < p.K) p.out[((size_t)nb * p.K + k) * p.S + v] = acc[k];
+            }
+        }
+    }
+}
+
 // Backward of the head (on raw logits): dx = dl . W (bf16), dW += dl^T x, db += sum dl.
 // thread = (voxel, 8-channel group); block-level reduction of dW / db, then fp32 atomics.
 struct HeadBwdParams {

@@ -5,9 +5,10 @@ chunks = the patch size (with all channels in one chunk), fill_value 0, all-zero
 
 `zarr` / `numcodecs` / Blosc are not installed in this image, so the zarr **v2** directory format is written
 directly (`.zgroup`, `<array>/.zarray`, one file per chunk named "i.j.k").  The reference compresses with
-Blosc(zstd, clevel 5, bitshuffle) (inference.py:92,224); without a Blosc encoder available here the writer uses the
-`zlib` codec (numcodecs id "zlib") or no compressor, both of which stock zarr reads; the codec is recorded in
-`.zarray`, so the arrays open unchanged with `zarr.open(path)`.  Chunk compression and file writes run on a host
+Blosc(zstd, clevel 5, bitshuffle) (inference.py:92,224): compressor "blosc" writes exactly that configuration
+(`blosc_codec.py`: the Blosc-1 container around zstd frames from the system libzstd) and records numcodecs' Blosc
+config in `.zarray`; "zlib" (numcodecs id "zlib") and None are kept as codecs with no third-party format involved.
+All three open unchanged with `zarr.open(path)`.  Chunk compression and file writes run on a host
 thread pool while the GPU keeps sweeping / finalising the next z-range (`submit` returns immediately; `close` joins).
 Each rank of a z-slab-sharded sweep writes the chunks of the z-range it owns; ranges are aligned to the chunk grid
 by the caller or fall back to read-modify-write of the boundary chunks on one rank at a time.
@@ -22,6 +23,8 @@ from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import blosc_codec
+
 _DTYPES = {np.dtype("uint8"): "|u1", np.dtype("uint16"): "<u2", np.dtype("float32"): "<f4"}
 
 
@@ -29,8 +32,12 @@ def _zarray_meta(shape, chunks, dtype, compressor):
     comp = None
     if compressor == "zlib":
         comp = {"id": "zlib", "level": 1}
+    elif compressor == "blosc":                    # numcodecs.Blosc(cname='zstd', clevel=5, shuffle=BITSHUFFLE).get_config()
+        if not blosc_codec.available():
+            raise NotImplementedError("compressor 'blosc' needs a zstd implementation (libzstd.so.1 or pyarrow)")
+        comp = {"id": "blosc", "cname": "zstd", "clevel": 5, "shuffle": 2, "blocksize": 0}
     elif compressor is not None:
-        raise NotImplementedError(f"compressor {compressor!r}: 'zlib' or None (no Blosc encoder in this image)")
+        raise NotImplementedError(f"compressor {compressor!r}: 'blosc' (zstd, bit-shuffle), 'zlib' or None")
     return {"zarr_format": 2, "shape": list(shape), "chunks": list(chunks), "dtype": _DTYPES[np.dtype(dtype)],
             "compressor": comp, "fill_value": 0, "order": "C", "filters": None, "dimension_separator": "."}
 
@@ -58,10 +65,13 @@ class ZarrArrayWriter:
     # -- chunk codec -----------------------------------------------------------------------------
     def _encode(self, block: np.ndarray) -> bytes:
         raw = np.ascontiguousarray(block, dtype=self.dtype.newbyteorder("<") if self.dtype.itemsize > 1 else self.dtype).tobytes()
+        if self.compressor == "blosc":
+            return blosc_codec.compress(raw, typesize=self.dtype.itemsize, clevel=5, shuffle=blosc_codec.BITSHUFFLE)
         return zlib.compress(raw, 1) if self.compressor == "zlib" else raw
 
     def _decode(self, data: bytes) -> np.ndarray:
-        raw = zlib.decompress(data) if self.compressor == "zlib" else data
+        raw = (blosc_codec.decompress(data) if self.compressor == "blosc" else
+               zlib.decompress(data) if self.compressor == "zlib" else data)
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks).copy()
 
     def _chunk_file(self, idx: Tuple[int, ...]) -> str:
@@ -204,8 +214,8 @@ class FinalVolumeWriter:
 class ZarrArrayReader:
     """Read-only view of a zarr v2 array directory with zarr's slicing interface (`.shape`, `.dtype`, `a[z0:z1]`,
     `a[..., z0:z1, y0:y1, x0:x1]`), enough for `DeviceVolume` / `SlidingWindowInferer` to consume a volume without the
-    `zarr` package.  Codecs: none and zlib (what `ZarrArrayWriter` writes); a Blosc-compressed array raises
-    `NotImplementedError` (no Blosc decoder in this image - open it with zarr itself)."""
+    `zarr` package.  Codecs: none, zlib and Blosc with zstd frames (what `ZarrArrayWriter` writes and what the
+    reference's own outputs use); other Blosc codecs (lz4, blosclz) raise `NotImplementedError`."""
 
     def __init__(self, path: str):
         with open(os.path.join(path, ".zarray")) as f:
@@ -213,15 +223,15 @@ class ZarrArrayReader:
         if meta.get("zarr_format") != 2 or meta.get("order", "C") != "C" or meta.get("filters"):
             raise NotImplementedError("only unfiltered C-order zarr v2 arrays are supported")
         comp = meta.get("compressor")
-        if comp is not None and comp.get("id") != "zlib":
-            raise NotImplementedError(f"compressor {comp.get('id')!r}: only zlib / none can be decoded here")
+        if comp is not None and comp.get("id") not in ("zlib", "blosc"):
+            raise NotImplementedError(f"compressor {comp.get('id')!r}: only blosc (zstd) / zlib / none can be decoded here")
         self.path = path
         self.shape = tuple(meta["shape"])
         self.chunks = tuple(meta["chunks"])
         self.dtype = np.dtype(meta["dtype"])
         self.fill_value = meta.get("fill_value") or 0
         self.sep = meta.get("dimension_separator", ".")
-        self._zlib = comp is not None
+        self._codec = comp.get("id") if comp is not None else None
         self.ndim = len(self.shape)
 
     def _chunk(self, idx):
@@ -230,8 +240,10 @@ class ZarrArrayReader:
             return np.full(self.chunks, self.fill_value, self.dtype)
         with open(fn, "rb") as f:
             raw = f.read()
-        if self._zlib:
+        if self._codec == "zlib":
             raw = zlib.decompress(raw)
+        elif self._codec == "blosc":
+            raw = blosc_codec.decompress(raw)
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks)
 
     def __getitem__(self, key):

@@ -995,6 +995,61 @@ def conv_norm_act(x, weight, stride=1, x_cat=None, res=None, gamma=None, beta=No
     return _ConvNormActFn.apply(weight, cfg, x, x_cat, res, gamma, beta, drop, *(se or ()))
 
 
+FUSE_HEAD = os.environ.get("RESENC_FUSE_HEAD", "1") != "0"
+
+
+def can_fuse_head(conv_weight, head, se=None, drop=None) -> bool:
+    """True when conv -> InstanceNorm -> LeakyReLU -> 1x1x1 head can run without storing the activation in between
+    (`conv_norm_act_head`): autograd off (inference), no gate, no stochastic depth, channel count the kernel takes."""
+    if head is None or not FUSE_HEAD or torch.is_grad_enabled() or _PreciseState.on or se is not None or drop is not None:
+        return False
+    if torch.compiler.is_compiling() or FORCE_CUSTOM_OPS:
+        return False
+    cg, k = conv_weight.shape[0] // 8, head[0].shape[0]
+    return conv_weight.shape[0] % 8 == 0 and cg & (cg - 1) == 0 and cg <= 32 and k <= 8
+
+
+def conv_norm_act_head(x, weight, stride, x_cat, res, gamma, beta, eps, act, slope, stem, head):
+    """Inference tail of a task decoder (decoder.py:144-152): head( act( IN( conv(cat(x, x_cat)) ) [+ res] ) ) with the
+    decoder's last activation never written to HBM - the normalise pass and the head are one kernel
+    (`rb_norm_act_head_fwd`) that reads the pre-norm conv output once.  No autograd (see `can_fuse_head`);
+    head = (weight [K, C, 1, 1, 1], bias [K] | None, activation None | 'sigmoid' | 'softmax').  Returns NCDHW fp32."""
+    hw, hb, hact = head
+    lib = L.load()
+    if stem:
+        src0 = _stem_im2col(x, tuple(weight.shape[2:]))
+        y, stats = _stem_forward(weight, None, src0, out_f32=True, want_stats=True)
+    else:
+        src0 = as_cl(x)
+        src1 = as_cl(x_cat) if x_cat is not None else None
+        L.require_cuda(src0, "conv3d")
+        y, stats = _conv_forward(weight, _triple(stride), None, src0, src1, out_f32=True, want_stats=True)
+    res = as_cl(res) if res is not None else None
+    if res is not None and res.shape != y.shape:
+        raise ValueError(f"residual shape {tuple(res.shape)} != {tuple(y.shape)}")
+    n, c, d, h, w = y.shape
+    S = d * h * w
+    sums = None if stats is not None else _plane_reduce(0, y, None, None, False, slope)
+    small = torch.empty((4, n, c), dtype=torch.float32, device=y.device)     # mean, rstd, scale, shift
+    L.check(lib.rb_in_finalize_fwd(L.ptr(sums), L.ptr(stats[0]) if stats else None, L.ptr(stats[1]) if stats else None,
+                                   L.ptr(gamma), L.ptr(beta), small[0].data_ptr(), small[1].data_ptr(),
+                                   small[2].data_ptr(), small[3].data_ptr(), n, c, float(S), float(eps),
+                                   L.stream_ptr()), "rb_in_finalize_fwd")
+    k = hw.shape[0]
+    w2 = hw.detach().reshape(k, c).float().contiguous()
+    b = hb.detach().float().contiguous() if hb is not None else None
+    out = torch.empty((n, k, d, h, w), dtype=torch.float32, device=y.device)
+    el = float(n * c * S)
+    yb = 4 if y.dtype == torch.float32 else 2
+    with KERNEL_TIMER.span("norm_apply", nbytes=el * (2 + (2 if res is not None else 0)) + 4.0 * n * k * S,
+                           moved=el * (yb + (2 if res is not None else 0)) + 4.0 * n * k * S):
+        rc = lib.rb_norm_act_head_fwd(y.data_ptr(), _YMODE[y.dtype], L.ptr(res), small[2].data_ptr(), small[3].data_ptr(),
+                                      w2.data_ptr(), L.ptr(b), out.data_ptr(), n, S, c, k, 1 if act else 0, float(slope),
+                                      _ACT[hact if hact is None else str(hact).lower()], L.stream_ptr())
+    L.check(rc, "rb_norm_act_head_fwd")
+    return out
+
+
 class _ZeroGradParamFn(torch.autograd.Function):
     """Ties a parameter whose effect cancels exactly (a conv bias in front of InstanceNorm) into the
     graph so that it receives the exact gradient, zero, as it (up to rounding) does in the reference."""

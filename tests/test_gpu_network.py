@@ -234,6 +234,32 @@ def test_eval_activation_semantics(rb):
     assert torch.allclose(act.sum(1), torch.ones_like(act.sum(1)), atol=1e-5)
 
 
+def test_inference_tail_fusion_is_transparent(rb):
+    """no_grad forward: the decoders' last norm + act + head run as one pass (ops.conv_norm_act_head, no stored
+    activation); switching the fusion off (the two-pass path the training forward uses) gives the same logits up to
+    the run-to-run atomics noise of two forward passes (5e-3, as in test_eval_activation_semantics)."""
+    model, mgr = _build(rb, "aniso_8x32x32")
+    x = torch.rand(2, 1, 8, 32, 32, device="cuda")
+    model.eval()
+    with torch.no_grad():
+        model(x)                                        # weight packs are built (and cached) by the first forward
+    n0 = rb._lib.launch_count()
+    with torch.no_grad():
+        fused = {t: v.clone() for t, v in model(x).items()}
+    n_fused = rb._lib.launch_count() - n0
+    rb.ops.FUSE_HEAD = False
+    try:
+        n0 = rb._lib.launch_count()
+        with torch.no_grad():
+            plain = model(x)
+        n_plain = rb._lib.launch_count() - n0
+    finally:
+        rb.ops.FUSE_HEAD = True
+    assert n_fused == n_plain - len(mgr.tasks)          # one launch less per task decoder
+    for t in mgr.tasks:
+        assert rel_l2(fused[t], plain[t]) < 5e-3, t
+
+
 def test_training_step_is_cuda_graph_capturable(rb):
     """bench.py replays the whole step (fwd + loss + bwd + clip + AdamW) as one CUDA graph: nothing on the path may
     synchronise, copy from pageable host memory or allocate index tensors on the host (weight packs included, which are

@@ -276,6 +276,59 @@ def test_head(rb, k, act):
         assert rel_l2(b.grad, br.grad) < TOL_F32
 
 
+@pytest.mark.parametrize("c", [8, 24, 64, 256])
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_head_channel_counts(rb, c, k):
+    """C / 8 a power of two takes the (voxel, channel-group) lane kernel, C = 24 the per-voxel one; S = 5*7*9 is not a
+    multiple of the voxels a warp instruction covers (ragged tail)."""
+    torch.manual_seed(60 + c + k)
+    x = q(torch.randn(2, c, 5, 7, 9, device="cuda"))
+    w = torch.randn(k, c, 1, 1, 1, device="cuda") * 0.2
+    b = torch.randn(k, device="cuda") * 0.1
+    for act, fn in ((None, lambda t: t), ("sigmoid", torch.sigmoid), ("softmax", lambda t: torch.softmax(t, 1))):
+        out = rb.ops.head_conv1x1(x, w, b, act)
+        assert rel_l2(out, fn(F.conv3d(x, w, b))) < 1e-5
+
+
+@pytest.mark.parametrize("case", [
+    # n, cin, cat, cout, dims, k, with_res, head activation
+    (2, 32, 0, 32, (8, 8, 8), 1, False, None),
+    (1, 32, 32, 32, (5, 6, 10), 3, False, None),
+    (2, 16, 0, 64, (4, 6, 6), 3, True, "softmax"),
+    (1, 32, 0, 256, (4, 4, 4), 8, False, "sigmoid"),
+    (1, 8, 0, 8, (3, 5, 7), 2, True, None),
+])
+def test_fused_norm_act_head_tail(rb, case):
+    """Inference tail of a decoder: conv -> IN -> LeakyReLU -> 1x1x1 head with the activation never stored
+    (ops.conv_norm_act_head / rb_norm_act_head_fwd) against (a) the two-pass path of the same library - same bf16
+    rounding of the activation, only the summation order of the 1x1 dot product differs: 1e-5 - and (b) torch fp32."""
+    n, cin, cat, cout, dims, k, with_res, hact = case
+    torch.manual_seed(61)
+    x = q(torch.randn(n, cin, *dims, device="cuda"))
+    xc = q(torch.randn(n, cat, *dims, device="cuda")) if cat else None
+    w = torch.randn(cout, cin + cat, 3, 3, 3, device="cuda") / (27 * (cin + cat)) ** 0.5
+    gamma = 1 + 0.2 * torch.randn(cout, device="cuda")
+    beta = 0.1 * torch.randn(cout, device="cuda")
+    res = q(torch.randn(n, cout, *dims, device="cuda")) if with_res else None
+    hw = torch.randn(k, cout, 1, 1, 1, device="cuda") * 0.2
+    hb = torch.randn(k, device="cuda") * 0.1
+    head = (hw, hb, hact)
+    with torch.no_grad():
+        assert rb.ops.can_fuse_head(w, head)
+        fused = rb.ops.conv_norm_act_head(x, w, 1, xc, res, gamma, beta, 1e-5, True, 0.01, False, head)
+        z = rb.ops.conv_norm_act(x, w, 1, x_cat=xc, res=res, gamma=gamma, beta=beta, act=True)
+        two_pass = rb.ops.head_conv1x1(z, hw, hb, hact)
+        xin = torch.cat((x, xc), 1) if cat else x
+        o = F.instance_norm(F.conv3d(xin, q(w), None, 1, 1), None, None, gamma, beta, True, 0.0, 1e-5)
+        ref = F.conv3d(F.leaky_relu(o + res if with_res else o, 0.01), hw, hb)
+        ref = torch.sigmoid(ref) if hact == "sigmoid" else torch.softmax(ref, 1) if hact == "softmax" else ref
+    assert fused.shape == two_pass.shape == ref.shape and fused.dtype == torch.float32 and fused.is_contiguous()
+    assert rel_l2(fused, two_pass) < 1e-5
+    assert rel_l2(fused, ref) < TOL_BF16
+    with torch.enable_grad():
+        assert not rb.ops.can_fuse_head(w, head)     # training keeps the stored activation for backward
+
+
 @pytest.mark.parametrize("cin", [1, 2, 4])
 def test_stem_conv(rb, cin):
     torch.manual_seed(7)

@@ -241,7 +241,7 @@ def test_zarr_v2_final_writer_roundtrip(rb, tmp_path):
     sheet = rng.integers(0, 256, vol, dtype=np.uint8)
     sheet[16:32, 8:16, 12:24] = 0                       # one all-zero chunk: must not exist on disk
     normals = rng.integers(0, 65536, (3, *vol), dtype=np.uint16)
-    for comp in ("zlib", None):
+    for comp in ("blosc", "zlib", None):
         root = str(tmp_path / f"out_{comp}.zarr")
         w = inf.FinalVolumeWriter(root, targets, vol, patch, compressor=comp, threads=4)
         for z0, z1 in [(0, 16), (16, 21), (21, 32), (32, 37)]:      # aligned, two partial pieces of one row, ragged tail
@@ -268,8 +268,78 @@ def test_zarr_v2_final_writer_roundtrip(rb, tmp_path):
         if comp is None:                                  # raw chunk = C-order bytes of the padded chunk
             raw = np.fromfile(os.path.join(root, "sheet_final", "2.2.2"), dtype=np.uint8).reshape(patch)
             assert np.array_equal(raw[:5, :4, :2], sheet[32:, 16:, 24:]) and not raw[5:].any()
+        if comp == "blosc":                              # the reference's codec configuration (inference.py:92,224)
+            assert ms["compressor"] == {"id": "blosc", "cname": "zstd", "clevel": 5, "shuffle": 2, "blocksize": 0}
+            from importlib import import_module
+            bc = import_module(inf.__name__ + ".blosc_codec")
+            h = bc.header(open(os.path.join(root, "normals_final", "0.1.1.1"), "rb").read())
+            assert h["typesize"] == 2 and h["nbytes"] == 3 * 16 * 8 * 12 * 2 and h["version"] == 2
     with pytest.raises(NotImplementedError):
-        inf.FinalVolumeWriter(str(tmp_path / "x.zarr"), targets, vol, patch, compressor="blosc")
+        inf.FinalVolumeWriter(str(tmp_path / "x.zarr"), targets, vol, patch, compressor="lz4")
+
+
+def _bitshuffle_literal(buf, ts):
+    """bitshuffle's bshuf_trans_bit_elem spelled out bit by bit: out[(j*8 + b) * (n/8) + k] bit i = bit b of byte j of
+    element 8k + i (blocks whose element count is not a multiple of 8 are copied, as c-blosc 1.x does)."""
+    n = len(buf) // ts
+    out = bytearray(buf)
+    if n % 8:
+        return bytes(out)                  # c-blosc 1.x copies such a block
+    for j in range(ts):
+        for b in range(8):
+            for k in range(n // 8):
+                v = 0
+                for i in range(8):
+                    v |= ((buf[(8 * k + i) * ts + j] >> b) & 1) << i
+                out[(j * 8 + b) * (n // 8) + k] = v
+    return bytes(out)
+
+
+def test_blosc_zstd_bitshuffle_container(rb):
+    """The reference's output codec, Blosc(cname='zstd', clevel=5, shuffle=BITSHUFFLE) (inference.py:92,224), written
+    without libblosc: byte-level checks of the Blosc-1 header / block table, the bit-shuffle against a literal
+    restatement, zstd frames that the system libzstd decodes, and round trips over the edge cases (empty, shorter
+    than the 128-byte minimum, incompressible, ragged last block, typesize 1 / 2 / 4, every shuffle mode)."""
+    import struct
+    from importlib import import_module
+    bc = import_module(rb.inference.__name__ + ".blosc_codec")
+    rng = np.random.default_rng(11)
+    # bit-shuffle == the literal definition, for element counts that are and are not multiples of 8
+    for ts, n in ((1, 64), (2, 40), (4, 24), (4, 27), (2, 7)):
+        raw = rng.integers(0, 256, ts * n, dtype=np.uint8)
+        assert bc._bit_shuffle(raw, ts).tobytes() == _bitshuffle_literal(raw.tobytes(), ts)
+        assert np.array_equal(bc._bit_unshuffle(bc._bit_shuffle(raw, ts), ts), raw)
+        assert np.array_equal(bc._byte_unshuffle(bc._byte_shuffle(raw, ts), ts), raw)
+    # a smooth uint16 volume compresses; header fields and block table are what c-blosc documents
+    vol = (np.add.outer(np.arange(300), np.arange(500)) * 3).astype("<u2")
+    buf = bc.compress(vol.tobytes(), typesize=2, clevel=5, shuffle=bc.BITSHUFFLE)
+    ver, verlz, flags, ts, nbytes, bs, cbytes = struct.unpack("<BBBBiii", buf[:16])
+    assert (ver, verlz, ts, nbytes, cbytes) == (2, 1, 2, vol.nbytes, len(buf)) and len(buf) < vol.nbytes // 4
+    assert flags == 0x04 | 0x10 | (4 << 5)              # bit-shuffle, unsplit blocks, codec zstd
+    nblocks = -(-nbytes // bs)
+    bstarts = struct.unpack("<%di" % nblocks, buf[16:16 + 4 * nblocks])
+    assert bstarts[0] == 16 + 4 * nblocks and list(bstarts) == sorted(bstarts) and nblocks > 1
+    (cs0,) = struct.unpack("<i", buf[bstarts[0]:bstarts[0] + 4])
+    assert bstarts[1] == bstarts[0] + 4 + cs0
+    assert buf[bstarts[0] + 4:bstarts[0] + 8] == b"\x28\xb5\x2f\xfd"      # zstd frame magic
+    first = bc._zstd().decompress(buf[bstarts[0] + 4:bstarts[0] + 4 + cs0], bs)
+    assert first == bc._bit_shuffle(np.frombuffer(vol.tobytes()[:bs], np.uint8), 2).tobytes()
+    assert bc.decompress(buf) == vol.tobytes()
+    # edge cases
+    for data, ts in ((b"", 1), (bytes(range(100)), 1), (rng.integers(0, 256, 70001, dtype=np.uint8).tobytes(), 1),
+                     (rng.integers(0, 256, 300000, dtype=np.uint8).tobytes(), 4), (bytes(1 << 20), 2),
+                     (np.arange(100003, dtype="<u4").tobytes()[:-1], 4)):
+        for sh in (bc.NOSHUFFLE, bc.SHUFFLE, bc.BITSHUFFLE):
+            for blocksize in (0, 4096):
+                b = bc.compress(data, typesize=ts, clevel=5, shuffle=sh, blocksize=blocksize)
+                h = bc.header(b)
+                assert h["nbytes"] == len(data) and h["cbytes"] == len(b) and len(b) <= len(data) + 16
+                assert bc.decompress(b) == data
+    assert bc.header(bc.compress(bytes(range(100)), 1))["memcpyed"]                     # < 128 bytes: stored
+    assert bc.header(bc.compress(rng.integers(0, 256, 70001, dtype=np.uint8).tobytes(), 1))["memcpyed"]   # random: stored
+    assert bc.header(bc.compress(bytes(1 << 20), 2, clevel=0))["memcpyed"]
+    with pytest.raises(ValueError):
+        bc.decompress(buf[:len(buf) // 2])
 
 
 def test_weight_pack_cache_sees_fused_optimizer_updates(rb):
