@@ -1178,6 +1178,13 @@ int rb_plane_reduce(int kind, const void* y, int y_f32, const void* dz, const vo
         gx = (int)(want < 1 ? 1 : want);
     }
     const size_t smem = (size_t)256 * 16 * sizeof(float);
+    // two voxels in flight per thread (RESENC_NORM_U2=0 restores the one-voxel kernels)
+    static const bool u2 = !(getenv("RESENC_NORM_U2") && atoi(getenv("RESENC_NORM_U2")) == 0);
+    if (u2 && !perW && y_f32 != 1 && cg <= 256 && 256 % cg == 0 && S * cg < (1LL << 31)) {
+        if (sign_scale) rb::plane_reduce_u2_kernel<true><<<dim3(gx, NB), 256, smem, st>>>(p);
+        else rb::plane_reduce_u2_kernel<false><<<dim3(gx, NB), 256, smem, st>>>(p);
+        return check_launch("plane_reduce_u2_kernel");
+    }
     if (sign_scale) rb::plane_reduce_kernel<true><<<dim3(gx, NB), 256, smem, st>>>(p);
     else rb::plane_reduce_kernel<false><<<dim3(gx, NB), 256, smem, st>>>(p);
     return check_launch("plane_reduce_kernel");
@@ -1232,6 +1239,20 @@ int rb_norm_act_fwd(const void* y, int y_f32, const void* res, void* z, const fl
         rb::norm_act_fwd_x2_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_fwd_x2_kernel");
     }
+    static const bool un = !(getenv("RESENC_NORM_U2") && atoi(getenv("RESENC_NORM_U2")) == 0);
+    if (un && y_f32 != 1) {
+        const cudaStream_t st = (cudaStream_t)stream;
+        if (res) {
+            const dim3 grid(grid_for((per + 1) / 2, 256, 8), NB);
+            if (y_f32 == 2) rb::norm_act_fwd_un_kernel<true, true, 2><<<grid, 256, 0, st>>>(p);
+            else rb::norm_act_fwd_un_kernel<false, true, 2><<<grid, 256, 0, st>>>(p);
+        } else {
+            const dim3 grid(grid_for((per + 3) / 4, 256, 8), NB);
+            if (y_f32 == 2) rb::norm_act_fwd_un_kernel<true, false, 4><<<grid, 256, 0, st>>>(p);
+            else rb::norm_act_fwd_un_kernel<false, false, 4><<<grid, 256, 0, st>>>(p);
+        }
+        return check_launch("norm_act_fwd_un_kernel");
+    }
     rb::norm_act_fwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_act_fwd_kernel");
 }
@@ -1253,6 +1274,23 @@ int rb_norm_act_bwd(const void* dz, const void* z, const float* sign_scale, cons
         gx = grid_for((per + 1) / 2, 256, 8);
         rb::norm_act_bwd_v1_kernel<2><<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("norm_act_bwd_v1_kernel");
+    }
+    static const bool u2 = !(getenv("RESENC_NORM_U2") && atoi(getenv("RESENC_NORM_U2")) == 0);
+    if (u2 && y_f32 != 1) {
+        gx = grid_for((per + 1) / 2, 256, 8);
+        const int zm = !act ? 0 : z ? 1 : 2;
+        const dim3 grid(gx, NB);
+        const cudaStream_t st = (cudaStream_t)stream;
+        if (y_f32 == 2) {
+            if (zm == 0) rb::norm_act_bwd_u2_kernel<true, 0><<<grid, 256, 0, st>>>(p);
+            else if (zm == 1) rb::norm_act_bwd_u2_kernel<true, 1><<<grid, 256, 0, st>>>(p);
+            else rb::norm_act_bwd_u2_kernel<true, 2><<<grid, 256, 0, st>>>(p);
+        } else {
+            if (zm == 0) rb::norm_act_bwd_u2_kernel<false, 0><<<grid, 256, 0, st>>>(p);
+            else if (zm == 1) rb::norm_act_bwd_u2_kernel<false, 1><<<grid, 256, 0, st>>>(p);
+            else rb::norm_act_bwd_u2_kernel<false, 2><<<grid, 256, 0, st>>>(p);
+        }
+        return check_launch("norm_act_bwd_u2_kernel");
     }
     rb::norm_act_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("norm_act_bwd_kernel");
@@ -1294,12 +1332,19 @@ static int launch_norm_head(const void* y, int y_mode, const void* res, const fl
     const size_t smem = (size_t)(K * C + K) * sizeof(float);
     const int vpw = 32 / (C / 8);                                   // voxels per warp instruction
     const long long warpIters = (S + vpw - 1) / vpw;                // per sample
-    int gx = (int)std::min<long long>((warpIters + 15) / 16, (long long)num_sms() * 8);   // 8 warps x 2 voxel sets per block pass
+    int gx = (int)std::min<long long>((warpIters + 8 * rb::NH_U - 1) / (8 * rb::NH_U), (long long)num_sms() * 6);   // 8 warps x NH_U voxel sets per block pass
     if (gx < 1) gx = 1;
     const dim3 grid(gx, NB);
-    if (K == 1) rb::norm_act_head_fwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-    else if (K <= 4) rb::norm_act_head_fwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-    else rb::norm_act_head_fwd_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    const cudaStream_t st = (cudaStream_t)stream;
+#define RB_NH_LAUNCH(KM, NORM, YM, RES) rb::norm_act_head_fwd_kernel<KM, NORM, YM, RES><<<grid, 256, smem, st>>>(p)
+#define RB_NH_K(NORM, YM, RES) do { if (K == 1) RB_NH_LAUNCH(1, NORM, YM, RES); else if (K <= 4) RB_NH_LAUNCH(4, NORM, YM, RES); \
+                                    else RB_NH_LAUNCH(8, NORM, YM, RES); } while (0)
+    if (scale == nullptr) RB_NH_K(0, 0, 0);
+    else if (y_mode == 2) { if (res) RB_NH_K(1, 2, 1); else RB_NH_K(1, 2, 0); }
+    else if (y_mode == 1) { if (res) RB_NH_K(1, 1, 1); else RB_NH_K(1, 1, 0); }
+    else { if (res) RB_NH_K(1, 0, 1); else RB_NH_K(1, 0, 0); }
+#undef RB_NH_K
+#undef RB_NH_LAUNCH
     return check_launch("norm_act_head_fwd_kernel");
 }
 

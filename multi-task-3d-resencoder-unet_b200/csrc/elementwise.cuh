@@ -184,6 +184,99 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const ReduceParams p)
     }
 }
 
+// Round-2 variant of the per-(n, c) reduction for 2-byte pre-norm tensors (one coefficient set per sample, not the
+// per-w variant).  ncu on the kernel above at 32 ch @128^3 x2 (profiles/r2_ncu_norm_passes.csv): 137 us for 537 MB =
+// 3.9 TB/s, issue slots 30 % busy, 32 resident warps per SM, every warp waiting on its two 16-byte loads (long
+// scoreboard) - ~32 KB in flight per SM, not enough to cover the DRAM latency at 6.5 TB/s.  Here a thread issues the
+// loads of TWO voxels before it touches either (raw 16-byte registers, unpacked one voxel at a time), which doubles the
+// bytes in flight at +8 registers.
+template <bool SGN>
+__global__ void __launch_bounds__(256, 4) plane_reduce_u2_kernel(const ReduceParams p) {
+    extern __shared__ float red[];  // [rows][cg*16]
+    const int cg = p.C >> 3;        // <= 256 (host-checked)
+    const int rows = 256 / cg;
+    const int nb = blockIdx.y;
+    const int mycg = threadIdx.x % cg;
+    const int myrow = threadIdx.x / cg;
+    const bool active = myrow < rows;
+    const bool yh = p.yF32 == 2;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    if (active) {
+        // 32-bit index math inside one sample (S * C/8 < 2^31, checked on the host)
+        const size_t base = (size_t)nb * p.S * cg + mycg;
+        const uint4* yv = reinterpret_cast<const uint4*>(p.y) + base;
+        const uint4* dzv = reinterpret_cast<const uint4*>(p.dz) + base;
+        const uint4* zv = reinterpret_cast<const uint4*>(p.z) + base;
+        const uint32_t S = (uint32_t)p.S;
+        const uint32_t step = gridDim.x * (uint32_t)rows;
+        const size_t cs = (size_t)nb * p.C + (size_t)mycg * 8;
+        auto accum = [&](const uint4& ry, const uint4& rdz, const uint4& rz) {
+            float a[8], b[8];
+            if (yh) {
+                a[0] = f16lo(ry.x); a[1] = f16hi(ry.x); a[2] = f16lo(ry.y); a[3] = f16hi(ry.y);
+                a[4] = f16lo(ry.z); a[5] = f16hi(ry.z); a[6] = f16lo(ry.w); a[7] = f16hi(ry.w);
+            } else {
+                unpack8(ry, a);
+            }
+            if (p.kind == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] = fmaf(a[j], a[j], s2[j]); }
+                return;
+            }
+            unpack8(rdz, b);
+            if (!SGN && p.z != nullptr) {
+                float zz[8];
+                unpack8(rz, zz);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = zz[j] > 0.f ? b[j] : b[j] * p.slope;
+            } else if (SGN) {
+                // scale / shift re-read per voxel (L1 hits) instead of 16 live registers per thread
+                float sA[8], sB[8];
+                *reinterpret_cast<float4*>(sA) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs));
+                *reinterpret_cast<float4*>(sA + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs + 4));
+                *reinterpret_cast<float4*>(sB) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs));
+                *reinterpret_cast<float4*>(sB + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs + 4));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = fmaf(a[j], sA[j], sB[j]) > 0.f ? b[j] : b[j] * p.slope;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] += b[j]; s2[j] = fmaf(b[j], a[j], s2[j]); }
+        };
+        for (uint32_t v = blockIdx.x * (uint32_t)rows + myrow; v < S; v += 2u * step) {
+            const bool two = v + step < S;
+            const uint32_t o0 = v * (uint32_t)cg, o1 = (v + step) * (uint32_t)cg;
+            uint4 y0, y1, d0, d1, z0, z1;
+            y0 = ld_stream(yv + o0);
+            if (p.kind != 0) d0 = ld_stream(dzv + o0);
+            if (!SGN && p.kind != 0 && p.z != nullptr) z0 = ld_stream(zv + o0);
+            if (two) {
+                y1 = ld_stream(yv + o1);
+                if (p.kind != 0) d1 = ld_stream(dzv + o1);
+                if (!SGN && p.kind != 0 && p.z != nullptr) z1 = ld_stream(zv + o1);
+            }
+            accum(y0, d0, z0);
+            if (two) accum(y1, d1, z1);
+        }
+    }
+    const int width = cg * 16;
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[myrow * width + mycg * 16 + j] = s1[j];
+            red[myrow * width + mycg * 16 + 8 + j] = s2[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < rows; ++r) acc += red[r * width + i];
+        const int g = i >> 4, j = i & 15;
+        atomicAdd(p.out + ((size_t)nb * p.C + g * 8 + (j & 7)) * 2 + (j >> 3), (double)acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Fused apply:   z = act( y * scale[n,(w),c] + shift[n,(w),c] + res )
 // scale/shift fold mean, rstd, affine gamma/beta and the SE gate (host glue builds them
@@ -278,6 +371,65 @@ __global__ void __launch_bounds__(256) norm_act_fwd_x2_kernel(const ApplyParams 
     }
 }
 
+// Several vectors in flight per thread for the forward apply pass (2-byte pre-norm tensor): all loads of an iteration
+// are issued first and held as raw 16-byte registers, then unpacked and finished one vector at a time.  The one-vector
+// kernel keeps 48 warps x one 16-byte load = 24 KB per SM in flight (long-scoreboard bound, issue slots 50 % busy,
+// 4.4 TB/s at 32 ch @128^3 x2); U = 4 without a residual / U = 2 with one put 64 KB in flight at 4 blocks per SM.
+template <bool YH, bool HAS_RES, int U>
+__global__ void __launch_bounds__(256, 4) norm_act_fwd_un_kernel(const ApplyParams p) {
+    const uint32_t cg = (uint32_t)p.C >> 3;
+    const uint32_t per = (uint32_t)p.S * cg;
+    const int nb = blockIdx.y;
+    const size_t base = (size_t)nb * per;
+    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + base;
+    const uint4* rv = HAS_RES ? reinterpret_cast<const uint4*>(p.res) + base : nullptr;
+    uint4* zv = reinterpret_cast<uint4*>(p.z) + base;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < per; i0 += (uint32_t)U * stride) {
+        uint4 ry[U], rr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * stride;
+            if (i < per) {
+                ry[u] = ld_stream(yv + i);
+                if (HAS_RES) rr[u] = ld_stream(rv + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * stride;
+            if (i >= per) break;
+            const uint32_t g = i % cg;
+            const uint32_t v = i / cg;
+            const size_t cidx = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
+            float a[8], sc[8], sh[8];
+            if (YH) {
+                a[0] = f16lo(ry[u].x); a[1] = f16hi(ry[u].x); a[2] = f16lo(ry[u].y); a[3] = f16hi(ry[u].y);
+                a[4] = f16lo(ry[u].z); a[5] = f16hi(ry[u].z); a[6] = f16lo(ry[u].w); a[7] = f16hi(ry[u].w);
+            } else {
+                unpack8(ry[u], a);
+            }
+            *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx));
+            *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cidx + 4));
+            *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx));
+            *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + cidx + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sh[j]);
+            if (HAS_RES) {
+                float r[8];
+                unpack8(rr[u], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += r[j];
+            }
+            if (p.act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = a[j] > 0.f ? a[j] : a[j] * p.slope;
+            }
+            zv[i] = pack8(a);
+        }
+    }
+}
+
 // Backward of the fused apply + InstanceNorm:
 //   g    = dz * lrelu'(z)                 (z = saved output; act==0 => g = dz)
 //   dres = g                              (only when dres != null)
@@ -342,6 +494,81 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const ApplyBwdParams 
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(gd[j], a1[j], fmaf(yy[j], a2[j], a3[j]));
         dyv[i] = pack8(o);
+    }
+}
+
+// Two vectors in flight per thread for the backward apply pass (2-byte pre-norm tensor): the loads of both vectors are
+// issued first and held as raw 16-byte registers (8-12 registers instead of the 32-48 floats the hoisted-coefficient
+// variant below kept live), unpacked one vector at a time; coefficients stay L1 reads.  ncu on the kernel above at
+// 32 ch @128^3 x2: 180 us, 4.5 TB/s, issue slots 38 % busy, long-scoreboard bound with 40 warps x 2 loads in flight.
+// ZM: how lrelu'(z) is obtained - 0 no activation, 1 from the stored z, 2 from the sign of fmaf(y, sgnA, sgnB)
+template <bool YH, int ZM>
+__global__ void __launch_bounds__(256, 4) norm_act_bwd_u2_kernel(const ApplyBwdParams p) {
+    const uint32_t cg = (uint32_t)p.C >> 3;
+    const uint32_t per = (uint32_t)p.S * cg;
+    const int nb = blockIdx.y;
+    const size_t base = (size_t)nb * per;
+    const uint4* dzv = reinterpret_cast<const uint4*>(p.dz) + base;
+    const uint4* yv = reinterpret_cast<const uint4*>(p.y) + base;
+    constexpr bool hasz = ZM == 1;
+    constexpr bool sgn = ZM == 2;
+    const uint4* zv = hasz ? reinterpret_cast<const uint4*>(p.z) + base : nullptr;
+    uint4* dyv = reinterpret_cast<uint4*>(p.dy) + base;
+    uint4* drv = p.dres ? reinterpret_cast<uint4*>(p.dres) + base : nullptr;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    auto apply = [&](uint32_t i, const uint4& rdz, const uint4& ry, const uint4& rz) {
+        const uint32_t g = i % cg;
+        const uint32_t v = i / cg;
+        const size_t c1 = p.perW ? (((size_t)nb * p.W + (v % (uint32_t)p.W)) * p.C + g * 8) : ((size_t)nb * p.C + g * 8);
+        float gd[8], yy[8], a1[8], a2[8], a3[8];
+        unpack8(rdz, gd);
+        if (YH) {
+            yy[0] = f16lo(ry.x); yy[1] = f16hi(ry.x); yy[2] = f16lo(ry.y); yy[3] = f16hi(ry.y);
+            yy[4] = f16lo(ry.z); yy[5] = f16hi(ry.z); yy[6] = f16lo(ry.w); yy[7] = f16hi(ry.w);
+        } else {
+            unpack8(ry, yy);
+        }
+        if (hasz) {
+            float zz[8];
+            unpack8(rz, zz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd[j] = zz[j] > 0.f ? gd[j] : gd[j] * p.slope;
+        } else if (sgn) {
+            const size_t cs = (size_t)nb * p.C + g * 8;
+            float sa[8], sb[8];
+            *reinterpret_cast<float4*>(sa) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs));
+            *reinterpret_cast<float4*>(sa + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnA + cs + 4));
+            *reinterpret_cast<float4*>(sb) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs));
+            *reinterpret_cast<float4*>(sb + 4) = __ldg(reinterpret_cast<const float4*>(p.sgnB + cs + 4));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gd[j] = fmaf(yy[j], sa[j], sb[j]) > 0.f ? gd[j] : gd[j] * p.slope;
+        }
+        if (drv != nullptr) drv[i] = pack8(gd);
+        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1));
+        *reinterpret_cast<float4*>(a1 + 4) = __ldg(reinterpret_cast<const float4*>(p.k1 + c1 + 4));
+        *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(p.k2 + c1));
+        *reinterpret_cast<float4*>(a2 + 4) = __ldg(reinterpret_cast<const float4*>(p.k2 + c1 + 4));
+        *reinterpret_cast<float4*>(a3) = __ldg(reinterpret_cast<const float4*>(p.k3 + c1));
+        *reinterpret_cast<float4*>(a3 + 4) = __ldg(reinterpret_cast<const float4*>(p.k3 + c1 + 4));
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(gd[j], a1[j], fmaf(yy[j], a2[j], a3[j]));
+        dyv[i] = pack8(o);
+    };
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < per; i0 += 2u * stride) {
+        const uint32_t i1 = i0 + stride;
+        const bool two = i1 < per;
+        uint4 d0, y0, z0, d1, y1, z1;
+        d0 = ld_stream(dzv + i0);
+        y0 = ld_stream(yv + i0);
+        if (hasz) z0 = ld_stream(zv + i0);
+        if (two) {
+            d1 = ld_stream(dzv + i1);
+            y1 = ld_stream(yv + i1);
+            if (hasz) z1 = ld_stream(zv + i1);
+        }
+        apply(i0, d0, y0, z0);
+        if (two) apply(i1, d1, y1, z1);
     }
 }
 
@@ -611,8 +838,12 @@ struct NormHeadParams {
     int yF32;
 };
 
-template <int KMAX>
-__global__ void __launch_bounds__(256, 4) norm_act_head_fwd_kernel(const NormHeadParams p) {
+// Template flags keep every per-element decision out of the instruction stream: the first version tested the pre-norm
+// type, residual and activation per element and needed ~300 instructions per 16-byte vector - issue bound at 1.9 TB/s.
+//   NORM: 0 = plain head on a stored bf16 activation, 1 = normalise + activation first;  YMODE: element type of y
+static constexpr int NH_U = 4;   // voxel sets (16-byte loads) in flight per thread: 3 blocks x 8 warps x 4 x 512 B = 48 KB per SM
+template <int KMAX, int NORM, int YMODE, int HAS_RES>
+__global__ void __launch_bounds__(256, 3) norm_act_head_fwd_kernel(const NormHeadParams p) {
     extern __shared__ float hw[];  // [K][C] + [K]
     for (int i = threadIdx.x; i < p.K * p.C; i += blockDim.x) hw[i] = p.w[i];
     for (int i = threadIdx.x; i < p.K; i += blockDim.x) hw[p.K * p.C + i] = p.b ? p.b[i] : 0.f;
@@ -620,29 +851,32 @@ __global__ void __launch_bounds__(256, 4) norm_act_head_fwd_kernel(const NormHea
     const uint32_t cg = (uint32_t)p.C >> 3;          // lanes per voxel
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t g = lane & (cg - 1u);
+    const uint32_t vsub = lane / cg;                 // voxel of this lane within the warp's group
     const uint32_t vpw = 32u / cg;                   // voxels per warp instruction
     const int nb = blockIdx.y;
     const uint32_t S = (uint32_t)p.S;
     const size_t base = (size_t)nb * p.S;
     const uint32_t stride = gridDim.x * 8u * vpw;
+    const float slope = p.act ? p.slope : 1.f;       // act == 0: the select below is the identity
+    const float* wrow = hw + g * 8;
+    const size_t cs = (size_t)nb * p.C + g * 8;
     // the loop variable is warp-uniform (first voxel of the warp's group): the shuffles below run with all lanes
-    for (uint32_t v0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * vpw; v0 < S; v0 += 2u * stride) {
-        float a[2][8], r[2][8];
-        bool ok[2];
+    for (uint32_t v0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * vpw; v0 < S; v0 += (uint32_t)NH_U * stride) {
+        float a[NH_U][8], r[NH_U][8];
+        bool ok[NH_U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const uint32_t v = v0 + u * stride + lane / cg;
+        for (int u = 0; u < NH_U; ++u) {
+            const uint32_t v = v0 + u * stride + vsub;
             ok[u] = v < S;
             const size_t off = (base + (ok[u] ? v : 0u)) * p.C + g * 8;
-            load8_prenorm(p.y, off, p.scale != nullptr ? p.yF32 : 0, a[u]);
-            if (p.res != nullptr) unpack8(ld_stream(reinterpret_cast<const uint4*>(p.res + off)), r[u]);
+            load8_prenorm(p.y, off, NORM ? YMODE : 0, a[u]);
+            if (HAS_RES) unpack8(ld_stream(reinterpret_cast<const uint4*>(p.res + off)), r[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (v0 + u * stride >= S) break;   // warp-uniform
-            if (p.scale != nullptr) {
-                // coefficients re-read per vector (L1 hits) rather than held in 16 registers (occupancy: 4 blocks per SM)
-                const size_t cs = (size_t)nb * p.C + g * 8;
+        for (int u = 0; u < NH_U; ++u) {
+            if (u > 0 && v0 + u * stride >= S) break;   // warp-uniform
+            if (NORM) {
+                // coefficients re-read per vector (L1 hits) rather than held in 16 registers
                 float sc[8], sh[8];
                 *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + cs));
                 *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + cs + 4));
@@ -651,21 +885,18 @@ __global__ void __launch_bounds__(256, 4) norm_act_head_fwd_kernel(const NormHea
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float t = fmaf(a[u][j], sc[j], sh[j]);
-                    if (p.res != nullptr) t += r[u][j];
-                    if (p.act) t = t > 0.f ? t : t * p.slope;
-                    a[u][j] = t;
+                    if (HAS_RES) t += r[u][j];
+                    a[u][j] = t > 0.f ? t : t * slope;
                 }
-                // what the stored activation would hold: round to bf16 (packed converts - the scalar F2F.BF16 form is a
-                // quarter-rate instruction and held the first version of this kernel at 1.9 TB/s)
-                unpack8(pack8(a[u]), a[u]);
+                unpack8(pack8(a[u]), a[u]);          // what the stored activation would hold: one rounding to bf16
             }
             float acc[KMAX];
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 acc[k] = 0.f;
                 if (k < p.K) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(hw + k * p.C + g * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(hw + k * p.C + g * 8 + 4);
+                    const float4 w0 = *reinterpret_cast<const float4*>(wrow + k * p.C);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wrow + k * p.C + 4);
                     acc[k] = fmaf(a[u][0], w0.x, fmaf(a[u][1], w0.y, fmaf(a[u][2], w0.z, a[u][3] * w0.w))) +
                              fmaf(a[u][4], w1.x, fmaf(a[u][5], w1.y, fmaf(a[u][6], w1.z, a[u][7] * w1.w)));
                 }
@@ -689,10 +920,10 @@ __global__ void __launch_bounds__(256, 4) norm_act_head_fwd_kernel(const NormHea
 #pragma unroll
                     for (int k = 0; k < KMAX; ++k) acc[k] /= sum;
                 }
-                const uint32_t v = v0 + u * stride + lane / cg;
+                float* o = p.out + (size_t)nb * p.K * p.S + (v0 + u * stride + vsub);
 #pragma unroll
                 for (int k = 0; k < KMAX; ++k)
-                    if (k < p.K) p.out[((size_t)nb * p.K + k) * p.S + v] = acc[k];
+                    if (k < p.K) o[(size_t)k * p.S] = acc[k];
             }
         }
     }
