@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--infer-overlap", type=float, default=0.5)
     ap.add_argument("--infer-weight", default="gaussian", choices=["gaussian", "uniform"])
     ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="--impl reference: time budget of the K + W sample steps")
+    ap.add_argument("--torch-optimizer", action="store_true",
+                    help="clip_grad_norm_ + torch.optim.AdamW(fused) instead of the library's ClippedAdamW (A/B)")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"],
                     help="N > 1: dtype of the gradient all-reduce on the wire (bf16 halves the NVLink bytes, DDP-style compression)")
     return ap.parse_args()
@@ -543,7 +545,11 @@ def run_train(args, rb, par, loss_mod, model, dev, rank, world, local, dist):
     crit = loss_mod.task_losses(make_mgr(P, B).tasks)
     model.train()
     use_graph = not args.no_graph   # N > 1: the bucketed NCCL all-reduces on the side stream are captured with the step
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
+    if args.torch_optimizer:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
+    else:
+        # clip_grad_norm_(3) + AdamW (train.py:79-83,227-228) as two multi-tensor passes of the library
+        opt = rb.optim.ClippedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=3.0)
     if world > 1:
         par.broadcast_parameters(model)          # replicas identical whatever each rank's RNG state was
     buckets = par.GradientBuckets(model, comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None) if world > 1 else None
@@ -566,7 +572,8 @@ def run_train(args, rb, par, loss_mod, model, dev, rank, world, local, dist):
         loss.backward()
         if buckets is not None:
             buckets.finish()
-        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 3.0)
+        if args.torch_optimizer:
+            torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 3.0)
         opt.step()
         return loss
 

@@ -204,6 +204,25 @@ int rb_stem_im2col_split(const float* x, void* col, int NB, int Cin, int D, int 
 int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int Cin, int taps, void* stream);
 int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int taps, void* stream);
 
+/* Optimiser step of the training loop: torch.nn.utils.clip_grad_norm_(model.parameters(), 3) followed by
+ * torch.optim.AdamW.step() (train.py:79-83,227-228) as two multi-tensor passes over fp32 tensors.
+ *   rb_grad_sumsq      *sumsq (device double, zeroed here) = sum over all listed gradients of g^2
+ *   rb_adamw_clip_step  g' = g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (sumsq NULL: no clipping), then the decoupled-
+ *                       weight-decay Adam update of p, m (exp_avg), v (exp_avg_sq) with bias correction for step *step
+ *                       (device float, the 1-based count of THIS update); lr is a device float (LR schedules under CUDA
+ *                       graphs).  Gradients are read, not modified.
+ * `tensors` is a HOST array; p / m / v may be NULL for rb_grad_sumsq. */
+typedef struct rb_opt_tensor {
+    void* p;
+    const void* g;
+    void* m;
+    void* v;
+    long long n;
+} rb_opt_tensor;
+int rb_grad_sumsq(const rb_opt_tensor* tensors, int count, double* sumsq, void* stream);
+int rb_adamw_clip_step(const rb_opt_tensor* tensors, int count, const float* lr, const float* step, const double* sumsq,
+                       float max_norm, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* Layout conversion at module boundaries: NCDHW fp32 <-> NDHWC bf16 (C % 8 == 0). */
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream);
 int rb_cl_to_ncdhw(const void* src, float* dst, int NB, int C, long long S, void* stream);

@@ -21,6 +21,7 @@
 #include "elementwise.cuh"
 #include "split.cuh"
 #include "blend.cuh"
+#include "optim.cuh"
 
 namespace {
 
@@ -1463,6 +1464,60 @@ int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int T, void* st
     else if (T == 8) rb::unpack_wgrad_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     else rb::unpack_wgrad_kernel<0><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     return check_launch("unpack_wgrad_kernel");
+}
+
+// ---- optimiser step (train.py:79-83 AdamW, train.py:227 clip_grad_norm_) ---------------------------------------
+static int opt_fill(rb::OptTensorList& L, const rb_opt_tensor* t, int cnt, bool need_state, long long* max_n) {
+    *max_n = 0;
+    for (int i = 0; i < cnt; ++i) {
+        if (!t[i].g || t[i].n <= 0 || (need_state && (!t[i].p || !t[i].m || !t[i].v))) return fail(RB_ERR_INVALID, "optimiser tensor list: null pointer or empty tensor");
+        L.p[i] = (float*)t[i].p; L.g[i] = (const float*)t[i].g; L.m[i] = (float*)t[i].m; L.v[i] = (float*)t[i].v; L.n[i] = t[i].n;
+        if (t[i].n > *max_n) *max_n = t[i].n;
+    }
+    for (int i = cnt; i < rb::OPT_MAX_TENSORS; ++i) { L.p[i] = nullptr; L.g[i] = nullptr; L.m[i] = nullptr; L.v[i] = nullptr; L.n[i] = 0; }
+    return RB_OK;
+}
+
+int rb_grad_sumsq(const rb_opt_tensor* tensors, int count, double* sumsq, void* stream) {
+    if (!tensors || count <= 0 || !sumsq) return fail(RB_ERR_INVALID, "grad_sumsq: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double), st));
+    for (int i0 = 0; i0 < count; i0 += rb::OPT_MAX_TENSORS) {
+        const int cnt = count - i0 < rb::OPT_MAX_TENSORS ? count - i0 : rb::OPT_MAX_TENSORS;
+        rb::OptTensorList L;
+        long long max_n;
+        int rc = opt_fill(L, tensors + i0, cnt, false, &max_n);
+        if (rc) return rc;
+        long long gx = (max_n / 4 + 256 * 4 - 1) / (256 * 4);      // four vectors per thread and pass
+        const long long cap = std::max<long long>(1, (long long)num_sms() * 8 / cnt);
+        gx = std::min<long long>(std::max<long long>(gx, 1), std::max<long long>(cap, 8));
+        rb::grad_sumsq_kernel<<<dim3((unsigned)gx, cnt), 256, 0, st>>>(L, sumsq);
+        rc = check_launch("grad_sumsq_kernel");
+        if (rc) return rc;
+    }
+    return RB_OK;
+}
+
+int rb_adamw_clip_step(const rb_opt_tensor* tensors, int count, const float* lr, const float* step, const double* sumsq,
+                       float max_norm, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (!tensors || count <= 0 || !lr || !step) return fail(RB_ERR_INVALID, "adamw_clip_step: bad arguments");
+    if (sumsq && !(max_norm > 0.f)) return fail(RB_ERR_INVALID, "adamw_clip_step: max_norm must be positive when clipping");
+    cudaStream_t st = (cudaStream_t)stream;
+    rb::OptHyper h{lr, step, sumsq, beta1, beta2, eps, weight_decay, max_norm};
+    for (int i0 = 0; i0 < count; i0 += rb::OPT_MAX_TENSORS) {
+        const int cnt = count - i0 < rb::OPT_MAX_TENSORS ? count - i0 : rb::OPT_MAX_TENSORS;
+        rb::OptTensorList L;
+        long long max_n;
+        int rc = opt_fill(L, tensors + i0, cnt, true, &max_n);
+        if (rc) return rc;
+        long long gx = (max_n / 4 + 256 * 2 - 1) / (256 * 2);      // two vectors per stream, thread and pass
+        const long long cap = std::max<long long>(1, (long long)num_sms() * 8 / cnt);
+        gx = std::min<long long>(std::max<long long>(gx, 1), std::max<long long>(cap, 8));
+        rb::adamw_clip_kernel<<<dim3((unsigned)gx, cnt), 256, 0, st>>>(L, h);
+        rc = check_launch("adamw_clip_kernel");
+        if (rc) return rc;
+    }
+    return RB_OK;
 }
 
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream) {

@@ -32,6 +32,7 @@ import torch.distributed as dist
 from . import ops
 from .losses import build_task_losses, task_losses
 from . import _lib as L
+from .optim import ClippedAdamW
 from .parallel import GradientBuckets, broadcast_parameters
 
 CLIP_NORM = 3.0          # train.py:227
@@ -81,7 +82,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model: torch.nn.Module, mgr, use_cuda_graph: bool = False, fused_losses: bool = True,
-                 process_group=None, grad_comm_dtype: Optional[torch.dtype] = None):
+                 process_group=None, grad_comm_dtype: Optional[torch.dtype] = None, fused_optimizer: bool = True):
         self.model = model
         self.group = process_group
         self.mgr = mgr
@@ -111,11 +112,17 @@ class DataParallelTrainer:
             # SGD bakes a Python-float lr into the captured kernels: the graph is re-captured whenever the schedule moves
             # the lr (end_epoch), see _lr_signature
             self.optimizer = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, nesterov=True, weight_decay=wd)
+            self._clip_in_step = False
         else:
             if self.use_graph and on_gpu:
                 lr = torch.tensor(lr, dtype=torch.float32, device=dev)   # a tensor lr stays adjustable after capture
-            self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd, fused=on_gpu,
-                                               capturable=self.use_graph and on_gpu)
+            if fused_optimizer and on_gpu:
+                # clip_grad_norm_(3) + AdamW as two multi-tensor passes (optim.ClippedAdamW; same state_dict format)
+                self.optimizer = ClippedAdamW(model.parameters(), lr=lr, weight_decay=wd, max_grad_norm=CLIP_NORM)
+            else:
+                self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd, fused=on_gpu,
+                                                   capturable=self.use_graph and on_gpu)
+        self._clip_in_step = isinstance(self.optimizer, ClippedAdamW)
         self._lr_tensors = [g["lr"] for g in self.optimizer.param_groups if torch.is_tensor(g["lr"])]
         self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=int(getattr(mgr, "max_epoch", 1000)),
                                                                     eta_min=0)
@@ -153,7 +160,8 @@ class DataParallelTrainer:
         if do_update:
             if self.buckets is not None:
                 self.buckets.finish()
-            torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], CLIP_NORM)
+            if not self._clip_in_step:
+                torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], CLIP_NORM)
             self.optimizer.step()
             self._micro = 0
         return total, per

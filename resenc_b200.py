@@ -17,6 +17,7 @@ builders = _pkg.builders
 inference = _pkg.inference
 ops = _pkg.ops
 losses = importlib.import_module(_pkg.__name__ + ".losses")
+optim = importlib.import_module(_pkg.__name__ + ".optim")
 parallel = importlib.import_module(_pkg.__name__ + ".parallel")
 precise = importlib.import_module(_pkg.__name__ + ".precise")
 training = importlib.import_module(_pkg.__name__ + ".training")

@@ -1,0 +1,139 @@
+"""optim.ClippedAdamW: clip_grad_norm_(3) + torch.optim.AdamW.step() (reference train.py:79-83,227-228) as two
+multi-tensor passes of the library.  CPU part: hyper-parameter validation, state_dict interchange with torch.optim.AdamW
+and the float64 restatement used as the checker; GPU part: the kernels against PyTorch's own clip + fused AdamW."""
+import math
+
+import pytest
+import torch
+
+
+def _mk(shapes, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(s, generator=g).to(device) for s in shapes]
+
+
+def test_hyperparameter_validation_and_state_dict_keys(rb):
+    O = rb.optim
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(NotImplementedError):
+        O.ClippedAdamW([p], amsgrad=True)
+    with pytest.raises(ValueError):
+        O.ClippedAdamW([p], betas=(1.0, 0.9))
+    with pytest.raises(ValueError):
+        O.ClippedAdamW([p], max_grad_norm=0.0)
+    opt = O.ClippedAdamW([p], lr=2e-3, weight_decay=1e-4, max_grad_norm=3.0)
+    ref = torch.optim.AdamW([p], lr=2e-3, weight_decay=1e-4)
+    mine, theirs = opt.state_dict()["param_groups"][0], ref.state_dict()["param_groups"][0]
+    assert set(theirs) <= set(mine)                                      # every key torch.optim.AdamW writes is there
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):
+        assert mine[k] == theirs[k], k
+    # a CPU parameter is refused loudly (there is no fallback path)
+    p.grad = torch.ones(4)
+    with pytest.raises(NotImplementedError):
+        opt.step()
+    # a torch.optim.AdamW checkpoint loads (and the other way round)
+    ref.step()
+    opt.load_state_dict(ref.state_dict())
+    assert set(opt.state[p]) == {"step", "exp_avg", "exp_avg_sq"}
+    ref.load_state_dict(opt.state_dict())
+
+
+def test_reference_step_is_clip_then_adamw(rb):
+    """The float64 restatement the GPU test checks against == clip_grad_norm_ + torch.optim.AdamW on the CPU."""
+    O = rb.optim
+    shapes = [(7, 5), (33,), (2, 3, 3, 3, 3)]
+    ps = [torch.nn.Parameter(t.double()) for t in _mk(shapes, 1, "cpu")]
+    ref = torch.optim.AdamW(ps, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+    mine_p = [p.detach().clone() for p in ps]
+    m = [torch.zeros_like(p) for p in ps]
+    v = [torch.zeros_like(p) for p in ps]
+    for step in range(1, 5):
+        gs = [t.double() * (4.0 if step % 2 else 0.05) for t in _mk(shapes, 10 + step, "cpu")]     # clipped / not clipped
+        for p, g in zip(ps, gs):
+            p.grad = g.clone()
+        total_ref = torch.nn.utils.clip_grad_norm_(ps, 3.0)
+        ref.step()
+        out, total = O.reference_step(mine_p, gs, m, v, step, 3e-3, (0.9, 0.99), 1e-8, 0.05, 3.0)
+        mine_p, m, v = [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
+        assert abs(total - float(total_ref)) < 1e-9 * total
+        for a, b in zip(mine_p, ps):
+            assert torch.allclose(a, b.detach(), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_norm", [3.0, None])
+def test_clipped_adamw_matches_torch(rb, max_norm):
+    """Five steps on tensors that cover the vector path, its scalar tail, a misaligned view (gradient bucket slot), a
+    tensor larger than one launch chunk's grid and > 48 tensors (two launches); gradients alternate between clipped
+    and unclipped.  Bound: 2e-6 relative to PyTorch's clip_grad_norm_ + AdamW(fused) (both fp32; PyTorch evaluates
+    the scalar coefficients in double), 1e-6 against the float64 restatement."""
+    O = rb.optim
+    dev = "cuda"
+    shapes = [(512, 64, 3, 3, 3), (1 << 20,), (33, 7), (5,), (1,), (64, 32, 1, 1, 1)] + [(17 + i,) for i in range(50)]
+    init = _mk(shapes, 2, dev)
+    big = torch.zeros(4 * 1000 + 3, device=dev)
+    ps = [torch.nn.Parameter(t.clone()) for t in init]
+    qs = [torch.nn.Parameter(t.clone()) for t in init]
+    opt = O.ClippedAdamW(ps, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=max_norm)
+    ref = torch.optim.AdamW(qs, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, fused=True)
+    p64 = [t.double() for t in init]
+    m64 = [torch.zeros_like(t) for t in p64]
+    v64 = [torch.zeros_like(t) for t in p64]
+    for step in range(1, 6):
+        gs = [t * (3.0 if step % 2 else 1e-3) for t in _mk(shapes, 20 + step, dev)]
+        for i, (p, q, g) in enumerate(zip(ps, qs, gs)):
+            if i == 2:      # a gradient that lives at a 4-byte-aligned offset of a flat buffer (DDP bucket slot)
+                slot = big[1:1 + g.numel()].view_as(g)
+                slot.copy_(g)
+                p.grad = slot
+            else:
+                p.grad = g.clone()
+            q.grad = g.clone()
+        before = [p.grad.clone() for p in ps]
+        opt.step()
+        if max_norm is not None:
+            total_ref = torch.nn.utils.clip_grad_norm_(qs, max_norm)
+            assert abs(float(opt.last_grad_norm()) - float(total_ref)) < 1e-5 * float(total_ref)
+        ref.step()
+        for p, b in zip(ps, before):
+            assert torch.equal(p.grad, b)                    # gradients are read, never rescaled in place
+        out, _ = O.reference_step(p64, [g.double() for g in gs], m64, v64, step, 2e-3, (0.9, 0.999), 1e-8, 1e-2, max_norm)
+        p64, m64, v64 = [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
+        for i, (p, q, e) in enumerate(zip(ps, qs, p64)):
+            scale = float(e.abs().max()) + 1e-12
+            assert float((p.detach().double() - e).abs().max()) < 1e-6 * scale + 1e-7, (step, i)
+            assert float((p.detach() - q.detach()).abs().max()) < 2e-6 * scale + 2e-7, (step, i)
+            for key in ("exp_avg", "exp_avg_sq"):      # absolute bound: the lerp cancels for entries near zero
+                a, b = opt.state[p][key], ref.state[q][key]
+                assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-12, (step, i, key)
+        assert float(opt.state[ps[0]]["step"]) == step
+    rb._lib.device_error_check()
+
+
+@pytest.mark.gpu
+def test_clipped_adamw_under_cuda_graph_follows_a_tensor_lr(rb):
+    """A captured step reads lr and the step count from device memory: replays keep counting, and filling the lr
+    tensor changes the size of the next update."""
+    O = rb.optim
+    p = torch.nn.Parameter(torch.ones(1024, device="cuda"))
+    lr = torch.tensor(1e-2, device="cuda")
+    opt = O.ClippedAdamW([p], lr=lr, weight_decay=0.0, max_grad_norm=None)
+    p.grad = torch.ones_like(p)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        opt.step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        opt.step()
+    a = p.detach().clone()
+    g.replay()
+    b = p.detach().clone()
+    lr.fill_(1e-3)
+    g.replay()
+    c = p.detach().clone()
+    torch.cuda.synchronize()
+    assert float(opt.state[p]["step"]) == 3.0                 # one eager step + two replays (capturing runs nothing)
+    d1, d2 = float((a - b).abs().mean()), float((b - c).abs().mean())
+    assert abs(d1 - 1e-2) < 1e-4 and abs(d2 - 1e-3) < 1e-5     # constant gradient: every Adam update is lr
