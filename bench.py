@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--infer-overlap", type=float, default=0.5)
     ap.add_argument("--infer-weight", default="gaussian", choices=["gaussian", "uniform"])
     ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="--impl reference: time budget of the K + W sample steps")
+    ap.add_argument("--opt-packs", action="store_true",
+                    help="ClippedAdamW(manage_packs=True): the update kernel writes next step's operand packs (measured slower)")
     ap.add_argument("--torch-optimizer", action="store_true",
                     help="clip_grad_norm_ + torch.optim.AdamW(fused) instead of the library's ClippedAdamW (A/B)")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"],
@@ -549,7 +551,8 @@ def run_train(args, rb, par, loss_mod, model, dev, rank, world, local, dist):
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, capturable=use_graph, fused=True)
     else:
         # clip_grad_norm_(3) + AdamW (train.py:79-83,227-228) as two multi-tensor passes of the library
-        opt = rb.optim.ClippedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=3.0)
+        opt = rb.optim.ClippedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=3.0,
+                                    manage_packs=args.opt_packs)
     if world > 1:
         par.broadcast_parameters(model)          # replicas identical whatever each rank's RNG state was
     buckets = par.GradientBuckets(model, comm_dtype=torch.bfloat16 if args.grad_comm == "bf16" else None) if world > 1 else None

@@ -222,6 +222,12 @@ typedef struct rb_opt_tensor {
 int rb_grad_sumsq(const rb_opt_tensor* tensors, int count, double* sumsq, void* stream);
 int rb_adamw_clip_step(const rb_opt_tensor* tensors, int count, const float* lr, const float* step, const double* sumsq,
                        float max_norm, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* The same update for ONE conv weight w[Cout][Cin][taps] (Cin % 32 == 0, taps <= 27, 16-byte aligned tensors),
+ * fused with rb_pack_conv_weights of the updated weight: out_f / out_d receive the bf16 operands of the next step, so
+ * the pack kernel does not re-read the parameter.  Bit-identical to rb_adamw_clip_step + rb_pack_conv_weights. */
+int rb_adamw_clip_pack_step(float* w, const float* g, float* m, float* v, void* out_f, void* out_d, int Cout, int Cin,
+                            int taps, const float* lr, const float* step, const double* sumsq, float max_norm,
+                            float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* Layout conversion at module boundaries: NCDHW fp32 <-> NDHWC bf16 (C % 8 == 0). */
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream);

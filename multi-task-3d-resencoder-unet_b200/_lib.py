@@ -66,6 +66,7 @@ SIGNATURES = {
     "rb_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P]),
     "rb_grad_sumsq": (_I, [_P, _I, _P, _P]),
     "rb_adamw_clip_step": (_I, [_P, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
+    "rb_adamw_clip_pack_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
     "rb_norm_act_head_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _F, _I, _P]),
     "rb_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_split_apply": (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _I, _F, _P]),

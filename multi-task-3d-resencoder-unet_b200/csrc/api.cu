@@ -21,7 +21,7 @@
 #include "elementwise.cuh"
 #include "split.cuh"
 #include "blend.cuh"
-#include "optim.cuh"
+#include "optim.cuh"   // after elementwise.cuh: the fused update + pack kernel shares the pack store phase
 
 namespace {
 
@@ -1518,6 +1518,25 @@ int rb_adamw_clip_step(const rb_opt_tensor* tensors, int count, const float* lr,
         if (rc) return rc;
     }
     return RB_OK;
+}
+
+int rb_adamw_clip_pack_step(float* w, const float* g, float* m, float* v, void* out_f, void* out_d, int Cout, int Cin,
+                            int taps, const float* lr, const float* step, const double* sumsq, float max_norm, float beta1,
+                            float beta2, float eps, float weight_decay, void* stream) {
+    if (!w || !g || !m || !v || !lr || !step || (!out_f && !out_d)) return fail(RB_ERR_INVALID, "adamw_clip_pack_step: null pointer");
+    if (Cout <= 0 || Cin <= 0 || Cin % 32 != 0 || taps <= 0 || taps > 27)
+        return fail(RB_ERR_UNSUPPORTED, "adamw_clip_pack_step: need Cin %% 32 == 0 and 1 <= taps <= 27");
+    if (sumsq && !(max_norm > 0.f)) return fail(RB_ERR_INVALID, "adamw_clip_pack_step: max_norm must be positive when clipping");
+    if (!aligned16(w) || !aligned16(g) || !aligned16(m) || !aligned16(v))
+        return fail(RB_ERR_UNSUPPORTED, "adamw_clip_pack_step: 16-byte aligned tensors only");
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(rb::adamw_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); });
+    rb::AdamPackParams p{w, g, m, v, (rb::bf16*)out_f, (rb::bf16*)out_d, Cout, Cin, taps};
+    rb::OptHyper h{lr, step, sumsq, beta1, beta2, eps, weight_decay, max_norm};
+    const size_t smem = (size_t)32 * (32 * taps + 2) * sizeof(rb::bf16);
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+    rb::adamw_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p, h);
+    return check_launch("adamw_pack_kernel");
 }
 
 int rb_ncdhw_to_cl(const float* src, void* dst, int NB, int C, long long S, void* stream) {

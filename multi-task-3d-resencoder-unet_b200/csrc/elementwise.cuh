@@ -1308,6 +1308,44 @@ __global__ void __launch_bounds__(256) pack_conv_weights_kernel(const WPackParam
     }
 }
 
+// Store phase shared by the pack kernels: bf16 tile [32 co][32 ci][T] (pitch 32*T + 2) in shared memory -> both operand
+// layouts, two 64-byte rows per warp instruction.
+__device__ __forceinline__ void wpack_store_tile(const bf16* tileW, bf16* out_f, bf16* out_d, int Cout, int Cin, int T,
+                                                 int co0, int ci0) {
+    const int pitch = 32 * T + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned short* tw = reinterpret_cast<const unsigned short*>(tileW);
+    const int half = lane >> 4, l16 = lane & 15;
+    // fprop pack [t][co][ci]: a warp instruction stores two (t, co) rows of 32 ci (2 x 64 B)
+    if (out_f != nullptr) {
+        for (int j = warp * 2 + half; j < 32 * T; j += 16) {
+            const int t = j >> 5, r = j & 31;
+            const int co = co0 + r;
+            if (co < Cout) {
+                const unsigned a = tw[r * pitch + (2 * l16) * T + t], b = tw[r * pitch + (2 * l16 + 1) * T + t];
+                reinterpret_cast<uint32_t*>(out_f + ((size_t)t * Cout + co) * Cin + ci0)[l16] = a | (b << 16);
+            }
+        }
+    }
+    // dgrad pack [T-1-t][ci][co]: two (t, ci) rows of 32 co per warp instruction
+    if (out_d != nullptr) {
+        const bool pairOk = (Cout & 1) == 0;
+        for (int j = warp * 2 + half; j < 32 * T; j += 16) {
+            const int t = j >> 5, c = j & 31;
+            const int ci = ci0 + c;
+            const int coA = co0 + 2 * l16;
+            bf16* row = out_d + ((size_t)(T - 1 - t) * Cin + ci) * Cout;
+            if (pairOk && coA + 1 < Cout) {
+                const unsigned a = tw[(2 * l16) * pitch + c * T + t], b = tw[(2 * l16 + 1) * pitch + c * T + t];
+                *reinterpret_cast<uint32_t*>(row + coA) = a | (b << 16);
+            } else {
+                if (coA < Cout) reinterpret_cast<unsigned short*>(row)[coA] = tw[(2 * l16) * pitch + c * T + t];
+                if (coA + 1 < Cout) reinterpret_cast<unsigned short*>(row)[coA + 1] = tw[(2 * l16 + 1) * pitch + c * T + t];
+            }
+        }
+    }
+}
+
 // Vectorised variant for Cin % 32 == 0 (every layer but the stem): 16-byte global loads with the whole row batch in
 // flight (the scalar kernel above keeps ~4 x 4 B per thread in flight and ran the 512 x 512 x 27 layers at 0.5 TB/s),
 // 4-byte (bf16x2) shared-memory and global stores, two output rows per warp instruction.
@@ -1350,36 +1388,7 @@ __global__ void __launch_bounds__(256) pack_conv_weights_vec_kernel(const WPackP
         }
     }
     __syncthreads();
-    const unsigned short* tw = reinterpret_cast<const unsigned short*>(tileW);
-    const int half = lane >> 4, l16 = lane & 15;
-    // fprop pack [t][co][ci]: a warp instruction stores two (t, co) rows of 32 ci (2 x 64 B)
-    if (p.out_f != nullptr) {
-        for (int j = warp * 2 + half; j < 32 * T; j += 16) {
-            const int t = j >> 5, r = j & 31;
-            const int co = co0 + r;
-            if (co < p.Cout) {
-                const unsigned a = tw[r * pitch + (2 * l16) * T + t], b = tw[r * pitch + (2 * l16 + 1) * T + t];
-                reinterpret_cast<uint32_t*>(p.out_f + ((size_t)t * p.Cout + co) * p.Cin + ci0)[l16] = a | (b << 16);
-            }
-        }
-    }
-    // dgrad pack [T-1-t][ci][co]: two (t, ci) rows of 32 co per warp instruction
-    if (p.out_d != nullptr) {
-        const bool pairOk = (p.Cout & 1) == 0;
-        for (int j = warp * 2 + half; j < 32 * T; j += 16) {
-            const int t = j >> 5, c = j & 31;
-            const int ci = ci0 + c;
-            const int coA = co0 + 2 * l16;
-            bf16* row = p.out_d + ((size_t)(T - 1 - t) * p.Cin + ci) * p.Cout;
-            if (pairOk && coA + 1 < p.Cout) {
-                const unsigned a = tw[(2 * l16) * pitch + c * T + t], b = tw[(2 * l16 + 1) * pitch + c * T + t];
-                *reinterpret_cast<uint32_t*>(row + coA) = a | (b << 16);
-            } else {
-                if (coA < p.Cout) reinterpret_cast<unsigned short*>(row)[coA] = tw[(2 * l16) * pitch + c * T + t];
-                if (coA + 1 < p.Cout) reinterpret_cast<unsigned short*>(row)[coA + 1] = tw[(2 * l16 + 1) * pitch + c * T + t];
-            }
-        }
-    }
+    wpack_store_tile(tileW, p.out_f, p.out_d, p.Cout, p.Cin, T, co0, ci0);
 }
 
 struct WUnpackParams {

@@ -88,13 +88,35 @@ struct AdamCoef {
     float coef, lr_wd, one_m_b1, b2, one_m_b2, step_size, inv_bc2_sqrt, eps;
 };
 
+__device__ __forceinline__ void adam_coef_init(const OptHyper& h, AdamCoef& cs) {
+    const float lr = *h.lr;
+    const double t = (double)*h.step;
+    const double bc1 = 1.0 - pow((double)h.beta1, t);
+    const double bc2 = 1.0 - pow((double)h.beta2, t);
+    float coef = 1.f;
+    if (h.sumsq != nullptr) {
+        const float total = (float)sqrt(*h.sumsq);
+        coef = fminf(h.max_norm / (total + 1e-6f), 1.f);
+    }
+    cs.coef = coef;
+    cs.lr_wd = lr * h.weight_decay;
+    cs.one_m_b1 = 1.f - h.beta1;
+    cs.b2 = h.beta2;
+    cs.one_m_b2 = 1.f - h.beta2;
+    cs.step_size = (float)((double)lr / bc1);
+    cs.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    cs.eps = h.eps;
+}
+
+// explicit rounding intrinsics: the compiler may not contract or reassociate them, so the two kernels that inline this
+// function (multi-tensor update, update fused with the operand packs) produce the same bits
 __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const AdamCoef& c) {
-    g *= c.coef;
-    p -= c.lr_wd * p;
-    m = m + c.one_m_b1 * (g - m);
-    v = c.b2 * v + c.one_m_b2 * g * g;
-    const float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
-    p -= c.step_size * (m / denom);
+    g = __fmul_rn(g, c.coef);
+    p = __fmaf_rn(-c.lr_wd, p, p);
+    m = __fmaf_rn(c.one_m_b1, __fsub_rn(g, m), m);
+    v = __fmaf_rn(__fmul_rn(c.one_m_b2, g), g, __fmul_rn(c.b2, v));
+    const float denom = __fmaf_rn(__fsqrt_rn(v), c.inv_bc2_sqrt, c.eps);
+    p = __fmaf_rn(-c.step_size, __fdiv_rn(m, denom), p);
 }
 
 __device__ __forceinline__ void adamw_vec(float4& p, const float4& g, float4& m, float4& v, const AdamCoef& c) {
@@ -107,25 +129,7 @@ __device__ __forceinline__ void adamw_vec(float4& p, const float4& g, float4& m,
 // grid = (blocks, tensors); a block strides over its tensor, two float4 per stream in flight per thread
 __global__ void __launch_bounds__(256) adamw_clip_kernel(const __grid_constant__ OptTensorList L, const OptHyper h) {
     __shared__ AdamCoef cs;
-    if (threadIdx.x == 0) {
-        const float lr = *h.lr;
-        const double t = (double)*h.step;
-        const double bc1 = 1.0 - pow((double)h.beta1, t);
-        const double bc2 = 1.0 - pow((double)h.beta2, t);
-        float coef = 1.f;
-        if (h.sumsq != nullptr) {
-            const float total = (float)sqrt(*h.sumsq);
-            coef = fminf(h.max_norm / (total + 1e-6f), 1.f);
-        }
-        cs.coef = coef;
-        cs.lr_wd = lr * h.weight_decay;
-        cs.one_m_b1 = 1.f - h.beta1;
-        cs.b2 = h.beta2;
-        cs.one_m_b2 = 1.f - h.beta2;
-        cs.step_size = (float)((double)lr / bc1);
-        cs.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-        cs.eps = h.eps;
-    }
+    if (threadIdx.x == 0) adam_coef_init(h, cs);
     __syncthreads();
     const AdamCoef c = cs;
     const int t = blockIdx.y;
@@ -167,6 +171,77 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(const __grid_constant__
     } else {
         for (long long j = tid; j < n; j += stride) adamw_elem(p[j], g[j], m[j], v[j], c);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// AdamW update of ONE conv weight fused with the bf16 operand packs of the next step (elementwise.cuh, "Weight
+// (un)packing"): the update already streams the fp32 weight through registers, so the [taps][Cout][Cin] fprop operand
+// and the flipped [taps][Cin][Cout] data-gradient operand are written from there instead of by a second kernel that
+// re-reads the weight (pack_conv_weights_vec_kernel: 0.94 GB read + 0.94 GB written per step on the 128^3 network).
+// One block = a 32 x 32 (co, ci) tile with all taps; Cin % 32 == 0, taps <= 27.  The arithmetic is adamw_elem, so the
+// result is bit-identical to adamw_clip_kernel followed by the pack kernel.
+// MEASURED SLOWER in the whole step (interleaved 30-step runs of bench.py on one B200: 25.60 / 25.81 ms with the fused
+// kernel against 25.39 / 25.33 ms with the multi-tensor update + pack kernel): 32 x 32 tiles give the 512-channel layers
+// 256 blocks on 148 SMs at two blocks per SM, and a block alternates between its streaming phase and its transposing
+// store phase instead of overlapping them.  Opt-in only (ClippedAdamW(manage_packs=True)).
+// ---------------------------------------------------------------------------------------
+struct AdamPackParams {
+    float* w;         // [Cout][Cin][T]
+    const float* g;
+    float* m;
+    float* v;
+    bf16* out_f;      // [T][Cout][Cin] or null
+    bf16* out_d;      // [T][Cin][Cout] (taps flipped) or null
+    int Cout, Cin, T;
+};
+
+__global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamPackParams p, const OptHyper h) {
+    extern __shared__ bf16 tileA[];   // [32 co][32 ci][T] (+2 padding), as in pack_conv_weights_vec_kernel
+    __shared__ AdamCoef cs;
+    if (threadIdx.x == 0) adam_coef_init(h, cs);
+    __syncthreads();
+    const AdamCoef c = cs;
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int T = p.T;
+    const int pitch = 32 * T + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n4 = 8 * T;             // float4 per (co, 32 ci) row
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp + 8 * rr;
+        const int co = co0 + r;
+        if (co >= p.Cout) continue;
+        const size_t row = ((size_t)co * p.Cin + ci0) * T;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tileA + r * pitch);
+#pragma unroll
+        for (int it0 = 0; it0 < 8; it0 += 4) {           // four float4 per stream in flight: 16 x 16 B per thread
+            float4 w4[4], g4[4], m4[4], v4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = lane + 32 * (it0 + k);
+                if (idx < n4) {
+                    w4[k] = ld_f4(p.w + row + 4 * idx);
+                    m4[k] = ld_f4(p.m + row + 4 * idx);
+                    v4[k] = ld_f4(p.v + row + 4 * idx);
+                    g4[k] = ld_f4_stream(p.g + row + 4 * idx);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = lane + 32 * (it0 + k);
+                if (idx < n4) {
+                    adamw_vec(w4[k], g4[k], m4[k], v4[k], c);
+                    *reinterpret_cast<float4*>(p.w + row + 4 * idx) = w4[k];
+                    *reinterpret_cast<float4*>(p.m + row + 4 * idx) = m4[k];
+                    *reinterpret_cast<float4*>(p.v + row + 4 * idx) = v4[k];
+                    dst[2 * idx] = pack_bf16(w4[k].x, w4[k].y);
+                    dst[2 * idx + 1] = pack_bf16(w4[k].z, w4[k].w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    wpack_store_tile(tileA, p.out_f, p.out_d, p.Cout, p.Cin, T, co0, ci0);
 }
 
 }  // namespace rb

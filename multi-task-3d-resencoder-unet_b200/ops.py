@@ -377,12 +377,37 @@ def _step_packs():
     return _STEP_PACKS["packs"]
 
 
+# Optimiser-managed packs (optim.ClippedAdamW(manage_packs=True)): the update kernel of a conv weight writes the bf16
+# operands of the NEXT step itself (rb_adamw_clip_pack_step), into buffers that live as long as the parameter
+# (`weight._rb_opt_packs`), so neither an eager step nor a captured one launches the pack kernel for that weight.  The
+# entry is trusted only while nothing else can have touched the parameter: same storage, same `Tensor._version`, and
+# the optimiser epoch it was written for (any other optimiser step, `invalidate_weight_packs()`, an in-place edit or a
+# `load_state_dict` makes it stale and the pack kernel runs again).  CUDA-graph replays run no Python: whoever modifies
+# parameters between replays behind the optimiser's back (the trainer restoring its snapshot after a capture) calls
+# `ClippedAdamW.refresh_packs()`.
+def opt_packs(weight):
+    ent = getattr(weight, "_rb_opt_packs", None)
+    if ent is None:
+        return None
+    if ent["epoch"] != _PACK_EPOCH[0] or ent["version"] != weight._version or ent["ptr"] != weight.data_ptr():
+        return None
+    return ent
+
+
+def opt_packs_store(weight, f, d, epoch_after_step):
+    weight._rb_opt_packs = {"f": f, "d": d, "epoch": epoch_after_step, "version": weight._version, "ptr": weight.data_ptr()}
+
+
 def pack_conv_fprop(weight):
     """[Cout, Cin, kd, kh, kw] -> [taps][Cout][Cin] bf16."""
     if not weight.is_cuda or weight.dtype != torch.float32:
         co, ci, kd, kh, kw = weight.shape
         return _cached_pack(weight, "f", lambda: weight.detach().permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci)
                             .to(BF16).contiguous())
+    weight._rb_wants_fd = True           # tells the optimiser which parameters are consumed as packed conv operands
+    ent = opt_packs(weight)
+    if ent is not None:
+        return ent["f"]
     if not PACK_CACHE:
         want_d = weight.requires_grad      # (grad mode is off inside autograd.Function.forward: not a usable signal)
         if not want_d:
@@ -396,6 +421,9 @@ def pack_conv_fprop(weight):
 
 def pack_conv_dgrad_full(weight):
     """Stride-1 data-gradient operand: all taps, flipped, [taps][Cin][Cout] bf16."""
+    ent = opt_packs(weight) if weight.is_cuda else None
+    if ent is not None:
+        return ent["d"]
     if not PACK_CACHE:
         hit = _step_packs().pop(id(weight), None)
         if hit is not None and hit[0] is weight:

@@ -34,7 +34,7 @@ class ClippedAdamW(torch.optim.Optimizer):
     returns)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
-                 amsgrad=False, maximize=False):
+                 amsgrad=False, maximize=False, manage_packs=False):
         if amsgrad or maximize:
             raise NotImplementedError("ClippedAdamW: amsgrad / maximize are not implemented on the B200 path")
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
@@ -48,6 +48,11 @@ class ClippedAdamW(torch.optim.Optimizer):
                         foreach=None, capturable=True, differentiable=False, fused=True, decoupled_weight_decay=True)
         super().__init__(params, defaults)
         self.max_grad_norm = None if max_grad_norm is None else float(max_grad_norm)
+        # manage_packs: conv weights that the network consumes as packed bf16 operands (ops.pack_conv_fprop marks them)
+        # are updated by rb_adamw_clip_pack_step, which writes next step's operands too (ops.opt_packs).  Bit-identical
+        # results; measured 0.3 ms per step SLOWER than the multi-tensor update + pack kernel on the 128^3 network
+        # (csrc/optim.cuh), hence off by default
+        self.manage_packs = bool(manage_packs)
         self._sumsq = None
         self._lr_dev = {}
         self._tables = {}
@@ -141,16 +146,72 @@ class ClippedAdamW(torch.optim.Optimizer):
                     flat[k] = e
                     k += 1
             L.check(lib.rb_grad_sumsq(flat, total, self._sumsq.data_ptr(), stream), "rb_grad_sumsq")
+        sumsq_ptr = self._sumsq.data_ptr() if self.max_grad_norm is not None else None
         for (gi, group, ps), arr in zip(active, tables):
             step_t = self._group_step(gi, ps)
             step_t.add_(1.0)
             lr_t = self._lr_tensor(gi, group, device)
             b1, b2 = group["betas"]
-            L.check(lib.rb_adamw_clip_step(arr, len(ps), lr_t.data_ptr(), step_t.data_ptr(),
-                                           self._sumsq.data_ptr() if self.max_grad_norm is not None else None,
-                                           float(self.max_grad_norm or 0.0), float(b1), float(b2), float(group["eps"]),
-                                           float(group["weight_decay"]), stream), "rb_adamw_clip_step")
+            hyper = (lr_t.data_ptr(), step_t.data_ptr(), sumsq_ptr, float(self.max_grad_norm or 0.0), float(b1), float(b2),
+                     float(group["eps"]), float(group["weight_decay"]), stream)
+            if self.manage_packs:
+                rest = (_OptTensor * len(ps))()
+                k = 0
+                for i, p in enumerate(ps):
+                    if self._packable(p):
+                        self._fused_pack_step(lib, p, arr[i], hyper)
+                    else:
+                        rest[k] = arr[i]
+                        k += 1
+                arr, n = rest, k
+            else:
+                n = len(ps)
+            if n:
+                L.check(lib.rb_adamw_clip_step(arr, n, *hyper), "rb_adamw_clip_step")
         return loss
+
+    # ---- optimiser-managed operand packs ------------------------------------------------------------------------
+    @staticmethod
+    def _packable(p):
+        return (getattr(p, "_rb_wants_fd", False) and p.dim() == 5 and p.shape[1] % 32 == 0
+                and p.shape[2] * p.shape[3] * p.shape[4] <= 27 and p.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0)
+
+    @staticmethod
+    def _pack_buffers(p):
+        ent = getattr(p, "_rb_opt_packs", None)
+        co, ci, kd, kh, kw = p.shape
+        T = kd * kh * kw
+        if ent is not None and ent["ptr"] == p.data_ptr() and tuple(ent["f"].shape) == (T, co, ci):
+            return ent["f"], ent["d"]            # same buffers for the life of the parameter (captured graphs read them)
+        f = torch.empty((T, co, ci), dtype=torch.bfloat16, device=p.device)
+        d = torch.empty((T, ci, co), dtype=torch.bfloat16, device=p.device)
+        return f, d
+
+    def _fused_pack_step(self, lib, p, e, hyper):
+        from . import ops
+        f, d = self._pack_buffers(p)
+        co, ci, kd, kh, kw = p.shape
+        L.check(lib.rb_adamw_clip_pack_step(e.p, e.g, e.m, e.v, f.data_ptr(), d.data_ptr(), co, ci, kd * kh * kw, *hyper),
+                "rb_adamw_clip_pack_step")
+        # valid for the epoch the global post-step hook (ops._on_optimizer_step) is about to open
+        ops.opt_packs_store(p, f, d, ops._PACK_EPOCH[0] + 1)
+
+    @torch.no_grad()
+    def refresh_packs(self):
+        """Re-pack every managed weight from its CURRENT value into its persistent buffers (after parameters were
+        modified behind the optimiser's back - copy_, load_state_dict, broadcast - while a captured graph that reads
+        those buffers is still in use)."""
+        from . import ops
+        lib = L.load()
+        for group in self.param_groups:
+            for p in group["params"]:
+                ent = getattr(p, "_rb_opt_packs", None)
+                if ent is None or ent["ptr"] != p.data_ptr():
+                    continue
+                co, ci, kd, kh, kw = p.shape
+                L.check(lib.rb_pack_conv_weights(p.data_ptr(), ent["f"].data_ptr(), ent["d"].data_ptr(), co, ci,
+                                                 kd * kh * kw, L.stream_ptr()), "rb_pack_conv_weights")
+                ops.opt_packs_store(p, ent["f"], ent["d"], ops._PACK_EPOCH[0])
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

@@ -82,7 +82,8 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model: torch.nn.Module, mgr, use_cuda_graph: bool = False, fused_losses: bool = True,
-                 process_group=None, grad_comm_dtype: Optional[torch.dtype] = None, fused_optimizer: bool = True):
+                 process_group=None, grad_comm_dtype: Optional[torch.dtype] = None, fused_optimizer: bool = True,
+                 manage_packs: bool = False):
         self.model = model
         self.group = process_group
         self.mgr = mgr
@@ -118,7 +119,8 @@ class DataParallelTrainer:
                 lr = torch.tensor(lr, dtype=torch.float32, device=dev)   # a tensor lr stays adjustable after capture
             if fused_optimizer and on_gpu:
                 # clip_grad_norm_(3) + AdamW as two multi-tensor passes (optim.ClippedAdamW; same state_dict format)
-                self.optimizer = ClippedAdamW(model.parameters(), lr=lr, weight_decay=wd, max_grad_norm=CLIP_NORM)
+                self.optimizer = ClippedAdamW(model.parameters(), lr=lr, weight_decay=wd, max_grad_norm=CLIP_NORM,
+                                              manage_packs=bool(manage_packs))
             else:
                 self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd, fused=on_gpu,
                                                    capturable=self.use_graph and on_gpu)
@@ -229,6 +231,8 @@ class DataParallelTrainer:
                 for k, v in st.items():
                     if torch.is_tensor(v):
                         v.copy_(old[k]) if k in old else v.zero_()     # zero == freshly initialised AdamW / SGD state
+        if self._clip_in_step:
+            self.optimizer.refresh_packs()     # the captured step reads the optimiser-managed operand packs
 
     # -- epoch bookkeeping ------------------------------------------------------------------------
     def _restore_device_lr(self):

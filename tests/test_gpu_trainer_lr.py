@@ -79,3 +79,39 @@ def test_graph_step_follows_the_schedule_after_resume(rb, tmp_path):
     tr3.load_checkpoint(path)
     g3 = tr3.optimizer.param_groups[0]
     assert torch.is_tensor(g3["lr"]) and g3["lr"].is_cuda and abs(float(g3["lr"]) - 5e-4) < 1e-9
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_with_optimizer_managed_packs(rb, graph):
+    """ClippedAdamW(manage_packs=True) inside the trainer: the captured step reads operand packs that only the
+    optimiser kernel and `refresh_packs()` (after the capture's parameter restore) write.  Six steps must reproduce the
+    loss curve of the pack-kernel path (same kernels otherwise: run-to-run noise of the statistics atomics)."""
+    x, tgt = _batch()
+    curves = {}
+    for managed in (False, True):
+        case = "sheet_normals_16"
+        mgr, _ = case_mgr(case)
+        model = quiet_build(rb.NetworkFromConfig, mgr)
+        model.load_state_dict(state_dict_from_params(model, golden_state(case)))
+        model = model.cuda()
+        tm = SimpleNamespace(tasks=mgr.tasks, optimizer="AdamW", initial_lr=1e-3, weight_decay=1e-4, max_epoch=4)
+        tr = rb.training.DataParallelTrainer(model, tm, use_cuda_graph=graph, manage_packs=managed)
+        assert tr.optimizer.manage_packs == managed
+        cur = []
+        for step in range(6):
+            total, _ = tr.train_step(x, tgt)
+            cur.append(float(total))
+            if step == 2:
+                tr.end_epoch()
+                model.eval()
+                with torch.no_grad():
+                    model(x)                       # an eager forward between replays must not disturb the managed packs
+        curves[managed] = cur
+        if managed:
+            n = sum(1 for p in model.parameters() if getattr(p, "_rb_opt_packs", None) is not None)
+            assert n > 0                           # the fused update really ran for the conv weights
+    dev = max(abs(a - b) for a, b in zip(curves[True], curves[False]))
+    print(f"graph={graph}: managed packs vs pack kernel, max loss deviation {dev:.2e}; {curves[True]}")
+    assert dev < 2e-3 * max(1.0, abs(curves[False][0]))
+    assert curves[True][-1] < curves[True][0]
+    rb._lib.device_error_check()

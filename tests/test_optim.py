@@ -137,3 +137,87 @@ def test_clipped_adamw_under_cuda_graph_follows_a_tensor_lr(rb):
     assert float(opt.state[p]["step"]) == 3.0                 # one eager step + two replays (capturing runs nothing)
     d1, d2 = float((a - b).abs().mean()), float((b - c).abs().mean())
     assert abs(d1 - 1e-2) < 1e-4 and abs(d2 - 1e-3) < 1e-5     # constant gradient: every Adam update is lr
+
+
+@pytest.mark.gpu
+def test_fused_update_writes_next_steps_operand_packs(rb):
+    """rb_adamw_clip_pack_step == rb_adamw_clip_step followed by rb_pack_conv_weights, bit for bit (weights, moments and
+    both bf16 operand layouts), including a Cout that is not a multiple of the 32-row tile and a 1x3x3 kernel."""
+    O, ops = rb.optim, rb.ops
+    for shape in ((64, 32, 3, 3, 3), (40, 64, 3, 3, 3), (32, 32, 1, 3, 3), (16, 96, 1, 1, 1)):
+        torch.manual_seed(sum(shape))
+        w0 = torch.randn(shape, device="cuda") * 0.1
+        a, b = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(w0.clone())
+        ops.pack_conv_fprop(a)                                  # the network consumes `a` as a packed operand
+        assert getattr(a, "_rb_wants_fd", False)
+        fused = O.ClippedAdamW([a], lr=1e-2, weight_decay=1e-2, max_grad_norm=1.0, manage_packs=True)
+        plain = O.ClippedAdamW([b], lr=1e-2, weight_decay=1e-2, max_grad_norm=1.0)
+        for step in range(3):
+            g = torch.randn(shape, device="cuda") * (2.0 if step != 1 else 1e-3)
+            a.grad, b.grad = g.clone(), g.clone()
+            plain.step()
+            fused.step()                                         # last: any optimiser step opens a new pack epoch
+            assert torch.equal(a.detach(), b.detach()), (shape, step)
+            for key in ("exp_avg", "exp_avg_sq"):
+                assert torch.equal(fused.state[a][key], plain.state[b][key]), (shape, step, key)
+            ent = ops.opt_packs(a)
+            assert ent is not None                               # fresh for the epoch the step opened
+            f_ref, d_ref = ops._pack_kernel(b, True, True)
+            assert torch.equal(ent["f"], f_ref) and torch.equal(ent["d"], d_ref), (shape, step)
+            assert ops.pack_conv_fprop(a) is ent["f"] and ops.pack_conv_dgrad_full(a) is ent["d"]
+            if step == 1:                                        # somebody else's optimiser step: stale, pack kernel again
+                other = torch.nn.Parameter(torch.zeros(8, device="cuda"))
+                other.grad = torch.ones_like(other)
+                torch.optim.SGD([other], lr=0.1).step()
+                assert ops.opt_packs(a) is None
+                assert torch.equal(ops.pack_conv_fprop(a), f_ref)
+        # anything that can change the parameter behind the optimiser's back makes the entry stale ...
+        with torch.no_grad():
+            a.mul_(0.5)
+        assert ops.opt_packs(a) is None
+        assert torch.equal(ops.pack_conv_fprop(a), ops._pack_kernel(a, True, False)[0])
+        # ... and refresh_packs() re-packs into the SAME buffers (what a captured graph keeps reading)
+        f_buf = a._rb_opt_packs["f"]
+        fused.refresh_packs()
+        ent = ops.opt_packs(a)
+        assert ent is not None and ent["f"] is f_buf and torch.equal(ent["f"], ops._pack_kernel(a, True, False)[0])
+        ops.invalidate_weight_packs()
+        assert ops.opt_packs(a) is None
+    rb._lib.device_error_check()
+
+
+@pytest.mark.gpu
+def test_training_with_managed_packs_tracks_the_pack_kernel_path(rb):
+    """Ten eager steps of a small network: ClippedAdamW(manage_packs=True) (no pack kernel launches after the first
+    step) against manage_packs=False.  Same kernels otherwise, so the losses agree to the run-to-run noise of the conv
+    statistics atomics (1e-3)."""
+    from helpers import make_mgr, quiet_build
+    losses = {}
+    launches = {}
+    for managed in (False, True):
+        torch.manual_seed(0)
+        mgr = make_mgr((32, 32, 32), {"sheet": {"channels": 1, "activation": "none"}, "normals": {"channels": 3, "activation": "none"}})
+        model = quiet_build(rb.NetworkFromConfig, mgr).cuda().train()
+        opt = rb.optim.ClippedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=3.0, manage_packs=managed)
+        g = torch.Generator().manual_seed(1)
+        x = torch.rand(2, 1, 32, 32, 32, generator=g).cuda()
+        ts = (torch.rand(2, 1, 32, 32, 32, generator=g) > 0.5).float().cuda()
+        tn = torch.nn.functional.normalize(torch.randn(2, 3, 32, 32, 32, generator=g), dim=1).cuda()
+        crit = rb.losses.task_losses(mgr.tasks)
+        cur = []
+        for step in range(10):
+            if step == 9:
+                n0 = rb._lib.launch_count()
+            out = model(x)
+            loss = crit["sheet"](out["sheet"], ts) + crit["normals"](out["normals"], tn)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            cur.append(float(loss))
+        launches[managed] = rb._lib.launch_count() - n0
+        losses[managed] = cur
+    assert launches[True] < launches[False]                      # the pack launches are gone, nothing else appeared
+    dev = max(abs(a - b) for a, b in zip(losses[True], losses[False]))
+    print("managed-pack loss curve deviation", dev, losses[True][-1], losses[False][-1])
+    assert dev < 1e-3 * max(1.0, abs(losses[False][0]))
+    assert losses[True][-1] < losses[True][0]
