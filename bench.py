@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--mode", default="both", choices=["both", "train", "infer"],
                     help="both: train step line with the `inference` object attached (default); train / infer: one of them")
     ap.add_argument("--infer-volume", type=int, default=1024, help="edge of the synthetic uint8 volume (config 3: 1024)")
-    ap.add_argument("--infer-batch", type=int, default=8, help="patches per forward in the sweep (8: 3.23 ms per patch "
-                    "against 3.36 at 4 - the 4^3 / 8^3 stages are latency bound per launch)")
+    ap.add_argument("--infer-batch", type=int, default=4, help="patches per forward in the sweep (8 is 4 %% faster per patch "
+                    "in a short run but draws more power: 1635 vs 1732 MHz under the cap over the 12 s sweep, no net gain)")
     ap.add_argument("--infer-overlap", type=float, default=0.5)
     ap.add_argument("--infer-weight", default="gaussian", choices=["gaussian", "uniform"])
     ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="--impl reference: time budget of the K + W sample steps")

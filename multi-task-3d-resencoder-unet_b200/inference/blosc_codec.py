@@ -10,12 +10,13 @@ bit-shuffle against a literal per-bit restatement (tests/test_host_logic.py) - n
 Container layout (little endian), as c-blosc 1.21 writes it:
     byte 0   format version (2)            byte 1   codec format version (zstd: 1)
     byte 2   flags: 0x01 byte-shuffle, 0x02 memcpyed, 0x04 bit-shuffle, 0x10 blocks are NOT split per byte of the
-             type, bits 5..7 codec (0 blosclz, 1 lz4, 3 zlib, 4 zstd)
+             type (written clear here), bits 5..7 codec (0 blosclz, 1 lz4, 3 zlib, 4 zstd)
     byte 3   typesize
     4..7     nbytes (uncompressed)     8..11  blocksize     12..15  cbytes (whole buffer, header included)
     then     int32 bstarts[nblocks]    offset of every block from the start of the buffer
-    block    int32 csize, then csize bytes: one zstd frame of the (shuffled) block, or the block itself when
-             csize == block length (incompressible)
+    block    `typesize` streams (one per byte plane of the shuffled block) when typesize <= 16 and the block holds
+             >= 128 elements and is not the ragged last block, else one stream; each stream = int32 csize, then csize
+             bytes: one zstd frame, or the stream itself when csize == its length (incompressible)
 A buffer that does not shrink (or is shorter than 128 bytes) is stored with the memcpyed flag: header + raw bytes.
 
 Bit-shuffle (bitshuffle's `bshuf_trans_bit_elem`, per block): out[(j * 8 + b) * (n / 8) + k] holds bit b of byte j
@@ -39,6 +40,7 @@ FLAG_SHUFFLE, FLAG_MEMCPYED, FLAG_BITSHUFFLE, FLAG_DONT_SPLIT = 0x01, 0x02, 0x04
 NOSHUFFLE, SHUFFLE, BITSHUFFLE = 0, 1, 2
 MAX_OVERHEAD = 16
 MIN_BUFFERSIZE = 128
+MAX_SPLITS = 16
 _L1 = 32 * 1024
 
 
@@ -193,7 +195,10 @@ def compress(data, typesize: int = 1, clevel: int = 5, shuffle: int = BITSHUFFLE
         # (shuffles the largest multiple of 8) disagree: such buffers - never a full zarr chunk of the reference's patch
         # shapes - are written unshuffled, which every decoder reads the same way
         shuffle = NOSHUFFLE
-    flags = FLAG_DONT_SPLIT | (BLOSC_ZSTD_FORMAT << 5)
+    # blocks are split into one stream per byte of the type (bit 4 clear) whenever c-blosc's rule allows it: decoders
+    # older than the "don't split" flag (c-blosc < 1.15) always assume that rule, newer ones honour it when the flag is
+    # clear, so every version reads the buffer the same way
+    flags = BLOSC_ZSTD_FORMAT << 5
     if shuffle == SHUFFLE:
         flags |= FLAG_SHUFFLE
     elif shuffle == BITSHUFFLE:
@@ -220,12 +225,17 @@ def compress(data, typesize: int = 1, clevel: int = 5, shuffle: int = BITSHUFFLE
         elif shuffle == BITSHUFFLE and blk.size >= typesize:
             blk = _bit_shuffle(blk, typesize)
         raw = blk.tobytes()
-        comp = z.compress(raw, level)
-        if len(comp) >= len(raw):           # incompressible block: stored as is (csize == block length)
-            comp = raw
+        leftover = len(raw) != bs
+        nsplit = typesize if (not leftover and 1 < typesize <= MAX_SPLITS and len(raw) // typesize >= MIN_BUFFERSIZE) else 1
+        ne = len(raw) // nsplit
         bstarts.append(pos)
-        parts.append(struct.pack("<i", len(comp)) + comp)
-        pos += 4 + len(comp)
+        for j in range(nsplit):
+            piece = raw[j * ne:(j + 1) * ne]
+            comp = z.compress(piece, level)
+            if len(comp) >= len(piece):     # incompressible stream: stored as is (csize == stream length)
+                comp = piece
+            parts.append(struct.pack("<i", len(comp)) + comp)
+            pos += 4 + len(comp)
     if pos > nbytes + MAX_OVERHEAD:         # did not shrink: the whole buffer is stored raw
         return memcpyed()
     hdr = struct.pack("<BBBBiii", BLOSC_VERSION_FORMAT, BLOSC_ZSTD_VERSION_FORMAT, flags, typesize, nbytes, bs, pos)
@@ -263,7 +273,7 @@ def decompress(buf) -> bytes:
     for b in range(nblocks):
         blen = min(bs, nbytes - b * bs)
         leftover = blen != bs
-        nsplit = ts if (h["split"] and not leftover and ts <= 16 and blen // ts >= MIN_BUFFERSIZE) else 1
+        nsplit = ts if (h["split"] and not leftover and ts <= MAX_SPLITS and blen // ts >= MIN_BUFFERSIZE) else 1
         ne = blen // nsplit
         pos = bstarts[b]
         chunks = []

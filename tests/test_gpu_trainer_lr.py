@@ -81,11 +81,26 @@ def test_graph_step_follows_the_schedule_after_resume(rb, tmp_path):
     assert torch.is_tensor(g3["lr"]) and g3["lr"].is_cuda and abs(float(g3["lr"]) - 5e-4) < 1e-9
 
 
+def _managed_packs_match_weights(rb, model):
+    """Every optimiser-managed operand buffer holds exactly the pack of the CURRENT parameter value."""
+    n = 0
+    for name, p in model.named_parameters():
+        ent = getattr(p, "_rb_opt_packs", None)
+        if ent is None or ent["ptr"] != p.data_ptr():
+            continue
+        f, d = rb.ops._pack_kernel(p, True, True)
+        assert torch.equal(ent["f"], f) and torch.equal(ent["d"], d), name
+        n += 1
+    return n
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_trainer_with_optimizer_managed_packs(rb, graph):
-    """ClippedAdamW(manage_packs=True) inside the trainer: the captured step reads operand packs that only the
-    optimiser kernel and `refresh_packs()` (after the capture's parameter restore) write.  Six steps must reproduce the
-    loss curve of the pack-kernel path (same kernels otherwise: run-to-run noise of the statistics atomics)."""
+    """ClippedAdamW(manage_packs=True) inside the trainer: the (captured) step reads operand packs that only the
+    optimiser kernel and `refresh_packs()` (after the capture's parameter restore) write.  The invariant that matters
+    is deterministic: after every step - eager or replayed, with a schedule step and an eager eval forward in between -
+    each managed buffer equals the pack of the current weight, bit for bit.  (Loss curves of two runs of this 16^3
+    network differ by ~1e-2 after a few Adam steps from the statistics atomics alone, so they only get a loose bound.)"""
     x, tgt = _batch()
     curves = {}
     for managed in (False, True):
@@ -101,17 +116,18 @@ def test_trainer_with_optimizer_managed_packs(rb, graph):
         for step in range(6):
             total, _ = tr.train_step(x, tgt)
             cur.append(float(total))
+            torch.cuda.synchronize()
+            n = _managed_packs_match_weights(rb, model)
+            assert (n > 0) == managed, (managed, step, n)        # the fused update really ran for the conv weights
             if step == 2:
                 tr.end_epoch()
                 model.eval()
                 with torch.no_grad():
                     model(x)                       # an eager forward between replays must not disturb the managed packs
+                _managed_packs_match_weights(rb, model)
         curves[managed] = cur
-        if managed:
-            n = sum(1 for p in model.parameters() if getattr(p, "_rb_opt_packs", None) is not None)
-            assert n > 0                           # the fused update really ran for the conv weights
     dev = max(abs(a - b) for a, b in zip(curves[True], curves[False]))
     print(f"graph={graph}: managed packs vs pack kernel, max loss deviation {dev:.2e}; {curves[True]}")
-    assert dev < 2e-3 * max(1.0, abs(curves[False][0]))
+    assert dev < 5e-2
     assert curves[True][-1] < curves[True][0]
     rb._lib.device_error_check()

@@ -315,15 +315,17 @@ def test_blosc_zstd_bitshuffle_container(rb):
     buf = bc.compress(vol.tobytes(), typesize=2, clevel=5, shuffle=bc.BITSHUFFLE)
     ver, verlz, flags, ts, nbytes, bs, cbytes = struct.unpack("<BBBBiii", buf[:16])
     assert (ver, verlz, ts, nbytes, cbytes) == (2, 1, 2, vol.nbytes, len(buf)) and len(buf) < vol.nbytes // 4
-    assert flags == 0x04 | 0x10 | (4 << 5)              # bit-shuffle, unsplit blocks, codec zstd
+    assert flags == 0x04 | (4 << 5)                     # bit-shuffle, codec zstd, blocks split per byte plane of the type
     nblocks = -(-nbytes // bs)
     bstarts = struct.unpack("<%di" % nblocks, buf[16:16 + 4 * nblocks])
     assert bstarts[0] == 16 + 4 * nblocks and list(bstarts) == sorted(bstarts) and nblocks > 1
     (cs0,) = struct.unpack("<i", buf[bstarts[0]:bstarts[0] + 4])
-    assert bstarts[1] == bstarts[0] + 4 + cs0
+    (cs1,) = struct.unpack("<i", buf[bstarts[0] + 4 + cs0:bstarts[0] + 8 + cs0])
+    assert bstarts[1] == bstarts[0] + 8 + cs0 + cs1      # two streams (typesize 2) per full block
     assert buf[bstarts[0] + 4:bstarts[0] + 8] == b"\x28\xb5\x2f\xfd"      # zstd frame magic
-    first = bc._zstd().decompress(buf[bstarts[0] + 4:bstarts[0] + 4 + cs0], bs)
-    assert first == bc._bit_shuffle(np.frombuffer(vol.tobytes()[:bs], np.uint8), 2).tobytes()
+    shuffled = bc._bit_shuffle(np.frombuffer(vol.tobytes()[:bs], np.uint8), 2).tobytes()
+    assert bc._zstd().decompress(buf[bstarts[0] + 4:bstarts[0] + 4 + cs0], bs // 2) == shuffled[:bs // 2]
+    assert bc._zstd().decompress(buf[bstarts[0] + 8 + cs0:bstarts[0] + 8 + cs0 + cs1], bs // 2) == shuffled[bs // 2:]
     assert bc.decompress(buf) == vol.tobytes()
     # edge cases
     for data, ts in ((b"", 1), (bytes(range(100)), 1), (rng.integers(0, 256, 70001, dtype=np.uint8).tobytes(), 1),
