@@ -216,7 +216,15 @@ def test_training_with_managed_packs_tracks_the_pack_kernel_path(rb):
             cur.append(float(loss))
         launches[managed] = rb._lib.launch_count() - n0
         losses[managed] = cur
-    assert launches[True] < launches[False]                      # the pack launches are gone, nothing else appeared
+        n_managed = 0
+        for name, p in model.named_parameters():
+            ent = rb.ops.opt_packs(p)
+            if ent is not None:                                   # fresh after the last step, and exactly pack(weight)
+                f, d = rb.ops._pack_kernel(p, True, True)
+                assert torch.equal(ent["f"], f) and torch.equal(ent["d"], d), name
+                n_managed += 1
+        assert (n_managed > 0) == managed
+    assert launches[True] <= launches[False]                     # one fused update per weight replaces one pack launch
     dev = max(abs(a - b) for a, b in zip(losses[True], losses[False]))
     print("managed-pack loss curve deviation", dev, losses[True][-1], losses[False][-1])
     assert dev < 5e-2            # two runs of one configuration already differ by ~1e-2 (atomics order + Adam's sign-like steps)
