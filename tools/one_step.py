@@ -12,7 +12,7 @@ torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     model = rb.NetworkFromConfig(bench.make_mgr(P, B)).cuda().train()
 crit = rb.losses.task_losses(bench.make_mgr(P, B).tasks)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+opt = rb.optim.ClippedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=3.0)   # clip + AdamW (train.py:227-228)
 x, tgt = bench.synthetic_batch(B, P, "cpu", 0)
 x = x.cuda(); tgt = {k: v.cuda() for k, v in tgt.items()}
 for _ in range(steps):
@@ -20,7 +20,6 @@ for _ in range(steps):
     loss = bench.gpu_losses(out, tgt, crit)
     opt.zero_grad(set_to_none=True)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(list(model.parameters()), 3.0)
     opt.step()
 torch.cuda.synchronize()
 print("loss", float(loss))
