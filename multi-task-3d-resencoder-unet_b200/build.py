@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libresenc_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "conv_tc5.cuh", "conv_tc5t.cuh", "conv_slab.cuh", "loss.cuh", "conv_generic.cuh", "wgrad_tc5.cuh", "wgrad2_tc5.cuh", "elementwise.cuh", "split.cuh", "blend.cuh",
+HEADERS = ["common.cuh", "conv_tc5.cuh", "conv_tc5t.cuh", "conv_slab.cuh", "loss.cuh", "conv_generic.cuh", "wgrad_tc5.cuh", "wgrad2_tc5.cuh", "elementwise.cuh", "split.cuh", "blend.cuh", "optim.cuh",
            os.path.join("..", "..", "include", "resenc_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-cudart", "static"]
