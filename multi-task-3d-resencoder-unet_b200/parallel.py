@@ -127,14 +127,17 @@ class GradientBuckets:
         self._index = {}
         self._slots = {}
         for bi, ps in enumerate(groups):
-            total = sum(p.numel() for p in ps)
-            b = {"params": ps, "flat": torch.zeros(total, dtype=torch.float32, device=dev), "pending": len(ps),
-                 "touched": 0, "work": None, "wire": None}
-            off = 0
+            # every slot starts on a 16-byte boundary (4 fp32): a 1- or 3-element head bias would otherwise leave all
+            # later slots of its bucket misaligned for the 16-byte vector paths of the optimiser kernels
+            offs, off = [], 0
             for p in ps:
-                self._slots[id(p)] = b["flat"][off:off + p.numel()].view_as(p)
+                offs.append(off)
+                off += (p.numel() + 3) & ~3
+            b = {"params": ps, "flat": torch.zeros(off, dtype=torch.float32, device=dev), "pending": len(ps),
+                 "touched": 0, "work": None, "wire": None}
+            for p, o in zip(ps, offs):
+                self._slots[id(p)] = b["flat"][o:o + p.numel()].view_as(p)
                 p.grad = None
-                off += p.numel()
                 self._index[id(p)] = bi
             self.buckets.append(b)
         for p in self.params:

@@ -685,7 +685,12 @@ def test_gradient_buckets_skip_the_never_used_heads_of_the_real_network(rb):
     assert not (bucketed & {id(p) for p in unused})
     assert len(bucketed) + 16 == len(list(model.parameters()))
     assert all(p.grad is None for p in model.parameters())
-    # fp32 on the wire: 4 bytes per bucketed parameter; bf16: 2
-    n = sum(p.numel() for p in model.parameters()) - sum(p.numel() for p in unused)
+    # fp32 on the wire: 4 bytes per bucketed parameter (slots padded to 16-byte boundaries); bf16: 2
+    ids = {id(p) for p in unused}
+    n = sum((p.numel() + 3) & ~3 for p in model.parameters() if id(p) not in ids)
     assert buckets.bytes_per_step == 4 * n
+    assert n - sum(p.numel() for p in model.parameters() if id(p) not in ids) < 64          # a handful of bias slots
     assert par.GradientBuckets(model, comm_dtype=torch.bfloat16).bytes_per_step == 2 * n
+    for b in buckets.buckets:
+        for p in b["params"]:
+            assert (buckets._slots[id(p)].data_ptr() - b["flat"].data_ptr()) % 16 == 0
