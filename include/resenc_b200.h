@@ -203,6 +203,12 @@ int rb_stem_im2col_split(const float* x, void* col, int NB, int Cin, int D, int 
  *   grad[A][B][taps] = dwp[taps][A][B] (rb_wgrad_gather result -> canonical gradient). Either output may be NULL. */
 int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int Cin, int taps, void* stream);
 int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int taps, void* stream);
+/* Data-gradient operand of a strided conv (builders/simple_conv_blocks.py:43-51 with stride 2; autograd's
+ * conv_backward in the reference) for the one-launch pixel-shuffle gather: out[window tap][(parity, ci)][co] bf16,
+ * zero blocks where a (parity, tap) pair has no kernel index.  ntaps / stride: int[3]; kidx: signed char [3][2][4],
+ * kidx[axis][parity][window tap] = kernel index or -1. */
+int rb_pack_conv_dgrad_merged(const float* w, void* out, int Cout, int Cin, int K0, int K1, int K2, const int* ntaps,
+                              const int* stride, const signed char* kidx, void* stream);
 
 /* Optimiser step of the training loop: torch.nn.utils.clip_grad_norm_(model.parameters(), 3) followed by
  * torch.optim.AdamW.step() (train.py:79-83,227-228) as two multi-tensor passes over fp32 tensors.

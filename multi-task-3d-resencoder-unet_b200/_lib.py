@@ -64,6 +64,7 @@ SIGNATURES = {
     "rb_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rb_head_fwd": (_I, [_P, _P, _P, _P, _I, _LL, _I, _I, _I, _P]),
     "rb_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _LL, _I, _I, _P]),
+    "rb_pack_conv_dgrad_merged": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rb_grad_sumsq": (_I, [_P, _I, _P, _P]),
     "rb_adamw_clip_step": (_I, [_P, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
     "rb_adamw_clip_pack_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _F, _F, _F, _P]),

@@ -1454,6 +1454,29 @@ int rb_pack_conv_weights(const float* w, void* out_f, void* out_d, int Cout, int
     return check_launch("pack_conv_weights_kernel");
 }
 
+int rb_pack_conv_dgrad_merged(const float* w, void* out, int Cout, int Cin, int K0, int K1, int K2, const int* ntaps,
+                              const int* stride, const signed char* kidx, void* stream) {
+    if (!w || !out || !ntaps || !stride || !kidx) return fail(RB_ERR_INVALID, "pack_conv_dgrad_merged: null pointer");
+    if (Cout <= 0 || Cin <= 0 || (Cout & 1)) return fail(RB_ERR_UNSUPPORTED, "pack_conv_dgrad_merged: Cout must be even");
+    rb::DMergePackParams p;
+    p.w = w; p.out = (rb::bf16*)out; p.Cout = Cout; p.Cin = Cin; p.K0 = K0; p.K1 = K1; p.K2 = K2;
+    p.nt0 = ntaps[0]; p.nt1 = ntaps[1]; p.nt2 = ntaps[2]; p.s0 = stride[0]; p.s1 = stride[1]; p.s2 = stride[2];
+    const int K[3] = {K0, K1, K2};
+    for (int a = 0; a < 3; ++a) {
+        if (ntaps[a] < 1 || ntaps[a] > 4 || stride[a] < 1 || stride[a] > 2 || K[a] < 1 || K[a] > 3)
+            return fail(RB_ERR_INVALID, "pack_conv_dgrad_merged: window taps 1..4, stride 1..2, kernel 1..3 per axis");
+        for (int r = 0; r < 2; ++r)
+            for (int u = 0; u < 4; ++u) {
+                const signed char k = kidx[(a * 2 + r) * 4 + u];
+                if (k >= K[a]) return fail(RB_ERR_INVALID, "pack_conv_dgrad_merged: kernel index out of range");
+                p.kidx[a][r][u] = k;
+            }
+    }
+    const long long total = (long long)p.nt0 * p.nt1 * p.nt2 * p.s0 * p.s1 * p.s2 * Cin * (Cout / 2);
+    rb::pack_dgrad_merged_kernel<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("pack_dgrad_merged_kernel");
+}
+
 int rb_unpack_wgrad(const float* dwp, float* grad, int A, int B, int T, void* stream) {
     if (!dwp || !grad) return fail(RB_ERR_INVALID, "unpack_wgrad: null pointer");
     if (A <= 0 || B <= 0 || T <= 0 || T > 27) return fail(RB_ERR_INVALID, "unpack_wgrad: need 1 <= taps <= 27");

@@ -1391,6 +1391,46 @@ __global__ void __launch_bounds__(256) pack_conv_weights_vec_kernel(const WPackP
     wpack_store_tile(tileW, p.out_f, p.out_d, p.Cout, p.Cin, T, co0, ci0);
 }
 
+// Data-gradient operand of a STRIDED conv as one pixel-shuffle gather (ops._merged_dgrad_plan): out[window tap
+// (ud, uh, uw)][(rd, rh, rw, ci)][co] = w[co][ci][kd][kh][kw] where the kernel index of an axis follows from the output
+// parity r and the window tap u of that axis (kidx[axis][r][u], -1 = this (parity, tap) pair has no kernel index: a
+// zero block).  One launch per weight instead of the ~17 torch launches (flip, zero fill, one strided slice copy and one
+// cast per parity class) that built the same tensor; reads are 4-byte gathers served by the L2 (the 27 taps of a
+// (co, ci) pair share their sectors), stores are coalesced bf16 pairs along co.
+struct DMergePackParams {
+    const float* w;      // [Cout][Cin][K0][K1][K2]
+    bf16* out;           // [nt0*nt1*nt2][s0*s1*s2*Cin][Cout]
+    int Cout, Cin, K0, K1, K2;
+    int nt0, nt1, nt2, s0, s1, s2;
+    signed char kidx[3][2][4];
+};
+
+__global__ void __launch_bounds__(256) pack_dgrad_merged_kernel(const __grid_constant__ DMergePackParams p) {
+    const int half = p.Cout >> 1;
+    const long long total = (long long)p.nt0 * p.nt1 * p.nt2 * p.s0 * p.s1 * p.s2 * p.Cin * half;
+    const int T = p.K0 * p.K1 * p.K2;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        long long r = o;
+        const int co = (int)(r % half) * 2; r /= half;
+        const int ci = (int)(r % p.Cin); r /= p.Cin;
+        const int rw = (int)(r % p.s2); r /= p.s2;
+        const int rh = (int)(r % p.s1); r /= p.s1;
+        const int rd = (int)(r % p.s0); r /= p.s0;
+        const int uw = (int)(r % p.nt2); r /= p.nt2;
+        const int uh = (int)(r % p.nt1); r /= p.nt1;
+        const int ud = (int)r;
+        const int kd = p.kidx[0][rd][ud], kh = p.kidx[1][rh][uh], kw = p.kidx[2][rw][uw];
+        uint32_t v = 0u;
+        if (kd >= 0 && kh >= 0 && kw >= 0) {
+            const size_t tap = (size_t)(kd * p.K1 + kh) * p.K2 + kw;
+            const float a = __ldg(p.w + ((size_t)co * p.Cin + ci) * T + tap);
+            const float b = __ldg(p.w + ((size_t)(co + 1) * p.Cin + ci) * T + tap);
+            v = pack_bf16(a, b);
+        }
+        reinterpret_cast<uint32_t*>(p.out)[o] = v;
+    }
+}
+
 struct WUnpackParams {
     const float* dwp;  // [T][A][B]
     float* grad;       // [A][B][T]

@@ -499,10 +499,34 @@ def _merged_dgrad_plan(k, stride, pad, in_dims, od):
     return axes
 
 
-def pack_conv_dgrad_merged(weight, axes, stride):
+DMERGE_KERNEL = os.environ.get("RESENC_DMERGE_KERNEL", "1") != "0"
+
+
+def _pack_dgrad_merged_kernel(weight, axes, stride):
+    """rb_pack_conv_dgrad_merged: the tensor `pack_conv_dgrad_merged` describes in ONE launch (the torch-op form below
+    costs a flip, a zero fill and a slice copy + cast per parity class: ~17 launches per strided conv and step)."""
+    import ctypes as C
+    co, ci, k0, k1, k2 = weight.shape
+    nt = [a[0] for a in axes]
+    kidx = (C.c_byte * 24)(*([-1] * 24))
+    for a in range(3):
+        for r, u0, ks in axes[a][2]:
+            for j, k in enumerate(ks):
+                kidx[(a * 2 + r) * 4 + u0 + j] = k
+    out = torch.empty((nt[0] * nt[1] * nt[2], stride[0] * stride[1] * stride[2] * ci, co), dtype=BF16, device=weight.device)
+    w = weight.detach()
+    L.check(L.load().rb_pack_conv_dgrad_merged(w.data_ptr(), out.data_ptr(), co, ci, k0, k1, k2, (C.c_int * 3)(*nt),
+                                                (C.c_int * 3)(*stride), kidx, L.stream_ptr()), "rb_pack_conv_dgrad_merged")
+    return out
+
+
+def pack_conv_dgrad_merged(weight, axes, stride, force_torch=False):
     """[window taps][(rd, rh, rw, ci)][co] bf16 for `_merged_dgrad_plan` (zero blocks included)."""
     def pack():
         co, ci = weight.shape[:2]
+        if (DMERGE_KERNEL and not force_torch and weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
+                and co % 2 == 0 and all(a[0] <= 4 for a in axes) and all(1 <= s <= 2 for s in stride)):
+            return _pack_dgrad_merged_kernel(weight, axes, stride)
         nt = [a[0] for a in axes]
         wp = torch.zeros((nt[0], nt[1], nt[2], stride[0], stride[1], stride[2], ci, co), dtype=BF16, device=weight.device)
         wf = _flipped(weight)
@@ -519,6 +543,9 @@ def pack_conv_dgrad_merged(weight, axes, stride):
                     blk = wf[:, :, sl(kd, K[0]), sl(kh, K[1]), sl(kw, K[2])]   # [co, ci, |kd|, |kh|, |kw|]
                     wp[ud:ud + len(kd), uh:uh + len(kh), uw:uw + len(kw), rd, rh, rw] = blk.permute(2, 3, 4, 1, 0).to(BF16)
         return wp.reshape(nt[0] * nt[1] * nt[2], stride[0] * stride[1] * stride[2] * ci, co)
+    if force_torch:
+        with torch.no_grad():
+            return pack()
     return _cached_pack(weight, "dmerge", pack)
 
 

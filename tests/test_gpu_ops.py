@@ -517,3 +517,30 @@ def test_split_precision_layout_kernels(rb):
     out = P.conv_norm_act(xin, ws, stem=True)
     ref = F.leaky_relu(F.instance_norm(F.conv3d(xin, ws, None, 1, 1)), 0.01)
     assert rel_l2(P.join(out), ref) < 3e-5
+
+
+@pytest.mark.parametrize("case", [
+    # cout, cin, kernel, stride, input dims
+    (64, 32, (3, 3, 3), (2, 2, 2), (16, 16, 16)),
+    (128, 64, (3, 3, 3), (2, 2, 2), (8, 8, 8)),
+    (64, 32, (3, 3, 3), (1, 2, 2), (8, 16, 16)),
+    (32, 32, (1, 3, 3), (1, 2, 2), (8, 16, 16)),
+    (512, 512, (3, 3, 3), (2, 2, 2), (8, 8, 8)),
+])
+def test_merged_dgrad_pack_kernel_equals_the_torch_construction(rb, case):
+    """rb_pack_conv_dgrad_merged (one launch) against the torch-op construction it replaces (flip, zero fill, one
+    strided slice copy + cast per parity class): bit-identical operand, zero blocks included."""
+    ops = rb.ops
+    co, ci, k, s, dims = case
+    torch.manual_seed(co + ci)
+    w = torch.randn(co, ci, *k, device="cuda")
+    pad = tuple((kk - 1) // 2 for kk in k)
+    od = ops._conv_out_dims(dims, k, s)
+    axes = ops._merged_dgrad_plan(k, s, pad, dims, od)
+    assert axes is not None
+    ref = ops.pack_conv_dgrad_merged(w, axes, s, force_torch=True)
+    assert ops.DMERGE_KERNEL
+    new = ops._pack_dgrad_merged_kernel(w, axes, s)
+    assert new.shape == ref.shape and new.dtype == ref.dtype and new.is_contiguous()
+    assert torch.equal(new, ref)
+    assert int((ref == 0).sum()) > 0          # the zero blocks are part of the comparison
