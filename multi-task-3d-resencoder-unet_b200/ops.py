@@ -1126,6 +1126,16 @@ def attach_cancelled_bias(y, bias):
 # ------------------------------------------------------------------------------------------
 # ConvTranspose3d with kernel == stride (non-overlapping "pixel shuffle" upsampling)
 # ------------------------------------------------------------------------------------------
+def _permuted_bf16(weight, perm, shape):
+    """bf16(weight.permute(perm)) laid out contiguously and viewed as `shape`, in ONE strided copy + cast kernel
+    (`permute().reshape().to(bf16)` materialises the fp32 permutation first: two launches per pack, 20 per step for the
+    transposed convs of the two decoders)."""
+    src = weight.detach().permute(*perm)
+    out = torch.empty(src.shape, dtype=BF16, device=weight.device)
+    out.copy_(src)
+    return out.view(shape)
+
+
 class _ConvT3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, stride, impl, x):
@@ -1141,8 +1151,7 @@ class _ConvT3dFn(torch.autograd.Function):
         full = tuple(i * s for i, s in zip(in_dims, stride))
         npar = sd * sh * sw
         y = new_cl(n, co, *full, x.device)
-        wpk = _cached_pack(weight, "t", lambda: weight.detach().permute(2, 3, 4, 1, 0).reshape(1, npar * co, ci)
-                           .to(BF16).contiguous())
+        wpk = _cached_pack(weight, "t", lambda: _permuted_bf16(weight, (2, 3, 4, 1, 0), (1, npar * co, ci)))
         _launch_gather(x, None, wpk, y, None, in_dims=in_dims, taps=(1, 1, 1), off=(0, 0, 0), istr=(1, 1, 1),
                        out_grid=in_dims, nout=npar * co, mode=1, ostr=stride, full=full, ps=stride, psC=co, impl=impl)
         ctx.save_for_backward(weight, x)
@@ -1170,7 +1179,7 @@ class _ConvT3dFn(torch.autograd.Function):
                 gw = unpack_wgrad(dw, ci, co, (sd, sh, sw))
         if ctx.needs_input_grad[3]:
             gx = new_cl(n, ci, *in_dims, x.device)
-            wpk = weight.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(BF16).contiguous()
+            wpk = _permuted_bf16(weight, (2, 3, 4, 0, 1), (npar, ci, co))
             _launch_gather(dy, None, wpk, gx, None, in_dims=full, taps=stride, off=(0, 0, 0), istr=stride,
                            out_grid=in_dims, nout=ci, impl=impl)
         if fork:

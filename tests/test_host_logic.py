@@ -694,3 +694,19 @@ def test_gradient_buckets_skip_the_never_used_heads_of_the_real_network(rb):
     for b in buckets.buckets:
         for p in b["params"]:
             assert (buckets._slots[id(p)].data_ptr() - b["flat"].data_ptr()) % 16 == 0
+
+
+def test_transposed_conv_operand_packs_in_one_copy(rb):
+    """ops._permuted_bf16 (one strided copy + cast) == the permute / reshape / cast / contiguous chain it replaces, for
+    both operand layouts of the transposed conv (decoder.py:110-113)."""
+    ops = rb.ops
+    torch.manual_seed(12)
+    for ci, co, s in ((64, 32, (2, 2, 2)), (16, 8, (1, 2, 2)), (8, 24, (2, 2, 1))):
+        w = torch.randn(ci, co, *s)
+        npar = s[0] * s[1] * s[2]
+        a = ops._permuted_bf16(w, (2, 3, 4, 1, 0), (1, npar * co, ci))
+        b = w.detach().permute(2, 3, 4, 1, 0).reshape(1, npar * co, ci).to(torch.bfloat16).contiguous()
+        assert a.is_contiguous() and a.dtype == torch.bfloat16 and torch.equal(a, b)
+        a = ops._permuted_bf16(w, (2, 3, 4, 0, 1), (npar, ci, co))
+        b = w.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(torch.bfloat16).contiguous()
+        assert a.is_contiguous() and torch.equal(a, b)
