@@ -710,3 +710,28 @@ def test_transposed_conv_operand_packs_in_one_copy(rb):
         a = ops._permuted_bf16(w, (2, 3, 4, 0, 1), (npar, ci, co))
         b = w.detach().permute(2, 3, 4, 0, 1).reshape(npar, ci, co).to(torch.bfloat16).contiguous()
         assert a.is_contiguous() and torch.equal(a, b)
+
+
+def test_blosc_container_roundtrip_property(rb):
+    """Any byte string, element size, shuffle mode, block size and level: decompress(compress(x)) == x, the header
+    describes the buffer, and the buffer never exceeds the input by more than the 16-byte header."""
+    import importlib
+    from hypothesis import given, settings, strategies as st
+    bc = importlib.import_module(rb.inference.__name__ + ".blosc_codec")
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.binary(min_size=0, max_size=5000), st.sampled_from([1, 2, 4, 8]), st.sampled_from([0, 1, 2]),
+           st.sampled_from([0, 64, 256, 1000, 4096]), st.integers(0, 9))
+    def check(data, typesize, shuffle, blocksize, clevel):
+        if blocksize and typesize > 1:
+            blocksize -= blocksize % typesize
+        buf = bc.compress(data, typesize=typesize, clevel=clevel, shuffle=shuffle, blocksize=blocksize or 0)
+        h = bc.header(buf)
+        assert h["nbytes"] == len(data) and h["cbytes"] == len(buf) and h["typesize"] == typesize
+        assert len(buf) <= len(data) + 16
+        assert bc.decompress(buf) == data
+        # repetitive input of a compressible size must actually shrink
+        rep = (data[:7] or b"\x01") * 400
+        assert len(bc.compress(rep, typesize=typesize, clevel=max(clevel, 1), shuffle=shuffle)) < len(rep)
+
+    check()
