@@ -735,3 +735,79 @@ def test_blosc_container_roundtrip_property(rb):
         assert len(bc.compress(rep, typesize=typesize, clevel=max(clevel, 1), shuffle=shuffle)) < len(rep)
 
     check()
+
+
+def test_decoder_routes_the_head_through_its_last_conv_unit(rb, monkeypatch):
+    """Host logic of the inference-tail fusion, without a GPU: `Decoder.forward` hands the task head to the LAST conv
+    unit of its LAST stage only; that unit calls `ops.conv_norm_act_head` when `ops.can_fuse_head` agrees (autograd off)
+    and `ops.conv_norm_act` + `ops.head_conv1x1` otherwise; deep supervision keeps one separate head call per stage."""
+    ops = rb.ops
+    tasks = {"sheet": {"channels": 1, "activation": "sigmoid"}}
+    model = quiet_build(rb.NetworkFromConfig, make_mgr([16, 16, 16], tasks))
+    dec = model.task_decoders["sheet"]
+    calls = []
+
+    def fake_cna(x, weight, stride=1, x_cat=None, res=None, *a, **k):
+        calls.append(("unit", weight.shape[0]))
+        n, d = x.shape[0], x.shape[2:]
+        return torch.zeros(n, weight.shape[0], *d)
+
+    def fake_fused(x, weight, stride, x_cat, res, gamma, beta, eps, act, slope, stem, head):
+        calls.append(("fused", weight.shape[0], head[0].shape[0], head[2]))
+        return torch.zeros(x.shape[0], head[0].shape[0], *x.shape[2:])
+
+    def fake_head(x, weight, bias, activation=None):
+        calls.append(("head", weight.shape[0], activation))
+        return torch.zeros(x.shape[0], weight.shape[0], *x.shape[2:])
+
+    def fake_up(x, weight, stride, impl=None, bias=None):
+        calls.append(("up", weight.shape[1]))
+        return torch.zeros(x.shape[0], weight.shape[1], *[i * s for i, s in zip(x.shape[2:], stride)])
+
+    monkeypatch.setattr(ops, "conv_norm_act", fake_cna)
+    monkeypatch.setattr(ops, "conv_norm_act_head", fake_fused)
+    monkeypatch.setattr(ops, "head_conv1x1", fake_head)
+    monkeypatch.setattr(ops, "conv_transpose3d", fake_up)
+    monkeypatch.setattr(ops, "attach_cancelled_bias", lambda z, b: z)
+    enc = model.shared_encoder
+    chans, strides = enc.output_channels, enc.strides
+    dims, skips = [16, 16, 16], []
+    for c, s in zip(chans, strides):
+        dims = [d // ss for d, ss in zip(dims, s)]
+        skips.append(torch.zeros(1, c, *dims))
+    n_stage = len(dec.stages)
+
+    monkeypatch.setattr(ops, "can_fuse_head", lambda w, head, se=None, drop=None: head is not None)
+    calls.clear()
+    out = dec(skips, activation="sigmoid")
+    assert out.shape == (1, 1, 16, 16, 16)
+    assert [c[0] for c in calls].count("fused") == 1 and calls[-1][0] == "fused" and calls[-1][2:] == (1, "sigmoid")
+    assert not any(c[0] == "head" for c in calls)
+    assert [c[0] for c in calls].count("up") == n_stage
+
+    monkeypatch.setattr(ops, "can_fuse_head", lambda w, head, se=None, drop=None: False)      # training / compile / gate
+    calls.clear()
+    dec(skips, activation=None)
+    assert not any(c[0] == "fused" for c in calls)
+    assert calls[-1] == ("head", 1, None) and [c[0] for c in calls].count("head") == 1
+    assert calls[-2][0] == "unit"
+
+    dec.deep_supervision = True
+    calls.clear()
+    outs = dec(skips, activation="sigmoid")
+    assert len(outs) == n_stage and [c[0] for c in calls].count("head") == n_stage
+    assert not any(c[0] == "fused" for c in calls)
+    heads = [c for c in calls if c[0] == "head"]
+    assert heads[-1][2] == "sigmoid" and all(h[2] is None for h in heads[:-1])       # activation on the full-res head only
+    dec.deep_supervision = False
+
+    # the real predicate: never with autograd on, never for gated / stochastic-depth units, only supported widths
+    monkeypatch.undo()
+    w32, head = torch.zeros(32, 32, 3, 3, 3), (torch.zeros(3, 32, 1, 1, 1), None, None)
+    with torch.no_grad():
+        assert ops.can_fuse_head(w32, head)
+        assert not ops.can_fuse_head(w32, None)
+        assert not ops.can_fuse_head(w32, head, se=(1, 2, 3, 4)) and not ops.can_fuse_head(w32, head, drop=torch.ones(1))
+        assert not ops.can_fuse_head(torch.zeros(24, 32, 3, 3, 3), (torch.zeros(3, 24, 1, 1, 1), None, None))   # C/8 = 3
+        assert not ops.can_fuse_head(torch.zeros(512, 32, 3, 3, 3), (torch.zeros(3, 512, 1, 1, 1), None, None))  # C/8 = 64
+    assert not ops.can_fuse_head(w32, head)          # autograd on
