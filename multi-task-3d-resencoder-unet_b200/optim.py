@@ -14,7 +14,6 @@ graph follows LR schedules that write `param_group["lr"]` as a tensor, and never
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import torch
 
@@ -220,21 +219,3 @@ class ClippedAdamW(torch.optim.Optimizer):
             for p in group["params"]:
                 if p in self.state and len(self.state[p]):
                     self._init_state(p)
-
-
-def reference_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas, eps, weight_decay, max_grad_norm):
-    """The same update spelled with torch ops in float64 (test infrastructure for tests/: clip_grad_norm_ followed by
-    the single-tensor AdamW of torch/optim/adamw.py)."""
-    total = math.sqrt(sum(float((g.double() ** 2).sum()) for g in grads))
-    coef = 1.0 if max_grad_norm is None else min(1.0, max_grad_norm / (total + 1e-6))
-    b1, b2 = betas
-    out = []
-    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
-        p, g, m, v = p.double(), g.double() * coef, m.double(), v.double()
-        p = p * (1 - lr * weight_decay)
-        m = m + (1 - b1) * (g - m)
-        v = b2 * v + (1 - b2) * g * g
-        denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
-        p = p - (lr / (1 - b1 ** step)) * m / denom
-        out.append((p, m, v))
-    return out, total

@@ -2,9 +2,14 @@
 multi-tensor passes of the library.  CPU part: hyper-parameter validation, state_dict interchange with torch.optim.AdamW
 and the float64 restatement used as the checker; GPU part: the kernels against PyTorch's own clip + fused AdamW."""
 import math
+import os
+import sys
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import optim_oracle  # noqa: E402  (checker only)
 
 
 def _mk(shapes, seed, device):
@@ -53,7 +58,7 @@ def test_reference_step_is_clip_then_adamw(rb):
             p.grad = g.clone()
         total_ref = torch.nn.utils.clip_grad_norm_(ps, 3.0)
         ref.step()
-        out, total = O.reference_step(mine_p, gs, m, v, step, 3e-3, (0.9, 0.99), 1e-8, 0.05, 3.0)
+        out, total = optim_oracle.reference_step(mine_p, gs, m, v, step, 3e-3, (0.9, 0.99), 1e-8, 0.05, 3.0)
         mine_p, m, v = [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
         assert abs(total - float(total_ref)) < 1e-9 * total
         for a, b in zip(mine_p, ps):
@@ -97,7 +102,7 @@ def test_clipped_adamw_matches_torch(rb, max_norm):
         ref.step()
         for p, b in zip(ps, before):
             assert torch.equal(p.grad, b)                    # gradients are read, never rescaled in place
-        out, _ = O.reference_step(p64, [g.double() for g in gs], m64, v64, step, 2e-3, (0.9, 0.999), 1e-8, 1e-2, max_norm)
+        out, _ = optim_oracle.reference_step(p64, [g.double() for g in gs], m64, v64, step, 2e-3, (0.9, 0.999), 1e-8, 1e-2, max_norm)
         p64, m64, v64 = [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
         for i, (p, q, e) in enumerate(zip(ps, qs, p64)):
             scale = float(e.abs().max()) + 1e-12
