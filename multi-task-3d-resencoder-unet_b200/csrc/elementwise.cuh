@@ -819,8 +819,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadParams p) {
 //     logits = head( act( y * scale[n,c] + shift[n,c] + res ) )          decoder.py:144-152 (last stage -> seg_layers[-1])
 // The last activation z of a decoder is consumed only by its 1x1x1 head, so writing it (2 B / element) and reading it
 // back (2 B) is pure HBM traffic: this kernel reads the pre-norm tensor once and writes K fp32 logit planes.  z is
-// rounded to bf16 in registers, so the logits match the two-kernel path up to the summation order of the dot product.
-// scale == nullptr: plain head on a stored bf16 activation (rb_head_fwd's coalesced path).
+// rounded to bf16 in registers and the plain head (rb_head_fwd) runs on this same kernel (NORM = 0, the launcher's choice
+// when scale == nullptr), so the logits are bit-identical to the two-kernel path.
 // Thread = (voxel, 8-channel group): a warp instruction reads 512 contiguous bytes; the C/8 lanes of a voxel combine
 // their partial dot products with a butterfly (C/8 a power of two <= 32, host-checked).
 // ---------------------------------------------------------------------------------------
